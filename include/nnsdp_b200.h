@@ -1,0 +1,201 @@
+/*
+ * nnsdp_b200.h -- C ABI of libnnsdp_b200.so
+ *
+ * B200-native (sm_100a) implementation of the Chordal-DeepSDP constraint-construction
+ * hot path of AntonXue/nn-sdp: interval bounds -> ReLU QC blocks -> per-clique LMI
+ * assembly, batched over queries.  This is the drop-in boundary: Julia `ccall`s it
+ * (see INTEGRATION.md), Python `ctypes` loads it in this repository's tests.
+ *
+ * The reference has no FFI for this path; each entry point cites the reference
+ * function(s) it replaces (paths relative to the reference repository root).
+ *
+ * Conventions
+ *  - every function returns int32 status: 0 = OK, < 0 = error; the message is
+ *    available (thread-local) from nnsdp_last_error().  No C++ exception crosses.
+ *  - all matrices are column-major FP64; all index arrays are Int64 and 1-BASED on
+ *    the wire (Julia-native) so clique sets compare bit-exactly with makeCliques.
+ *  - per-query arrays are stored query-major: column q of an (n x Q) array is the
+ *    contiguous vector of query q.  A `*_stride` of 0 in nnsdp_query_inputs shares
+ *    one column between all queries (reach batches, src/NnSdp.jl:73-95).
+ *  - the caller owns every host buffer; the library owns device memory behind the
+ *    opaque handles.  Calls are blocking unless stated otherwise.
+ *  - there is NO CPU fallback: without a CUDA device every compute entry point
+ *    returns NNSDP_ERR_CUDA.
+ */
+#ifndef NNSDP_B200_H
+#define NNSDP_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NNSDP_OK 0
+#define NNSDP_ERR_ARG (-1)    /* bad argument / shape                                  */
+#define NNSDP_ERR_CUDA (-2)   /* CUDA runtime failure, or no device                     */
+#define NNSDP_ERR_NOMEM (-3)  /* host or device allocation failed                       */
+#define NNSDP_ERR_STATE (-4)  /* call sequence error (e.g. emit before prepare)         */
+#define NNSDP_ERR_ASSERT (-5) /* an @assert of the reference would have failed          */
+
+/* Output QC kinds, src/Qc/output.jl:3-31 */
+#define NNSDP_OUT_SAFETY 0    /* QcSafety(S)                                            */
+#define NNSDP_OUT_HPLANE 1    /* QcReachHplane(normal)                                  */
+#define NNSDP_OUT_CIRCLE 2    /* QcReachCircle(yc)                                      */
+#define NNSDP_OUT_ELLIPSOID 3 /* QcReachEllipsoid(invP, yc)                             */
+
+typedef struct nnsdp_ctx nnsdp_ctx;     /* devices + streams                             */
+typedef struct nnsdp_net nnsdp_net;     /* FeedFwdNet uploaded (replicated per device)   */
+typedef struct nnsdp_batch nnsdp_batch; /* device-resident state of a batch of queries   */
+
+/* Sizes derived from (net, beta).  Mirrors: FeedFwdNet.zdims (MyNeuralNetwork.jl:17),
+ * QcActivSector._lambda_dim / vardim (src/Qc/activ_sector.jl:18-19), makeCliques. */
+typedef struct {
+  int64_t K;         /* number of affine layers, length(Ms)                              */
+  int64_t Zdim;      /* sum(zdims) = sum(xdims[1:K]) + 1                                 */
+  int64_t acdim;     /* sum(xdims[2:K]) : stacked hidden activations                     */
+  int64_t xtot;      /* sum(xdims[1:K+1]) : stacked x_intvs length                       */
+  int64_t lamdim;    /* _lambda_dim = sum((acdim-beta):acdim)                            */
+  int64_t secdim;    /* sector vardim = lamdim + 2*acdim                                 */
+  int64_t n_in;      /* xdims[1]                                                         */
+  int64_t n_out;     /* xdims[K+1]                                                       */
+  int64_t sdim;      /* n_in + n_out + 1 : side of the output matrix S                   */
+  int64_t ncliques;  /* p                                                                */
+  int64_t sum_ck;    /* sum_k |C_k|                                                      */
+  int64_t sum_ck_sq; /* sum_k |C_k|^2 : doubles per query of dense block output          */
+  int64_t sum_dk;    /* sum_k (|D_k1| + |D_k2|)                                          */
+  int64_t max_ck;    /* max_k |C_k|                                                      */
+} nnsdp_sizes;
+
+/* One batch of Q numeric-gamma queries.  Pointers are HOST pointers for the one-shot
+ * entry points and for nnsdp_batch_set_inputs.  stride = doubles between consecutive
+ * queries (0 = shared by all queries; otherwise must be >= the vector length).
+ *
+ * Bounds: if ymin == NULL the library computes interval bounds on the device from
+ * (x1min, x1max) with IBP (IntervalsWorstCase, src/Intervals/intervals_easy.jl:2-37)
+ * and derives smin/smax with makeSectorMinMax (src/Qc/activ_sector.jl:63-72); this is
+ * makeQcActivsIntvs (src/Qc/activ.jl:45-67) with method = IntervalsWorstCase.
+ * Otherwise the caller supplies what the two activation QCs hold:
+ *   ymin/ymax : QcActivBounded.acymin/acymax (POST-activation bounds of x_2..x_K)
+ *   smin/smax : QcActivSector.smin/smax.
+ */
+typedef struct {
+  const double* x1min;     int64_t x1min_stride;     /* n_in   QcInputBox.x1min (src/Qc/input.jl:3-8) */
+  const double* x1max;     int64_t x1max_stride;     /* n_in   QcInputBox.x1max                       */
+  const double* ymin;      int64_t ymin_stride;      /* acdim  or NULL                                */
+  const double* ymax;      int64_t ymax_stride;      /* acdim                                          */
+  const double* smin;      int64_t smin_stride;      /* acdim                                          */
+  const double* smax;      int64_t smax_stride;      /* acdim                                          */
+  const double* gamma_in;  int64_t gamma_in_stride;  /* n_in   gamma of makeZin                        */
+  const double* gamma_bnd; int64_t gamma_bnd_stride; /* acdim  gamma of makeZac(QcActivBounded)        */
+  const double* gamma_sec; int64_t gamma_sec_stride; /* secdim gamma of makeZac(QcActivSector):
+                                                        [lambda(acdim); v(pairs i<j<=i+beta, i asc, j asc);
+                                                         eta(acdim); nu(acdim)]  activ_sector.jl:26-54 */
+  int32_t out_kind;        int32_t reserved;
+  const double* out_S;     int64_t out_S_stride;     /* SAFETY: sdim*sdim col-major (symmetric)        */
+  const double* out_vec;   int64_t out_vec_stride;   /* HPLANE: normal(n_out); CIRCLE/ELLIPSOID: yc    */
+  const double* out_invP;  int64_t out_invP_stride;  /* ELLIPSOID: n_out*n_out col-major               */
+  const double* gamma_out; int64_t gamma_out_stride; /* reach kinds: 1 per query                       */
+} nnsdp_query_inputs;
+
+/* ---- error / environment ------------------------------------------------------------ */
+const char* nnsdp_last_error(void);
+int32_t nnsdp_version(void);
+int32_t nnsdp_device_count(int32_t* count);
+
+/* ---- context ------------------------------------------------------------------------
+ * ndev devices (CUDA ordinals in dev_ids; NULL = 0..ndev-1).  One non-blocking stream
+ * per device.  Queries of the one-shot entry points are sharded over the devices in
+ * contiguous ranges with one host thread per device; no collective is used. */
+int32_t nnsdp_ctx_create(int32_t ndev, const int32_t* dev_ids, nnsdp_ctx** ctx);
+int32_t nnsdp_ctx_destroy(nnsdp_ctx* ctx);
+int32_t nnsdp_ctx_num_devices(const nnsdp_ctx* ctx, int32_t* ndev);
+/* Pinned host memory for fast host<->device copies (optional; any host memory works). */
+int32_t nnsdp_host_alloc(uint64_t bytes, void** ptr);
+int32_t nnsdp_host_free(void* ptr);
+
+/* ---- network: FeedFwdNet (src/MyNeuralNetwork/MyNeuralNetwork.jl:12-27) ---------------
+ * xdims has K+1 entries; Ms[k] is the column-major xdims[k+1] x (xdims[k]+1) matrix
+ * [W_k b_k].  ReLU activations.  Weights are copied to every device of ctx. */
+int32_t nnsdp_net_upload(nnsdp_ctx* ctx, int64_t K, const int64_t* xdims, const double* const* Ms,
+                         nnsdp_net** net);
+int32_t nnsdp_net_destroy(nnsdp_net* net);
+
+/* ---- integer work on the host, bit-exact --------------------------------------------- */
+int32_t nnsdp_query_sizes(const nnsdp_net* net, int64_t beta, nnsdp_sizes* sizes);
+/* makeCliques (src/Methods/chordal_cliques.jl:13-59).  Outputs (1-based):
+ *   ck_off[ncliques+1]  offsets (0-based) into ck_idx;  ck_idx[sum_ck] = C_k concatenated
+ *   ck1_len[ncliques]   |C_k1| (= |C_k| for the last clique, which has one part)
+ *   d_off[2*ncliques+1] offsets into d_idx of D_k1, D_k2 (empty D_k2 for k = 1 and k = p)
+ *   d_idx[sum_dk]       local indices into C_k */
+int32_t nnsdp_cliques(const nnsdp_net* net, int64_t beta, int64_t* ck_off, int64_t* ck_idx,
+                      int64_t* ck1_len, int64_t* d_off, int64_t* d_idx);
+
+/* ---- one-shot entry points with HOST buffers ------------------------------------------
+ * intervalsWorstCase (src/Intervals/intervals_easy.jl:2-37), batched over Q boxes.
+ *   x1min,x1max : n_in x Q;  xmin,xmax : xtot x Q (x_intvs stacked, x_1 first);
+ *   acxmin,acxmax : acdim x Q (acx_intvs stacked).  Any output may be NULL. */
+int32_t nnsdp_bounds_ibp(nnsdp_ctx* ctx, const nnsdp_net* net, int64_t Q, const double* x1min,
+                         const double* x1max, double* xmin, double* xmax, double* acxmin,
+                         double* acxmax);
+/* One-step pre-activation IBP from given x_intvs
+ * (src/Intervals/intervals_auto_lirpa.jl:55-62): reads xmin/xmax (xtot x Q), writes
+ * acxmin/acxmax (acdim x Q).  Fails with NNSDP_ERR_ASSERT if some ymin > ymax (:60). */
+int32_t nnsdp_preact_from_x(nnsdp_ctx* ctx, const nnsdp_net* net, int64_t Q, const double* xmin,
+                            const double* xmax, double* acxmin, double* acxmax);
+/* makeSectorMinMax, ReLU branch (src/Qc/activ_sector.jl:63-72). n = acdim * Q entries. */
+int32_t nnsdp_sector_minmax(nnsdp_ctx* ctx, int64_t n, const double* acxmin, const double* acxmax,
+                            double* smin, double* smax);
+/* Z[C_k, C_k] for every clique and query, dense column-major, for numeric gamma:
+ * blocks_out[q * sum_ck_sq + off_k + i + j*|C_k|], off_k = sum_{k'<k} |C_k'|^2.
+ * Z = makeZin + makeZout + makeZac(bounded) + makeZac(sector)
+ * (src/Qc/input.jl:19-42, output.jl:52-106, activ.jl:30-41; summed as in
+ * src/Methods/chordal_sdp.jl:114,145) restricted to the cliques of makeCliques. */
+int32_t nnsdp_assemble_blocks(nnsdp_ctx* ctx, const nnsdp_net* net, int64_t beta, int64_t Q,
+                              const nnsdp_query_inputs* in, double* blocks_out);
+/* The full dense Z (Zdim x Zdim per query), i.e. Zin + Zout + sum(Zacs) of
+ * src/Methods/chordal_sdp.jl:114 / scripts/test_acas.jl:81-85.  For moderate Zdim. */
+int32_t nnsdp_assemble_dense(nnsdp_ctx* ctx, const nnsdp_net* net, int64_t beta, int64_t Q,
+                             const nnsdp_query_inputs* in, double* Z_out);
+
+/* ---- device-resident batch (what bench.py times with inputs already in HBM) -----------
+ * A batch lives on ONE device of the ctx (dev_index into the ctx's device list).
+ * ring_queries = number of per-query output slots kept on the device (>= 1). */
+int32_t nnsdp_batch_create(nnsdp_ctx* ctx, int32_t dev_index, const nnsdp_net* net, int64_t beta,
+                           int64_t Qcap, int64_t ring_queries, int32_t dense_Z, nnsdp_batch** batch);
+int32_t nnsdp_batch_destroy(nnsdp_batch* batch);
+/* Host -> device copy of the inputs of Q <= Qcap queries (async on the batch stream). */
+int32_t nnsdp_batch_set_inputs(nnsdp_batch* batch, int64_t Q, const nnsdp_query_inputs* in);
+/* K1 + K2: IBP from the boxes and sector slopes, all on the device. */
+int32_t nnsdp_batch_bounds(nnsdp_batch* batch);
+/* QC diagonals, band multipliers, affine column (all queries of the batch). */
+int32_t nnsdp_batch_prepare(nnsdp_batch* batch);
+/* Gram contractions + block emission of queries [q0, q0+nq) into ring slots
+ * (q - q0) % ring_queries ... ; nq <= ring_queries.  Asynchronous. */
+int32_t nnsdp_batch_emit(nnsdp_batch* batch, int64_t q0, int64_t nq);
+/* Full pass: bounds (if the batch has no caller-supplied bounds) + prepare + emit of all
+ * Q queries through the ring, chunk by chunk.  If host_out != NULL every chunk is copied
+ * to host_out[q * per_query_doubles] (device -> host inside the call).  Blocking. */
+int32_t nnsdp_batch_run(nnsdp_batch* batch, double* host_out);
+int32_t nnsdp_batch_sync(nnsdp_batch* batch);
+/* Copy results back (any pointer may be NULL). Blocking. */
+int32_t nnsdp_batch_get_bounds(nnsdp_batch* batch, double* xmin, double* xmax, double* acxmin,
+                               double* acxmax, double* smin, double* smax);
+int32_t nnsdp_batch_get_slot(nnsdp_batch* batch, int64_t slot, double* host_out);
+/* Device pointer of the ring (for zero-copy consumers, e.g. torch.from_blob / CuArray). */
+int32_t nnsdp_batch_ring_ptr(nnsdp_batch* batch, uint64_t* dev_ptr, int64_t* slot_doubles);
+/* CUDA-event timing on the batch stream.  which: 0 = start, 1 = stop. */
+int32_t nnsdp_batch_event_record(nnsdp_batch* batch, int32_t which);
+int32_t nnsdp_batch_elapsed_ms(nnsdp_batch* batch, float* ms);
+/* Per-stage device time (ms) accumulated by nnsdp_batch_run since the last reset:
+ * stage 0 bounds, 1 prepare, 2 gram, 3 emit, 4 d2h.  Also counts kernel launches. */
+int32_t nnsdp_batch_stage_ms(nnsdp_batch* batch, int32_t stage, float* ms, int64_t* launches);
+int32_t nnsdp_batch_stage_reset(nnsdp_batch* batch);
+/* Executed Gram work of the last prepare: number of (query, layer) contractions with a
+ * non-empty active set and the sum over them of |active|. */
+int32_t nnsdp_batch_gram_stats(nnsdp_batch* batch, int64_t* n_contractions, int64_t* sum_active);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NNSDP_B200_H */

@@ -1,0 +1,168 @@
+// K1 (interval bound propagation), K2 (sector slopes) and the batched affine-column
+// contraction.  FP64 throughout.
+//
+// Reference semantics:
+//   intervalsWorstCase            src/Intervals/intervals_easy.jl:21-33
+//   one-step pre-activation IBP   src/Intervals/intervals_auto_lirpa.jl:55-62
+//   makeSectorMinMax (ReLU)       src/Qc/activ_sector.jl:63-72
+//
+// The IBP of one layer for Q boxes is a GEMM-shaped contraction
+//   ymin = W+ xmin + W- xmax + b,   ymax = W+ xmax + W- xmin + b
+// with M = n_{k+1}, N = Q, K = n_k; W+ = max(W,0), W- = min(W,0) are formed in registers
+// (the reference re-materialises both matrices on every call).
+#include "internal.h"
+
+namespace nnsdp {
+
+namespace {
+
+constexpr int BM = 64, BN = 64, BK = 16;
+constexpr int GEMM_THREADS = 256;
+
+// MODE 0: IBP layer.  MODE 1: C += A * B (affine column).
+template <int MODE>
+__global__ void __launch_bounds__(GEMM_THREADS)
+gemm_nn_kernel(const double* __restrict__ A, int lda, int M, int Kdim,
+               const double* __restrict__ B0, const double* __restrict__ B1, long long ldb, int N,
+               const double* __restrict__ bias,
+               double* __restrict__ C0, double* __restrict__ C1, long long ldc,       // x_{k+1} / aff
+               double* __restrict__ D0, double* __restrict__ D1, long long ldd,       // acx (may be null)
+               int relu, int write_x, int* __restrict__ flag_bad) {
+  __shared__ double As[BK][BM];
+  __shared__ double Bs0[BK][BN + 1];
+  __shared__ double Bs1[MODE == 0 ? BK : 1][BN + 1];
+
+  const int tid = threadIdx.x;
+  const int tx = tid & 15, ty = tid >> 4;
+  const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
+
+  double acc0[4][4], acc1[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc0[i][j] = 0.0, acc1[i][j] = 0.0;
+
+  for (int k0 = 0; k0 < Kdim; k0 += BK) {
+    // A tile: BK x BM, m contiguous in global
+#pragma unroll
+    for (int i = 0; i < (BK * BM) / GEMM_THREADS; ++i) {
+      const int idx = tid + i * GEMM_THREADS;
+      const int m = idx % BM, k = idx / BM;
+      const int gm = m0 + m, gk = k0 + k;
+      As[k][m] = (gm < M && gk < Kdim) ? A[gm + (long long)gk * lda] : 0.0;
+    }
+    // B tile: BK x BN, k contiguous in global (one query vector per column)
+#pragma unroll
+    for (int i = 0; i < (BK * BN) / GEMM_THREADS; ++i) {
+      const int idx = tid + i * GEMM_THREADS;
+      const int k = idx % BK, n = idx / BK;
+      const int gn = n0 + n, gk = k0 + k;
+      const bool ok = (gn < N && gk < Kdim);
+      Bs0[k][n] = ok ? B0[(long long)gn * ldb + gk] : 0.0;
+      if (MODE == 0) Bs1[k][n] = ok ? B1[(long long)gn * ldb + gk] : 0.0;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < BK; ++k) {
+      double a[4], b0[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) a[i] = As[k][tx * 4 + i];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) b0[j] = Bs0[k][ty * 4 + j];
+      if (MODE == 0) {
+        double b1[4], ap[4], an[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) b1[j] = Bs1[k][ty * 4 + j];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) ap[i] = fmax(a[i], 0.0), an[i] = fmin(a[i], 0.0);
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            acc0[i][j] = fma(ap[i], b0[j], acc0[i][j]);
+            acc0[i][j] = fma(an[i], b1[j], acc0[i][j]);
+            acc1[i][j] = fma(ap[i], b1[j], acc1[i][j]);
+            acc1[i][j] = fma(an[i], b0[j], acc1[i][j]);
+          }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) acc0[i][j] = fma(a[i], b0[j], acc0[i][j]);
+      }
+    }
+    __syncthreads();
+  }
+
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int gn = n0 + ty * 4 + j;
+    if (gn >= N) continue;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int gm = m0 + tx * 4 + i;
+      if (gm >= M) continue;
+      if (MODE == 0) {
+        const double bb = bias[gm];
+        const double ymin = acc0[i][j] + bb, ymax = acc1[i][j] + bb;
+        if (!(ymin <= ymax) && flag_bad) atomicOr(flag_bad, 1);
+        if (D0) {
+          D0[(long long)gn * ldd + gm] = ymin;
+          D1[(long long)gn * ldd + gm] = ymax;
+        }
+        if (write_x) {
+          C0[(long long)gn * ldc + gm] = relu ? fmax(ymin, 0.0) : ymin;
+          C1[(long long)gn * ldc + gm] = relu ? fmax(ymax, 0.0) : ymax;
+        }
+      } else {
+        C0[(long long)gn * ldc + gm] += acc0[i][j];
+      }
+    }
+  }
+}
+
+__global__ void sector_minmax_kernel(long long n, const double* __restrict__ lo,
+                                     const double* __restrict__ hi, double* __restrict__ smin,
+                                     double* __restrict__ smax) {
+  const double eps = 1e-4;  // activ_sector.jl:65
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x) {
+    smin[i] = (lo[i] > eps) ? 1.0 : 0.0;
+    smax[i] = (hi[i] < -eps) ? 0.0 : 1.0;
+  }
+}
+
+}  // namespace
+
+
+int ibp_layer_launch(const double* Mk, int n_out_k, int n_in_k, const double* xin_min,
+                     const double* xin_max, long long x_stride, double* xout_min, double* xout_max,
+                     double* acx_min, double* acx_max, long long acx_stride, int Q, int relu,
+                     int write_x, int* flag_bad, cudaStream_t st) {
+  dim3 grid((n_out_k + BM - 1) / BM, (Q + BN - 1) / BN);
+  gemm_nn_kernel<0><<<grid, GEMM_THREADS, 0, st>>>(
+      Mk, n_out_k, n_out_k, n_in_k, xin_min, xin_max, x_stride, Q, Mk + (long long)n_in_k * n_out_k,
+      xout_min, xout_max, x_stride, acx_min, acx_max, acx_stride, relu, write_x, flag_bad);
+  return 1;
+}
+
+int affine_layer_launch(const double* Wt, int ldT, int n_rows, int n_neurons, const double* u,
+                        long long u_stride, double* aff, long long aff_stride, int Q,
+                        cudaStream_t st) {
+  dim3 grid((n_rows + BM - 1) / BM, (Q + BN - 1) / BN);
+  gemm_nn_kernel<1><<<grid, GEMM_THREADS, 0, st>>>(Wt, ldT, n_rows, n_neurons, u, nullptr, u_stride,
+                                                  Q, nullptr, aff, nullptr, aff_stride, nullptr,
+                                                  nullptr, 0, 0, 0, nullptr);
+  return 1;
+}
+
+int launch_sector_minmax(long long n, const double* acxmin, const double* acxmax, double* smin,
+                         double* smax, cudaStream_t st) {
+  if (n <= 0) return 0;
+  long long blocks = (n + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  sector_minmax_kernel<<<(int)blocks, 256, 0, st>>>(n, acxmin, acxmax, smin, smax);
+  return 1;
+}
+
+}  // namespace nnsdp
