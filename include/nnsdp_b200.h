@@ -92,7 +92,8 @@ typedef struct {
                                                         [lambda(acdim); v(pairs i<j<=i+beta, i asc, j asc);
                                                          eta(acdim); nu(acdim)]  activ_sector.jl:26-54 */
   int32_t out_kind;        int32_t reserved;
-  const double* out_S;     int64_t out_S_stride;     /* SAFETY: sdim*sdim col-major (symmetric)        */
+  const double* out_S;     int64_t out_S_stride;     /* SAFETY: sdim*sdim col-major; like Julia's
+                                                        Symmetric(S) the UPPER triangle is read        */
   const double* out_vec;   int64_t out_vec_stride;   /* HPLANE: normal(n_out); CIRCLE/ELLIPSOID: yc    */
   const double* out_invP;  int64_t out_invP_stride;  /* ELLIPSOID: n_out*n_out col-major               */
   const double* gamma_out; int64_t gamma_out_stride; /* reach kinds: 1 per query                       */
@@ -130,6 +131,10 @@ int32_t nnsdp_query_sizes(const nnsdp_net* net, int64_t beta, nnsdp_sizes* sizes
  *   d_idx[sum_dk]       local indices into C_k */
 int32_t nnsdp_cliques(const nnsdp_net* net, int64_t beta, int64_t* ck_off, int64_t* ck_idx,
                       int64_t* ck1_len, int64_t* d_off, int64_t* d_idx);
+/* The same two functions from xdims alone (K+1 entries): no device, no uploaded network. */
+int32_t nnsdp_sizes_from_xdims(int64_t K, const int64_t* xdims, int64_t beta, nnsdp_sizes* sizes);
+int32_t nnsdp_cliques_from_xdims(int64_t K, const int64_t* xdims, int64_t beta, int64_t* ck_off,
+                                 int64_t* ck_idx, int64_t* ck1_len, int64_t* d_off, int64_t* d_idx);
 
 /* ---- one-shot entry points with HOST buffers ------------------------------------------
  * intervalsWorstCase (src/Intervals/intervals_easy.jl:2-37), batched over Q boxes.
@@ -160,7 +165,9 @@ int32_t nnsdp_assemble_dense(nnsdp_ctx* ctx, const nnsdp_net* net, int64_t beta,
 
 /* ---- device-resident batch (what bench.py times with inputs already in HBM) -----------
  * A batch lives on ONE device of the ctx (dev_index into the ctx's device list).
- * ring_queries = number of per-query output slots kept on the device (>= 1). */
+ * ring_queries = number of per-query output slots kept on the device; 0 = bounds only
+ * (no gamma inputs are read and nothing can be emitted).  dense_Z != 0 makes the output
+ * of every query the whole Zdim x Zdim matrix instead of the clique blocks. */
 int32_t nnsdp_batch_create(nnsdp_ctx* ctx, int32_t dev_index, const nnsdp_net* net, int64_t beta,
                            int64_t Qcap, int64_t ring_queries, int32_t dense_Z, nnsdp_batch** batch);
 int32_t nnsdp_batch_destroy(nnsdp_batch* batch);
@@ -182,6 +189,8 @@ int32_t nnsdp_batch_sync(nnsdp_batch* batch);
 int32_t nnsdp_batch_get_bounds(nnsdp_batch* batch, double* xmin, double* xmax, double* acxmin,
                                double* acxmax, double* smin, double* smax);
 int32_t nnsdp_batch_get_slot(nnsdp_batch* batch, int64_t slot, double* host_out);
+/* The affine column Z[:, a] of every query (Zdim x Q) after nnsdp_batch_prepare. */
+int32_t nnsdp_batch_get_affine(nnsdp_batch* batch, double* aff_out);
 /* Device pointer of the ring (for zero-copy consumers, e.g. torch.from_blob / CuArray). */
 int32_t nnsdp_batch_ring_ptr(nnsdp_batch* batch, uint64_t* dev_ptr, int64_t* slot_doubles);
 /* CUDA-event timing on the batch stream.  which: 0 = start, 1 = stop. */

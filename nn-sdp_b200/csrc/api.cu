@@ -1,0 +1,1090 @@
+// Host runtime behind the C ABI of include/nnsdp_b200.h: contexts (devices + streams), uploaded
+// networks, device-resident batches of queries, and the one-shot entry points that shard queries
+// over the devices of a context (one host thread per device, no collective).
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <memory>
+#include <mutex>
+#include <thread>
+
+#include "internal.h"
+
+namespace nnsdp {
+
+static thread_local std::string g_err;
+
+void set_error(const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  g_err = buf;
+}
+
+int32_t cuda_fail(cudaError_t e, const char* what, const char* file, int line) {
+  set_error("CUDA error %d (%s) in %s at %s:%d", (int)e, cudaGetErrorString(e), what, file, line);
+  return e == cudaErrorMemoryAllocation ? NNSDP_ERR_NOMEM : NNSDP_ERR_CUDA;
+}
+
+}  // namespace nnsdp
+
+using namespace nnsdp;
+
+// -----------------------------------------------------------------------------------------
+// handles
+// -----------------------------------------------------------------------------------------
+struct nnsdp_ctx {
+  std::vector<int> devs;
+  std::vector<cudaStream_t> streams;
+};
+
+namespace {
+
+struct DevBuf {  // growable device allocation bound to one device
+  void* p = nullptr;
+  size_t cap = 0;
+  int32_t ensure(size_t bytes) {
+    if (bytes <= cap && p) return NNSDP_OK;
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+    if (bytes == 0) bytes = 8;
+    NN_CUDA(cudaMalloc(&p, bytes));
+    cap = bytes;
+    return NNSDP_OK;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+  }
+  template <class T>
+  T* as() const {
+    return reinterpret_cast<T*>(p);
+  }
+};
+
+struct NetPerDev {
+  int dev = -1;
+  std::vector<DevBuf> M, Wt;
+  DevBuf n, off, xoff, blk_of, Mptr, Wtptr, ldT, bias;
+  NetDev nd{};
+  void release() {
+    for (auto& x : M) x.release();
+    for (auto& x : Wt) x.release();
+    n.release(); off.release(); xoff.release(); blk_of.release();
+    Mptr.release(); Wtptr.release(); ldT.release(); bias.release();
+  }
+};
+
+int round_up(int64_t v, int64_t m) { return (int)(((v + m - 1) / m) * m); }
+
+}  // namespace
+
+struct nnsdp_net {
+  nnsdp_ctx* ctx = nullptr;
+  Shape sh;
+  std::vector<int> ldT;
+  std::vector<NetPerDev> per;
+  int64_t max_block = 0;  // max_b n[b], b <= K-2 (Gram side)
+};
+
+namespace {
+
+enum Stage { ST_BOUNDS = 0, ST_PREP = 1, ST_GRAM = 2, ST_EMIT = 3, ST_D2H = 4, ST_COUNT = 5 };
+
+struct StageSpan {
+  int stage;
+  cudaEvent_t e0, e1;
+};
+
+}  // namespace
+
+struct nnsdp_batch {
+  nnsdp_ctx* ctx = nullptr;
+  int dev_index = 0, dev = 0;
+  const nnsdp_net* net = nullptr;
+  const NetPerDev* nd = nullptr;
+  int64_t beta = 0, Qcap = 0, ring = 0, Q = 0;
+  bool dense = false;
+  nnsdp_sizes sz{};
+  PlanHost plan;
+  DevBuf d_tiles, d_mats, d_goff, d_ldG;
+  std::vector<long long> goff;
+  std::vector<int> ldG;
+  long long gram_per_query = 0;
+  // inputs
+  DevBuf x1min, x1max, ymin, ymax, smin, smax, gin, gbnd, gsec, outS, outvec, outinvP, gout;
+  // bounds
+  DevBuf xmin, xmax, acxmin, acxmax, smin_c, smax_c;
+  // prepared
+  DevBuf d11, Md, T0, Bt, u, aff, part, act, cnt, Z11, Z1K, U;
+  DevBuf gram, ringbuf, flags;
+  BatchDev bd{};
+  GramDev gd{};
+  PlanDev pd{};
+  bool have_inputs = false, bounds_supplied = false, bounds_done = false, prepared = false;
+  cudaStream_t st = nullptr, st_copy = nullptr;
+  cudaEvent_t ev_start = nullptr, ev_stop = nullptr;
+  cudaEvent_t ev_done[2] = {nullptr, nullptr}, ev_free[2] = {nullptr, nullptr};
+  std::vector<StageSpan> spans;
+  std::vector<cudaEvent_t> ev_pool;
+  float stage_ms[ST_COUNT] = {0, 0, 0, 0, 0};
+  int64_t stage_launches[ST_COUNT] = {0, 0, 0, 0, 0};
+
+  cudaEvent_t get_event() {
+    if (!ev_pool.empty()) {
+      cudaEvent_t e = ev_pool.back();
+      ev_pool.pop_back();
+      return e;
+    }
+    cudaEvent_t e = nullptr;
+    cudaEventCreate(&e);
+    return e;
+  }
+  void span_begin(int stage, cudaStream_t s) {
+    if (spans.size() >= 8192) return;
+    StageSpan sp{stage, get_event(), get_event()};
+    cudaEventRecord(sp.e0, s);
+    spans.push_back(sp);
+  }
+  void span_end(cudaStream_t s, int launches) {
+    if (spans.empty() || spans.size() > 8192) return;
+    cudaEventRecord(spans.back().e1, s);
+    stage_launches[spans.back().stage] += launches;
+  }
+  void resolve_spans() {  // requires the streams to be idle
+    for (auto& sp : spans) {
+      float ms = 0.f;
+      if (cudaEventElapsedTime(&ms, sp.e0, sp.e1) == cudaSuccess) stage_ms[sp.stage] += ms;
+      ev_pool.push_back(sp.e0);
+      ev_pool.push_back(sp.e1);
+    }
+    spans.clear();
+  }
+  std::vector<DevBuf*> all_bufs() {
+    return {&d_tiles, &d_mats, &d_goff, &d_ldG, &x1min, &x1max, &ymin, &ymax, &smin, &smax,
+            &gin, &gbnd, &gsec, &outS, &outvec, &outinvP, &gout, &xmin, &xmax, &acxmin, &acxmax,
+            &smin_c, &smax_c, &d11, &Md, &T0, &Bt, &u, &aff, &part, &act, &cnt, &Z11, &Z1K, &U,
+            &gram, &ringbuf, &flags};
+  }
+};
+
+namespace {
+
+int32_t require_device() {
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n <= 0) {
+    cudaGetLastError();
+    set_error("no CUDA device available (%s); this library has no CPU fallback",
+              e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+    return NNSDP_ERR_CUDA;
+  }
+  return NNSDP_OK;
+}
+
+int32_t upload(DevBuf& buf, const void* src, size_t bytes, cudaStream_t st) {
+  NN_TRY(buf.ensure(bytes));
+  if (bytes) NN_CUDA(cudaMemcpyAsync(buf.p, src, bytes, cudaMemcpyHostToDevice, st));
+  return NNSDP_OK;
+}
+
+// host (len x Q, given stride) -> device; returns the device stride through *dstride
+int32_t upload_cols(DevBuf& buf, const double* src, int64_t stride, int64_t len, int64_t Q,
+                    cudaStream_t st, long long* dstride, const char* name) {
+  NN_CHECK(src != nullptr, NNSDP_ERR_ARG, "query input '%s' is NULL", name);
+  NN_CHECK(stride == 0 || stride >= len, NNSDP_ERR_ARG,
+           "query input '%s': stride %lld < length %lld", name, (long long)stride, (long long)len);
+  if (stride == 0 || Q == 1) {
+    NN_TRY(buf.ensure((size_t)len * 8));
+    if (len) NN_CUDA(cudaMemcpyAsync(buf.p, src, (size_t)len * 8, cudaMemcpyHostToDevice, st));
+    *dstride = (stride == 0) ? 0 : len;
+    return NNSDP_OK;
+  }
+  NN_TRY(buf.ensure((size_t)len * Q * 8));
+  if (len == 0) {
+    *dstride = 0;
+    return NNSDP_OK;
+  }
+  if (stride == len)
+    NN_CUDA(cudaMemcpyAsync(buf.p, src, (size_t)len * Q * 8, cudaMemcpyHostToDevice, st));
+  else
+    NN_CUDA(cudaMemcpy2DAsync(buf.p, (size_t)len * 8, src, (size_t)stride * 8, (size_t)len * 8,
+                              (size_t)Q, cudaMemcpyHostToDevice, st));
+  *dstride = len;
+  return NNSDP_OK;
+}
+
+int32_t check_flags(nnsdp_batch* b, const char* where) {
+  int h[4] = {0, 0, 0, 0};
+  NN_CUDA(cudaMemcpyAsync(h, b->flags.p, sizeof(h), cudaMemcpyDeviceToHost, b->st));
+  NN_CUDA(cudaStreamSynchronize(b->st));
+  if (h[0] | h[1]) {
+    NN_CUDA(cudaMemsetAsync(b->flags.p, 0, sizeof(h), b->st));
+    if (h[0] & 1)
+      NN_CHECK(false, NNSDP_ERR_ASSERT, "%s: acymin <= acymax violated (src/Qc/activ_bounded.jl:8)",
+               where);
+    if (h[0] & 2)
+      NN_CHECK(false, NNSDP_ERR_ASSERT,
+               "%s: 0 <= smin <= smax <= 1 violated (src/Qc/activ_sector.jl:14-16)", where);
+    NN_CHECK(false, NNSDP_ERR_ASSERT,
+             "%s: ykmin <= ykmax violated (src/Intervals/intervals_auto_lirpa.jl:60)", where);
+  }
+  return NNSDP_OK;
+}
+
+}  // namespace
+
+// -----------------------------------------------------------------------------------------
+// C ABI
+// -----------------------------------------------------------------------------------------
+extern "C" {
+
+const char* nnsdp_last_error(void) { return g_err.c_str(); }
+int32_t nnsdp_version(void) { return 100; }
+
+int32_t nnsdp_device_count(int32_t* count) {
+  NN_CHECK(count != nullptr, NNSDP_ERR_ARG, "count is NULL");
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    n = 0;
+  }
+  *count = n;
+  return NNSDP_OK;
+}
+
+int32_t nnsdp_ctx_create(int32_t ndev, const int32_t* dev_ids, nnsdp_ctx** out) {
+  NN_CHECK(out != nullptr, NNSDP_ERR_ARG, "ctx output pointer is NULL");
+  *out = nullptr;
+  NN_CHECK(ndev >= 1, NNSDP_ERR_ARG, "ndev must be >= 1");
+  NN_TRY(require_device());
+  int avail = 0;
+  NN_CUDA(cudaGetDeviceCount(&avail));
+  std::unique_ptr<nnsdp_ctx> ctx(new nnsdp_ctx());
+  for (int i = 0; i < ndev; ++i) {
+    const int d = dev_ids ? dev_ids[i] : i;
+    NN_CHECK(d >= 0 && d < avail, NNSDP_ERR_ARG, "device ordinal %d out of range (have %d)", d, avail);
+    ctx->devs.push_back(d);
+  }
+  for (int d : ctx->devs) {
+    NN_CUDA(cudaSetDevice(d));
+    cudaStream_t s = nullptr;
+    NN_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+    ctx->streams.push_back(s);
+  }
+  *out = ctx.release();
+  return NNSDP_OK;
+}
+
+int32_t nnsdp_ctx_destroy(nnsdp_ctx* ctx) {
+  if (!ctx) return NNSDP_OK;
+  for (size_t i = 0; i < ctx->streams.size(); ++i) {
+    cudaSetDevice(ctx->devs[i]);
+    cudaStreamSynchronize(ctx->streams[i]);
+    cudaStreamDestroy(ctx->streams[i]);
+  }
+  delete ctx;
+  return NNSDP_OK;
+}
+
+int32_t nnsdp_ctx_num_devices(const nnsdp_ctx* ctx, int32_t* ndev) {
+  NN_CHECK(ctx && ndev, NNSDP_ERR_ARG, "NULL argument");
+  *ndev = (int32_t)ctx->devs.size();
+  return NNSDP_OK;
+}
+
+int32_t nnsdp_host_alloc(uint64_t bytes, void** ptr) {
+  NN_CHECK(ptr != nullptr, NNSDP_ERR_ARG, "ptr is NULL");
+  *ptr = nullptr;
+  NN_TRY(require_device());
+  NN_CUDA(cudaHostAlloc(ptr, bytes ? bytes : 8, cudaHostAllocPortable));
+  return NNSDP_OK;
+}
+
+int32_t nnsdp_host_free(void* ptr) {
+  if (ptr) NN_CUDA(cudaFreeHost(ptr));
+  return NNSDP_OK;
+}
+
+// ---- network -----------------------------------------------------------------------------
+static int32_t shape_from_xdims(int64_t K, const int64_t* xdims, Shape* sh) {
+  NN_CHECK(xdims != nullptr, NNSDP_ERR_ARG, "xdims is NULL");
+  // FeedFwdNet: length(xdims) >= 3 (MyNeuralNetwork.jl:18), K = length(Ms) = length(xdims)-1 (:22-23)
+  NN_CHECK(K >= 2, NNSDP_ERR_ASSERT, "FeedFwdNet needs length(xdims) >= 3 (K >= 2)");
+  NN_CHECK(K < 32768, NNSDP_ERR_ARG, "K too large");
+  sh->K = (int)K;
+  sh->n.assign(xdims, xdims + K + 1);
+  for (auto v : sh->n) NN_CHECK(v >= 1 && v < (1 << 24), NNSDP_ERR_ARG, "bad layer width %lld", (long long)v);
+  sh->off.assign(K + 1, 0);
+  for (int b = 1; b <= K; ++b) sh->off[b] = sh->off[b - 1] + sh->n[b - 1];
+  sh->xoff.assign(K + 2, 0);
+  for (int b = 1; b <= K + 1; ++b) sh->xoff[b] = sh->xoff[b - 1] + sh->n[b - 1];
+  sh->Zdim = sh->off[K] + 1;
+  sh->acdim = sh->off[K] - sh->n[0];
+  sh->xtot = sh->xoff[K + 1];
+  NN_CHECK(sh->Zdim < (int64_t(1) << 30), NNSDP_ERR_ARG, "Zdim too large");
+  return NNSDP_OK;
+}
+
+int32_t nnsdp_net_upload(nnsdp_ctx* ctx, int64_t K, const int64_t* xdims, const double* const* Ms,
+                         nnsdp_net** out) {
+  NN_CHECK(out != nullptr, NNSDP_ERR_ARG, "net output pointer is NULL");
+  *out = nullptr;
+  NN_CHECK(ctx != nullptr && Ms != nullptr, NNSDP_ERR_ARG, "NULL argument");
+  std::unique_ptr<nnsdp_net> net(new nnsdp_net());
+  net->ctx = ctx;
+  NN_TRY(shape_from_xdims(K, xdims, &net->sh));
+  const Shape& sh = net->sh;
+  for (int k = 0; k < sh.K; ++k) NN_CHECK(Ms[k] != nullptr, NNSDP_ERR_ARG, "Ms[%d] is NULL", k);
+  net->ldT.resize(sh.K);
+  for (int k = 0; k < sh.K; ++k) net->ldT[k] = round_up(sh.n[k], 128);
+  for (int b = 0; b <= sh.K - 2; ++b) net->max_block = std::max(net->max_block, sh.n[b]);
+
+  std::vector<int> n32(sh.n.begin(), sh.n.end()), off32(sh.off.begin(), sh.off.end()),
+      xoff32(sh.xoff.begin(), sh.xoff.end()), blk((size_t)sh.Zdim);
+  for (int64_t z = 0; z < sh.Zdim; ++z) blk[z] = sh.block_of(z);
+  std::vector<double> bias((size_t)sh.acdim);
+  for (int k = 0; k <= sh.K - 2; ++k)
+    for (int64_t i = 0; i < sh.n[k + 1]; ++i)
+      bias[sh.noff(k + 1) + i] = Ms[k][i + sh.n[k] * sh.n[k + 1]];
+
+  net->per.resize(ctx->devs.size());
+  for (size_t di = 0; di < ctx->devs.size(); ++di) {
+    NetPerDev& pd = net->per[di];
+    pd.dev = ctx->devs[di];
+    cudaStream_t st = ctx->streams[di];
+    NN_CUDA(cudaSetDevice(pd.dev));
+    pd.M.resize(sh.K);
+    pd.Wt.resize(sh.K);
+    std::vector<const double*> mp(sh.K), wp(sh.K);
+    for (int k = 0; k < sh.K; ++k) {
+      const size_t mbytes = (size_t)sh.n[k + 1] * (sh.n[k] + 1) * 8;
+      NN_TRY(upload(pd.M[k], Ms[k], mbytes, st));
+      const size_t wbytes = (size_t)net->ldT[k] * sh.n[k + 1] * 8;
+      NN_TRY(pd.Wt[k].ensure(wbytes));
+      NN_CUDA(cudaMemsetAsync(pd.Wt[k].p, 0, wbytes, st));
+      launch_transpose_w(pd.M[k].as<double>(), (int)sh.n[k + 1], (int)sh.n[k], pd.Wt[k].as<double>(),
+                         net->ldT[k], st);
+      mp[k] = pd.M[k].as<double>();
+      wp[k] = pd.Wt[k].as<double>();
+    }
+    NN_TRY(upload(pd.n, n32.data(), n32.size() * 4, st));
+    NN_TRY(upload(pd.off, off32.data(), off32.size() * 4, st));
+    NN_TRY(upload(pd.xoff, xoff32.data(), xoff32.size() * 4, st));
+    NN_TRY(upload(pd.blk_of, blk.data(), blk.size() * 4, st));
+    NN_TRY(upload(pd.Mptr, mp.data(), mp.size() * sizeof(double*), st));
+    NN_TRY(upload(pd.Wtptr, wp.data(), wp.size() * sizeof(double*), st));
+    NN_TRY(upload(pd.ldT, net->ldT.data(), net->ldT.size() * 4, st));
+    NN_TRY(upload(pd.bias, bias.data(), bias.size() * 8, st));
+    NN_CUDA(cudaStreamSynchronize(st));  // host staging vectors go out of scope below
+    NN_CUDA(cudaGetLastError());
+    NetDev& nd = pd.nd;
+    nd.K = sh.K;
+    nd.n_in = (int)sh.n_in();
+    nd.n_out = (int)sh.n_out();
+    nd.Zdim = (int)sh.Zdim;
+    nd.acdim = (int)sh.acdim;
+    nd.xtot = (int)sh.xtot;
+    nd.n = pd.n.as<int>();
+    nd.off = pd.off.as<int>();
+    nd.xoff = pd.xoff.as<int>();
+    nd.blk_of = pd.blk_of.as<int>();
+    nd.M = pd.Mptr.as<const double*>();
+    nd.Wt = pd.Wtptr.as<const double*>();
+    nd.ldT = pd.ldT.as<int>();
+    nd.bias_all = pd.bias.as<double>();
+  }
+  *out = net.release();
+  return NNSDP_OK;
+}
+
+int32_t nnsdp_net_destroy(nnsdp_net* net) {
+  if (!net) return NNSDP_OK;
+  for (auto& pd : net->per) {
+    cudaSetDevice(pd.dev);
+    pd.release();
+  }
+  delete net;
+  return NNSDP_OK;
+}
+
+// ---- integer work on the host ---------------------------------------------------------------
+int32_t nnsdp_query_sizes(const nnsdp_net* net, int64_t beta, nnsdp_sizes* sizes) {
+  NN_CHECK(net && sizes, NNSDP_ERR_ARG, "NULL argument");
+  return fill_sizes(net->sh, beta, sizes);
+}
+
+int32_t nnsdp_sizes_from_xdims(int64_t K, const int64_t* xdims, int64_t beta, nnsdp_sizes* sizes) {
+  NN_CHECK(sizes != nullptr, NNSDP_ERR_ARG, "NULL argument");
+  Shape sh;
+  NN_TRY(shape_from_xdims(K, xdims, &sh));
+  return fill_sizes(sh, beta, sizes);
+}
+
+static int32_t cliques_out(const Shape& sh, int64_t beta, int64_t* ck_off, int64_t* ck_idx,
+                           int64_t* ck1_len, int64_t* d_off, int64_t* d_idx) {
+  NN_CHECK(beta >= 0, NNSDP_ERR_ASSERT, "0 <= beta violated (activ_sector.jl:12)");
+  CliqueInfoHost ci;
+  NN_TRY(make_cliques_host(sh, beta, &ci));
+  int64_t o = 0, od = 0;
+  for (size_t k = 0; k < ci.ck.size(); ++k) {
+    const CliqueRanges& c = ci.ck[k];
+    if (ck_off) ck_off[k] = o;
+    if (ck1_len) ck1_len[k] = c.hi[0] - c.lo[0] + 1;
+    for (int s = 0; s < c.nseg; ++s)
+      for (int64_t g = c.lo[s]; g <= c.hi[s]; ++g, ++o)
+        if (ck_idx) ck_idx[o] = g + 1;  // 1-based on the wire
+    if (d_off) d_off[2 * k] = od;
+    for (int64_t v : ci.d1[k]) {
+      if (d_idx) d_idx[od] = v;
+      ++od;
+    }
+    if (d_off) d_off[2 * k + 1] = od;
+    for (int64_t v : ci.d2[k]) {
+      if (d_idx) d_idx[od] = v;
+      ++od;
+    }
+  }
+  if (ck_off) ck_off[ci.ck.size()] = o;
+  if (d_off) d_off[2 * ci.ck.size()] = od;
+  return NNSDP_OK;
+}
+
+int32_t nnsdp_cliques(const nnsdp_net* net, int64_t beta, int64_t* ck_off, int64_t* ck_idx,
+                      int64_t* ck1_len, int64_t* d_off, int64_t* d_idx) {
+  NN_CHECK(net != nullptr, NNSDP_ERR_ARG, "net is NULL");
+  return cliques_out(net->sh, beta, ck_off, ck_idx, ck1_len, d_off, d_idx);
+}
+
+int32_t nnsdp_cliques_from_xdims(int64_t K, const int64_t* xdims, int64_t beta, int64_t* ck_off,
+                                 int64_t* ck_idx, int64_t* ck1_len, int64_t* d_off, int64_t* d_idx) {
+  Shape sh;
+  NN_TRY(shape_from_xdims(K, xdims, &sh));
+  return cliques_out(sh, beta, ck_off, ck_idx, ck1_len, d_off, d_idx);
+}
+
+// ---- batch ----------------------------------------------------------------------------------
+int32_t nnsdp_batch_destroy(nnsdp_batch* b) {
+  if (!b) return NNSDP_OK;
+  cudaSetDevice(b->dev);
+  if (b->st) cudaStreamSynchronize(b->st);
+  if (b->st_copy) cudaStreamSynchronize(b->st_copy);
+  b->resolve_spans();
+  for (DevBuf* x : b->all_bufs()) x->release();
+  for (cudaEvent_t e : b->ev_pool) cudaEventDestroy(e);
+  for (cudaEvent_t e : {b->ev_start, b->ev_stop, b->ev_done[0], b->ev_done[1], b->ev_free[0], b->ev_free[1]})
+    if (e) cudaEventDestroy(e);
+  if (b->st) cudaStreamDestroy(b->st);
+  if (b->st_copy) cudaStreamDestroy(b->st_copy);
+  delete b;
+  return NNSDP_OK;
+}
+
+int32_t nnsdp_batch_create(nnsdp_ctx* ctx, int32_t dev_index, const nnsdp_net* net, int64_t beta,
+                           int64_t Qcap, int64_t ring_queries, int32_t dense_Z, nnsdp_batch** out) {
+  NN_CHECK(out != nullptr, NNSDP_ERR_ARG, "batch output pointer is NULL");
+  *out = nullptr;
+  NN_CHECK(ctx && net, NNSDP_ERR_ARG, "NULL argument");
+  NN_CHECK(net->ctx == ctx, NNSDP_ERR_ARG, "net was uploaded through a different ctx");
+  NN_CHECK(dev_index >= 0 && dev_index < (int)ctx->devs.size(), NNSDP_ERR_ARG, "bad dev_index");
+  NN_CHECK(Qcap >= 1 && Qcap < (1 << 30), NNSDP_ERR_ARG, "bad Qcap");
+  NN_CHECK(ring_queries >= 0 && ring_queries <= 65535, NNSDP_ERR_ARG, "ring_queries must be in [0, 65535]");
+  const Shape& sh = net->sh;
+  nnsdp_batch* b = new nnsdp_batch();
+  struct Guard {
+    nnsdp_batch* b;
+    ~Guard() { if (b) nnsdp_batch_destroy(b); }
+  } guard{b};
+  b->ctx = ctx;
+  b->dev_index = dev_index;
+  b->dev = ctx->devs[dev_index];
+  b->net = net;
+  b->nd = &net->per[dev_index];
+  b->beta = beta;
+  b->Qcap = Qcap;
+  b->ring = std::min<int64_t>(ring_queries, Qcap);
+  b->dense = dense_Z != 0;
+  NN_TRY(fill_sizes(sh, beta, &b->sz));
+  NN_CHECK(b->sz.sdim * b->sz.sdim * 8 + b->sz.n_out * 8 <= 40000, NNSDP_ERR_ARG,
+           "n_in + n_out + 1 = %lld too large for the output-QC kernel", (long long)b->sz.sdim);
+  NN_CUDA(cudaSetDevice(b->dev));
+  NN_CUDA(cudaStreamCreateWithFlags(&b->st, cudaStreamNonBlocking));
+  NN_CUDA(cudaStreamCreateWithFlags(&b->st_copy, cudaStreamNonBlocking));
+  NN_CUDA(cudaEventCreate(&b->ev_start));
+  NN_CUDA(cudaEventCreate(&b->ev_stop));
+  for (int i = 0; i < 2; ++i) {
+    NN_CUDA(cudaEventCreateWithFlags(&b->ev_done[i], cudaEventDisableTiming));
+    NN_CUDA(cudaEventCreateWithFlags(&b->ev_free[i], cudaEventDisableTiming));
+  }
+  NN_TRY(b->flags.ensure(16));
+  NN_CUDA(cudaMemsetAsync(b->flags.p, 0, 16, b->st));
+
+  const int64_t Q = Qcap, ac = sh.acdim;
+  // bounds + prepared vectors
+  NN_TRY(b->xmin.ensure((size_t)sh.xtot * Q * 8));
+  NN_TRY(b->xmax.ensure((size_t)sh.xtot * Q * 8));
+  NN_TRY(b->acxmin.ensure((size_t)ac * Q * 8));
+  NN_TRY(b->acxmax.ensure((size_t)ac * Q * 8));
+  NN_TRY(b->smin_c.ensure((size_t)ac * Q * 8));
+  NN_TRY(b->smax_c.ensure((size_t)ac * Q * 8));
+  if (b->ring > 0) {
+    const int npart = (int)((ac + PREP_THREADS - 1) / PREP_THREADS);
+    NN_TRY(b->d11.ensure((size_t)ac * Q * 8));
+    NN_TRY(b->Md.ensure((size_t)ac * Q * 8));
+    NN_TRY(b->T0.ensure((size_t)ac * Q * 8));
+    NN_TRY(b->Bt.ensure((size_t)ac * Q * 8 * std::max<int64_t>(beta, 1)));
+    NN_TRY(b->u.ensure((size_t)ac * Q * 8));
+    NN_TRY(b->aff.ensure((size_t)sh.Zdim * Q * 8));
+    NN_TRY(b->part.ensure((size_t)npart * Q * 8));
+    NN_TRY(b->act.ensure((size_t)ac * Q * 4));
+    NN_TRY(b->cnt.ensure((size_t)sh.K * Q * 4));
+    NN_TRY(b->Z11.ensure((size_t)sh.n_in() * sh.n_in() * Q * 8));
+    NN_TRY(b->Z1K.ensure((size_t)sh.n_in() * sh.n[sh.K - 1] * Q * 8));
+    NN_TRY(b->U.ensure((size_t)sh.n_out() * sh.n[sh.K - 1] * Q * 8));
+    b->bd.npart = npart;
+    // Gram scratch layout (one slot per ring entry)
+    b->goff.assign(sh.K, 0);
+    b->ldG.assign(sh.K, 0);
+    long long go = 0;
+    for (int blk = 0; blk <= sh.K - 2; ++blk) {
+      b->ldG[blk] = round_up(sh.n[blk], 16);
+      b->goff[blk] = go;
+      go += (long long)b->ldG[blk] * sh.n[blk];
+    }
+    b->gram_per_query = go;
+    NN_TRY(upload(b->d_goff, b->goff.data(), b->goff.size() * 8, b->st));
+    NN_TRY(upload(b->d_ldG, b->ldG.data(), b->ldG.size() * 4, b->st));
+    NN_TRY(b->gram.ensure((size_t)go * b->ring * 8));
+    // plan
+    std::vector<CliqueRanges> mats;
+    if (b->dense) {
+      CliqueRanges c;
+      c.nseg = 1;
+      c.lo[0] = 0;
+      c.hi[0] = sh.Zdim - 1;
+      mats.push_back(c);
+    } else {
+      CliqueInfoHost ci;
+      NN_TRY(make_cliques_host(sh, beta, &ci));
+      mats = ci.ck;
+    }
+    const char* noclass = getenv("NNSDP_NO_TILE_CLASSES");  // validation aid: evaluate every term everywhere
+    NN_TRY(build_plan(sh, beta, mats, !(noclass && noclass[0] == '1'), &b->plan));
+    NN_TRY(upload(b->d_tiles, b->plan.tiles.data(), b->plan.tiles.size() * sizeof(TileDev), b->st));
+    NN_TRY(upload(b->d_mats, b->plan.mats.data(), b->plan.mats.size() * sizeof(MatDev), b->st));
+    NN_TRY(b->ringbuf.ensure((size_t)b->plan.per_query_doubles * b->ring * 8));
+    b->pd.tiles = b->d_tiles.as<TileDev>();
+    b->pd.mats = b->d_mats.as<MatDev>();
+    b->pd.ntiles = (int)b->plan.tiles.size();
+    b->pd.tile_rows = b->plan.tile_rows;
+    b->pd.per_query = b->plan.per_query_doubles;
+    b->gd.scratch = b->gram.as<double>();
+    b->gd.per_query = go;
+    b->gd.goff = b->d_goff.as<long long>();
+    b->gd.ldG = b->d_ldG.as<int>();
+  }
+  NN_CUDA(cudaStreamSynchronize(b->st));
+  guard.b = nullptr;
+  *out = b;
+  return NNSDP_OK;
+}
+
+int32_t nnsdp_batch_set_inputs(nnsdp_batch* b, int64_t Q, const nnsdp_query_inputs* in) {
+  NN_CHECK(b && in, NNSDP_ERR_ARG, "NULL argument");
+  NN_CHECK(Q >= 1 && Q <= b->Qcap, NNSDP_ERR_ARG, "Q = %lld outside [1, Qcap = %lld]", (long long)Q,
+           (long long)b->Qcap);
+  NN_CUDA(cudaSetDevice(b->dev));
+  const Shape& sh = b->net->sh;
+  const nnsdp_sizes& sz = b->sz;
+  BatchDev& bd = b->bd;
+  cudaStream_t st = b->st;
+  b->have_inputs = false;
+  b->bounds_done = b->prepared = false;
+  b->Q = Q;
+  bd.Q = (int)Q;
+  bd.beta = (int)b->beta;
+  bd.lamdim = sz.lamdim;
+  bd.sdim = (int)sz.sdim;
+  NN_TRY(upload_cols(b->x1min, in->x1min, in->x1min_stride, sz.n_in, Q, st, &bd.s_x1min, "x1min"));
+  NN_TRY(upload_cols(b->x1max, in->x1max, in->x1max_stride, sz.n_in, Q, st, &bd.s_x1max, "x1max"));
+  bd.x1min = b->x1min.as<double>();
+  bd.x1max = b->x1max.as<double>();
+  b->bounds_supplied = (in->ymin != nullptr);
+  if (b->bounds_supplied) {
+    NN_TRY(upload_cols(b->ymin, in->ymin, in->ymin_stride, sz.acdim, Q, st, &bd.s_ymin, "ymin"));
+    NN_TRY(upload_cols(b->ymax, in->ymax, in->ymax_stride, sz.acdim, Q, st, &bd.s_ymax, "ymax"));
+    NN_TRY(upload_cols(b->smin, in->smin, in->smin_stride, sz.acdim, Q, st, &bd.s_smin, "smin"));
+    NN_TRY(upload_cols(b->smax, in->smax, in->smax_stride, sz.acdim, Q, st, &bd.s_smax, "smax"));
+    bd.ymin = b->ymin.as<double>();
+    bd.ymax = b->ymax.as<double>();
+    bd.smin = b->smin.as<double>();
+    bd.smax = b->smax.as<double>();
+  } else {  // device IBP: post-activation bounds of x_2..x_K live inside the stacked x bounds
+    bd.ymin = b->xmin.as<double>() + sh.n_in();
+    bd.ymax = b->xmax.as<double>() + sh.n_in();
+    bd.s_ymin = bd.s_ymax = sh.xtot;
+    bd.smin = b->smin_c.as<double>();
+    bd.smax = b->smax_c.as<double>();
+    bd.s_smin = bd.s_smax = sh.acdim;
+  }
+  if (b->ring > 0) {
+    NN_TRY(upload_cols(b->gin, in->gamma_in, in->gamma_in_stride, sz.n_in, Q, st, &bd.s_gin, "gamma_in"));
+    NN_TRY(upload_cols(b->gbnd, in->gamma_bnd, in->gamma_bnd_stride, sz.acdim, Q, st, &bd.s_gbnd, "gamma_bnd"));
+    NN_TRY(upload_cols(b->gsec, in->gamma_sec, in->gamma_sec_stride, sz.secdim, Q, st, &bd.s_gsec, "gamma_sec"));
+    bd.gin = b->gin.as<double>();
+    bd.gbnd = b->gbnd.as<double>();
+    bd.gsec = b->gsec.as<double>();
+    bd.out_kind = in->out_kind;
+    bd.outS = bd.outvec = bd.outinvP = bd.gout = nullptr;
+    bd.s_outS = bd.s_outvec = bd.s_outinvP = bd.s_gout = 0;
+    bd.has_s12 = bd.has_s22 = 0;
+    switch (in->out_kind) {
+      case NNSDP_OUT_SAFETY: {
+        NN_TRY(upload_cols(b->outS, in->out_S, in->out_S_stride, sz.sdim * sz.sdim, Q, st, &bd.s_outS, "out_S"));
+        bd.outS = b->outS.as<double>();
+        // does any query carry S12 / S22 ?  (upper triangle is authoritative, Symmetric(S))
+        const int64_t nq = in->out_S_stride == 0 ? 1 : Q, sd = sz.sdim, ni = sz.n_in, no = sz.n_out;
+        for (int64_t q = 0; q < nq && !(bd.has_s12 && bd.has_s22); ++q) {
+          const double* S = in->out_S + q * in->out_S_stride;
+          for (int64_t c = ni; c < ni + no; ++c) {
+            for (int64_t r = 0; r < ni; ++r) bd.has_s12 |= (S[r + c * sd] != 0.0);
+            for (int64_t r = ni; r <= c; ++r) bd.has_s22 |= (S[r + c * sd] != 0.0);
+          }
+        }
+        break;
+      }
+      case NNSDP_OUT_ELLIPSOID:
+        NN_TRY(upload_cols(b->outinvP, in->out_invP, in->out_invP_stride, sz.n_out * sz.n_out, Q, st, &bd.s_outinvP, "out_invP"));
+        bd.outinvP = b->outinvP.as<double>();
+        // fallthrough
+      case NNSDP_OUT_CIRCLE:
+        bd.has_s22 = 1;
+        // fallthrough
+      case NNSDP_OUT_HPLANE:
+        NN_TRY(upload_cols(b->outvec, in->out_vec, in->out_vec_stride, sz.n_out, Q, st, &bd.s_outvec, "out_vec"));
+        NN_TRY(upload_cols(b->gout, in->gamma_out, in->gamma_out_stride, 1, Q, st, &bd.s_gout, "gamma_out"));
+        bd.outvec = b->outvec.as<double>();
+        bd.gout = b->gout.as<double>();
+        break;
+      default:
+        NN_CHECK(false, NNSDP_ERR_ARG, "unrecognized out_kind %d (src/Qc/output.jl:95)", in->out_kind);
+    }
+    bd.d11 = b->d11.as<double>();
+    bd.Md = b->Md.as<double>();
+    bd.T0 = b->T0.as<double>();
+    bd.Bt = b->Bt.as<double>();
+    bd.u = b->u.as<double>();
+    bd.aff = b->aff.as<double>();
+    bd.part = b->part.as<double>();
+    bd.act = b->act.as<int>();
+    bd.cnt = b->cnt.as<int>();
+    bd.Z11 = b->Z11.as<double>();
+    bd.Z1K = b->Z1K.as<double>();
+    bd.U = b->U.as<double>();
+  }
+  NN_CUDA(cudaStreamSynchronize(st));  // caller may reuse its host buffers after return
+  b->have_inputs = true;
+  return NNSDP_OK;
+}
+
+int32_t nnsdp_batch_bounds(nnsdp_batch* b) {
+  NN_CHECK(b != nullptr, NNSDP_ERR_ARG, "batch is NULL");
+  NN_CHECK(b->have_inputs, NNSDP_ERR_STATE, "nnsdp_batch_bounds before nnsdp_batch_set_inputs");
+  NN_CUDA(cudaSetDevice(b->dev));
+  const Shape& sh = b->net->sh;
+  const NetPerDev& nd = *b->nd;
+  const int Q = (int)b->Q;
+  double* xmin = b->xmin.as<double>();
+  double* xmax = b->xmax.as<double>();
+  b->span_begin(ST_BOUNDS, b->st);
+  int launches = 0;
+  launches += launch_place_x1(b->bd.x1min, b->bd.s_x1min, b->bd.x1max, b->bd.s_x1max, xmin, xmax,
+                              sh.xtot, (int)sh.n_in(), Q, b->st);
+  for (int k = 0; k < sh.K; ++k) {
+    const bool last = (k == sh.K - 1);
+    launches += ibp_layer_launch(
+        nd.M[k].as<double>(), (int)sh.n[k + 1], (int)sh.n[k], xmin + sh.xoff[k], xmax + sh.xoff[k],
+        sh.xtot, xmin + sh.xoff[k + 1], xmax + sh.xoff[k + 1],
+        last ? nullptr : b->acxmin.as<double>() + sh.noff(k + 1),
+        last ? nullptr : b->acxmax.as<double>() + sh.noff(k + 1), sh.acdim, Q, last ? 0 : 1, 1,
+        nullptr, b->st);
+  }
+  launches += launch_sector_minmax(sh.acdim * (long long)Q, b->acxmin.as<double>(),
+                                   b->acxmax.as<double>(), b->smin_c.as<double>(),
+                                   b->smax_c.as<double>(), b->st);
+  b->span_end(b->st, launches);
+  NN_CUDA(cudaGetLastError());
+  b->bounds_done = true;
+  return NNSDP_OK;
+}
+
+int32_t nnsdp_batch_prepare(nnsdp_batch* b) {
+  NN_CHECK(b != nullptr, NNSDP_ERR_ARG, "batch is NULL");
+  NN_CHECK(b->have_inputs, NNSDP_ERR_STATE, "nnsdp_batch_prepare before nnsdp_batch_set_inputs");
+  NN_CHECK(b->ring > 0, NNSDP_ERR_STATE, "batch was created without an output ring");
+  NN_CHECK(b->bounds_supplied || b->bounds_done, NNSDP_ERR_STATE,
+           "nnsdp_batch_prepare needs bounds: supply ymin/ymax/smin/smax or call nnsdp_batch_bounds");
+  NN_CUDA(cudaSetDevice(b->dev));
+  const Shape& sh = b->net->sh;
+  const NetPerDev& nd = *b->nd;
+  b->span_begin(ST_PREP, b->st);
+  int launches = launch_prep(nd.nd, b->bd, b->flags.as<int>(), b->st);
+  for (int blk = 0; blk <= sh.K - 2; ++blk)
+    launches += affine_layer_launch(nd.Wt[blk].as<double>(), b->net->ldT[blk], (int)sh.n[blk],
+                                    (int)sh.n[blk + 1], b->bd.u + sh.noff(blk + 1), sh.acdim,
+                                    b->bd.aff + sh.off[blk], sh.Zdim, (int)b->Q, b->st);
+  b->span_end(b->st, launches);
+  NN_CUDA(cudaGetLastError());
+  NN_TRY(check_flags(b, "nnsdp_batch_prepare"));
+  b->prepared = true;
+  return NNSDP_OK;
+}
+
+int32_t nnsdp_batch_emit(nnsdp_batch* b, int64_t q0, int64_t nq) {
+  NN_CHECK(b != nullptr, NNSDP_ERR_ARG, "batch is NULL");
+  NN_CHECK(b->prepared, NNSDP_ERR_STATE, "nnsdp_batch_emit before nnsdp_batch_prepare");
+  NN_CHECK(q0 >= 0 && nq >= 1 && q0 + nq <= b->Q && nq <= b->ring, NNSDP_ERR_ARG,
+           "bad query range [%lld, %lld) for Q = %lld, ring = %lld", (long long)q0,
+           (long long)(q0 + nq), (long long)b->Q, (long long)b->ring);
+  NN_CUDA(cudaSetDevice(b->dev));
+  const NetPerDev& nd = *b->nd;
+  b->span_begin(ST_GRAM, b->st);
+  int l = launch_gram(nd.nd, b->bd, b->gd, (int)b->net->max_block, (int)q0, (int)nq, b->st);
+  b->span_end(b->st, l);
+  b->span_begin(ST_EMIT, b->st);
+  l = launch_emit(nd.nd, b->bd, b->gd, b->pd, (int)q0, (int)nq, b->ringbuf.as<double>(), b->st);
+  b->span_end(b->st, l);
+  NN_CUDA(cudaGetLastError());
+  return NNSDP_OK;
+}
+
+int32_t nnsdp_batch_sync(nnsdp_batch* b) {
+  NN_CHECK(b != nullptr, NNSDP_ERR_ARG, "batch is NULL");
+  NN_CUDA(cudaSetDevice(b->dev));
+  NN_CUDA(cudaStreamSynchronize(b->st));
+  NN_CUDA(cudaStreamSynchronize(b->st_copy));
+  b->resolve_spans();
+  return NNSDP_OK;
+}
+
+int32_t nnsdp_batch_run(nnsdp_batch* b, double* host_out) {
+  NN_CHECK(b != nullptr, NNSDP_ERR_ARG, "batch is NULL");
+  NN_CHECK(b->have_inputs, NNSDP_ERR_STATE, "nnsdp_batch_run before nnsdp_batch_set_inputs");
+  NN_CHECK(b->ring > 0, NNSDP_ERR_STATE, "batch was created without an output ring");
+  NN_CUDA(cudaSetDevice(b->dev));
+  if (!b->bounds_supplied) NN_TRY(nnsdp_batch_bounds(b));
+  NN_TRY(nnsdp_batch_prepare(b));
+  const NetPerDev& nd = *b->nd;
+  const int64_t per = b->plan.per_query_doubles;
+  // the ring is used as two halves so the device->host copy of one half overlaps the
+  // emission of the other
+  const int nhalf = (host_out && b->ring >= 2) ? 2 : 1;
+  const int64_t chunk = (nhalf == 2) ? b->ring / 2 : b->ring;
+  bool used[2] = {false, false};
+  int h = 0;
+  for (int64_t q0 = 0; q0 < b->Q; q0 += chunk, h = (h + 1) % nhalf) {
+    const int64_t nq = std::min(chunk, b->Q - q0);
+    double* dst = b->ringbuf.as<double>() + (int64_t)h * chunk * per;
+    GramDev gd = b->gd;
+    gd.scratch += (int64_t)h * chunk * gd.per_query;
+    if (host_out && used[h]) NN_CUDA(cudaStreamWaitEvent(b->st, b->ev_free[h], 0));
+    b->span_begin(ST_GRAM, b->st);
+    int l = launch_gram(nd.nd, b->bd, gd, (int)b->net->max_block, (int)q0, (int)nq, b->st);
+    b->span_end(b->st, l);
+    b->span_begin(ST_EMIT, b->st);
+    l = launch_emit(nd.nd, b->bd, gd, b->pd, (int)q0, (int)nq, dst, b->st);
+    b->span_end(b->st, l);
+    if (host_out) {
+      NN_CUDA(cudaEventRecord(b->ev_done[h], b->st));
+      NN_CUDA(cudaStreamWaitEvent(b->st_copy, b->ev_done[h], 0));
+      b->span_begin(ST_D2H, b->st_copy);
+      NN_CUDA(cudaMemcpyAsync(host_out + q0 * per, dst, (size_t)nq * per * 8, cudaMemcpyDeviceToHost,
+                              b->st_copy));
+      b->span_end(b->st_copy, 0);
+      NN_CUDA(cudaEventRecord(b->ev_free[h], b->st_copy));
+      used[h] = true;
+    }
+  }
+  NN_CUDA(cudaGetLastError());
+  NN_CUDA(cudaStreamSynchronize(b->st));
+  NN_CUDA(cudaStreamSynchronize(b->st_copy));
+  b->resolve_spans();
+  return NNSDP_OK;
+}
+
+int32_t nnsdp_batch_get_bounds(nnsdp_batch* b, double* xmin, double* xmax, double* acxmin,
+                               double* acxmax, double* smin, double* smax) {
+  NN_CHECK(b != nullptr, NNSDP_ERR_ARG, "batch is NULL");
+  NN_CHECK(b->bounds_done, NNSDP_ERR_STATE, "bounds have not been computed on the device");
+  NN_CUDA(cudaSetDevice(b->dev));
+  const Shape& sh = b->net->sh;
+  const size_t Q = (size_t)b->Q;
+  auto get = [&](double* dst, const DevBuf& src, size_t len) -> int32_t {
+    if (dst) NN_CUDA(cudaMemcpyAsync(dst, src.p, len * Q * 8, cudaMemcpyDeviceToHost, b->st));
+    return NNSDP_OK;
+  };
+  NN_TRY(get(xmin, b->xmin, sh.xtot));
+  NN_TRY(get(xmax, b->xmax, sh.xtot));
+  NN_TRY(get(acxmin, b->acxmin, sh.acdim));
+  NN_TRY(get(acxmax, b->acxmax, sh.acdim));
+  NN_TRY(get(smin, b->smin_c, sh.acdim));
+  NN_TRY(get(smax, b->smax_c, sh.acdim));
+  NN_CUDA(cudaStreamSynchronize(b->st));
+  return NNSDP_OK;
+}
+
+int32_t nnsdp_batch_get_slot(nnsdp_batch* b, int64_t slot, double* host_out) {
+  NN_CHECK(b && host_out, NNSDP_ERR_ARG, "NULL argument");
+  NN_CHECK(slot >= 0 && slot < b->ring, NNSDP_ERR_ARG, "slot out of range");
+  NN_CUDA(cudaSetDevice(b->dev));
+  const int64_t per = b->plan.per_query_doubles;
+  NN_CUDA(cudaMemcpyAsync(host_out, b->ringbuf.as<double>() + slot * per, (size_t)per * 8,
+                          cudaMemcpyDeviceToHost, b->st));
+  NN_CUDA(cudaStreamSynchronize(b->st));
+  return NNSDP_OK;
+}
+
+int32_t nnsdp_batch_get_affine(nnsdp_batch* b, double* aff_out) {
+  NN_CHECK(b && aff_out, NNSDP_ERR_ARG, "NULL argument");
+  NN_CHECK(b->prepared, NNSDP_ERR_STATE, "batch is not prepared");
+  NN_CUDA(cudaSetDevice(b->dev));
+  NN_CUDA(cudaMemcpyAsync(aff_out, b->aff.p, (size_t)b->net->sh.Zdim * b->Q * 8,
+                          cudaMemcpyDeviceToHost, b->st));
+  NN_CUDA(cudaStreamSynchronize(b->st));
+  return NNSDP_OK;
+}
+
+int32_t nnsdp_batch_ring_ptr(nnsdp_batch* b, uint64_t* dev_ptr, int64_t* slot_doubles) {
+  NN_CHECK(b != nullptr, NNSDP_ERR_ARG, "batch is NULL");
+  if (dev_ptr) *dev_ptr = (uint64_t)(uintptr_t)b->ringbuf.p;
+  if (slot_doubles) *slot_doubles = b->plan.per_query_doubles;
+  return NNSDP_OK;
+}
+
+int32_t nnsdp_batch_event_record(nnsdp_batch* b, int32_t which) {
+  NN_CHECK(b != nullptr, NNSDP_ERR_ARG, "batch is NULL");
+  NN_CUDA(cudaSetDevice(b->dev));
+  NN_CUDA(cudaEventRecord(which == 0 ? b->ev_start : b->ev_stop, b->st));
+  return NNSDP_OK;
+}
+
+int32_t nnsdp_batch_elapsed_ms(nnsdp_batch* b, float* ms) {
+  NN_CHECK(b && ms, NNSDP_ERR_ARG, "NULL argument");
+  NN_CUDA(cudaSetDevice(b->dev));
+  NN_CUDA(cudaEventSynchronize(b->ev_stop));
+  NN_CUDA(cudaEventElapsedTime(ms, b->ev_start, b->ev_stop));
+  return NNSDP_OK;
+}
+
+int32_t nnsdp_batch_stage_ms(nnsdp_batch* b, int32_t stage, float* ms, int64_t* launches) {
+  NN_CHECK(b != nullptr, NNSDP_ERR_ARG, "batch is NULL");
+  NN_CHECK(stage >= 0 && stage < ST_COUNT, NNSDP_ERR_ARG, "bad stage");
+  NN_TRY(nnsdp_batch_sync(b));
+  if (ms) *ms = b->stage_ms[stage];
+  if (launches) *launches = b->stage_launches[stage];
+  return NNSDP_OK;
+}
+
+int32_t nnsdp_batch_stage_reset(nnsdp_batch* b) {
+  NN_CHECK(b != nullptr, NNSDP_ERR_ARG, "batch is NULL");
+  NN_TRY(nnsdp_batch_sync(b));
+  for (int i = 0; i < ST_COUNT; ++i) b->stage_ms[i] = 0.f, b->stage_launches[i] = 0;
+  return NNSDP_OK;
+}
+
+int32_t nnsdp_batch_gram_stats(nnsdp_batch* b, int64_t* n_contractions, int64_t* sum_active) {
+  NN_CHECK(b != nullptr, NNSDP_ERR_ARG, "batch is NULL");
+  NN_CHECK(b->prepared, NNSDP_ERR_STATE, "batch is not prepared");
+  NN_CUDA(cudaSetDevice(b->dev));
+  const int K = b->net->sh.K;
+  std::vector<int> cnt((size_t)K * b->Q);
+  NN_CUDA(cudaMemcpyAsync(cnt.data(), b->cnt.p, cnt.size() * 4, cudaMemcpyDeviceToHost, b->st));
+  NN_CUDA(cudaStreamSynchronize(b->st));
+  int64_t nc = 0, sa = 0;
+  for (int64_t q = 0; q < b->Q; ++q)
+    for (int blk = 0; blk <= K - 2; ++blk) {
+      const int c = cnt[q * K + blk];
+      if (c > 0) ++nc, sa += c;
+    }
+  if (n_contractions) *n_contractions = nc;
+  if (sum_active) *sum_active = sa;
+  return NNSDP_OK;
+}
+
+}  // extern "C"
+
+// ---- one-shot entry points --------------------------------------------------------------------
+namespace {
+
+// Split Q queries over the devices of ctx in contiguous ranges and run fn(dev_index, q0, nq) with
+// one host thread per device.  Errors of worker threads are forwarded to the caller's thread.
+template <class F>
+int32_t shard_queries(nnsdp_ctx* ctx, int64_t Q, F fn) {
+  const int nd = (int)ctx->devs.size();
+  if (nd == 1 || Q < nd) return fn(0, (int64_t)0, Q);
+  std::vector<int32_t> status(nd, NNSDP_OK);
+  std::vector<std::string> errs(nd);
+  std::vector<std::thread> th;
+  const int64_t base = Q / nd, rem = Q % nd;
+  int64_t q0 = 0;
+  for (int d = 0; d < nd; ++d) {
+    const int64_t nq = base + (d < rem ? 1 : 0);
+    th.emplace_back([&, d, q0, nq]() {
+      status[d] = fn(d, q0, nq);
+      if (status[d] != NNSDP_OK) errs[d] = nnsdp_last_error();
+    });
+    q0 += nq;
+  }
+  for (auto& t : th) t.join();
+  for (int d = 0; d < nd; ++d)
+    if (status[d] != NNSDP_OK) {
+      set_error("device %d: %s", ctx->devs[d], errs[d].c_str());
+      return status[d];
+    }
+  return NNSDP_OK;
+}
+
+struct BatchHolder {
+  nnsdp_batch* b = nullptr;
+  ~BatchHolder() { nnsdp_batch_destroy(b); }
+};
+
+const double* col(const double* p, int64_t stride, int64_t q0) { return p ? p + stride * q0 : p; }
+
+nnsdp_query_inputs shift_inputs(const nnsdp_query_inputs& in, int64_t q0) {
+  nnsdp_query_inputs o = in;
+  o.x1min = col(in.x1min, in.x1min_stride, q0);
+  o.x1max = col(in.x1max, in.x1max_stride, q0);
+  o.ymin = col(in.ymin, in.ymin_stride, q0);
+  o.ymax = col(in.ymax, in.ymax_stride, q0);
+  o.smin = col(in.smin, in.smin_stride, q0);
+  o.smax = col(in.smax, in.smax_stride, q0);
+  o.gamma_in = col(in.gamma_in, in.gamma_in_stride, q0);
+  o.gamma_bnd = col(in.gamma_bnd, in.gamma_bnd_stride, q0);
+  o.gamma_sec = col(in.gamma_sec, in.gamma_sec_stride, q0);
+  o.out_S = col(in.out_S, in.out_S_stride, q0);
+  o.out_vec = col(in.out_vec, in.out_vec_stride, q0);
+  o.out_invP = col(in.out_invP, in.out_invP_stride, q0);
+  o.gamma_out = col(in.gamma_out, in.gamma_out_stride, q0);
+  return o;
+}
+
+int32_t assemble_impl(nnsdp_ctx* ctx, const nnsdp_net* net, int64_t beta, int64_t Q,
+                      const nnsdp_query_inputs* in, double* out, int dense) {
+  NN_CHECK(ctx && net && in && out, NNSDP_ERR_ARG, "NULL argument");
+  NN_CHECK(Q >= 1, NNSDP_ERR_ARG, "Q must be >= 1");
+  nnsdp_sizes sz;
+  NN_TRY(fill_sizes(net->sh, beta, &sz));
+  const int64_t per = dense ? sz.Zdim * sz.Zdim : sz.sum_ck_sq;
+  return shard_queries(ctx, Q, [&](int d, int64_t q0, int64_t nq) -> int32_t {
+    // ring: two halves of up to ~2 GiB each, at least one query per half
+    int64_t ring = std::max<int64_t>(2, (int64_t)((4ll << 30) / (per * 8)));
+    ring = std::min<int64_t>(std::min<int64_t>(ring, nq), 4096);
+    BatchHolder h;
+    NN_TRY(nnsdp_batch_create(ctx, d, net, beta, nq, ring, dense, &h.b));
+    nnsdp_query_inputs sub = shift_inputs(*in, q0);
+    NN_TRY(nnsdp_batch_set_inputs(h.b, nq, &sub));
+    return nnsdp_batch_run(h.b, out + q0 * per);
+  });
+}
+
+}  // namespace
+
+extern "C" {
+
+int32_t nnsdp_bounds_ibp(nnsdp_ctx* ctx, const nnsdp_net* net, int64_t Q, const double* x1min,
+                         const double* x1max, double* xmin, double* xmax, double* acxmin,
+                         double* acxmax) {
+  NN_CHECK(ctx && net && x1min && x1max, NNSDP_ERR_ARG, "NULL argument");
+  NN_CHECK(Q >= 1, NNSDP_ERR_ARG, "Q must be >= 1");
+  const Shape& sh = net->sh;
+  return shard_queries(ctx, Q, [&](int d, int64_t q0, int64_t nq) -> int32_t {
+    BatchHolder h;
+    NN_TRY(nnsdp_batch_create(ctx, d, net, 0, nq, 0, 0, &h.b));
+    nnsdp_query_inputs in;
+    memset(&in, 0, sizeof(in));
+    in.x1min = x1min + q0 * sh.n_in();
+    in.x1max = x1max + q0 * sh.n_in();
+    in.x1min_stride = in.x1max_stride = sh.n_in();
+    NN_TRY(nnsdp_batch_set_inputs(h.b, nq, &in));
+    NN_TRY(nnsdp_batch_bounds(h.b));
+    return nnsdp_batch_get_bounds(h.b, xmin ? xmin + q0 * sh.xtot : nullptr,
+                                  xmax ? xmax + q0 * sh.xtot : nullptr,
+                                  acxmin ? acxmin + q0 * sh.acdim : nullptr,
+                                  acxmax ? acxmax + q0 * sh.acdim : nullptr, nullptr, nullptr);
+  });
+}
+
+int32_t nnsdp_preact_from_x(nnsdp_ctx* ctx, const nnsdp_net* net, int64_t Q, const double* xmin,
+                            const double* xmax, double* acxmin, double* acxmax) {
+  NN_CHECK(ctx && net && xmin && xmax && acxmin && acxmax, NNSDP_ERR_ARG, "NULL argument");
+  NN_CHECK(Q >= 1, NNSDP_ERR_ARG, "Q must be >= 1");
+  const Shape& sh = net->sh;
+  return shard_queries(ctx, Q, [&](int d, int64_t q0, int64_t nq) -> int32_t {
+    BatchHolder h;
+    NN_TRY(nnsdp_batch_create(ctx, d, net, 0, nq, 0, 0, &h.b));
+    nnsdp_batch* b = h.b;
+    NN_CUDA(cudaSetDevice(b->dev));
+    const NetPerDev& nd = *b->nd;
+    NN_CUDA(cudaMemcpyAsync(b->xmin.p, xmin + q0 * sh.xtot, (size_t)sh.xtot * nq * 8,
+                            cudaMemcpyHostToDevice, b->st));
+    NN_CUDA(cudaMemcpyAsync(b->xmax.p, xmax + q0 * sh.xtot, (size_t)sh.xtot * nq * 8,
+                            cudaMemcpyHostToDevice, b->st));
+    for (int k = 0; k <= sh.K - 2; ++k)
+      ibp_layer_launch(nd.M[k].as<double>(), (int)sh.n[k + 1], (int)sh.n[k],
+                       b->xmin.as<double>() + sh.xoff[k], b->xmax.as<double>() + sh.xoff[k], sh.xtot,
+                       nullptr, nullptr, b->acxmin.as<double>() + sh.noff(k + 1),
+                       b->acxmax.as<double>() + sh.noff(k + 1), sh.acdim, (int)nq, 0, 0,
+                       b->flags.as<int>() + 1, b->st);
+    NN_CUDA(cudaGetLastError());
+    NN_CUDA(cudaMemcpyAsync(acxmin + q0 * sh.acdim, b->acxmin.p, (size_t)sh.acdim * nq * 8,
+                            cudaMemcpyDeviceToHost, b->st));
+    NN_CUDA(cudaMemcpyAsync(acxmax + q0 * sh.acdim, b->acxmax.p, (size_t)sh.acdim * nq * 8,
+                            cudaMemcpyDeviceToHost, b->st));
+    return check_flags(b, "nnsdp_preact_from_x");
+  });
+}
+
+int32_t nnsdp_sector_minmax(nnsdp_ctx* ctx, int64_t n, const double* acxmin, const double* acxmax,
+                            double* smin, double* smax) {
+  NN_CHECK(ctx && acxmin && acxmax && smin && smax, NNSDP_ERR_ARG, "NULL argument");
+  NN_CHECK(n >= 0, NNSDP_ERR_ARG, "n must be >= 0");
+  if (n == 0) return NNSDP_OK;
+  NN_CUDA(cudaSetDevice(ctx->devs[0]));
+  cudaStream_t st = ctx->streams[0];
+  DevBuf lo, hi, a, b;
+  struct Rel {
+    DevBuf *w, *x, *y, *z;
+    ~Rel() { w->release(); x->release(); y->release(); z->release(); }
+  } rel{&lo, &hi, &a, &b};
+  NN_TRY(upload(lo, acxmin, (size_t)n * 8, st));
+  NN_TRY(upload(hi, acxmax, (size_t)n * 8, st));
+  NN_TRY(a.ensure((size_t)n * 8));
+  NN_TRY(b.ensure((size_t)n * 8));
+  launch_sector_minmax(n, lo.as<double>(), hi.as<double>(), a.as<double>(), b.as<double>(), st);
+  NN_CUDA(cudaGetLastError());
+  NN_CUDA(cudaMemcpyAsync(smin, a.p, (size_t)n * 8, cudaMemcpyDeviceToHost, st));
+  NN_CUDA(cudaMemcpyAsync(smax, b.p, (size_t)n * 8, cudaMemcpyDeviceToHost, st));
+  NN_CUDA(cudaStreamSynchronize(st));
+  return NNSDP_OK;
+}
+
+int32_t nnsdp_assemble_blocks(nnsdp_ctx* ctx, const nnsdp_net* net, int64_t beta, int64_t Q,
+                              const nnsdp_query_inputs* in, double* blocks_out) {
+  return assemble_impl(ctx, net, beta, Q, in, blocks_out, 0);
+}
+
+int32_t nnsdp_assemble_dense(nnsdp_ctx* ctx, const nnsdp_net* net, int64_t beta, int64_t Q,
+                             const nnsdp_query_inputs* in, double* Z_out) {
+  return assemble_impl(ctx, net, beta, Q, in, Z_out, 1);
+}
+
+}  // extern "C"

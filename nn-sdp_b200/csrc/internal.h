@@ -1,5 +1,11 @@
 // Internal declarations shared by the host runtime and the sm_100a kernels.
 // Nothing in here is part of the C ABI (see include/nnsdp_b200.h).
+//
+// Index conventions (0-based internally, 1-based only on the C ABI):
+//   block b = 0..K-1 holds x_{b+1} (size n[b]); index a = off[K] = Zdim-1 is the affine entry.
+//   layer matrix M[k] = [W_k b_k] (k = 0..K-1) maps block k to the n[k+1] rows it produces.
+//   hidden neuron j = 0..acdim-1 is z-index n[0]+j; the neurons of block b (1 <= b <= K-1)
+//   are [noff(b), noff(b)+n[b]) with noff(b) = off[b]-n[0]; they are the rows of M[b-1].
 #pragma once
 
 #include <cuda_runtime.h>
@@ -18,18 +24,18 @@ namespace nnsdp {
 void set_error(const char* fmt, ...);
 int32_t cuda_fail(cudaError_t e, const char* what, const char* file, int line);
 
-#define NN_CUDA(call)                                                         \
-  do {                                                                        \
-    cudaError_t _e = (call);                                                  \
+#define NN_CUDA(call)                                                                \
+  do {                                                                               \
+    cudaError_t _e = (call);                                                         \
     if (_e != cudaSuccess) return ::nnsdp::cuda_fail(_e, #call, __FILE__, __LINE__); \
   } while (0)
 
-#define NN_CHECK(cond, code, ...)       \
-  do {                                  \
-    if (!(cond)) {                      \
-      ::nnsdp::set_error(__VA_ARGS__);  \
-      return (code);                    \
-    }                                   \
+#define NN_CHECK(cond, code, ...)      \
+  do {                                 \
+    if (!(cond)) {                     \
+      ::nnsdp::set_error(__VA_ARGS__); \
+      return (code);                   \
+    }                                  \
   } while (0)
 
 #define NN_TRY(expr)               \
@@ -39,10 +45,7 @@ int32_t cuda_fail(cudaError_t e, const char* what, const char* file, int line);
   } while (0)
 
 // ---------------------------------------------------------------------------------
-// host-side shape bookkeeping (0-based internally)
-//   block b = 0..K-1 holds x_{b+1} (size n[b]); "block" K is the affine index a.
-//   neuron j = 0..acdim-1 is z-index n[0]+j; the neurons of block b (b>=1) are
-//   [noff(b), noff(b)+n[b]) with noff(b) = off[b]-n[0]; they are the rows of W_{b-1}.
+// host-side shape bookkeeping
 // ---------------------------------------------------------------------------------
 struct Shape {
   int K = 0;
@@ -52,7 +55,12 @@ struct Shape {
   int64_t Zdim = 0, acdim = 0, xtot = 0;
   int64_t n_in() const { return n[0]; }
   int64_t n_out() const { return n[K]; }
-  int64_t n_last_hidden() const { return n[K - 1]; }
+  int64_t noff(int b) const { return off[b] - n[0]; }
+  int block_of(int64_t z) const {  // z in [0, Zdim)
+    int b = 0;
+    while (b < K && z >= off[b + 1]) ++b;
+    return b;
+  }
 };
 
 // A clique = one or two contiguous global index ranges [lo, hi] (0-based, inclusive).
@@ -67,68 +75,55 @@ struct CliqueRanges {
 };
 
 struct CliqueInfoHost {
-  std::vector<CliqueRanges> ck;            // p cliques
+  std::vector<CliqueRanges> ck;              // p cliques
   std::vector<std::vector<int64_t>> d1, d2;  // 1-based local indices (Dk1, Dk2)
 };
 
 int32_t make_cliques_host(const Shape& sh, int64_t beta, CliqueInfoHost* out);
 int64_t lambda_dim(int64_t acdim, int64_t beta);
+int32_t fill_sizes(const Shape& sh, int64_t beta, nnsdp_sizes* out);
 
 // ---------------------------------------------------------------------------------
-// emission plan: every clique block is cut into strips (<= STRIP_ROWS rows inside one
-// Z block) x chunks (<= CHUNK_COLS columns inside one Z block); each tile gets a class.
+// emission plan: every output matrix (a clique block, or the dense Z) is cut into
+// rectangular tiles; each tile carries the set of terms of Z that can be non-zero in it.
 // ---------------------------------------------------------------------------------
-constexpr int STRIP_ROWS = 128;
-constexpr int CHUNK_COLS = 32;
-
-enum TileClass : uint8_t {
-  TILE_ZERO = 0,      // structurally zero
-  TILE_AFFCOL = 1,    // the affine column (1 column)
-  TILE_DIAGPLAIN = 2, // same block, away from band/slivers: Gram copy / output Gram / zero
-  TILE_WT = 3,        // rows in block b, cols = neurons of block b+1: W_b' * M  (window sum)
-  TILE_WTT = 4,       // transpose of the above
-  TILE_GENERAL = 5,   // everything else: per-entry evaluation
+enum TileFlags : uint32_t {
+  TF_AFF = 1u << 0,    // contains the affine row and/or column
+  TF_SAME = 1u << 1,   // rows and columns share a block: Gram / Zin / S11 / W_K' S22 W_K
+  TF_1K = 1u << 2,     // x_1 against x_K coupling S12 W_K (either orientation)
+  TF_RC = 1u << 3,     // F(r,c) = sum_j W_b[j,r] M[j,c] with r in block b, c a neuron near layer b+1
+  TF_CR = 1u << 4,     // F(c,r), the transposed term
+  TF_BAND = 1u << 5,   // neuron-neuron band: -2 T and the -2 gamma_bnd diagonal
+  TF_ALL = 0x3Fu,
+  TF_UNIFORM = 1u << 8,  // rows lie in one block and columns lie in one block (rblk, cblk valid)
 };
 
-struct StripDev {
-  int32_t clique;     // clique index
-  int32_t row0;       // first local row in the clique block
-  int32_t nrows;      // <= STRIP_ROWS
-  int32_t grow0;      // global z index of the first row
-  int32_t blk;        // Z block of the rows
-  int32_t arow;       // 1: this strip also writes the affine row of its clique
-  int32_t tile0;      // index of this strip's first tile class in the tile table
-  int32_t pad;
+struct TileDev {
+  int32_t mat;          // index of the output matrix (clique) this tile belongs to
+  int32_t row0, nrows;  // local row range
+  int32_t col0, ncols;  // local column range
+  int32_t grow0;        // global z index of the first row
+  int32_t gcol0;        // global z index of the first column
+  uint32_t flags;
+  int32_t rblk, cblk;   // block of the rows / columns when TF_UNIFORM
 };
 
-struct ChunkDev {
-  int32_t col0;       // first local column in the clique block
-  int32_t ncols;      // <= CHUNK_COLS
-  int32_t gcol0;      // global z index of the first column
-  int32_t blk;        // Z block of the columns (K = affine)
-};
-
-struct CliqueDev {
-  int64_t out_off;    // offset (doubles) of this block inside one query's output
-  int32_t n;          // |C_k|
-  int32_t ld;         // leading dimension of the block
-  int32_t chunk0;     // first chunk of this clique in the chunk table
-  int32_t nchunks;
-  int32_t len1;       // length of the first segment
-  int32_t g1, g2;     // global start of segment 1 / 2
-  int32_t pad;
+struct MatDev {
+  int64_t out_off;  // offset (doubles) of this matrix inside one query's output
+  int32_t n;        // side
+  int32_t ld;       // leading dimension (= n)
 };
 
 struct PlanHost {
-  std::vector<StripDev> strips;
-  std::vector<ChunkDev> chunks;
-  std::vector<CliqueDev> cliques;
-  std::vector<uint8_t> tiles;
+  std::vector<TileDev> tiles;
+  std::vector<MatDev> mats;
   int64_t per_query_doubles = 0;
+  int tile_rows = 0, tile_cols = 0;
 };
 
-int32_t build_plan(const Shape& sh, int64_t beta, const std::vector<CliqueRanges>& cliques,
-                   PlanHost* plan);
+// tile_rows in {32, 64, 128}; classify = false marks every tile TF_ALL (validation mode).
+int32_t build_plan(const Shape& sh, int64_t beta, const std::vector<CliqueRanges>& mats,
+                   bool classify, PlanHost* plan);
 
 // ---------------------------------------------------------------------------------
 // device-side descriptors (passed by value to kernels)
@@ -138,55 +133,61 @@ struct NetDev {
   const int* n;               // K+1
   const int* off;             // K+1
   const int* xoff;            // K+2
-  const double* const* M;     // K   : [W_k b_k], ld = n[k+1]            (neuron-contiguous)
-  const double* const* Wt;    // K   : W_k', (n[k] x n[k+1]), ld = ldT[k] (input-contiguous)
-  const int* ldT;             // K
+  const int* blk_of;          // Zdim : block of every z index (K for the affine index)
+  const double* const* M;     // K   : [W_k b_k], ld = n[k+1]              (neuron-contiguous)
+  const double* const* Wt;    // K   : W_k' (n[k] x n[k+1]), ld = ldT[k]   (input-contiguous, zero padded)
+  const int* ldT;             // K   : n[k] rounded up to 128
   const double* bias_all;     // acdim : b_1..b_{K-1} stacked
 };
 
 // Per-batch device arrays.  Strides are in doubles between queries (0 = shared).
 struct BatchDev {
   int Q, beta;
-  int out_kind, has_s22, has_s1x;
-  // inputs
-  const double* x1min;  long long s_x1min;
-  const double* x1max;  long long s_x1max;
-  const double* ymin;   long long s_ymin;
-  const double* ymax;   long long s_ymax;
-  const double* smin;   long long s_smin;
-  const double* smax;   long long s_smax;
-  const double* gin;    long long s_gin;
-  const double* gbnd;   long long s_gbnd;
-  const double* gsec;   long long s_gsec;
-  const double* outS;   long long s_outS;
-  const double* outvec; long long s_outvec;
-  const double* outinvP; long long s_outinvP;
-  const double* gout;   long long s_gout;
+  int out_kind, has_s22, has_s12;
+  int sdim;
   long long lamdim;
+  // inputs
+  const double* x1min;   long long s_x1min;
+  const double* x1max;   long long s_x1max;
+  const double* ymin;    long long s_ymin;
+  const double* ymax;    long long s_ymax;
+  const double* smin;    long long s_smin;
+  const double* smax;    long long s_smax;
+  const double* gin;     long long s_gin;
+  const double* gbnd;    long long s_gbnd;
+  const double* gsec;    long long s_gsec;
+  const double* outS;    long long s_outS;
+  const double* outvec;  long long s_outvec;
+  const double* outinvP; long long s_outinvP;
+  const double* gout;    long long s_gout;
   // prepared per-query vectors (stride = natural size)
-  double* d11;    // acdim
-  double* Mb;     // (beta+1) * acdim
-  double* dg;     // acdim
-  double* u;      // acdim
-  double* aff;    // Zdim
-  int* cnt;       // K   (active-neuron count feeding the Gram of block b)
-  double* Z11;    // n_in * n_in
-  double* Z1K;    // n_in * n[K-1]
-  double* U;      // n_out * n[K-1]
+  double* d11;     // acdim                 -2 smin smax lambda
+  double* Md;      // acdim                 (smin+smax) lambda + T[j,j]
+  double* T0;      // acdim                 T[j,j]
+  double* Bt;      // beta * acdim          Bt[(t-1)*acdim + i] = T[i, i+t]
+  double* u;       // acdim                 d11 b + c13
+  double* aff;     // Zdim                  the affine column Z[:, a]
+  double* part;    // npart                 per-CTA partial sums of Z[a, a]
+  int npart;
+  int* act;        // acdim                 compacted local indices of Gram-active neurons, per layer
+  int* cnt;        // K                     cnt[b] = active neurons among the rows of M[b]
+  double* Z11;     // n_in * n_in           S11 - 2 diag(gamma_in)
+  double* Z1K;     // n_in * n[K-1]         S12 W_K
+  double* U;       // n_out * n[K-1]        S22 W_K
 };
 
 struct GramDev {
-  double* scratch;           // chunk * gram_per_query
+  double* scratch;           // nslots * per_query
   long long per_query;       // doubles
-  const long long* goff;     // K-1 : offset of block b's Gram inside one query's scratch
+  const long long* goff;     // K : offset of block b's Gram inside one query's scratch (b <= K-2)
+  const int* ldG;            // K : leading dimension of block b's Gram
 };
 
 struct PlanDev {
-  const StripDev* strips;
-  const ChunkDev* chunks;
-  const CliqueDev* cliques;
-  const uint8_t* tiles;
-  int nstrips;
+  const TileDev* tiles;
+  const MatDev* mats;
+  int ntiles;
+  int tile_rows;
   long long per_query;       // doubles per query in the output
 };
 
@@ -205,13 +206,20 @@ int affine_layer_launch(const double* Wt, int ldT, int n_rows, int n_neurons, co
 // K2: smin/smax from acx bounds.
 int launch_sector_minmax(long long n, const double* acxmin, const double* acxmax, double* smin,
                          double* smax, cudaStream_t st);
-// K2b: per-query QC diagonals, band multipliers, affine-column seeds.
+int launch_place_x1(const double* x1min, long long s_min, const double* x1max, long long s_max,
+                    double* xmin, double* xmax, long long xtot, int n_in, int Q, cudaStream_t st);
+// transposed, zero-padded copy of W_k out of [W_k b_k]
+int launch_transpose_w(const double* Mk, int n_out_k, int n_in_k, double* Wt, int ldT,
+                       cudaStream_t st);
+// K2b: per-query QC diagonals, band multipliers, affine column, Gram active sets.
 int launch_prep(const NetDev& net, const BatchDev& b, int* err_flag, cudaStream_t st);
-// K3: Gram contractions (DMMA) for queries [q0, q0+nq).
-int launch_gram(const NetDev& net, const BatchDev& b, const GramDev& g, int q0, int nq,
+// K3: Gram contractions (DMMA) for queries [q0, q0+nq) into scratch slots 0..nq-1.
+int launch_gram(const NetDev& net, const BatchDev& b, const GramDev& g, int max_n, int q0, int nq,
                 cudaStream_t st);
-// K4+K5: emit all clique blocks of queries [q0, q0+nq) to out (slot s = q - q0).
+// K4+K5: emit all tiles of queries [q0, q0+nq) to out + slot * per_query, slot = q - q0.
 int launch_emit(const NetDev& net, const BatchDev& b, const GramDev& g, const PlanDev& plan,
                 int q0, int nq, double* out, cudaStream_t st);
+
+constexpr int PREP_THREADS = 256;
 
 }  // namespace nnsdp

@@ -132,8 +132,50 @@ __global__ void sector_minmax_kernel(long long n, const double* __restrict__ lo,
   }
 }
 
+// x_1 bounds of every query into the stacked x layout (stride 0 = one box shared by all queries)
+__global__ void place_x1_kernel(const double* __restrict__ x1min, long long s_min,
+                                const double* __restrict__ x1max, long long s_max,
+                                double* __restrict__ xmin, double* __restrict__ xmax,
+                                long long xtot, int n_in, int Q) {
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= (long long)n_in * Q) return;
+  const long long q = i / n_in, r = i % n_in;
+  xmin[q * xtot + r] = x1min[q * s_min + r];
+  xmax[q * xtot + r] = x1max[q * s_max + r];
+}
+
+// Wt[r + j*ldT] = W[j, r] : input-contiguous copy of W_k (rows r >= n_in_k stay zero).
+__global__ void transpose_w_kernel(const double* __restrict__ Mk, int n_out_k, int n_in_k,
+                                   double* __restrict__ Wt, int ldT) {
+  __shared__ double tile[32][33];
+  const int j0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {  // i: input index r, x: neuron j
+    const int j = j0 + threadIdx.x, r = r0 + i;
+    tile[i][threadIdx.x] = (j < n_out_k && r < n_in_k) ? Mk[j + (long long)r * n_out_k] : 0.0;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {  // i: neuron j, x: input index r
+    const int j = j0 + i, r = r0 + threadIdx.x;
+    if (j < n_out_k && r < n_in_k) Wt[r + (long long)j * ldT] = tile[threadIdx.x][i];
+  }
+}
+
 }  // namespace
 
+int launch_place_x1(const double* x1min, long long s_min, const double* x1max, long long s_max,
+                    double* xmin, double* xmax, long long xtot, int n_in, int Q, cudaStream_t st) {
+  const long long n = (long long)n_in * Q;
+  place_x1_kernel<<<(int)((n + 255) / 256), 256, 0, st>>>(x1min, s_min, x1max, s_max, xmin, xmax,
+                                                          xtot, n_in, Q);
+  return 1;
+}
+
+int launch_transpose_w(const double* Mk, int n_out_k, int n_in_k, double* Wt, int ldT,
+                       cudaStream_t st) {
+  dim3 grid((n_out_k + 31) / 32, (n_in_k + 31) / 32), block(32, 8);
+  transpose_w_kernel<<<grid, block, 0, st>>>(Mk, n_out_k, n_in_k, Wt, ldT);
+  return 1;
+}
 
 int ibp_layer_launch(const double* Mk, int n_out_k, int n_in_k, const double* xin_min,
                      const double* xin_max, long long x_stride, double* xout_min, double* xout_max,

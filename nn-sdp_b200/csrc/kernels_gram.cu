@@ -1,0 +1,167 @@
+// K3: Gram contractions  G_b = W_b' diag(d11) W_b  restricted to the Gram-active neurons
+// (d11 = -2 smin smax lambda != 0, i.e. stably-active ReLUs with a non-zero multiplier).
+// This is the A' Q11 A part of  Zac = R' Q R  (reference: src/Qc/activ.jl:40 with
+// Q11 from src/Qc/activ_sector.jl:42).
+//
+// FP64 tensor cores: tcgen05 has no f64 kind, so the contraction uses the DMMA path
+// (mma.sync.aligned.m8n8k4.f64).  Operands come from the input-contiguous copy Wt of W, so a
+// gathered neuron j is one contiguous column (cp.async 16 B chunks, fully coalesced whatever
+// the active set looks like).  Only upper-triangular 128x128 tile pairs are computed; every tile
+// is written to G[r,c] and mirrored to G[c,r] from the same accumulators, so G is bit-symmetric.
+#include "internal.h"
+
+namespace nnsdp {
+
+namespace {
+
+constexpr int GT = 128;        // tile side
+constexpr int GK = 16;         // neurons per pipeline stage
+constexpr int GSTAGES = 3;
+constexpr int GLD = GT + 8;    // smem leading dimension: (k*GLD + row) hits 32 distinct banks pairs
+constexpr int GTHREADS = 256;  // 8 warps: 4 (rows) x 2 (cols), warp tile 32 x 64
+
+struct GramSmem {
+  double A[GSTAGES][GK][GLD];
+  double B[GSTAGES][GK][GLD];
+  double d[GSTAGES][GK];
+};
+
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem, bool valid) {
+  const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+  const int sz = valid ? 16 : 0;  // src-size 0 zero-fills the 16 bytes
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(s), "l"(gmem), "r"(sz));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;\n" ::"n"(N));
+}
+
+__device__ __forceinline__ void dmma_m8n8k4(double& c0, double& c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+               : "+d"(c0), "+d"(c1)
+               : "d"(a), "d"(b));
+}
+
+__global__ void __launch_bounds__(GTHREADS, 1)
+gram_kernel(NetDev net, BatchDev b, GramDev g, int q0) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  GramSmem& sm = *reinterpret_cast<GramSmem*>(smem_raw);
+
+  const int blk = blockIdx.y;                 // Gram of block blk uses layer matrix M[blk]
+  const int slot = blockIdx.z, q = q0 + slot;
+  const int cnt = b.cnt[(long long)q * net.K + blk];
+  if (cnt == 0) return;
+  const int nb = net.n[blk];
+  const int ntile = (nb + GT - 1) / GT;
+  // decode the upper-triangular tile pair (ti <= tj) from blockIdx.x
+  int ti = 0, rem = blockIdx.x;
+  while (ti < ntile && rem >= ntile - ti) {
+    rem -= ntile - ti;
+    ++ti;
+  }
+  if (ti >= ntile) return;
+  const int tj = ti + rem;
+  const bool diag = (ti == tj);
+  const int m0 = ti * GT, n0 = tj * GT;
+
+  const double* Wt = net.Wt[blk];
+  const int ldT = net.ldT[blk];
+  const int L0 = net.off[blk + 1] - net.n_in;
+  const int* act = b.act + (long long)q * net.acdim + L0;
+  const double* d11 = b.d11 + (long long)q * net.acdim + L0;
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int wm = (warp & 3) * 32, wn = (warp >> 2) * 64;
+  const int nsteps = (cnt + GK - 1) / GK;
+
+  auto load_stage = [&](int stage, int step) {
+    const int k0 = step * GK;
+    // 16 neurons x 128 rows = 16 x 64 chunks of 16 B per operand
+    for (int c = tid; c < GK * (GT / 2); c += GTHREADS) {
+      const int kk = c / (GT / 2), ch = c % (GT / 2);
+      const bool valid = (k0 + kk) < cnt;
+      const int jl = valid ? act[k0 + kk] : 0;
+      const double* col = Wt + (long long)jl * ldT;
+      cp_async16(&sm.A[stage][kk][ch * 2], col + m0 + ch * 2, valid);
+      if (!diag) cp_async16(&sm.B[stage][kk][ch * 2], col + n0 + ch * 2, valid);
+    }
+    if (tid < GK) sm.d[stage][tid] = (k0 + tid < cnt) ? d11[act[k0 + tid]] : 0.0;
+  };
+
+  double acc[4][8][2];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+  for (int s = 0; s < GSTAGES - 1; ++s) {
+    if (s < nsteps) load_stage(s, s);
+    cp_async_commit();
+  }
+  for (int step = 0; step < nsteps; ++step) {
+    cp_async_wait<GSTAGES - 2>();
+    __syncthreads();
+    {  // prefetch into the stage consumed in the previous iteration
+      const int nxt = step + GSTAGES - 1;
+      if (nxt < nsteps) load_stage(nxt % GSTAGES, nxt);
+      cp_async_commit();
+    }
+    const int st = step % GSTAGES;
+    const double(*As)[GLD] = sm.A[st];
+    const double(*Bs)[GLD] = diag ? sm.A[st] : sm.B[st];
+#pragma unroll
+    for (int k4 = 0; k4 < GK; k4 += 4) {
+      const int k = k4 + (lane & 3);
+      const double dk = sm.d[st][k];
+      double af[4], bf[8];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) af[i] = As[k][wm + i * 8 + (lane >> 2)] * dk;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) bf[j] = Bs[k][wn + j * 8 + (lane >> 2)];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) dmma_m8n8k4(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+    }
+  }
+  cp_async_wait<0>();
+
+  // epilogue: G[r, c] and the mirror G[c, r]; on diagonal tiles only r <= c is authoritative.
+  double* G = g.scratch + (long long)slot * g.per_query + g.goff[blk];
+  const int ldG = g.ldG[blk];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int r = m0 + wm + i * 8 + (lane >> 2);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int c = n0 + wn + j * 8 + (lane & 3) * 2;
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int cc = c + e;
+        if (r < nb && cc < nb && (!diag || r <= cc)) {
+          const double v = acc[i][j][e];
+          G[r + (long long)cc * ldG] = v;
+          if (r != cc) G[cc + (long long)r * ldG] = v;
+        }
+      }
+    }
+  }
+}
+
+}  // namespace
+
+int launch_gram(const NetDev& net, const BatchDev& b, const GramDev& g, int max_n, int q0, int nq,
+                cudaStream_t st) {
+  if (net.K < 2 || nq <= 0) return 0;
+  static bool attr_set = false;  // per process; harmless if repeated per device
+  (void)attr_set;
+  cudaFuncSetAttribute(gram_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                       (int)sizeof(GramSmem));
+  const int ntile = (max_n + GT - 1) / GT;
+  dim3 grid(ntile * (ntile + 1) / 2, net.K - 1, nq);
+  gram_kernel<<<grid, GTHREADS, sizeof(GramSmem), st>>>(net, b, g, q0);
+  return 1;
+}
+
+}  // namespace nnsdp

@@ -1,4 +1,4 @@
-// Host-side integer work: clique index sets and the emission plan.
+// Host-side integer work: sizes, clique index sets and the emission plan.
 //
 // make_cliques_host restates makeCliques (reference: src/Methods/chordal_cliques.jl:13-59)
 // with index arithmetic only; nothing is materialised as a selector matrix (the reference
@@ -41,8 +41,10 @@ int32_t make_cliques_host(const Shape& sh, int64_t beta, CliqueInfoHost* out) {
     c.hi[0] = Sfun(sh, k + 1) + beta - 1;  // 0-based of S(k+1)+beta
     c.lo[1] = Sfun(sh, K - 1);
     c.hi[1] = Sfun(sh, K);                 // 0-based of S(K)+1 (the affine index)
-    NN_CHECK(c.hi[0] + 1 <= c.lo[1] + 1, NNSDP_ERR_ASSERT,
+    NN_CHECK(c.hi[0] <= c.lo[1], NNSDP_ERR_ASSERT,
              "makeCliques: Ck1[end] <= Ck2[1] violated (chordal_cliques.jl:35)");
+    // Ck = [Ck1; Ck2] must be sorted-unique for Ec (MyMath.jl:46); k < p guarantees it.
+    NN_CHECK(c.hi[0] < c.lo[1], NNSDP_ERR_ASSERT, "makeCliques: Ck1 and Ck2 overlap");
     const int64_t ckdim = c.size();
     std::vector<int64_t> d1, d2;
     if (k == 1) {
@@ -69,117 +71,152 @@ int32_t make_cliques_host(const Shape& sh, int64_t beta, CliqueInfoHost* out) {
   return NNSDP_OK;
 }
 
+int32_t fill_sizes(const Shape& sh, int64_t beta, nnsdp_sizes* s) {
+  NN_CHECK(beta >= 0, NNSDP_ERR_ASSERT, "QcActivSector: 0 <= beta violated (activ_sector.jl:12)");
+  NN_CHECK(beta <= sh.acdim, NNSDP_ERR_ASSERT,
+           "QcActivSector: acxdim + length(ijs) == _lambda_dim needs beta <= acxdim "
+           "(activ_sector.jl:18,32)");
+  CliqueInfoHost ci;
+  NN_TRY(make_cliques_host(sh, beta, &ci));
+  s->K = sh.K;
+  s->Zdim = sh.Zdim;
+  s->acdim = sh.acdim;
+  s->xtot = sh.xtot;
+  s->lamdim = lambda_dim(sh.acdim, beta);
+  s->secdim = s->lamdim + 2 * sh.acdim;
+  s->n_in = sh.n_in();
+  s->n_out = sh.n_out();
+  s->sdim = sh.n_in() + sh.n_out() + 1;
+  s->ncliques = (int64_t)ci.ck.size();
+  s->sum_ck = s->sum_ck_sq = s->sum_dk = s->max_ck = 0;
+  for (size_t k = 0; k < ci.ck.size(); ++k) {
+    const int64_t n = ci.ck[k].size();
+    s->sum_ck += n;
+    s->sum_ck_sq += n * n;
+    s->sum_dk += (int64_t)(ci.d1[k].size() + ci.d2[k].size());
+    s->max_ck = std::max(s->max_ck, n);
+  }
+  return NNSDP_OK;
+}
+
 namespace {
 
 struct Piece {
   int64_t g0, g1;  // global range (inclusive)
-  int blk;
-  int64_t l0;      // local index of g0 inside the clique block
+  int64_t l0;      // local index of g0 inside the output matrix
 };
 
 bool intersects(int64_t a0, int64_t a1, int64_t b0, int64_t b1) {
   return a0 <= a1 && b0 <= b1 && std::max(a0, b0) <= std::min(a1, b1);
 }
 
-uint8_t classify(const Shape& sh, int64_t beta, int Bi, int64_t r0, int64_t r1, int Bj, int64_t c0,
-                 int64_t c1) {
+// Terms of Z that can be non-zero for rows [r0,r1] of block Bi against columns [c0,c1] of
+// block Bj (global z indices).  Must be a superset of what the device evaluator tests per entry.
+uint32_t pair_flags(const Shape& sh, int64_t beta, int Bi, int64_t r0, int64_t r1, int Bj,
+                    int64_t c0, int64_t c1) {
   const int K = sh.K;
-  if (Bj == K) return TILE_AFFCOL;
-  const int64_t n0 = sh.n[0];
-  const bool f_same = (Bi == Bj);
-  bool f23 = false, f32 = false;
-  if (Bi <= K - 2) {
+  if (Bi == K || Bj == K) return TF_AFF;
+  uint32_t f = 0;
+  const int64_t n0 = sh.n[0], a = sh.off[K];
+  if (Bi == Bj) f |= TF_SAME;
+  if ((Bi == 0 && Bj == K - 1) || (Bi == K - 1 && Bj == 0)) f |= TF_1K;
+  if (Bi <= K - 2) {  // rows feed layer Bi+1: columns must be neurons within beta of that layer
     const int64_t lo = sh.off[Bi + 1] - beta, hi = sh.off[Bi + 2] - 1 + beta;
-    f23 = intersects(std::max(c0, n0), c1, lo, hi);
+    if (intersects(std::max(c0, n0), std::min(c1, a - 1), lo, hi)) f |= TF_RC;
   }
   if (Bj <= K - 2) {
     const int64_t lo = sh.off[Bj + 1] - beta, hi = sh.off[Bj + 2] - 1 + beta;
-    f32 = intersects(std::max(r0, n0), r1, lo, hi);
+    if (intersects(std::max(r0, n0), std::min(r1, a - 1), lo, hi)) f |= TF_CR;
   }
-  const int64_t dist = std::max<int64_t>(0, std::max(c0 - r1, r0 - c1));
-  const bool f_band = (r1 >= n0 && c1 >= n0 && dist <= beta);
-  const bool f_1K = (Bi == 0 && Bj == K - 1) || (Bi == K - 1 && Bj == 0);
-  if (!f_same && !f23 && !f32 && !f_band && !f_1K) return TILE_ZERO;
-  if (f_same && !f23 && !f32 && !f_band && !f_1K) return TILE_DIAGPLAIN;
-  if (f23 && !f_same && !f32 && !f_band && !f_1K && Bj == Bi + 1) return TILE_WT;
-  if (f32 && !f_same && !f23 && !f_band && !f_1K && Bi == Bj + 1) return TILE_WTT;
-  return TILE_GENERAL;
+  if (r1 >= n0 && c1 >= n0) {
+    const int64_t rr0 = std::max(r0, n0), cc0 = std::max(c0, n0);
+    const int64_t dist = std::max<int64_t>(0, std::max(cc0 - r1, rr0 - c1));
+    if (dist <= beta) f |= TF_BAND;
+  }
+  return f;
+}
+
+void cut(const Shape& sh, const CliqueRanges& c, bool split_blocks, int64_t step,
+         std::vector<Piece>* out) {
+  int64_t local = 0;
+  for (int s = 0; s < c.nseg; ++s) {
+    std::vector<std::pair<int64_t, int64_t>> ranges;
+    if (split_blocks) {
+      for (int b = 0; b <= sh.K; ++b) {
+        const int64_t b0 = sh.off[b], b1 = (b == sh.K) ? sh.off[sh.K] : sh.off[b + 1] - 1;
+        const int64_t g0 = std::max(c.lo[s], b0), g1 = std::min(c.hi[s], b1);
+        if (g0 <= g1) ranges.push_back({g0, g1});
+      }
+    } else {
+      ranges.push_back({c.lo[s], c.hi[s]});
+    }
+    for (auto& rg : ranges)
+      for (int64_t g = rg.first; g <= rg.second; g += step)
+        out->push_back({g, std::min(rg.second, g + step - 1), local + (g - c.lo[s])});
+    local += c.hi[s] - c.lo[s] + 1;
+  }
 }
 
 }  // namespace
 
-int32_t build_plan(const Shape& sh, int64_t beta, const std::vector<CliqueRanges>& cliques,
-                   PlanHost* plan) {
+int32_t build_plan(const Shape& sh, int64_t beta, const std::vector<CliqueRanges>& mats,
+                   bool classify, PlanHost* plan) {
   const int K = sh.K;
-  const int64_t a = sh.off[K];
-  plan->strips.clear();
-  plan->chunks.clear();
-  plan->cliques.clear();
   plan->tiles.clear();
+  plan->mats.clear();
+  int64_t max_n = 0;
+  for (auto& c : mats) max_n = std::max(max_n, c.size());
+  int64_t min_hidden = sh.n[1];
+  for (int b = 1; b <= K - 1; ++b) min_hidden = std::min(min_hidden, sh.n[b]);
+  plan->tile_rows = max_n >= 512 ? 128 : (max_n >= 48 ? 64 : 32);
+  plan->tile_cols = 32;
+  const bool split_blocks = min_hidden >= 48;
   int64_t out_off = 0;
-  for (size_t ci = 0; ci < cliques.size(); ++ci) {
-    const CliqueRanges& c = cliques[ci];
+  for (size_t ci = 0; ci < mats.size(); ++ci) {
+    const CliqueRanges& c = mats[ci];
     const int64_t n = c.size();
-    NN_CHECK(n < (int64_t(1) << 30), NNSDP_ERR_ARG, "clique too large");
-    // cut the segments into per-block pieces
-    std::vector<Piece> pieces;
-    int64_t local = 0;
-    bool has_a = false;
-    for (int s = 0; s < c.nseg; ++s) {
-      for (int b = 0; b <= K; ++b) {
-        const int64_t b0 = sh.off[b], b1 = (b == K) ? a : sh.off[b + 1] - 1;
-        const int64_t g0 = std::max(c.lo[s], b0), g1 = std::min(c.hi[s], b1);
-        if (g0 > g1) continue;
-        pieces.push_back({g0, g1, b, local + (g0 - c.lo[s])});
-        if (b == K) has_a = true;
-      }
-      local += c.hi[s] - c.lo[s] + 1;
-    }
-    NN_CHECK(has_a, NNSDP_ERR_ARG, "clique without the affine index");
-    CliqueDev cd{};
-    cd.out_off = out_off;
-    cd.n = (int32_t)n;
-    cd.ld = (int32_t)n;
-    cd.chunk0 = (int32_t)plan->chunks.size();
-    cd.len1 = (int32_t)(c.hi[0] - c.lo[0] + 1);
-    cd.g1 = (int32_t)c.lo[0];
-    cd.g2 = (int32_t)(c.nseg > 1 ? c.lo[1] : 0);
-    // chunks (columns), affine column included as a 1-wide chunk
-    for (const Piece& pc : pieces) {
-      for (int64_t g = pc.g0; g <= pc.g1; g += CHUNK_COLS) {
-        ChunkDev ch{};
-        ch.gcol0 = (int32_t)g;
-        ch.ncols = (int32_t)std::min<int64_t>(CHUNK_COLS, pc.g1 - g + 1);
-        ch.col0 = (int32_t)(pc.l0 + (g - pc.g0));
-        ch.blk = pc.blk;
-        plan->chunks.push_back(ch);
-      }
-    }
-    cd.nchunks = (int32_t)plan->chunks.size() - cd.chunk0;
-    // strips (rows), affine row excluded (written by the last strip's epilogue)
-    const size_t first_strip = plan->strips.size();
-    for (const Piece& pc : pieces) {
-      if (pc.blk == K) continue;
-      for (int64_t g = pc.g0; g <= pc.g1; g += STRIP_ROWS) {
-        StripDev st{};
-        st.clique = (int32_t)ci;
-        st.grow0 = (int32_t)g;
-        st.nrows = (int32_t)std::min<int64_t>(STRIP_ROWS, pc.g1 - g + 1);
-        st.row0 = (int32_t)(pc.l0 + (g - pc.g0));
-        st.blk = pc.blk;
-        st.arow = 0;
-        st.tile0 = (int32_t)plan->tiles.size();
-        for (int j = 0; j < cd.nchunks; ++j) {
-          const ChunkDev& ch = plan->chunks[cd.chunk0 + j];
-          plan->tiles.push_back(classify(sh, beta, st.blk, st.grow0, st.grow0 + st.nrows - 1, ch.blk,
-                                         ch.gcol0, ch.gcol0 + ch.ncols - 1));
+    NN_CHECK(n < (int64_t(1) << 30), NNSDP_ERR_ARG, "output matrix too large");
+    std::vector<Piece> rows, cols;
+    cut(sh, c, split_blocks, plan->tile_rows, &rows);
+    cut(sh, c, split_blocks, plan->tile_cols, &cols);
+    for (const Piece& cp : cols) {
+      for (const Piece& rp : rows) {
+        TileDev t{};
+        t.mat = (int32_t)ci;
+        t.row0 = (int32_t)rp.l0;
+        t.nrows = (int32_t)(rp.g1 - rp.g0 + 1);
+        t.grow0 = (int32_t)rp.g0;
+        t.col0 = (int32_t)cp.l0;
+        t.ncols = (int32_t)(cp.g1 - cp.g0 + 1);
+        t.gcol0 = (int32_t)cp.g0;
+        const int rb0 = sh.block_of(rp.g0), rb1 = sh.block_of(rp.g1);
+        const int cb0 = sh.block_of(cp.g0), cb1 = sh.block_of(cp.g1);
+        uint32_t f = 0;
+        for (int Bi = rb0; Bi <= rb1; ++Bi) {
+          const int64_t br0 = std::max<int64_t>(rp.g0, sh.off[Bi]);
+          const int64_t br1 = std::min<int64_t>(rp.g1, Bi == K ? sh.off[K] : sh.off[Bi + 1] - 1);
+          for (int Bj = cb0; Bj <= cb1; ++Bj) {
+            const int64_t bc0 = std::max<int64_t>(cp.g0, sh.off[Bj]);
+            const int64_t bc1 = std::min<int64_t>(cp.g1, Bj == K ? sh.off[K] : sh.off[Bj + 1] - 1);
+            f |= pair_flags(sh, beta, Bi, br0, br1, Bj, bc0, bc1);
+          }
         }
-        plan->strips.push_back(st);
+        if (!classify) f = TF_ALL;
+        t.rblk = t.cblk = -1;
+        if (rb0 == rb1 && cb0 == cb1 && rb0 < K && cb0 < K) {
+          f |= TF_UNIFORM;
+          t.rblk = rb0;
+          t.cblk = cb0;
+        }
+        t.flags = f;
+        plan->tiles.push_back(t);
       }
     }
-    NN_CHECK(plan->strips.size() > first_strip, NNSDP_ERR_ARG, "clique with only the affine index");
-    plan->strips.back().arow = 1;
-    plan->cliques.push_back(cd);
+    MatDev md{};
+    md.out_off = out_off;
+    md.n = (int32_t)n;
+    md.ld = (int32_t)n;
+    plan->mats.push_back(md);
     out_off += n * n;
   }
   plan->per_query_doubles = out_off;
