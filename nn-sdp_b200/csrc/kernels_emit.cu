@@ -98,9 +98,11 @@ emit_kernel(NetDev net, BatchDev b, GramDev g, PlanDev plan, int q0, double* __r
         if (Br <= K - 2 && v.cnt[Br] > 0) val += v.G[g.goff[Br] + rl + (long long)cl * g.ldG[Br]];
         if (Br == 0) val += v.Z11[rl + cl * n0];
         if (Br == K - 1 && b.has_s22) {
+          // evaluated as (min, max) so that Z[r,c] and Z[c,r] are bit-identical
+          const int lo = rl < cl ? rl : cl, hi = rl < cl ? cl : rl;
           double s = 0.0;
           for (int m = 0; m < n_out; ++m)
-            s = fma(WK[m + (long long)rl * n_out], v.U[m + (long long)cl * n_out], s);
+            s = fma(WK[m + (long long)lo * n_out], v.U[m + (long long)hi * n_out], s);
           val += s;
         }
       }
