@@ -98,6 +98,11 @@ enum TileFlags : uint32_t {
   TF_UNIFORM = 1u << 8,  // rows lie in one block and columns lie in one block (rblk, cblk valid)
 };
 
+// Tile programs of the emitter (kernels_emit.cu).  RC / CR need 128 x 32 tiles and beta <= 4.
+enum TileProg : int32_t {
+  PROG_ZERO = 0, PROG_SAME = 1, PROG_RC = 2, PROG_CR = 3, PROG_MIXED = 4, PROG_GENERAL = 5,
+};
+
 struct TileDev {
   int32_t mat;          // index of the output matrix (clique) this tile belongs to
   int32_t row0, nrows;  // local row range
@@ -106,6 +111,7 @@ struct TileDev {
   int32_t gcol0;        // global z index of the first column
   uint32_t flags;
   int32_t rblk, cblk;   // block of the rows / columns when TF_UNIFORM
+  int32_t prog;         // TileProg
 };
 
 struct MatDev {
@@ -221,5 +227,7 @@ int launch_emit(const NetDev& net, const BatchDev& b, const GramDev& g, const Pl
                 int q0, int nq, double* out, cudaStream_t st);
 
 constexpr int PREP_THREADS = 256;
+constexpr int MAX_WINDOW_BETA = 4;  // RC / CR register-window programs are instantiated for beta <= 4
+constexpr int MAX_FAST_BETA = 8;  // uniform-tile fast path of the emitter stages 2*beta+1 <= 17 band taps
 
 }  // namespace nnsdp

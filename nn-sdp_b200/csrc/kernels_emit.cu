@@ -8,9 +8,20 @@
 //          + F(r,c) + F(c,r)  +  [band] (-2 T[jr,jc] - 2 gamma_bnd [jr == jc])
 //   F(r,c) = sum_{j in layer(blk(r)+1), |j - jc| <= beta} W[j, r] M[j, jc],   M = diag(q lambda) + T
 //  and written once, column-major, with consecutive threads on consecutive rows.
-// The kernel is HBM-write bound: 8 |C_k|^2 bytes per block.  Tiles carry host-computed flags
-// saying which terms can be non-zero inside them, so the bulk tiles reduce to a zero fill, a
-// Gram copy or a (2 beta + 1)-wide window sum over coalesced columns of W' / W.
+// The kernel is HBM-write bound: 8 |C_k|^2 bytes per block.
+//
+// Every output matrix is cut into tiles (128 x 32 for wide nets); the host plan gives each tile a
+// PROGRAM.  One CTA runs its tile for a whole group of queries (ring slots), so whatever depends
+// on the network only -- the W tile of a window sum -- is loaded once and reused from registers /
+// shared memory for every query of the group:
+//   ZERO     structurally zero                                   -> fill
+//   SAME     interior of a diagonal block (no band, no sliver)   -> copy of the Gram scratch, or fill
+//   RC       rows x_b against neurons of layer b+1               -> (2 beta+1)-tap sliding window over
+//                                                                   columns of W' held in registers
+//   CR       the transposed case                                 -> window over rows of a W tile in smem
+//   MIXED    any combination, rows/cols each inside one block    -> per-entry evaluation, hoisted tests
+//   GENERAL  anything (small nets, affine row/column)            -> per-entry evaluation with block lookup
+// All programs produce bit-identical values (same fma sequences, ascending neuron index).
 #include "internal.h"
 
 namespace nnsdp {
@@ -18,8 +29,13 @@ namespace nnsdp {
 namespace {
 
 constexpr int ETHREADS = 256;
+constexpr int SLOT_GROUP = 8;   // queries handled by one CTA
+constexpr int FAST_TR = 128, FAST_TC = 32, FAST_NCOL = 16;
+constexpr int MAX_TAPS = 2 * MAX_FAST_BETA + 1;
+constexpr int MAX_TC = 32;
+constexpr int SMEM_DOUBLES = 4608;  // 36 KB: max(CR tile 32 x 136, RC coefs 8 x 32 x 9, MIXED coefs 160 x 17)
 
-struct QView {  // per-query pointers, resolved once per CTA
+struct QView {  // per-query pointers
   const double* Md;
   const double* T0;
   const double* Bt;
@@ -32,37 +48,14 @@ struct QView {  // per-query pointers, resolved once per CTA
   const double* G;
 };
 
-// M[j, c] = delta_jc q_j lambda_j + T[j, c],  |j - c| <= beta
-__device__ __forceinline__ double m_coef(const QView& v, long long acdim, int j, int c) {
-  if (j == c) return v.Md[j];
-  const int t = j > c ? j - c : c - j;
-  return v.Bt[(long long)(t - 1) * acdim + (j < c ? j : c)];
-}
-
-__global__ void __launch_bounds__(ETHREADS)
-emit_kernel(NetDev net, BatchDev b, GramDev g, PlanDev plan, int q0, double* __restrict__ out) {
-  const TileDev t = plan.tiles[blockIdx.x];
-  const int slot = blockIdx.y, q = q0 + slot;
-  const MatDev mat = plan.mats[t.mat];
-  const int K = net.K, n0 = net.n_in, a = net.Zdim - 1, beta = b.beta;
+__device__ __forceinline__ QView make_view(const NetDev& net, const BatchDev& b, const GramDev& g,
+                                           int q, int slot) {
   const long long acdim = net.acdim;
-
-  const int TR = plan.tile_rows;
-  const int tr = threadIdx.x % TR, cg = threadIdx.x / TR, ncg = ETHREADS / TR;
-  if (tr >= t.nrows) return;
-
-  double* o = out + (long long)slot * plan.per_query + mat.out_off + (t.row0 + tr) +
-              (long long)t.col0 * mat.ld;
-  const uint32_t flags = t.flags;
-  if ((flags & TF_ALL) == 0) {  // structurally zero tile
-    for (int c = cg; c < t.ncols; c += ncg) o[(long long)c * mat.ld] = 0.0;
-    return;
-  }
-
+  const int K = net.K, n0 = net.n_in;
   QView v;
   v.Md = b.Md + (long long)q * acdim;
   v.T0 = b.T0 + (long long)q * acdim;
-  v.Bt = b.Bt + (long long)q * beta * acdim;
+  v.Bt = b.Bt + (long long)q * b.beta * acdim;
   v.gbnd = b.gbnd + q * b.s_gbnd;
   v.aff = b.aff + (long long)q * net.Zdim;
   v.Z11 = b.Z11 + (long long)q * n0 * n0;
@@ -70,8 +63,122 @@ emit_kernel(NetDev net, BatchDev b, GramDev g, PlanDev plan, int q0, double* __r
   v.U = b.U + (long long)q * net.n_out * net.n[K - 1];
   v.cnt = b.cnt + (long long)q * K;
   v.G = g.scratch + (long long)slot * g.per_query;
+  return v;
+}
 
-  // row-dependent quantities
+// M[j, c] = delta_jc q_j lambda_j + T[j, c],  |j - c| <= beta
+__device__ __forceinline__ double m_coef(const double* Md, const double* Bt, long long acdim, int j,
+                                         int c) {
+  if (j == c) return Md[j];
+  const int t = j > c ? j - c : c - j;
+  return Bt[(long long)(t - 1) * acdim + (j < c ? j : c)];
+}
+
+// ---------------------------------------------------------------------------------------------
+// MIXED: uniform tile, every block-level decision hoisted, band coefficients staged in smem
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void emit_mixed(const NetDev& net, const BatchDev& b, const GramDev& g,
+                                           const TileDev& t, const MatDev& mat, const QView& v,
+                                           double* __restrict__ o, int tr, int cg, int ncg,
+                                           double* smem) {
+  const int K = net.K, n0 = net.n_in, beta = b.beta, ntap = 2 * beta + 1;
+  const long long acdim = net.acdim;
+  const uint32_t flags = t.flags;
+  const int Br = t.rblk, Bc = t.cblk;
+  const int rl0 = t.grow0 - net.off[Br], cl0 = t.gcol0 - net.off[Bc];
+  const int jr0 = t.grow0 - n0, jc0 = t.gcol0 - n0;  // neuron index of the first row / column
+  const bool same = (Br == Bc) && (flags & TF_SAME);
+  const bool gram = same && Br <= K - 2 && v.cnt[Br] > 0;
+  const bool z11 = same && Br == 0;
+  const bool s22 = same && Br == K - 1 && b.has_s22;
+  const bool k1a = (flags & TF_1K) && b.has_s12 && Br == 0 && Bc == K - 1;
+  const bool k1b = (flags & TF_1K) && b.has_s12 && Bc == 0 && Br == K - 1;
+  const bool rc = (flags & TF_RC) && Br <= K - 2 && Bc >= 1;
+  const bool cr = (flags & TF_CR) && Bc <= K - 2 && Br >= 1;
+  const bool band = (flags & TF_BAND) && Br >= 1 && Bc >= 1;
+  const int Lr0 = rc ? net.off[Br + 1] - n0 : 0, nLr = rc ? net.n[Br + 1] : 0;
+  const int Lc0 = cr ? net.off[Bc + 1] - n0 : 0, nLc = cr ? net.n[Bc + 1] : 0;
+  double* coefRC = smem;
+  double* coefCR = smem + MAX_TC * MAX_TAPS;
+
+  __syncthreads();  // smem may still be read by the previous query of the group
+  if (rc)
+    for (int i = threadIdx.x; i < t.ncols * ntap; i += ETHREADS) {
+      const int c = i / ntap, jc = jc0 + c, j = jc - beta + i % ntap;
+      coefRC[i] = (j >= Lr0 && j < Lr0 + nLr) ? m_coef(v.Md, v.Bt, acdim, j, jc) : 0.0;
+    }
+  if (cr)
+    for (int i = threadIdx.x; i < t.nrows * ntap; i += ETHREADS) {
+      const int r = i / ntap, jr = jr0 + r, j = jr - beta + i % ntap;
+      coefCR[i] = (j >= Lc0 && j < Lc0 + nLc) ? m_coef(v.Md, v.Bt, acdim, j, jr) : 0.0;
+    }
+  __syncthreads();
+  if (tr >= t.nrows) return;
+
+  const int rl = rl0 + tr, jr = jr0 + tr;
+  const double* Gp = gram ? v.G + g.goff[Br] + rl : nullptr;
+  const int ldG = gram ? g.ldG[Br] : 0;
+  const double* WtR = rc ? net.Wt[Br] + rl : nullptr;
+  const int ldTR = rc ? net.ldT[Br] : 0;
+  const double* Wc0 = cr ? net.M[Bc] : nullptr;
+  const double* WK = net.M[K - 1];
+  const int n_out = net.n_out;
+  // valid taps of the transposed term depend on the row only
+  const int cr_lo = cr ? max(0, Lc0 - (jr - beta)) : 0;
+  const int cr_hi = cr ? min(ntap - 1, Lc0 + nLc - 1 - (jr - beta)) : -1;
+  const double* myCR = coefCR + tr * ntap;
+  double bdiag = 0.0;
+  if (band && jr >= jc0 && jr < jc0 + t.ncols) bdiag = -2.0 * v.T0[jr] - 2.0 * v.gbnd[jr];
+
+  for (int c = cg; c < t.ncols; c += ncg) {
+    const int cl = cl0 + c, jc = jc0 + c;
+    double val = 0.0;
+    if (gram) val += Gp[(long long)cl * ldG];
+    if (z11) val += v.Z11[rl + cl * n0];
+    if (s22) {
+      // evaluated as (min, max) so that Z[r,c] and Z[c,r] are bit-identical
+      const int lo = rl < cl ? rl : cl, hi = rl < cl ? cl : rl;
+      double s = 0.0;
+      for (int m = 0; m < n_out; ++m)
+        s = fma(WK[m + (long long)lo * n_out], v.U[m + (long long)hi * n_out], s);
+      val += s;
+    }
+    if (k1a) val += v.Z1K[rl + (long long)cl * n0];
+    if (k1b) val += v.Z1K[cl + (long long)rl * n0];
+    double f1 = 0.0, f2 = 0.0;
+    if (rc) {
+      const int jb = jc - beta;  // tap tt <-> neuron jb + tt
+      const int lo = max(0, Lr0 - jb), hi = min(ntap - 1, Lr0 + nLr - 1 - jb);
+      const double* w = WtR + (long long)(jb - Lr0) * ldTR;
+      const double* cf = coefRC + c * ntap;
+      for (int tt = lo; tt <= hi; ++tt) f1 = fma(w[(long long)tt * ldTR], cf[tt], f1);
+    }
+    if (cr) {
+      const double* w = Wc0 + (long long)cl * nLc + (jr - beta - Lc0);
+      for (int tt = cr_lo; tt <= cr_hi; ++tt) f2 = fma(w[tt], myCR[tt], f2);
+    }
+    val += f1 + f2;  // commutative: Z[r,c] and Z[c,r] come out bit-identical
+    if (band) {
+      const int d = jr > jc ? jr - jc : jc - jr;
+      if (d == 0)
+        val += bdiag;
+      else if (d <= beta)
+        val += -2.0 * v.Bt[(long long)(d - 1) * acdim + (jr < jc ? jr : jc)];
+    }
+    o[(long long)c * mat.ld] = val;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// GENERAL: per-entry block lookup, every term tested per entry
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void emit_general(const NetDev& net, const BatchDev& b, const GramDev& g,
+                                             const TileDev& t, const MatDev& mat, const QView& v,
+                                             double* __restrict__ o, int tr, int cg, int ncg) {
+  if (tr >= t.nrows) return;
+  const int K = net.K, n0 = net.n_in, a = net.Zdim - 1, beta = b.beta;
+  const long long acdim = net.acdim;
+  const uint32_t flags = t.flags;
   const int gr = t.grow0 + tr;
   const int Br = net.blk_of[gr];
   const int rl = gr - (Br < K ? net.off[Br] : a);
@@ -98,7 +205,6 @@ emit_kernel(NetDev net, BatchDev b, GramDev g, PlanDev plan, int q0, double* __r
         if (Br <= K - 2 && v.cnt[Br] > 0) val += v.G[g.goff[Br] + rl + (long long)cl * g.ldG[Br]];
         if (Br == 0) val += v.Z11[rl + cl * n0];
         if (Br == K - 1 && b.has_s22) {
-          // evaluated as (min, max) so that Z[r,c] and Z[c,r] are bit-identical
           const int lo = rl < cl ? rl : cl, hi = rl < cl ? cl : rl;
           double s = 0.0;
           for (int m = 0; m < n_out; ++m)
@@ -114,15 +220,16 @@ emit_kernel(NetDev net, BatchDev b, GramDev g, PlanDev plan, int q0, double* __r
       if ((flags & TF_RC) && r_feeds && jc >= 0) {
         const int jlo = max(Lr0, jc - beta), jhi = min(Lr0 + nLr - 1, jc + beta);
         for (int j = jlo; j <= jhi; ++j)
-          f1 = fma(WtR[(long long)(j - Lr0) * ldTR], m_coef(v, acdim, j, jc), f1);
+          f1 = fma(WtR[(long long)(j - Lr0) * ldTR], m_coef(v.Md, v.Bt, acdim, j, jc), f1);
       }
       if ((flags & TF_CR) && Bc <= K - 2 && jr >= 0) {
         const int Lc0 = net.off[Bc + 1] - n0, nLc = net.n[Bc + 1];
         const double* Wc = net.M[Bc] + (long long)cl * nLc;  // column cl of W_Bc: neuron-contiguous
         const int jlo = max(Lc0, jr - beta), jhi = min(Lc0 + nLc - 1, jr + beta);
-        for (int j = jlo; j <= jhi; ++j) f2 = fma(Wc[j - Lc0], m_coef(v, acdim, j, jr), f2);
+        for (int j = jlo; j <= jhi; ++j)
+          f2 = fma(Wc[j - Lc0], m_coef(v.Md, v.Bt, acdim, j, jr), f2);
       }
-      val += f1 + f2;  // commutative: Z[r,c] and Z[c,r] come out bit-identical
+      val += f1 + f2;
       if ((flags & TF_BAND) && jr >= 0 && jc >= 0) {
         const int d = jr > jc ? jr - jc : jc - jr;
         if (d == 0)
@@ -135,13 +242,200 @@ emit_kernel(NetDev net, BatchDev b, GramDev g, PlanDev plan, int q0, double* __r
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// RC: out[r, c] = sum_t Wt[r, jc - beta + t] * M[jc - beta + t, jc].  Thread = (row, 16 contiguous
+// columns); the 16 + 2 beta values of W' it needs are loaded once (coalesced over rows) and reused
+// for every query of the group; the per-column taps of all queries are staged in shared memory.
+// ---------------------------------------------------------------------------------------------
+template <int BETA>
+__device__ __forceinline__ void emit_rc(const NetDev& net, const BatchDev& b, const PlanDev& plan,
+                                        const TileDev& t, const MatDev& mat, int q0, int slot0,
+                                        int nslots, double* __restrict__ out, double* smem) {
+  constexpr int NTAP = 2 * BETA + 1;
+  const int n0 = net.n_in;
+  const long long acdim = net.acdim;
+  const int Br = t.rblk;
+  const int tr = threadIdx.x & (FAST_TR - 1), cg = threadIdx.x / FAST_TR;
+  const int rl = t.grow0 - net.off[Br] + tr;
+  const int jc0 = t.gcol0 - n0;
+  const int Lr0 = net.off[Br + 1] - n0, nLr = net.n[Br + 1];
+
+  // taps of every query of the group: coef[s][c][tt]
+  const int per_slot = t.ncols * NTAP;
+  for (int i = threadIdx.x; i < nslots * per_slot; i += ETHREADS) {
+    const int s = i / per_slot, rem = i - s * per_slot;
+    const int c = rem / NTAP, tt = rem - c * NTAP, jc = jc0 + c, j = jc - BETA + tt;
+    double cf = 0.0;
+    if (j >= Lr0 && j < Lr0 + nLr) {
+      const long long q = q0 + slot0 + s;
+      cf = m_coef(b.Md + q * acdim, b.Bt + q * BETA * acdim, acdim, j, jc);
+    }
+    smem[(s * FAST_TC + c) * NTAP + tt] = cf;
+  }
+  __syncthreads();
+  if (tr >= t.nrows) return;
+
+  const int cbase = cg * FAST_NCOL;
+  double w[FAST_NCOL + NTAP - 1];
+  {
+    const double* WtR = net.Wt[Br] + rl;
+    const int ldTR = net.ldT[Br];
+    const int jb = jc0 + cbase - BETA;
+#pragma unroll
+    for (int i = 0; i < FAST_NCOL + NTAP - 1; ++i) {
+      const int j = jb + i;
+      w[i] = (j >= Lr0 && j < Lr0 + nLr) ? WtR[(long long)(j - Lr0) * ldTR] : 0.0;
+    }
+  }
+  for (int s = 0; s < nslots; ++s) {
+    double* o = out + (long long)(slot0 + s) * plan.per_query + mat.out_off + (t.row0 + tr) +
+                (long long)(t.col0 + cbase) * mat.ld;
+    const double* cf = smem + (s * FAST_TC + cbase) * NTAP;
+#pragma unroll
+    for (int c = 0; c < FAST_NCOL; ++c) {
+      if (cbase + c < t.ncols) {
+        double f = 0.0;
+#pragma unroll
+        for (int tt = 0; tt < NTAP; ++tt) f = fma(w[c + tt], cf[c * NTAP + tt], f);
+        o[(long long)c * mat.ld] = f;
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// CR: out[jr, c] = sum_t W[jr - beta + t, c] * M[jr - beta + t, jr].  The (128 + 2 beta) x 32 tile of
+// W (neuron-contiguous) is staged once in shared memory; the taps depend on the row only and live
+// in registers per query.
+// ---------------------------------------------------------------------------------------------
+template <int BETA>
+__device__ __forceinline__ void emit_cr(const NetDev& net, const BatchDev& b, const PlanDev& plan,
+                                        const TileDev& t, const MatDev& mat, int q0, int slot0,
+                                        int nslots, double* __restrict__ out, double* smem) {
+  constexpr int NTAP = 2 * BETA + 1;
+  constexpr int LDW = FAST_TR + 2 * BETA;  // rows per staged column
+  const int n0 = net.n_in;
+  const long long acdim = net.acdim;
+  const int Bc = t.cblk;
+  const int tr = threadIdx.x & (FAST_TR - 1), cg = threadIdx.x / FAST_TR;
+  const int jr0 = t.grow0 - n0, jr = jr0 + tr;
+  const int cl0 = t.gcol0 - net.off[Bc];
+  const int Lc0 = net.off[Bc + 1] - n0, nLc = net.n[Bc + 1];
+  const double* Wc0 = net.M[Bc] + (long long)cl0 * nLc;
+  for (int i = threadIdx.x; i < t.ncols * LDW; i += ETHREADS) {
+    const int c = i / LDW, ii = i - c * LDW;
+    const int j = jr0 - BETA + ii;
+    smem[i] = (j >= Lc0 && j < Lc0 + nLc) ? Wc0[(long long)c * nLc + (j - Lc0)] : 0.0;
+  }
+  __syncthreads();
+  if (tr >= t.nrows) return;
+  const int cbase = cg * FAST_NCOL;
+  for (int s = 0; s < nslots; ++s) {
+    const long long q = q0 + slot0 + s;
+    const double* Md = b.Md + q * acdim;
+    const double* Bt = b.Bt + q * BETA * acdim;
+    double cf[NTAP];
+#pragma unroll
+    for (int tt = 0; tt < NTAP; ++tt) {
+      const int j = jr - BETA + tt;
+      cf[tt] = (j >= Lc0 && j < Lc0 + nLc) ? m_coef(Md, Bt, acdim, j, jr) : 0.0;
+    }
+    double* o = out + (long long)(slot0 + s) * plan.per_query + mat.out_off + (t.row0 + tr) +
+                (long long)(t.col0 + cbase) * mat.ld;
+#pragma unroll 4
+    for (int c = 0; c < FAST_NCOL; ++c) {
+      if (cbase + c < t.ncols) {
+        const double* ws = smem + (cbase + c) * LDW + tr;
+        double f = 0.0;
+#pragma unroll
+        for (int tt = 0; tt < NTAP; ++tt) f = fma(ws[tt], cf[tt], f);
+        o[(long long)c * mat.ld] = f;
+      }
+    }
+  }
+}
+
+template <int BETA>
+__device__ __forceinline__ void emit_window(int prog, const NetDev& net, const BatchDev& b,
+                                            const PlanDev& plan, const TileDev& t, const MatDev& mat,
+                                            int q0, int slot0, int nslots, double* __restrict__ out,
+                                            double* smem) {
+  if (prog == PROG_RC)
+    emit_rc<BETA>(net, b, plan, t, mat, q0, slot0, nslots, out, smem);
+  else
+    emit_cr<BETA>(net, b, plan, t, mat, q0, slot0, nslots, out, smem);
+}
+
+__global__ void __launch_bounds__(ETHREADS)
+emit_kernel(NetDev net, BatchDev b, GramDev g, PlanDev plan, int q0, int nq,
+            double* __restrict__ out) {
+  __shared__ double smem[SMEM_DOUBLES];
+  const TileDev t = plan.tiles[blockIdx.x];
+  const MatDev mat = plan.mats[t.mat];
+  const int slot0 = blockIdx.y * SLOT_GROUP;
+  const int nslots = min(SLOT_GROUP, nq - slot0);
+  const int TR = plan.tile_rows;
+  const int tr = threadIdx.x % TR, cg = threadIdx.x / TR, ncg = ETHREADS / TR;
+  const long long tile_off = mat.out_off + (t.row0 + tr) + (long long)t.col0 * mat.ld;
+  int prog = t.prog;
+
+  if (prog == PROG_SAME) {  // interior of a diagonal block: Gram copy, plain fill, or the S22 Gram
+    const int Br = t.rblk;
+    if (Br == net.K - 1) prog = b.has_s22 ? PROG_MIXED : PROG_ZERO;
+    else if (Br == 0) prog = PROG_MIXED;
+  }
+  if (prog == PROG_ZERO) {
+    if (tr < t.nrows)
+      for (int s = 0; s < nslots; ++s) {
+        double* o = out + (long long)(slot0 + s) * plan.per_query + tile_off;
+        for (int c = cg; c < t.ncols; c += ncg) o[(long long)c * mat.ld] = 0.0;
+      }
+    return;
+  }
+  if (prog == PROG_SAME) {
+    if (tr >= t.nrows) return;
+    const int Br = t.rblk;
+    const int rl = t.grow0 - net.off[Br] + tr, cl0 = t.gcol0 - net.off[Br];
+    const int ldG = g.ldG[Br];
+    const long long goff = g.goff[Br] + rl + (long long)cl0 * ldG;
+    for (int s = 0; s < nslots; ++s) {
+      double* o = out + (long long)(slot0 + s) * plan.per_query + tile_off;
+      if (b.cnt[(long long)(q0 + slot0 + s) * net.K + Br] > 0) {
+        const double* G = g.scratch + (long long)(slot0 + s) * g.per_query + goff;
+        for (int c = cg; c < t.ncols; c += ncg) o[(long long)c * mat.ld] = G[(long long)c * ldG];
+      } else {
+        for (int c = cg; c < t.ncols; c += ncg) o[(long long)c * mat.ld] = 0.0;
+      }
+    }
+    return;
+  }
+  if (prog == PROG_RC || prog == PROG_CR) {
+    switch (b.beta) {
+      case 0: emit_window<0>(prog, net, b, plan, t, mat, q0, slot0, nslots, out, smem); return;
+      case 1: emit_window<1>(prog, net, b, plan, t, mat, q0, slot0, nslots, out, smem); return;
+      case 2: emit_window<2>(prog, net, b, plan, t, mat, q0, slot0, nslots, out, smem); return;
+      case 3: emit_window<3>(prog, net, b, plan, t, mat, q0, slot0, nslots, out, smem); return;
+      case 4: emit_window<4>(prog, net, b, plan, t, mat, q0, slot0, nslots, out, smem); return;
+      default: prog = PROG_MIXED;
+    }
+  }
+  for (int s = 0; s < nslots; ++s) {
+    const QView v = make_view(net, b, g, q0 + slot0 + s, slot0 + s);
+    double* o = out + (long long)(slot0 + s) * plan.per_query + tile_off;
+    if (prog == PROG_MIXED)
+      emit_mixed(net, b, g, t, mat, v, o, tr, cg, ncg, smem);
+    else
+      emit_general(net, b, g, t, mat, v, o, tr, cg, ncg);
+  }
+}
+
 }  // namespace
 
 int launch_emit(const NetDev& net, const BatchDev& b, const GramDev& g, const PlanDev& plan,
                 int q0, int nq, double* out, cudaStream_t st) {
   if (plan.ntiles <= 0 || nq <= 0) return 0;
-  dim3 grid(plan.ntiles, nq);
-  emit_kernel<<<grid, ETHREADS, 0, st>>>(net, b, g, plan, q0, out);
+  dim3 grid(plan.ntiles, (nq + SLOT_GROUP - 1) / SLOT_GROUP);
+  emit_kernel<<<grid, ETHREADS, 0, st>>>(net, b, g, plan, q0, nq, out);
   return 1;
 }
 

@@ -203,12 +203,21 @@ int32_t build_plan(const Shape& sh, int64_t beta, const std::vector<CliqueRanges
         }
         if (!classify) f = TF_ALL;
         t.rblk = t.cblk = -1;
-        if (rb0 == rb1 && cb0 == cb1 && rb0 < K && cb0 < K) {
+        if (rb0 == rb1 && cb0 == cb1 && rb0 < K && cb0 < K && beta <= MAX_FAST_BETA) {
           f |= TF_UNIFORM;
           t.rblk = rb0;
           t.cblk = cb0;
         }
         t.flags = f;
+        const uint32_t terms = f & TF_ALL;
+        const bool fast = (f & TF_UNIFORM) && plan->tile_rows == 128 && plan->tile_cols == 32 &&
+                          beta <= MAX_WINDOW_BETA;
+        if (terms == 0) t.prog = PROG_ZERO;
+        else if (!(f & TF_UNIFORM)) t.prog = PROG_GENERAL;
+        else if (terms == TF_SAME) t.prog = PROG_SAME;
+        else if (terms == TF_RC && fast) t.prog = PROG_RC;
+        else if (terms == TF_CR && fast) t.prog = PROG_CR;
+        else t.prog = PROG_MIXED;
         plan->tiles.push_back(t);
       }
     }

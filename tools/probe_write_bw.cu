@@ -1,0 +1,75 @@
+// Microbenchmarks behind the design of the block emitter: how fast can B200 take a
+// column-major tiled write stream, and what does a leading dimension that is not a multiple of
+// 4 doubles (32 B sectors) cost?   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o probe tools/probe_write_bw.cu
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <stdlib.h>
+#define CK(x) do { cudaError_t e = (x); if (e != cudaSuccess) { printf("CUDA %s at %d\n", cudaGetErrorString(e), __LINE__); exit(1);} } while (0)
+
+// tile = 128 rows x 32 cols, 256 threads, thread = (row, column group), 8 B stores
+__global__ void tile_fill8(double* out, int n, int ld, int tiles_r, double v) {
+  const int tr = threadIdx.x & 127, cg = threadIdx.x >> 7;
+  const int r0 = (blockIdx.x % tiles_r) * 128, c0 = (blockIdx.x / tiles_r) * 32;
+  double* o = out + (size_t)blockIdx.y * (size_t)ld * n;
+  const int r = r0 + tr;
+  if (r >= n) return;
+  for (int c = cg; c < 32; c += 2) if (c0 + c < n) o[r + (size_t)(c0 + c) * ld] = v;
+}
+// same tile, but rows are re-based per column so that every warp store covers whole 32 B sectors
+__global__ void tile_fill8_aligned(double* out, int n, int ld, int tiles_r, double v) {
+  const int tr = threadIdx.x & 127, cg = threadIdx.x >> 7;
+  const int r0 = (blockIdx.x % tiles_r) * 128, c0 = (blockIdx.x / tiles_r) * 32;
+  double* o = out + (size_t)blockIdx.y * (size_t)ld * n;
+  const int rend = min(r0 + 128, n);
+  for (int c = cg; c < 32; c += 2) {
+    if (c0 + c >= n) break;
+    double* col = o + (size_t)(c0 + c) * ld;
+    const int mis = (int)(((size_t)(col + r0) >> 3) & 3);     // doubles past a sector boundary
+    const int start = r0 - mis;                                 // sector-aligned virtual start
+    for (int r = start + tr; r < rend; r += 128) if (r >= r0) col[r] = v;
+    // rows [start+128, rend) are picked up by the second trip of the loop (at most 3 rows)
+  }
+}
+// 16 B stores where the address allows it (ld even)
+__global__ void tile_fill16(double* out, int n, int ld, int tiles_r, double v) {
+  const int tr = threadIdx.x & 63, cg = threadIdx.x >> 6;
+  const int r0 = (blockIdx.x % tiles_r) * 128, c0 = (blockIdx.x / tiles_r) * 32;
+  double* o = out + (size_t)blockIdx.y * (size_t)ld * n;
+  const int r = r0 + 2 * tr;
+  if (r + 1 >= n) return;
+  for (int c = cg; c < 32; c += 4) if (c0 + c < n) *reinterpret_cast<double2*>(o + r + (size_t)(c0 + c) * ld) = make_double2(v, v);
+}
+__global__ void linear_fill(double* out, size_t n, double v) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) out[i] = v;
+}
+
+int main() {
+  const int nmat = 64;
+  const int n = 3003;
+  size_t cap = (size_t)nmat * 3008 * 3008 + 1024;
+  double* buf; CK(cudaMalloc(&buf, cap * 8));
+  cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+  auto timeit = [&](const char* name, auto fn, double bytes) {
+    for (int i = 0; i < 2; ++i) fn();
+    CK(cudaDeviceSynchronize());
+    cudaEventRecord(e0);
+    const int reps = 5;
+    for (int i = 0; i < reps; ++i) fn();
+    cudaEventRecord(e1); CK(cudaEventSynchronize(e1));
+    float ms; cudaEventElapsedTime(&ms, e0, e1);
+    printf("%-44s %8.3f ms  %8.1f GB/s\n", name, ms / reps, bytes / (ms / reps * 1e-3) / 1e9);
+  };
+  const int tiles_r = (n + 127) / 128, tiles_c = (n + 31) / 32;
+  dim3 grid(tiles_r * tiles_c, nmat);
+  double bytes = (double)nmat * n * n * 8;
+  timeit("cudaMemsetAsync", [&] { cudaMemsetAsync(buf, 0, (size_t)nmat * n * n * 8); }, bytes);
+  timeit("linear_fill 8B grid-stride", [&] { linear_fill<<<148 * 16, 256>>>(buf, (size_t)nmat * n * n, 1.0); }, bytes);
+  timeit("tile_fill8 ld=3003", [&] { tile_fill8<<<grid, 256>>>(buf, n, 3003, tiles_r, 1.0); }, bytes);
+  timeit("tile_fill8 ld=3004", [&] { tile_fill8<<<grid, 256>>>(buf, n, 3004, tiles_r, 1.0); }, bytes);
+  timeit("tile_fill8 ld=3008", [&] { tile_fill8<<<grid, 256>>>(buf, n, 3008, tiles_r, 1.0); }, bytes);
+  timeit("tile_fill8_aligned ld=3003", [&] { tile_fill8_aligned<<<grid, 256>>>(buf, n, 3003, tiles_r, 1.0); }, bytes);
+  timeit("tile_fill16 ld=3004", [&] { tile_fill16<<<grid, 256>>>(buf, n, 3004, tiles_r, 1.0); }, bytes);
+  timeit("tile_fill16 ld=3008", [&] { tile_fill16<<<grid, 256>>>(buf, n, 3008, tiles_r, 1.0); }, bytes);
+  CK(cudaGetLastError());
+  return 0;
+}
