@@ -584,6 +584,9 @@ int32_t nnsdp_batch_create(nnsdp_ctx* ctx, int32_t dev_index, const nnsdp_net* n
     b->pd.tiles = b->d_tiles.as<TileDev>();
     b->pd.mats = b->d_mats.as<MatDev>();
     b->pd.ntiles = (int)b->plan.tiles.size();
+    b->pd.n_fill = b->plan.n_fill;
+    b->pd.n_window = b->plan.n_window;
+    b->pd.n_edge = b->plan.n_edge;
     b->pd.tile_rows = b->plan.tile_rows;
     b->pd.per_query = b->plan.per_query_doubles;
     b->gd.scratch = b->gram.as<double>();

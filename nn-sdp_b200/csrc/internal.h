@@ -101,6 +101,7 @@ enum TileFlags : uint32_t {
 // Tile programs of the emitter (kernels_emit.cu).  RC / CR need 128 x 32 tiles and beta <= 4.
 enum TileProg : int32_t {
   PROG_ZERO = 0, PROG_SAME = 1, PROG_RC = 2, PROG_CR = 3, PROG_MIXED = 4, PROG_GENERAL = 5,
+  PROG_DIAG = 6, PROG_AFF = 7,
 };
 
 struct TileDev {
@@ -125,6 +126,7 @@ struct PlanHost {
   std::vector<MatDev> mats;
   int64_t per_query_doubles = 0;
   int tile_rows = 0, tile_cols = 0;
+  int n_fill = 0, n_window = 0, n_edge = 0;  // tiles are sorted by kernel class
 };
 
 // tile_rows in {32, 64, 128}; classify = false marks every tile TF_ALL (validation mode).
@@ -192,7 +194,8 @@ struct GramDev {
 struct PlanDev {
   const TileDev* tiles;
   const MatDev* mats;
-  int ntiles;
+  int ntiles;                // tiles are sorted: [fill | window | edge]
+  int n_fill, n_window, n_edge;
   int tile_rows;
   long long per_query;       // doubles per query in the output
 };

@@ -22,6 +22,8 @@
 //   MIXED    any combination, rows/cols each inside one block    -> per-entry evaluation, hoisted tests
 //   GENERAL  anything (small nets, affine row/column)            -> per-entry evaluation with block lookup
 // All programs produce bit-identical values (same fma sequences, ascending neuron index).
+#include <stdlib.h>
+
 #include "internal.h"
 
 namespace nnsdp {
@@ -72,6 +74,15 @@ __device__ __forceinline__ double m_coef(const double* Md, const double* Bt, lon
   if (j == c) return Md[j];
   const int t = j > c ? j - c : c - j;
   return Bt[(long long)(t - 1) * acdim + (j < c ? j : c)];
+}
+
+// Band term of neuron pair (jr, jc), |jr - jc| <= beta: -2 T[jr,jc] - 2 gamma_bnd [jr == jc].
+// Written with non-contractible intrinsics so every program rounds it identically.
+__device__ __forceinline__ double band_term(const double* T0, const double* gbnd, const double* Bt,
+                                            long long acdim, int jr, int jc) {
+  if (jr == jc) return __dadd_rn(__dmul_rn(-2.0, T0[jr]), __dmul_rn(-2.0, gbnd[jr]));
+  const int d = jr > jc ? jr - jc : jc - jr;
+  return __dmul_rn(-2.0, Bt[(long long)(d - 1) * acdim + (jr < jc ? jr : jc)]);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -127,8 +138,6 @@ __device__ __forceinline__ void emit_mixed(const NetDev& net, const BatchDev& b,
   const int cr_lo = cr ? max(0, Lc0 - (jr - beta)) : 0;
   const int cr_hi = cr ? min(ntap - 1, Lc0 + nLc - 1 - (jr - beta)) : -1;
   const double* myCR = coefCR + tr * ntap;
-  double bdiag = 0.0;
-  if (band && jr >= jc0 && jr < jc0 + t.ncols) bdiag = -2.0 * v.T0[jr] - 2.0 * v.gbnd[jr];
 
   for (int c = cg; c < t.ncols; c += ncg) {
     const int cl = cl0 + c, jc = jc0 + c;
@@ -160,10 +169,7 @@ __device__ __forceinline__ void emit_mixed(const NetDev& net, const BatchDev& b,
     val += f1 + f2;  // commutative: Z[r,c] and Z[c,r] come out bit-identical
     if (band) {
       const int d = jr > jc ? jr - jc : jc - jr;
-      if (d == 0)
-        val += bdiag;
-      else if (d <= beta)
-        val += -2.0 * v.Bt[(long long)(d - 1) * acdim + (jr < jc ? jr : jc)];
+      if (d <= beta) val = __dadd_rn(val, band_term(v.T0, v.gbnd, v.Bt, acdim, jr, jc));
     }
     o[(long long)c * mat.ld] = val;
   }
@@ -232,10 +238,7 @@ __device__ __forceinline__ void emit_general(const NetDev& net, const BatchDev& 
       val += f1 + f2;
       if ((flags & TF_BAND) && jr >= 0 && jc >= 0) {
         const int d = jr > jc ? jr - jc : jc - jr;
-        if (d == 0)
-          val += -2.0 * v.T0[jr] - 2.0 * v.gbnd[jr];
-        else if (d <= beta)
-          val += -2.0 * v.Bt[(long long)(d - 1) * acdim + (jr < jc ? jr : jc)];
+        if (d <= beta) val = __dadd_rn(val, band_term(v.T0, v.gbnd, v.Bt, acdim, jr, jc));
       }
     }
     o[(long long)c * mat.ld] = val;
@@ -355,74 +358,111 @@ __device__ __forceinline__ void emit_cr(const NetDev& net, const BatchDev& b, co
   }
 }
 
+// ---- kernel 1: tiles whose bulk is a plain store stream; one (tile, query) per CTA -----------------
+//   ZERO  fill                 SAME  Gram copy | S22 Gram | fill
+//   DIAG  SAME + the (2 beta + 1)-wide band patched in afterwards by the thread that owns the entry
+//   AFF   the affine row / column Z[a, :], Z[:, a]
+__device__ __forceinline__ double s22_entry(const double* WK, const double* U, int n_out, int rl, int cl) {
+  const int lo = rl < cl ? rl : cl, hi = rl < cl ? cl : rl;  // (min, max): bit-symmetric
+  double acc = 0.0;
+  for (int m = 0; m < n_out; ++m)
+    acc = fma(WK[m + (long long)lo * n_out], U[m + (long long)hi * n_out], acc);
+  return acc;
+}
+
+__global__ void __launch_bounds__(ETHREADS)
+emit_fill_kernel(NetDev net, BatchDev b, GramDev g, PlanDev plan, int q0, int nq,
+                 double* __restrict__ out) {
+  const TileDev t = plan.tiles[blockIdx.x];
+  const MatDev mat = plan.mats[t.mat];
+  const int slot = blockIdx.y, q = q0 + slot;
+  const int TR = plan.tile_rows;
+  const int tr = threadIdx.x % TR, cg = threadIdx.x / TR, ncg = ETHREADS / TR;
+  if (tr >= t.nrows) return;
+  const long long ld = mat.ld;
+  double* o = out + (long long)slot * plan.per_query + mat.out_off + (t.row0 + tr) + t.col0 * ld;
+  const int K = net.K, prog = t.prog;
+  if (prog == PROG_ZERO) {
+    for (int c = cg; c < t.ncols; c += ncg) o[c * ld] = 0.0;
+    return;
+  }
+  if (prog == PROG_AFF) {
+    const double* aff = b.aff + (long long)q * net.Zdim;
+    const int a = net.Zdim - 1, gr = t.grow0 + tr;
+    for (int c = cg; c < t.ncols; c += ncg) o[c * ld] = aff[gr == a ? t.gcol0 + c : gr];
+    return;
+  }
+  // SAME / DIAG: rows and columns in block Br, 1 <= Br <= K-1
+  const int Br = t.rblk;
+  const int rl = t.grow0 - net.off[Br] + tr, cl0 = t.gcol0 - net.off[Br];
+  const bool copy = Br <= K - 2 && b.cnt[(long long)q * K + Br] > 0;  // Gram of an active layer
+  const bool s22 = Br == K - 1 && b.has_s22;                           // W_K' S22 W_K of the output QC
+  const double* G = nullptr;
+  int ldG = 0;
+  const double* WK = net.M[K - 1];
+  const double* U = b.U + (long long)q * net.n_out * net.n[K - 1];
+  if (copy) {
+    ldG = g.ldG[Br];
+    G = g.scratch + (long long)slot * g.per_query + g.goff[Br] + rl + (long long)cl0 * ldG;
+    for (int c = cg; c < t.ncols; c += ncg) o[c * ld] = G[(long long)c * ldG];
+  } else if (s22) {
+    for (int c = cg; c < t.ncols; c += ncg) o[c * ld] = s22_entry(WK, U, net.n_out, rl, cl0 + c);
+  } else {
+    for (int c = cg; c < t.ncols; c += ncg) o[c * ld] = 0.0;
+  }
+  if (prog == PROG_DIAG) {
+    // band entries of this row: columns jr - beta .. jr + beta; each is re-written by its owner
+    const int beta = b.beta, n0 = net.n_in;
+    const long long acdim = net.acdim;
+    const int jr = t.grow0 - n0 + tr, jc0 = t.gcol0 - n0;
+    const double* T0 = b.T0 + (long long)q * acdim;
+    const double* Bt = b.Bt + (long long)q * beta * acdim;
+    const double* gbnd = b.gbnd + q * b.s_gbnd;
+    for (int jc = max(jr - beta, jc0); jc <= min(jr + beta, jc0 + t.ncols - 1); ++jc) {
+      const int c = jc - jc0;
+      if (c % ncg != cg) continue;
+      double val = 0.0;
+      if (copy) val += G[(long long)c * ldG];
+      if (s22) val += s22_entry(WK, U, net.n_out, rl, cl0 + c);
+      val += 0.0;  // the (absent) window terms f1 + f2 of the general formula
+      o[c * ld] = __dadd_rn(val, band_term(T0, gbnd, Bt, acdim, jr, jc));
+    }
+  }
+}
+
+// ---- kernel 2: RC / CR window sums (128 x 32 tiles, beta <= 4) ------------------------------------
 template <int BETA>
-__device__ __forceinline__ void emit_window(int prog, const NetDev& net, const BatchDev& b,
-                                            const PlanDev& plan, const TileDev& t, const MatDev& mat,
-                                            int q0, int slot0, int nslots, double* __restrict__ out,
-                                            double* smem) {
-  if (prog == PROG_RC)
+__global__ void __launch_bounds__(ETHREADS)
+emit_window_kernel(NetDev net, BatchDev b, PlanDev plan, int tile0, int q0, int nq, int group,
+                   double* __restrict__ out) {
+  __shared__ double smem[SMEM_DOUBLES];
+  const TileDev t = plan.tiles[tile0 + blockIdx.x];
+  const MatDev mat = plan.mats[t.mat];
+  const int slot0 = blockIdx.y * group;
+  const int nslots = min(group, nq - slot0);
+  if (t.prog == PROG_RC)
     emit_rc<BETA>(net, b, plan, t, mat, q0, slot0, nslots, out, smem);
   else
     emit_cr<BETA>(net, b, plan, t, mat, q0, slot0, nslots, out, smem);
 }
 
+// ---- kernel 3: everything else (band / sliver / corner tiles, affine row and column, small nets) -
 __global__ void __launch_bounds__(ETHREADS)
-emit_kernel(NetDev net, BatchDev b, GramDev g, PlanDev plan, int q0, int nq,
-            double* __restrict__ out) {
-  __shared__ double smem[SMEM_DOUBLES];
-  const TileDev t = plan.tiles[blockIdx.x];
+emit_edge_kernel(NetDev net, BatchDev b, GramDev g, PlanDev plan, int tile0, int q0, int nq,
+                 int group, double* __restrict__ out) {
+  __shared__ double smem[MAX_TC * MAX_TAPS + 128 * MAX_TAPS];
+  const TileDev t = plan.tiles[tile0 + blockIdx.x];
   const MatDev mat = plan.mats[t.mat];
-  const int slot0 = blockIdx.y * SLOT_GROUP;
-  const int nslots = min(SLOT_GROUP, nq - slot0);
+  const int slot0 = blockIdx.y * group;
+  const int nslots = min(group, nq - slot0);
   const int TR = plan.tile_rows;
   const int tr = threadIdx.x % TR, cg = threadIdx.x / TR, ncg = ETHREADS / TR;
   const long long tile_off = mat.out_off + (t.row0 + tr) + (long long)t.col0 * mat.ld;
-  int prog = t.prog;
-
-  if (prog == PROG_SAME) {  // interior of a diagonal block: Gram copy, plain fill, or the S22 Gram
-    const int Br = t.rblk;
-    if (Br == net.K - 1) prog = b.has_s22 ? PROG_MIXED : PROG_ZERO;
-    else if (Br == 0) prog = PROG_MIXED;
-  }
-  if (prog == PROG_ZERO) {
-    if (tr < t.nrows)
-      for (int s = 0; s < nslots; ++s) {
-        double* o = out + (long long)(slot0 + s) * plan.per_query + tile_off;
-        for (int c = cg; c < t.ncols; c += ncg) o[(long long)c * mat.ld] = 0.0;
-      }
-    return;
-  }
-  if (prog == PROG_SAME) {
-    if (tr >= t.nrows) return;
-    const int Br = t.rblk;
-    const int rl = t.grow0 - net.off[Br] + tr, cl0 = t.gcol0 - net.off[Br];
-    const int ldG = g.ldG[Br];
-    const long long goff = g.goff[Br] + rl + (long long)cl0 * ldG;
-    for (int s = 0; s < nslots; ++s) {
-      double* o = out + (long long)(slot0 + s) * plan.per_query + tile_off;
-      if (b.cnt[(long long)(q0 + slot0 + s) * net.K + Br] > 0) {
-        const double* G = g.scratch + (long long)(slot0 + s) * g.per_query + goff;
-        for (int c = cg; c < t.ncols; c += ncg) o[(long long)c * mat.ld] = G[(long long)c * ldG];
-      } else {
-        for (int c = cg; c < t.ncols; c += ncg) o[(long long)c * mat.ld] = 0.0;
-      }
-    }
-    return;
-  }
-  if (prog == PROG_RC || prog == PROG_CR) {
-    switch (b.beta) {
-      case 0: emit_window<0>(prog, net, b, plan, t, mat, q0, slot0, nslots, out, smem); return;
-      case 1: emit_window<1>(prog, net, b, plan, t, mat, q0, slot0, nslots, out, smem); return;
-      case 2: emit_window<2>(prog, net, b, plan, t, mat, q0, slot0, nslots, out, smem); return;
-      case 3: emit_window<3>(prog, net, b, plan, t, mat, q0, slot0, nslots, out, smem); return;
-      case 4: emit_window<4>(prog, net, b, plan, t, mat, q0, slot0, nslots, out, smem); return;
-      default: prog = PROG_MIXED;
-    }
-  }
+  const bool uniform = (t.flags & TF_UNIFORM) != 0;
   for (int s = 0; s < nslots; ++s) {
     const QView v = make_view(net, b, g, q0 + slot0 + s, slot0 + s);
     double* o = out + (long long)(slot0 + s) * plan.per_query + tile_off;
-    if (prog == PROG_MIXED)
+    if (uniform)
       emit_mixed(net, b, g, t, mat, v, o, tr, cg, ncg, smem);
     else
       emit_general(net, b, g, t, mat, v, o, tr, cg, ncg);
@@ -433,10 +473,33 @@ emit_kernel(NetDev net, BatchDev b, GramDev g, PlanDev plan, int q0, int nq,
 
 int launch_emit(const NetDev& net, const BatchDev& b, const GramDev& g, const PlanDev& plan,
                 int q0, int nq, double* out, cudaStream_t st) {
-  if (plan.ntiles <= 0 || nq <= 0) return 0;
-  dim3 grid(plan.ntiles, (nq + SLOT_GROUP - 1) / SLOT_GROUP);
-  emit_kernel<<<grid, ETHREADS, 0, st>>>(net, b, g, plan, q0, nq, out);
-  return 1;
+  if (nq <= 0) return 0;
+  static const int wgroup = [] { const char* e = getenv("NNSDP_WINDOW_GROUP"); int v = e ? atoi(e) : SLOT_GROUP; return v < 1 ? 1 : (v > SLOT_GROUP ? SLOT_GROUP : v); }();
+  static const int egroup = [] { const char* e = getenv("NNSDP_EDGE_GROUP"); int v = e ? atoi(e) : SLOT_GROUP; return v < 1 ? 1 : (v > SLOT_GROUP ? SLOT_GROUP : v); }();
+  int launches = 0;
+  if (plan.n_fill > 0) {
+    emit_fill_kernel<<<dim3(plan.n_fill, nq), ETHREADS, 0, st>>>(net, b, g, plan, q0, nq, out);
+    ++launches;
+  }
+  if (plan.n_window > 0) {
+    const dim3 grid(plan.n_window, (nq + wgroup - 1) / wgroup);
+    const int t0 = plan.n_fill;
+    switch (b.beta) {
+      case 0: emit_window_kernel<0><<<grid, ETHREADS, 0, st>>>(net, b, plan, t0, q0, nq, wgroup, out); break;
+      case 1: emit_window_kernel<1><<<grid, ETHREADS, 0, st>>>(net, b, plan, t0, q0, nq, wgroup, out); break;
+      case 2: emit_window_kernel<2><<<grid, ETHREADS, 0, st>>>(net, b, plan, t0, q0, nq, wgroup, out); break;
+      case 3: emit_window_kernel<3><<<grid, ETHREADS, 0, st>>>(net, b, plan, t0, q0, nq, wgroup, out); break;
+      case 4: emit_window_kernel<4><<<grid, ETHREADS, 0, st>>>(net, b, plan, t0, q0, nq, wgroup, out); break;
+      default: return -1;  // the plan never emits window tiles for beta > MAX_WINDOW_BETA
+    }
+    ++launches;
+  }
+  if (plan.n_edge > 0) {
+    emit_edge_kernel<<<dim3(plan.n_edge, (nq + egroup - 1) / egroup), ETHREADS, 0, st>>>(
+        net, b, g, plan, plan.n_fill + plan.n_window, q0, nq, egroup, out);
+    ++launches;
+  }
+  return launches;
 }
 
 }  // namespace nnsdp

@@ -212,9 +212,14 @@ int32_t build_plan(const Shape& sh, int64_t beta, const std::vector<CliqueRanges
         const uint32_t terms = f & TF_ALL;
         const bool fast = (f & TF_UNIFORM) && plan->tile_rows == 128 && plan->tile_cols == 32 &&
                           beta <= MAX_WINDOW_BETA;
+        // SAME tiles of x_1 (Zin / S11) go to the edge kernel
+        const bool aff_only = (rp.g0 == sh.off[K] && rp.g1 == sh.off[K]) ||
+                              (cp.g0 == sh.off[K] && cp.g1 == sh.off[K]);
         if (terms == 0) t.prog = PROG_ZERO;
+        else if (aff_only && classify) t.prog = PROG_AFF;
         else if (!(f & TF_UNIFORM)) t.prog = PROG_GENERAL;
-        else if (terms == TF_SAME) t.prog = PROG_SAME;
+        else if (terms == (TF_SAME | TF_BAND) && t.rblk >= 1) t.prog = PROG_DIAG;
+        else if (terms == TF_SAME && t.rblk >= 1) t.prog = PROG_SAME;
         else if (terms == TF_RC && fast) t.prog = PROG_RC;
         else if (terms == TF_CR && fast) t.prog = PROG_CR;
         else t.prog = PROG_MIXED;
@@ -229,6 +234,17 @@ int32_t build_plan(const Shape& sh, int64_t beta, const std::vector<CliqueRanges
     out_off += n * n;
   }
   plan->per_query_doubles = out_off;
+  // sort by kernel class: fill (ZERO, SAME) | window (RC, CR) | edge (MIXED, GENERAL)
+  auto cls = [](const TileDev& t) {
+    return (t.prog == PROG_ZERO || t.prog == PROG_SAME || t.prog == PROG_DIAG || t.prog == PROG_AFF) ? 0 : (t.prog == PROG_RC || t.prog == PROG_CR) ? 1 : 2;
+  };
+  std::stable_sort(plan->tiles.begin(), plan->tiles.end(),
+                   [&](const TileDev& x, const TileDev& y) { return cls(x) < cls(y); });
+  plan->n_fill = plan->n_window = plan->n_edge = 0;
+  for (const TileDev& t : plan->tiles) {
+    const int c = cls(t);
+    (c == 0 ? plan->n_fill : c == 1 ? plan->n_window : plan->n_edge)++;
+  }
   return NNSDP_OK;
 }
 

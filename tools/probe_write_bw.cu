@@ -39,6 +39,26 @@ __global__ void tile_fill16(double* out, int n, int ld, int tiles_r, double v) {
   if (r + 1 >= n) return;
   for (int c = cg; c < 32; c += 4) if (c0 + c < n) *reinterpret_cast<double2*>(o + r + (size_t)(c0 + c) * ld) = make_double2(v, v);
 }
+// one CTA writes the same tile of `nslots` matrices that lie `slot_stride` doubles apart
+__global__ void tile_fill8_slots(double* out, int n, int ld, int tiles_r, size_t slot_stride, int nslots, double v) {
+  const int tr = threadIdx.x & 127, cg = threadIdx.x >> 7;
+  const int r0 = (blockIdx.x % tiles_r) * 128, c0 = (blockIdx.x / tiles_r) * 32;
+  const int r = r0 + tr;
+  if (r >= n) return;
+  for (int s = 0; s < nslots; ++s) {
+    double* o = out + ((size_t)blockIdx.y * nslots + s) * slot_stride;
+    for (int c = cg; c < 32; c += 2) if (c0 + c < n) o[r + (size_t)(c0 + c) * ld] = v;
+  }
+}
+// slot index fastest in the grid: blockIdx.x = slot, blockIdx.y = tile
+__global__ void tile_fill8_slotfast(double* out, int n, int ld, int tiles_r, size_t slot_stride, double v) {
+  const int tr = threadIdx.x & 127, cg = threadIdx.x >> 7;
+  const int r0 = (blockIdx.y % tiles_r) * 128, c0 = (blockIdx.y / tiles_r) * 32;
+  const int r = r0 + tr;
+  if (r >= n) return;
+  double* o = out + (size_t)blockIdx.x * slot_stride;
+  for (int c = cg; c < 32; c += 2) if (c0 + c < n) o[r + (size_t)(c0 + c) * ld] = v;
+}
 __global__ void linear_fill(double* out, size_t n, double v) {
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) out[i] = v;
 }
@@ -70,6 +90,16 @@ int main() {
   timeit("tile_fill8_aligned ld=3003", [&] { tile_fill8_aligned<<<grid, 256>>>(buf, n, 3003, tiles_r, 1.0); }, bytes);
   timeit("tile_fill16 ld=3004", [&] { tile_fill16<<<grid, 256>>>(buf, n, 3004, tiles_r, 1.0); }, bytes);
   timeit("tile_fill16 ld=3008", [&] { tile_fill16<<<grid, 256>>>(buf, n, 3008, tiles_r, 1.0); }, bytes);
+  {
+    // 8 slots of 19 cliques each (1.33 GB per slot, like the stress workload): slot stride 166e6 doubles
+    const size_t slot_stride = 166332179;  // sum |Ck|^2 at stress
+    double* big; CK(cudaMalloc(&big, slot_stride * 8 * 8 + 1024));
+    double b2 = 8.0 * n * (double)n * 8;
+    timeit("slots-in-CTA x8, stride 1.33 GB (1 matrix)", [&] { tile_fill8_slots<<<dim3(tiles_r * tiles_c, 1), 256>>>(big, n, 3003, tiles_r, slot_stride, 8, 1.0); }, b2);
+    timeit("slot-fastest grid x8, stride 1.33 GB", [&] { tile_fill8_slotfast<<<dim3(8, tiles_r * tiles_c), 256>>>(big, n, 3003, tiles_r, slot_stride, 1.0); }, b2);
+    timeit("slot-slowest grid x8, stride 1.33 GB", [&] { tile_fill8<<<dim3(tiles_r * tiles_c, 1), 256>>>(big, n, 3003, tiles_r, 1.0); }, b2 / 8);
+    cudaFree(big);
+  }
   CK(cudaGetLastError());
   return 0;
 }
