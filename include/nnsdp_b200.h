@@ -136,6 +136,12 @@ int32_t nnsdp_sizes_from_xdims(int64_t K, const int64_t* xdims, int64_t beta, nn
 int32_t nnsdp_cliques_from_xdims(int64_t K, const int64_t* xdims, int64_t beta, int64_t* ck_off,
                                  int64_t* ck_idx, int64_t* ck1_len, int64_t* d_off, int64_t* d_idx);
 
+/* Introspection of the emission plan (host only): tiles and output entries per tile program
+ * (8 slots: ZERO, SAME, RC, CR, MIXED, GENERAL, DIAG, AFF; see DESIGN.md, "emitter"). */
+int32_t nnsdp_plan_stats(int64_t K, const int64_t* xdims, int64_t beta, int32_t dense_Z,
+                         int64_t* tiles_per_prog, int64_t* entries_per_prog, int64_t* tile_rows,
+                         int64_t* tile_cols);
+
 /* ---- one-shot entry points with HOST buffers ------------------------------------------
  * intervalsWorstCase (src/Intervals/intervals_easy.jl:2-37), batched over Q boxes.
  *   x1min,x1max : n_in x Q;  xmin,xmax : xtot x Q (x_intvs stacked, x_1 first);

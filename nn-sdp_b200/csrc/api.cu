@@ -471,6 +471,40 @@ int32_t nnsdp_cliques_from_xdims(int64_t K, const int64_t* xdims, int64_t beta, 
   return cliques_out(sh, beta, ck_off, ck_idx, ck1_len, d_off, d_idx);
 }
 
+/* Host-only introspection of the emission plan: number of tiles and of output entries per tile
+ * program (index = TileProg, 8 entries each) and per flag combination is not exposed. */
+int32_t nnsdp_plan_stats(int64_t K, const int64_t* xdims, int64_t beta, int32_t dense_Z,
+                         int64_t* tiles_per_prog, int64_t* entries_per_prog, int64_t* tile_rows,
+                         int64_t* tile_cols) {
+  NN_CHECK(tiles_per_prog && entries_per_prog, NNSDP_ERR_ARG, "NULL argument");
+  Shape sh;
+  NN_TRY(shape_from_xdims(K, xdims, &sh));
+  nnsdp_sizes sz;
+  NN_TRY(fill_sizes(sh, beta, &sz));
+  std::vector<CliqueRanges> mats;
+  if (dense_Z) {
+    CliqueRanges c;
+    c.nseg = 1;
+    c.lo[0] = 0;
+    c.hi[0] = sh.Zdim - 1;
+    mats.push_back(c);
+  } else {
+    CliqueInfoHost ci;
+    NN_TRY(make_cliques_host(sh, beta, &ci));
+    mats = ci.ck;
+  }
+  PlanHost plan;
+  NN_TRY(build_plan(sh, beta, mats, true, &plan));
+  for (int i = 0; i < 8; ++i) tiles_per_prog[i] = entries_per_prog[i] = 0;
+  for (const TileDev& t : plan.tiles) {
+    tiles_per_prog[t.prog] += 1;
+    entries_per_prog[t.prog] += (int64_t)t.nrows * t.ncols;
+  }
+  if (tile_rows) *tile_rows = plan.tile_rows;
+  if (tile_cols) *tile_cols = plan.tile_cols;
+  return NNSDP_OK;
+}
+
 // ---- batch ----------------------------------------------------------------------------------
 int32_t nnsdp_batch_destroy(nnsdp_batch* b) {
   if (!b) return NNSDP_OK;

@@ -436,9 +436,11 @@ __global__ void __launch_bounds__(ETHREADS)
 emit_window_kernel(NetDev net, BatchDev b, PlanDev plan, int tile0, int q0, int nq, int group,
                    double* __restrict__ out) {
   __shared__ double smem[SMEM_DOUBLES];
-  const TileDev t = plan.tiles[tile0 + blockIdx.x];
+  // slot group is the fastest grid index: CTAs that share a W tile run back to back (L2 reuse)
+  const int ngroups = (nq + group - 1) / group;
+  const TileDev t = plan.tiles[tile0 + blockIdx.x / ngroups];
   const MatDev mat = plan.mats[t.mat];
-  const int slot0 = blockIdx.y * group;
+  const int slot0 = (blockIdx.x % ngroups) * group;
   const int nslots = min(group, nq - slot0);
   if (t.prog == PROG_RC)
     emit_rc<BETA>(net, b, plan, t, mat, q0, slot0, nslots, out, smem);
@@ -447,7 +449,7 @@ emit_window_kernel(NetDev net, BatchDev b, PlanDev plan, int tile0, int q0, int 
 }
 
 // ---- kernel 3: everything else (band / sliver / corner tiles, affine row and column, small nets) -
-__global__ void __launch_bounds__(ETHREADS)
+__global__ void __launch_bounds__(ETHREADS, 4)
 emit_edge_kernel(NetDev net, BatchDev b, GramDev g, PlanDev plan, int tile0, int q0, int nq,
                  int group, double* __restrict__ out) {
   __shared__ double smem[MAX_TC * MAX_TAPS + 128 * MAX_TAPS];
@@ -475,14 +477,14 @@ int launch_emit(const NetDev& net, const BatchDev& b, const GramDev& g, const Pl
                 int q0, int nq, double* out, cudaStream_t st) {
   if (nq <= 0) return 0;
   static const int wgroup = [] { const char* e = getenv("NNSDP_WINDOW_GROUP"); int v = e ? atoi(e) : SLOT_GROUP; return v < 1 ? 1 : (v > SLOT_GROUP ? SLOT_GROUP : v); }();
-  static const int egroup = [] { const char* e = getenv("NNSDP_EDGE_GROUP"); int v = e ? atoi(e) : SLOT_GROUP; return v < 1 ? 1 : (v > SLOT_GROUP ? SLOT_GROUP : v); }();
+  static const int egroup = [] { const char* e = getenv("NNSDP_EDGE_GROUP"); int v = e ? atoi(e) : 1; return v < 1 ? 1 : (v > SLOT_GROUP ? SLOT_GROUP : v); }();
   int launches = 0;
   if (plan.n_fill > 0) {
     emit_fill_kernel<<<dim3(plan.n_fill, nq), ETHREADS, 0, st>>>(net, b, g, plan, q0, nq, out);
     ++launches;
   }
   if (plan.n_window > 0) {
-    const dim3 grid(plan.n_window, (nq + wgroup - 1) / wgroup);
+    const dim3 grid(plan.n_window * ((nq + wgroup - 1) / wgroup));
     const int t0 = plan.n_fill;
     switch (b.beta) {
       case 0: emit_window_kernel<0><<<grid, ETHREADS, 0, st>>>(net, b, plan, t0, q0, nq, wgroup, out); break;

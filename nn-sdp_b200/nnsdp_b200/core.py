@@ -109,6 +109,22 @@ def cliques_from_xdims(xdims: Sequence[int], beta: int):
     return _cliques_call(lambda *a: L.lib.nnsdp_cliques_from_xdims(K, xd, beta, *a), sz)
 
 
+PROGRAMS = ("ZERO", "SAME", "RC", "CR", "MIXED", "GENERAL", "DIAG", "AFF")
+
+
+def plan_stats(xdims: Sequence[int], beta: int, dense: bool = False) -> dict:
+    """Tiles / output entries per tile program of the emission plan (host only)."""
+    K = len(xdims) - 1
+    xd = (L.c_i64 * (K + 1))(*[int(x) for x in xdims])
+    tiles = np.zeros(8, dtype=np.int64)
+    entries = np.zeros(8, dtype=np.int64)
+    tr, tc = L.c_i64(0), L.c_i64(0)
+    L.check(L.lib.nnsdp_plan_stats(K, xd, beta, int(dense), tiles.ctypes.data_as(L.c_i64p),
+                                   entries.ctypes.data_as(L.c_i64p), C.byref(tr), C.byref(tc)))
+    return {"tile_rows": int(tr.value), "tile_cols": int(tc.value),
+            "tiles": dict(zip(PROGRAMS, tiles.tolist())), "entries": dict(zip(PROGRAMS, entries.tolist()))}
+
+
 def _cliques_call(fn, sz):
     p = sz["ncliques"]
     ck_off = np.zeros(p + 1, dtype=np.int64)
