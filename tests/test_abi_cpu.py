@@ -1,0 +1,142 @@
+"""CPU tests of the drop-in boundary: libnnsdp_b200.so loads and exports every symbol that
+include/nnsdp_b200.h declares; the host-only integer entry points (sizes, makeCliques, emission plan)
+are bit-exact against the oracle; compute entry points fail loudly without a CUDA device."""
+import ctypes as C
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+from hypothesis import given, settings
+from hypothesis import strategies as st
+
+import nnsdp_oracle as o
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "nnsdp_b200.h")
+
+
+def _declared():
+    src = open(HEADER).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(nnsdp_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_header_symbols_exported_and_bound():
+    import nnsdp_b200._lib as L
+
+    names = _declared()
+    assert len(names) >= 35
+    out = subprocess.run(["nm", "-D", "--defined-only", os.path.abspath(L.LIB_PATH)], capture_output=True, text=True,
+                         check=True).stdout
+    exported = {ln.split()[-1] for ln in out.splitlines() if " T " in ln}
+    for n in names:
+        assert n in exported, f"{n} declared in include/nnsdp_b200.h but not exported"
+        assert n in L.PROTOTYPES, f"{n} has no ctypes prototype"
+    assert set(L.PROTOTYPES) <= set(names)
+    assert L.lib.nnsdp_version() >= 100
+
+
+def test_struct_layouts_match_header():
+    import nnsdp_b200._lib as L
+
+    assert C.sizeof(L.Sizes) == 14 * 8
+    # nnsdp_query_inputs: 13 (pointer, stride) pairs + (out_kind, reserved)
+    assert C.sizeof(L.QueryInputs) == 13 * 16 + 8
+    assert L.QueryInputs.out_kind.offset == 9 * 16
+    assert L.QueryInputs.out_S.offset == 9 * 16 + 8
+
+
+def test_no_cpu_fallback():
+    """Without a device every compute entry point returns NNSDP_ERR_CUDA with a message."""
+    import nnsdp_b200 as nb
+
+    if nb.device_count() > 0:
+        pytest.skip("a CUDA device is visible")
+    with pytest.raises(nb.NnsdpError) as e:
+        nb.Context([0])
+    assert e.value.code == -2 and "no CPU fallback" in str(e.value)
+
+
+def test_argument_and_assert_errors():
+    import nnsdp_b200 as nb
+
+    with pytest.raises(nb.NnsdpError) as e:  # length(xdims) >= 3, MyNeuralNetwork.jl:18
+        nb.sizes_from_xdims([2, 2], 0)
+    assert e.value.code == -5
+    with pytest.raises(nb.NnsdpError) as e:  # 0 <= beta, activ_sector.jl:12
+        nb.sizes_from_xdims([2, 3, 2], -1)
+    assert e.value.code == -5
+    with pytest.raises(nb.NnsdpError) as e:
+        nb.sizes_from_xdims([2, 0, 2], 1)
+    assert e.value.code == -1
+
+
+def _check_cliques(xdims, beta):
+    import nnsdp_b200 as nb
+
+    net = o.FeedFwdNet(xdims=xdims, Ms=[np.zeros((xdims[k + 1], xdims[k] + 1)) for k in range(len(xdims) - 1)])
+    ref = o.make_cliques(net, beta)
+    got = nb.cliques_from_xdims(xdims, beta)
+    sz = nb.sizes_from_xdims(xdims, beta)
+    assert len(got) == len(ref) == sz["ncliques"]
+    for (a, pa, da), (b, pb, db) in zip(got, ref):
+        assert a.dtype == np.int64 and np.array_equal(a, b)
+        assert len(pa) == len(pb) and all(np.array_equal(x, y) for x, y in zip(pa, pb))
+        assert len(da) == len(db) and all(np.array_equal(x, y) for x, y in zip(da, db))
+    assert sz["Zdim"] == net.Zdim and sz["acdim"] == net.acdim and sz["K"] == net.K
+    assert sz["lamdim"] == o.sector_lambda_dim(net.acdim, beta)
+    assert sz["secdim"] == sz["lamdim"] + 2 * net.acdim
+    assert sz["sum_ck"] == sum(len(c[0]) for c in ref)
+    assert sz["sum_ck_sq"] == sum(len(c[0]) ** 2 for c in ref)
+    assert sz["max_ck"] == max(len(c[0]) for c in ref)
+    return sz
+
+
+@pytest.mark.parametrize("xdims,beta", [
+    ([2, 3, 2], 0), ([2, 3, 2], 2), ([3, 3, 3, 3, 4, 3, 3], 2), ([2] + [10] * 10 + [2], 1), ([2] + [20] * 100 + [2], 2),
+    ([5] + [50] * 6 + [5], 2), ([2, 4, 7, 3, 5, 2], 5), ([2] + [1000] * 20 + [2], 2), ([2, 70, 130, 64, 3], 7),
+])
+def test_cliques_bit_exact_named_configs(xdims, beta):
+    sz = _check_cliques(xdims, beta)
+    if xdims == [2] + [1000] * 20 + [2]:
+        assert sz["ncliques"] == 19 and sz["sum_ck_sq"] * 8 == 1330657432 and sz["max_ck"] == 3003
+    if xdims == [2] + [20] * 100 + [2]:   # config 2'
+        assert sz["ncliques"] == 99 and sz["Zdim"] == 2003
+
+
+@settings(max_examples=150, deadline=None)
+@given(st.lists(st.integers(1, 9), min_size=3, max_size=9), st.integers(0, 12))
+def test_cliques_bit_exact_random_shapes(xdims, beta):
+    if beta > sum(xdims[1:-1]):
+        return
+    _check_cliques(xdims, beta)
+
+
+@pytest.mark.parametrize("xdims,beta", [([2, 3, 2], 1), ([2] + [10] * 10 + [2], 1), ([5] + [50] * 6 + [5], 2),
+                                        ([2, 70, 130, 64, 3], 2), ([2] + [1000] * 20 + [2], 2), ([2] + [100] * 50 + [2], 3)])
+@pytest.mark.parametrize("dense", [False, True])
+def test_emission_plan_covers_output_exactly_once(xdims, beta, dense):
+    """Every output entry belongs to exactly one tile (entry counts add up to the output size)."""
+    import nnsdp_b200 as nb
+
+    sz = nb.sizes_from_xdims(xdims, beta)
+    ps = nb.plan_stats(xdims, beta, dense=dense)
+    total = sum(ps["entries"].values())
+    assert total == (sz["Zdim"] ** 2 if dense else sz["sum_ck_sq"])
+    assert ps["tile_rows"] in (32, 64, 128) and ps["tile_cols"] == 32
+
+
+def test_shard_ranges_partition():
+    from nnsdp_b200.dist import all_ranges, shard_range
+
+    for Q in (1, 7, 64, 1024, 1025):
+        for world in (1, 2, 3, 4, 8):
+            rs = all_ranges(Q, world)
+            assert rs[0][0] == 0 and sum(n for _, n in rs) == Q
+            for (a, n), (b, _) in zip(rs, rs[1:]):
+                assert a + n == b
+            assert max(n for _, n in rs) - min(n for _, n in rs) <= 1
+    with pytest.raises(ValueError):
+        shard_range(4, 2, 2)

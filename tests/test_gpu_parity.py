@@ -273,3 +273,222 @@ def test_error_paths(ctx):
     with pytest.raises(nb.NnsdpError) as e:
         b.prepare()  # before set_inputs
     assert e.value.code == -4
+
+
+# ---------------------------------------------------------------------------------------------
+# committed golden fixtures (tests/golden/, made by tests/golden/make_golden.py)
+# ---------------------------------------------------------------------------------------------
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def _gold_net(d):
+    xd = d["xdims"].tolist()
+    return xd, [d[f"M{k}"] for k in range(len(xd) - 1)]
+
+
+@pytest.mark.parametrize("tag", ["safety", "ellipsoid", "tight"])
+def test_golden_config1(ctx, tag):
+    """BASELINE.json configs[0]: the reference's shipped scale-I2-O2-W10-D10 net, beta = 1."""
+    import nnsdp_b200 as nb
+
+    d = np.load(os.path.join(GOLD, "config1_W10_D10_beta1.npz"))
+    xd, Ms = _gold_net(d)
+    beta = int(d["beta"])
+    dnet = nb.Net(ctx, xd, Ms)
+    kw = dict(out_kind=nb.OUT_SAFETY, out_S=d["S"][None]) if tag != "ellipsoid" else dict(
+        out_kind=nb.OUT_ELLIPSOID, out_vec=d["yc"][None], out_invP=np.eye(2)[None], gamma_out=d["gout"][None])
+    batch = nb.NumericBatch(x1min=d[f"{tag}_x1min"][None], x1max=d[f"{tag}_x1max"][None], gamma_in=d[f"{tag}_gin"][None],
+                            gamma_bnd=d[f"{tag}_gbnd"][None], gamma_sec=d[f"{tag}_gsec"][None], **kw)
+    r = nb.bounds_ibp(dnet, d[f"{tag}_x1min"][None], d[f"{tag}_x1max"][None])
+    for k in ("xmin", "xmax", "acxmin", "acxmax"):
+        ref = d[f"{tag}_{k}"]
+        assert np.abs(r[k][0] - ref).max() <= TOL * max(np.abs(ref).max(), 1.0)
+    smin, smax = nb.sector_minmax(ctx, r["acxmin"][0], r["acxmax"][0])
+    assert np.array_equal(smin, d[f"{tag}_smin"]) and np.array_equal(smax, d[f"{tag}_smax"])
+    Z = nb.assemble_dense(dnet, beta, batch)[0]
+    assert relerr(Z, d[f"{tag}_Z"]) <= TOL
+    cliques = dnet.cliques(beta)
+    assert len(cliques) == int(d["ncliques"])
+    flat = nb.assemble_blocks(dnet, beta, batch)[0]
+    for k, (blk, (Ck, _, ds)) in enumerate(zip(nb.split_blocks(flat, cliques), cliques)):
+        assert np.array_equal(Ck, d[f"Ck{k}"])
+        for i, dd in enumerate(ds):
+            assert np.array_equal(dd, d[f"Dk{k}_{i}"])
+        rb = d[f"{tag}_Z"][np.ix_(Ck - 1, Ck - 1)]
+        assert relerr(blk, rb) <= TOL
+
+
+def test_golden_config3_reach_batch(ctx):
+    """BASELINE.json configs[2]: 64 hyperplane directions on reach-I2-O2-W20-D10, shared bounds and
+    multipliers (stride 0), per-direction normal and gamma_out."""
+    import nnsdp_b200 as nb
+
+    d = np.load(os.path.join(GOLD, "config3_reach_W20_D10_beta2.npz"))
+    xd, Ms = _gold_net(d)
+    beta = int(d["beta"])
+    dnet = nb.Net(ctx, xd, Ms)
+    batch = nb.NumericBatch(x1min=d["dir0_x1min"], x1max=d["dir0_x1max"], gamma_in=d["dir0_gin"], gamma_bnd=d["dir0_gbnd"],
+                            gamma_sec=d["dir0_gsec"], out_kind=nb.OUT_HPLANE, out_vec=d["normals"], gamma_out=d["gout"][:, None])
+    flat = nb.assemble_blocks(dnet, beta, batch, Q=64)
+    cliques = dnet.cliques(beta)
+    for i in range(64):
+        blocks = nb.split_blocks(flat[i], cliques)
+        fro = np.array([np.linalg.norm(b) for b in blocks])
+        assert np.abs(fro - d["block_fro"][i]).max() <= TOL * d["block_fro"][i].max()
+        # the affine column of Z restricted to each clique is the last column of its block
+        for blk, (Ck, _, _) in zip(blocks, cliques):
+            ref = d["affine_cols"][i][Ck - 1]
+            assert np.abs(blk[:, -1] - ref).max() <= TOL * max(np.abs(d["affine_cols"][i]).max(), 1.0)
+    for i in (0, 17):
+        Zr = d[f"dir{i}_Z"]
+        for blk, (Ck, _, _) in zip(nb.split_blocks(flat[i], cliques), cliques):
+            assert relerr(blk, Zr[np.ix_(Ck - 1, Ck - 1)]) <= TOL
+
+
+# ---------------------------------------------------------------------------------------------
+# full-size configs through size-independent properties (the oracle would need minutes and GBs)
+# ---------------------------------------------------------------------------------------------
+def test_stress_config_properties(ctx):
+    """BASELINE.json configs[4]: width 1000, depth 20, beta = 2.  Checked: (1) every block is
+    bit-symmetric; (2) overlapping cliques agree bit-for-bit on their shared index range;
+    (3) Z is affine in the multipliers: blocks(g1) + blocks(g2) - blocks(0) == blocks(g1 + g2) to
+    1e-12; (4) bounds are ordered; (5) one clique block against the closed-form oracle restricted
+    to that clique's rows (built without the dense Z)."""
+    import bench
+    import nnsdp_b200 as nb
+
+    xdims, Ms, beta, inp = bench.make_workload("stress-W1000-D20-beta2-Q1024", 0, Q=2)
+    dnet = nb.Net(ctx, xdims, Ms)
+    sz = dnet.sizes(beta)
+    assert sz["ncliques"] == 19 and sz["sum_ck_sq"] * 8 == 1330657432
+    cliques = dnet.cliques(beta)
+    # tight box on query 1 so that some layers carry stably-active neurons (Gram term)
+    inp["x1min"][1] = inp["x1min"][1] * 0 + 1.0 - 1e-4
+    inp["x1max"][1] = inp["x1min"][1] + 2e-4
+
+    def run(scale1, scale2):
+        g = {k: inp[k] * scale1 for k in ("gamma_in", "gamma_bnd", "gamma_sec")}
+        g2 = {k: inp[k][::-1] * scale2 for k in ("gamma_in", "gamma_bnd", "gamma_sec")}
+        batch = nb.NumericBatch(x1min=inp["x1min"], x1max=inp["x1max"], out_kind=nb.OUT_SAFETY, out_S=inp["out_S"],
+                                **{k: g[k] + g2[k] for k in g})
+        b = nb.Batch(dnet, beta, Qcap=2, ring=1)
+        b.set_inputs(batch, Q=2)
+        b.bounds()
+        b.prepare()
+        b.emit(1, 1)
+        b.sync()
+        out = b.get_slot(0)
+        bounds = b.get_bounds()
+        stats = b.gram_stats()
+        b.close()
+        return out, bounds, stats
+
+    f1, bounds, stats = run(1.0, 0.0)
+    assert stats[1] > 0  # the Gram path ran
+    assert np.all(bounds["xmin"] <= bounds["xmax"]) and np.all(bounds["acxmin"] <= bounds["acxmax"])
+    blocks = nb.split_blocks(f1, cliques)
+    for blk in blocks:
+        assert np.array_equal(blk, blk.T)
+    for (Ca, _, _), (Cb, _, _), A, B in zip(cliques, cliques[1:], blocks, blocks[1:]):
+        common = np.intersect1d(Ca, Cb)
+        ia, ib = np.searchsorted(Ca, common), np.searchsorted(Cb, common)
+        assert np.array_equal(A[np.ix_(ia, ia)], B[np.ix_(ib, ib)])
+    f2, _, _ = run(0.0, 1.0)
+    f0, _, _ = run(0.0, 0.0)
+    f12, _, _ = run(1.0, 1.0)
+    scale = np.abs(f12).max()
+    assert np.abs((f1 - f0) + (f2 - f0) - (f12 - f0)).max() <= 1e-12 * scale
+    del f2, f0, f12
+
+    # (5) clique 3 against the oracle, assembled from the closed form on that clique's rows only
+    k = 3
+    Ck = cliques[k][0] - 1
+    net = o.FeedFwdNet(xdims, Ms)
+    q = o.NumericQuery(x1min=inp["x1min"][1], x1max=inp["x1max"][1], gin=inp["gamma_in"][1], gbnd=inp["gamma_bnd"][1],
+                       gsec=inp["gamma_sec"][1], qc_out=o.QcSafety(S=inp["out_S"][0]))
+    ref = clique_block_oracle(net, beta, q, Ck)
+    assert relerr(blocks[k], ref) <= TOL
+
+
+def clique_block_oracle(net, beta, q, Ck):
+    """Z[Ck, Ck] from the closed form without materialising Z: only the
+    terms with both indices in Ck are evaluated.  Independent of assemble_Z_closed_form's code path
+    for the band (dense banded M here)."""
+    info = o.intervals_worst_case(q.x1min, q.x1max, net)
+    qb, qs = o.make_qc_activs_intvs(net, q.x1min, q.x1max, beta, info)
+    xd, K, n1, ac, a = net.xdims, net.K, net.xdims[0], net.acdim, net.Zdim - 1
+    s = o.split_sector_gamma(q.gsec, ac, beta)
+    p, qq = qs.smin * qs.smax, qs.smin + qs.smax
+    d11 = -2.0 * p * s.lam
+    c13, c23 = -qs.smin * s.eta - qs.smax * s.nu, s.eta + s.nu
+    Tb = o.band_T(s.v, ac, beta)
+    pos = {g: i for i, g in enumerate(Ck)}
+    n = len(Ck)
+    out = np.zeros((n, n))
+    off = np.concatenate([[0], np.cumsum(xd[:-1])])
+    bias = o.makeb(net)
+    S11, S12, S13, S22, S23, S33 = o.out_S_blocks(q.qc_out, net, q.gout)
+
+    def loc(idx):
+        return np.array([pos.get(int(g), -1) for g in idx])
+
+    def Mcoef(j, c):  # M = diag(q lam) + T
+        t = abs(j - c)
+        if t > beta:
+            return 0.0
+        v = Tb[t, min(j, c)]
+        return v + (qq[j] * s.lam[j] if t == 0 else 0.0)
+
+    aff = np.zeros(net.Zdim)
+    aff[:n1] += q.gin * (q.x1min + q.x1max) + S12 @ net.Ms[K - 1][:, -1] + S13
+    aff[n1:a] += q.gbnd * (qb.acymin + qb.acymax) + c23
+    aff[a] += -2.0 * np.sum(q.gin * q.x1min * q.x1max) - 2.0 * np.sum(q.gbnd * qb.acymin * qb.acymax)
+    for j in range(ac):
+        for c in range(max(0, j - beta), min(ac, j + beta + 1)):
+            aff[n1 + c] += bias[j] * Mcoef(j, c)
+    for k in range(1, K):  # W_k: block k-1 (0-based) -> neurons of layer k
+        W, bk = net.Ms[k - 1][:, :-1], net.Ms[k - 1][:, -1]
+        j0 = off[k] - n1
+        rows = np.arange(off[k - 1], off[k - 1] + xd[k - 1])
+        dj = d11[j0:j0 + xd[k]]
+        u = dj * bk + c13[j0:j0 + xd[k]]
+        aff[rows] += W.T @ u
+        aff[a] += np.sum(dj * bk * bk) + 2.0 * np.sum(bk * c13[j0:j0 + xd[k]])
+        lr = loc(rows)
+        sel = lr >= 0
+        if np.any(sel):
+            lrs, Ws = lr[sel], W[:, sel]
+            if np.any(dj != 0):
+                out[np.ix_(lrs, lrs)] += Ws.T @ (dj[:, None] * Ws)
+            for jl in range(xd[k]):
+                j = j0 + jl
+                for c in range(max(0, j - beta), min(ac, j + beta + 1)):
+                    lc = pos.get(n1 + c, -1)
+                    if lc >= 0:
+                        m = Mcoef(j, c)
+                        out[lrs, lc] += Ws[jl] * m
+                        out[lc, lrs] += Ws[jl] * m
+    for j in range(ac):
+        lj = pos.get(n1 + j, -1)
+        if lj < 0:
+            continue
+        out[lj, lj] += -2.0 * q.gbnd[j]
+        for c in range(max(0, j - beta), min(ac, j + beta + 1)):
+            lc = pos.get(n1 + c, -1)
+            if lc >= 0:
+                out[lj, lc] += -2.0 * Tb[abs(j - c), min(j, c)]
+    WK, bK = net.Ms[K - 1][:, :-1], net.Ms[K - 1][:, -1]
+    rK = np.arange(off[K - 1], off[K - 1] + xd[K - 1])
+    aff[rK] += WK.T @ (S22 @ bK + S23)
+    aff[a] += bK @ S22 @ bK + 2.0 * (bK @ S23) + S33
+    lK, l1 = loc(rK), loc(np.arange(n1))
+    sK, s1 = lK >= 0, l1 >= 0
+    out[np.ix_(lK[sK], lK[sK])] += (WK.T @ S22 @ WK)[np.ix_(sK, sK)]
+    out[np.ix_(l1[s1], l1[s1])] += (S11 - 2.0 * np.diag(q.gin))[np.ix_(s1, s1)]
+    t = (S12 @ WK)[np.ix_(s1, sK)]
+    out[np.ix_(l1[s1], lK[sK])] += t
+    out[np.ix_(lK[sK], l1[s1])] += t.T
+    la = pos[a]
+    out[:, la] = aff[Ck]
+    out[la, :] = aff[Ck]
+    return out

@@ -1,0 +1,234 @@
+"""CPU tests of the oracle (oracle/nnsdp_oracle.py): the known-answer material SURVEY.md section 8c
+lists -- hand-worked example, literal R'QR == closed form, the sparsity statement of the reference's
+plot_sparsity notebook, clique cover, the reference's @asserts -- and the committed golden fixtures.
+No GPU, no /root/reference at run time.
+"""
+import os
+
+import numpy as np
+import pytest
+
+import nnsdp_oracle as o
+from helpers import rand_net, rand_query
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+NETS = [
+    ([2, 3, 2], 0), ([2, 3, 2], 2), ([2, 3, 3, 2], 1), ([3, 3, 3, 3, 4, 3, 3], 0), ([3, 3, 3, 3, 4, 3, 3], 2),
+    ([3, 3, 3, 3, 4, 3, 3], 4), ([2, 4, 7, 3, 5, 2], 5), ([2] + [10] * 10 + [2], 3), ([5, 20, 20, 20, 5], 2),
+]
+KINDS = ["safety", "hplaneS", "hplane", "circle", "ellipsoid"]
+
+
+# ---------------------------------------------------------------------------------------------
+# hand-worked example: xdims = [1, 1, 1], W1 = 2, b1 = 1, W2 = 3, b2 = -1, box [1, 2]
+# ---------------------------------------------------------------------------------------------
+def test_hand_worked_1_1_1():
+    """Every number below was derived by hand from the Julia sources (not from this oracle):
+    z = [x1; x2; 1], Zdim = 3, acdim = 1, beta = 0 so gamma_sec = [lambda, eta, nu].
+      IBP (intervals_easy.jl:23-24): y1 in [2*1+1, 2*2+1] = [3, 5], x2 in [3, 5]; y2 = 3*x2-1 in [8, 14].
+      makeSectorMinMax: acxmin = 3 > 1e-4 -> smin = 1; smax = 1.
+      Zin  (input.jl:22-26), g = gamma_in:    Z11 += -2g, Z1a += g(1+2), Zaa += -2g*1*2.
+      bounded (activ_bounded.jl:19-21), d:    Z22 += -2d, Z2a += d(3+5), Zaa += -2d*15.
+      sector (activ_sector.jl:42-57): Q11 = -2*1*1*lam, Q12 = (1+1)*lam, Q22 = 0 (no pairs),
+        Q13 = -eta - nu, Q23 = eta + nu, Q33 = 0;  R = [A b; B 0; 0 1] = [[2,0,1],[0,1,0],[0,0,1]]:
+        Z11 += 4*Q11, Z12 += 2*Q12, Z1a += 2*(Q11*1 + Q13), Z2a += Q12*1 + Q23, Zaa += Q11 + 2*Q13.
+      Zout hplane (output.jl:72-76), normal = 1, gamma_out = t:  S23 = 1, S33 = -2t,
+        Z2a += W2*S23 = 3, Zaa += 2*b2*S23 + S33 = -2 - 2t."""
+    net = o.FeedFwdNet(xdims=[1, 1, 1], Ms=[np.array([[2.0, 1.0]]), np.array([[3.0, -1.0]])])
+    g, d, lam, eta, nu, t = 0.5, 0.25, 0.75, 0.125, 0.375, 0.625
+    q = o.NumericQuery(x1min=np.array([1.0]), x1max=np.array([2.0]), gin=np.array([g]), gbnd=np.array([d]),
+                       gsec=np.array([lam, eta, nu]), qc_out=o.QcReachHplane(np.array([1.0])), gout=np.array([t]))
+    Q11, Q12, Q13, Q23 = -2 * lam, 2 * lam, -eta - nu, eta + nu
+    Z = np.zeros((3, 3))
+    Z[0, 0] = -2 * g + 4 * Q11
+    Z[0, 1] = Z[1, 0] = 2 * Q12
+    Z[0, 2] = Z[2, 0] = 3 * g + 2 * (Q11 + Q13)
+    Z[1, 1] = -2 * d
+    Z[1, 2] = Z[2, 1] = 8 * d + Q12 + Q23 + 3.0
+    Z[2, 2] = -4 * g - 30 * d + Q11 + 2 * Q13 - 2.0 - 2 * t
+    for form in ("literal", "closed"):
+        r = o.run_query(net, 0, q, form=form)
+        assert np.array_equal(r["intv"].x_intvs[1][0], [3.0]) and np.array_equal(r["intv"].x_intvs[1][1], [5.0])
+        assert np.array_equal(r["intv"].x_intvs[2][0], [8.0]) and np.array_equal(r["intv"].x_intvs[2][1], [14.0])
+        assert np.array_equal(r["qc_sector"].smin, [1.0]) and np.array_equal(r["qc_sector"].smax, [1.0])
+        assert np.allclose(r["Z"], Z, rtol=0, atol=1e-15), form
+    # K = 2: p = 1 and the single clique is everything (chordal_cliques.jl:22-27,55-57)
+    (Ck, parts, ds), = r["cliques"]
+    assert np.array_equal(Ck, [1, 2, 3]) and np.array_equal(ds[0], [1, 2, 3])
+
+
+def test_hand_worked_cliques_notebook_dims():
+    """xdims of experiments/plot_sparsity.ipynb, beta = 2: S = 3,6,9,12,16,19; p = first i with
+    S(i+1)+2 >= S(5)=16 -> i = 4 (S(5)+2 = 18).  k=1: Ck1 = 1:8, Ck2 = 17:20; k=2: 4:11; k=3: 7:14;
+    last: S(3)+1 : 20 = 10:20 (chordal_cliques.jl:22-57, by hand)."""
+    net = rand_net([3, 3, 3, 3, 4, 3, 3], seed=0)
+    cl = o.make_cliques(net, 2)
+    assert len(cl) == 4
+    assert np.array_equal(cl[0][0], list(range(1, 9)) + [17, 18, 19, 20])
+    assert np.array_equal(cl[1][0], list(range(4, 12)) + [17, 18, 19, 20])
+    assert np.array_equal(cl[2][0], list(range(7, 15)) + [17, 18, 19, 20])
+    assert np.array_equal(cl[3][0], list(range(10, 21)))
+    # Dk of clique 2: [1 : 3+3+2 ; 12] and [3+3+1 : 12]  (:45-50)
+    assert np.array_equal(cl[1][2][0], list(range(1, 9)) + [12])
+    assert np.array_equal(cl[1][2][1], list(range(7, 13)))
+    assert len(cl[0][2]) == 1 and len(cl[3][2]) == 1
+
+
+# ---------------------------------------------------------------------------------------------
+# self-consistency identities
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("kind", KINDS)
+@pytest.mark.parametrize("xdims,beta", NETS)
+def test_literal_equals_closed_form(xdims, beta, kind):
+    net = rand_net(xdims, seed=7)
+    rng = np.random.default_rng(3)
+    for radius in (0.001, 0.3):
+        q = rand_query(net, beta, rng, kind=kind, radius=radius)
+        lit = o.run_query(net, beta, q, form="literal")["Z"]
+        clo = o.run_query(net, beta, q, form="closed")["Z"]
+        assert np.abs(lit - clo).max() <= 1e-14 * max(np.abs(lit).max(), 1.0)
+        assert np.abs(lit - lit.T).max() <= 1e-14 * max(np.abs(lit).max(), 1.0)
+
+
+@pytest.mark.parametrize("xdims,beta", NETS)
+def test_sparsity_inside_notebook_pattern_and_clique_cover(xdims, beta):
+    net = rand_net(xdims, seed=9)
+    rng = np.random.default_rng(1)
+    q = rand_query(net, beta, rng, kind="safety", radius=0.002)
+    r = o.run_query(net, beta, q, form="literal")
+    Z = r["Z"]
+    pat = o.structural_pattern_notebook(net.xdims, beta)
+    assert not np.any((Z != 0) & ~pat)
+    # cliques cover nnz(Z) and the scatter pattern of setupZksum! is that cover (chordal_sdp.jl:71-89)
+    cover = np.zeros_like(pat)
+    for Ck, _, _ in r["cliques"]:
+        cover[np.ix_(Ck - 1, Ck - 1)] = True
+        assert np.array_equal(Ck, np.unique(Ck))  # MyMath.jl:46
+    assert not np.any((Z != 0) & ~cover)
+    assert np.array_equal(o.zksum_pattern(net, r["cliques"]), cover)
+    # Ec(Ck) Z Ec(Ck)' is the block (MyMath.jl:45-52)
+    for (Ck, _, _), blk in zip(r["cliques"], r["blocks"]):
+        EcK = o.Ec(Ck, net.Zdim)
+        assert np.array_equal(np.asarray((EcK @ Z @ EcK.T)), blk)
+
+
+def test_Z_is_affine_in_gamma():
+    net = rand_net([2, 6, 5, 7, 2], seed=2)
+    beta = 2
+    rng = np.random.default_rng(0)
+    q = rand_query(net, beta, rng, kind="circle", radius=0.01)
+
+    def Zof(gin, gbnd, gsec, gout):
+        qq = o.NumericQuery(q.x1min, q.x1max, gin, gbnd, gsec, q.qc_out, gout)
+        return o.run_query(net, beta, qq, form="literal")["Z"]
+
+    z0 = Zof(0 * q.gin, 0 * q.gbnd, 0 * q.gsec, 0 * q.gout)
+    za = Zof(q.gin, q.gbnd, q.gsec, q.gout)
+    g2 = [rng.random(v.shape) for v in (q.gin, q.gbnd, q.gsec, q.gout)]
+    zb = Zof(*g2)
+    zab = Zof(q.gin + g2[0], q.gbnd + g2[1], q.gsec + g2[2], q.gout + g2[3])
+    assert np.abs((za - z0) + (zb - z0) - (zab - z0)).max() <= 1e-13 * np.abs(zab).max()
+
+
+def test_quirks_reproduced():
+    """Bug-for-bug items of SURVEY.md 8a: (i) lambda contributes no -2 lambda eps eps' term;
+    (ii) ellipsoid S33 = yc'yc - gamma_out (output.jl:93), not yc' invP' invP yc."""
+    net = rand_net([2, 4, 4, 2], seed=5)
+    rng = np.random.default_rng(2)
+    q = rand_query(net, 0, rng, kind="ellipsoid", radius=0.5)
+    ac = net.acdim
+    gsec = np.zeros_like(q.gsec)
+    gsec[:ac] = 1.0  # only lambda
+    qq = o.NumericQuery(q.x1min, q.x1max, 0 * q.gin, 0 * q.gbnd, gsec, o.QcSafety(S=np.zeros((5, 5))))
+    Z = o.run_query(net, 0, qq, form="literal")["Z"]
+    # x_K (the last hidden layer) receives no Gram term, so a -2 lambda_j eps_j eps_j' term would show here
+    nK = net.xdims[-2]
+    assert np.all(np.diag(Z)[net.Zdim - 1 - nK:net.Zdim - 1] == 0.0)
+    S = o.reach_S(np.array([0.25]), q.qc_out, net)
+    assert S[-1, -1] == pytest.approx(q.qc_out.yc @ q.qc_out.yc - 0.25, abs=1e-15)
+
+
+def test_reference_asserts():
+    with pytest.raises(AssertionError):  # MyNeuralNetwork.jl:18
+        o.FeedFwdNet(xdims=[2, 2], Ms=[np.zeros((2, 3))])
+    with pytest.raises(AssertionError):  # MyNeuralNetwork.jl:26
+        o.FeedFwdNet(xdims=[2, 3, 2], Ms=[np.zeros((3, 3)), np.zeros((2, 3))])
+    with pytest.raises(AssertionError):  # activ_bounded.jl:8
+        o.QcActivBounded(acydim=2, acymin=np.array([1.0, 0.0]), acymax=np.array([0.0, 1.0]))
+    with pytest.raises(AssertionError):  # activ_sector.jl:14
+        o.QcActivSector(acxdim=2, beta=1, smin=np.array([1.0, 0.0]), smax=np.array([0.0, 1.0]))
+    with pytest.raises(AssertionError):  # MyMath.jl:46
+        o.Ec([3, 2], 5)
+
+
+def test_sector_thresholds():
+    lo = np.array([1e-4, np.nextafter(1e-4, 1), -1.0, 0.0])
+    hi = np.array([1.0, 1.0, -1e-4, np.nextafter(-1e-4, -1)])
+    smin, smax = o.make_sector_min_max(lo, hi)
+    assert np.array_equal(smin, [0, 1, 0, 0]) and np.array_equal(smax, [1, 1, 1, 0])  # strict, activ_sector.jl:67-68
+
+
+# ---------------------------------------------------------------------------------------------
+# golden fixtures (tests/golden/make_golden.py)
+# ---------------------------------------------------------------------------------------------
+def _net_from(d):
+    xd = d["xdims"].tolist()
+    return o.FeedFwdNet(xdims=xd, Ms=[d[f"M{k}"] for k in range(len(xd) - 1)])
+
+
+def test_nnet_reader_matches_reference_reader():
+    """weights in the fixture were read by the reference's exts/NNet/utils/readNNet.py."""
+    d = np.load(os.path.join(GOLD, "scale_W5_D5_weights.npz"))
+    net = o.load_nnet(os.path.join(GOLD, "scale-I2-O2-W5-D5.nnet"))
+    assert net.xdims == d["xdims"].tolist() == [2, 5, 5, 5, 5, 5, 2]
+    for k, M in enumerate(net.Ms):
+        assert np.array_equal(M, d[f"M{k}"])
+    # fixture statistics, scripts/make_networks.jl:44,50
+    assert abs(float(d["std_scale_W20"]) - 2.0 / np.sqrt(20 * np.log(20))) < 0.01
+    assert abs(float(d["std_reach_W20"]) - 1.0 / np.sqrt(2.0)) < 0.02
+
+
+@pytest.mark.parametrize("tag,kind", [("safety", "safety"), ("ellipsoid", "ellipsoid"), ("tight", "safety")])
+def test_golden_config1(tag, kind):
+    d = np.load(os.path.join(GOLD, "config1_W10_D10_beta1.npz"))
+    net, beta = _net_from(d), int(d["beta"])
+    assert net.Zdim == 103 and net.acdim == 100 and net.K == 11
+    qc = o.QcSafety(S=d["S"]) if kind == "safety" else o.QcReachEllipsoid(invP=np.eye(2), yc=d["yc"])
+    q = o.NumericQuery(d[f"{tag}_x1min"], d[f"{tag}_x1max"], d[f"{tag}_gin"], d[f"{tag}_gbnd"], d[f"{tag}_gsec"],
+                       qc, d["gout"] if kind != "safety" else None)
+    for form, tol in (("literal", 0.0), ("closed", 1e-14)):
+        r = o.run_query(net, beta, q, form=form)
+        info = r["intv"]
+        assert np.array_equal(np.concatenate([p[0] for p in info.x_intvs]), d[f"{tag}_xmin"])
+        assert np.array_equal(np.concatenate([p[1] for p in info.acx_intvs]), d[f"{tag}_acxmax"])
+        assert np.array_equal(r["qc_sector"].smin, d[f"{tag}_smin"])
+        assert np.array_equal(r["qc_sector"].smax, d[f"{tag}_smax"])
+        assert np.abs(r["Z"] - d[f"{tag}_Z"]).max() <= tol * np.abs(d[f"{tag}_Z"]).max()
+    assert int(d["ncliques"]) == len(r["cliques"]) == 9
+    for k, (Ck, parts, ds) in enumerate(r["cliques"]):
+        assert np.array_equal(Ck, d[f"Ck{k}"])
+        for i, p in enumerate(ds):
+            assert np.array_equal(p, d[f"Dk{k}_{i}"])
+    assert sorted(len(c[0]) for c in r["cliques"])[0] == 24 and max(len(c[0]) for c in r["cliques"]) == 32
+    if tag == "tight":
+        assert d["tight_smin"].sum() > 0  # the Gram term is exercised
+
+
+def test_golden_config3_reach_directions():
+    d = np.load(os.path.join(GOLD, "config3_reach_W20_D10_beta2.npz"))
+    net, beta = _net_from(d), int(d["beta"])
+    assert net.Zdim == 203 and int(d["ncliques"]) == 9
+    for i in (0, 17, 40):
+        tag = f"dir{i}" if i in (0, 17) else "dir0"
+        q = o.NumericQuery(d[f"{tag}_x1min"], d[f"{tag}_x1max"], d[f"{tag}_gin"], d[f"{tag}_gbnd"], d[f"{tag}_gsec"],
+                           o.QcReachHplane(d["normals"][i]), d["gout"][i:i + 1])
+        r = o.run_query(net, beta, q, form="closed")
+        assert np.abs(r["Z"][:, -1] - d["affine_cols"][i]).max() <= 1e-13 * np.abs(d["affine_cols"][i]).max()
+        fro = np.array([np.linalg.norm(b) for b in r["blocks"]])
+        assert np.abs(fro - d["block_fro"][i]).max() <= 1e-13 * d["block_fro"][i].max()
+        if i in (0, 17):
+            assert np.abs(r["Z"] - d[f"{tag}_Z"]).max() <= 1e-14 * np.abs(d[f"{tag}_Z"]).max()
+    # across directions only the affine column / Z[a,a] change (src/NnSdp.jl:73-95)
+    diff = d["dir0_Z"] - d["dir17_Z"]
+    assert np.all(diff[:-1, :-1] == 0.0) and np.any(diff[:, -1] != 0.0)
