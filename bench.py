@@ -36,6 +36,9 @@ WORKLOADS = {
     "tiny-W10-D10-beta1-Q64": dict(W=10, D=10, beta=1, Q=64, ring=64),
 }
 DEFAULT_WORKLOAD = "stress-W1000-D20-beta2-Q1024"
+# dram__bytes_read.sum + dram__bytes_write.sum per launch from the `ncu --set full` capture of the same
+# command (profiles/): filled in when a capture exists for the current kernels, else null.
+NCU_TRAFFIC = {}
 
 
 def make_workload(name: str, rank: int, Q: int | None = None):
@@ -155,10 +158,9 @@ def run_reference(args):
     w = WORKLOADS[name]
     cores = os.cpu_count() or 1
     per_step = 1 if w["W"] >= 500 else 16
-    cpu_queries_per_sec(name, 1, 1e9)  # warm-up (BLAS threads, page faults)
     times = []
-    for _ in range(args.warmup):
-        pass  # the warm-up above is the only untimed work; CPU steps are seconds each
+    for _ in range(max(args.warmup, 1)):
+        cpu_queries_per_sec(name, per_step, 1e9)  # untimed warm-up steps (BLAS threads, page faults)
     for _ in range(args.steps):
         qps, done, dt = cpu_queries_per_sec(name, per_step, 1e9)
         times.append(dt / done)
@@ -230,7 +232,7 @@ def run_ours(args):
     barrier()
     ms = batch.elapsed_ms()
     clocks = sampler.stop() if rank == 0 else None
-    stage = {k: batch.stage_ms(k) for k in ("bounds", "prepare", "gram", "emit")}
+    stage = {k: batch.stage_ms(k) for k in ("bounds", "prepare", "gram", "emit")}  # emit = its three kernels
     ncon, nact = batch.gram_stats()
     if world > 1:
         t = torch.tensor([ms], device="cuda")
@@ -239,16 +241,39 @@ def run_ours(args):
     ms_per_step = ms / args.steps
     value = world * Q / (ms_per_step * 1e-3)
 
-    # ---- roofline of the dominant kernel (block emission): algorithmic bytes = 8 * sum |Ck|^2 per query
-    emit_ms, emit_launches = stage["emit"]
-    bytes_per_launch = 8.0 * sz["sum_ck_sq"] * ring
-    avg_launch_ms = emit_ms / max(emit_launches, 1)
-    achieved = bytes_per_launch / (avg_launch_ms * 1e-3) / 1e9
+    # ---- roofline of the emitter (HBM-write bound).  One pass = emit_fill_kernel, emit_window_kernel,
+    # emit_edge_kernel back to back over `ring` queries; each kernel is timed with its own CUDA-event
+    # span on the launching stream.  Algorithmic bytes of a kernel = 8 B x the output entries of the
+    # tiles it owns (host plan), x the queries of the pass; the three add up to 8 * sum|Ck|^2 per query.
+    ps = nb.plan_stats(xdims, beta)
+    ent = ps["entries"]
+    kernel_entries = {"emit_fill_kernel": ent["ZERO"] + ent["SAME"] + ent["DIAG"] + ent["AFF"],
+                      "emit_window_kernel": ent["RC"] + ent["CR"], "emit_edge_kernel": ent["MIXED"] + ent["GENERAL"]}
+    assert sum(kernel_entries.values()) == sz["sum_ck_sq"]
     peak, peak_src = measured_peaks()
-    roofline = {"bound": "hbm", "kernel": "emit_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
-                "algorithmic_bytes_per_launch": bytes_per_launch, "avg_launch_ms": avg_launch_ms,
-                "share_of_step": emit_ms / ms if ms > 0 else None}
+    q_per_pass = Q / max(1, -(-Q // ring))          # average queries per emitter pass
+    kernels = []
+    for kname, stage_name in (("emit_fill_kernel", "emit_fill"), ("emit_window_kernel", "emit_window"),
+                              ("emit_edge_kernel", "emit_edge")):
+        kms, kl = batch.stage_ms(stage_name)
+        if kl == 0:
+            continue
+        b_launch = 8.0 * kernel_entries[kname] * q_per_pass
+        avg = kms / kl
+        kernels.append({"kernel": kname, "launches": kl, "avg_launch_ms": avg, "algorithmic_bytes_per_launch": b_launch,
+                        "achieved": b_launch / (avg * 1e-3) / 1e9, "share_of_step": kms / ms if ms > 0 else None})
+    dom = max(kernels, key=lambda k: k["share_of_step"])
+    emit_ms, _ = stage["emit"]
+    passes = dom["launches"]
+    pass_bytes = 8.0 * sz["sum_ck_sq"] * q_per_pass
+    pass_gbs = pass_bytes / (emit_ms / passes * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "kernel": dom["kernel"], "achieved": dom["achieved"], "peak": peak, "unit": "GB/s",
+                "frac": dom["achieved"] / peak, "traffic": NCU_TRAFFIC.get(dom["kernel"]), "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": dom["algorithmic_bytes_per_launch"], "avg_launch_ms": dom["avg_launch_ms"],
+                "share_of_step": dom["share_of_step"],
+                "emitter_pass": {"kernels": kernels, "algorithmic_bytes": pass_bytes, "ms": emit_ms / passes,
+                                 "achieved": pass_gbs, "frac": pass_gbs / peak, "share_of_step": emit_ms / ms if ms > 0 else None,
+                                 "note": "8*sum|Ck|^2 bytes per query over the three kernels of a pass"}}
 
     line = None
     if rank == 0:
@@ -280,8 +305,9 @@ def run_ours(args):
         # ---- CPU baseline on this box's host cores (bounded sample)
         cpu = None
         if not args.no_cpu:
-            nq_cpu = 2 if w["W"] >= 500 else 32
-            qps, done, dt = cpu_queries_per_sec(name, nq_cpu, 25.0)
+            nq_cpu = 8 if w["W"] >= 500 else 256
+            cpu_queries_per_sec(name, 1, 1e9)  # warm-up
+            qps, done, dt = cpu_queries_per_sec(name, nq_cpu, 20.0)
             cpu = {"value": qps, "unit": "queries/s", "cores": os.cpu_count(), "kind": "port",
                    "sample": f"{done} queries of the same workload in {dt:.1f} s, numpy+BLAS closed-form oracle"}
         launches_per_step = sum(stage[k][1] for k in stage) / max(args.steps, 1)

@@ -142,6 +142,12 @@ int32_t nnsdp_plan_stats(int64_t K, const int64_t* xdims, int64_t beta, int32_t 
                          int64_t* tiles_per_prog, int64_t* entries_per_prog, int64_t* tile_rows,
                          int64_t* tile_cols);
 
+/* The tile list itself: 11 int32 per tile {mat, row0, nrows, col0, ncols, grow0, gcol0, flags, rblk,
+ * cblk, prog} (rows/cols local to output matrix `mat`, grow0/gcol0 global 0-based z indices).
+ * tiles_out == NULL queries the count. */
+int32_t nnsdp_plan_tiles(int64_t K, const int64_t* xdims, int64_t beta, int32_t dense_Z,
+                         int64_t max_tiles, int32_t* tiles_out, int64_t* ntiles);
+
 /* ---- one-shot entry points with HOST buffers ------------------------------------------
  * intervalsWorstCase (src/Intervals/intervals_easy.jl:2-37), batched over Q boxes.
  *   x1min,x1max : n_in x Q;  xmin,xmax : xtot x Q (x_intvs stacked, x_1 first);
@@ -202,8 +208,9 @@ int32_t nnsdp_batch_ring_ptr(nnsdp_batch* batch, uint64_t* dev_ptr, int64_t* slo
 /* CUDA-event timing on the batch stream.  which: 0 = start, 1 = stop. */
 int32_t nnsdp_batch_event_record(nnsdp_batch* batch, int32_t which);
 int32_t nnsdp_batch_elapsed_ms(nnsdp_batch* batch, float* ms);
-/* Per-stage device time (ms) accumulated by nnsdp_batch_run since the last reset:
- * stage 0 bounds, 1 prepare, 2 gram, 3 emit, 4 d2h.  Also counts kernel launches. */
+/* Per-stage device time (ms, CUDA events on the launching stream) accumulated since the last reset:
+ * stage 0 bounds, 1 prepare, 2 gram, 3 emit (= 5 + 6 + 7), 4 d2h, and the three kernels of an emitter
+ * pass: 5 emit_fill_kernel, 6 emit_window_kernel, 7 emit_edge_kernel.  Also counts kernel launches. */
 int32_t nnsdp_batch_stage_ms(nnsdp_batch* batch, int32_t stage, float* ms, int64_t* launches);
 int32_t nnsdp_batch_stage_reset(nnsdp_batch* batch);
 /* Executed Gram work of the last prepare: number of (query, layer) contractions with a

@@ -96,7 +96,11 @@ struct nnsdp_net {
 
 namespace {
 
-enum Stage { ST_BOUNDS = 0, ST_PREP = 1, ST_GRAM = 2, ST_EMIT = 3, ST_D2H = 4, ST_COUNT = 5 };
+enum Stage {
+  ST_BOUNDS = 0, ST_PREP = 1, ST_GRAM = 2, ST_EMIT = 3, ST_D2H = 4,
+  ST_EMIT_FILL = 5, ST_EMIT_WINDOW = 6, ST_EMIT_EDGE = 7,  // the three kernels of an emitter pass (sub-spans of ST_EMIT)
+  ST_COUNT = 8
+};
 
 struct StageSpan {
   int stage;
@@ -134,8 +138,8 @@ struct nnsdp_batch {
   cudaEvent_t ev_done[2] = {nullptr, nullptr}, ev_free[2] = {nullptr, nullptr};
   std::vector<StageSpan> spans;
   std::vector<cudaEvent_t> ev_pool;
-  float stage_ms[ST_COUNT] = {0, 0, 0, 0, 0};
-  int64_t stage_launches[ST_COUNT] = {0, 0, 0, 0, 0};
+  float stage_ms[ST_COUNT] = {};
+  int64_t stage_launches[ST_COUNT] = {};
 
   cudaEvent_t get_event() {
     if (!ev_pool.empty()) {
@@ -147,21 +151,27 @@ struct nnsdp_batch {
     cudaEventCreate(&e);
     return e;
   }
+  bool span_open = false;
   void span_begin(int stage, cudaStream_t s) {
-    if (spans.size() >= 8192) return;
+    span_open = spans.size() < 16384;  // spans are resolved at every sync; beyond the cap they are dropped
+    if (!span_open) return;
     StageSpan sp{stage, get_event(), get_event()};
     cudaEventRecord(sp.e0, s);
     spans.push_back(sp);
   }
   void span_end(cudaStream_t s, int launches) {
-    if (spans.empty() || spans.size() > 8192) return;
+    if (!span_open) return;
+    span_open = false;
     cudaEventRecord(spans.back().e1, s);
     stage_launches[spans.back().stage] += launches;
   }
   void resolve_spans() {  // requires the streams to be idle
     for (auto& sp : spans) {
       float ms = 0.f;
-      if (cudaEventElapsedTime(&ms, sp.e0, sp.e1) == cudaSuccess) stage_ms[sp.stage] += ms;
+      if (cudaEventElapsedTime(&ms, sp.e0, sp.e1) == cudaSuccess) {
+        stage_ms[sp.stage] += ms;
+        if (sp.stage >= 5 && sp.stage <= 7) stage_ms[3] += ms;  // ST_EMIT = sum of its three kernels
+      }
       ev_pool.push_back(sp.e0);
       ev_pool.push_back(sp.e1);
     }
@@ -505,6 +515,39 @@ int32_t nnsdp_plan_stats(int64_t K, const int64_t* xdims, int64_t beta, int32_t 
   return NNSDP_OK;
 }
 
+/* The tile list of the emission plan (host only): 11 int32 per tile
+ * {mat, row0, nrows, col0, ncols, grow0, gcol0, flags, rblk, cblk, prog}.  tiles_out may be NULL to
+ * query the count. */
+int32_t nnsdp_plan_tiles(int64_t K, const int64_t* xdims, int64_t beta, int32_t dense_Z,
+                         int64_t max_tiles, int32_t* tiles_out, int64_t* ntiles) {
+  NN_CHECK(ntiles != nullptr, NNSDP_ERR_ARG, "NULL argument");
+  Shape sh;
+  NN_TRY(shape_from_xdims(K, xdims, &sh));
+  nnsdp_sizes sz;
+  NN_TRY(fill_sizes(sh, beta, &sz));
+  std::vector<CliqueRanges> mats;
+  if (dense_Z) {
+    CliqueRanges c;
+    c.nseg = 1;
+    c.lo[0] = 0;
+    c.hi[0] = sh.Zdim - 1;
+    mats.push_back(c);
+  } else {
+    CliqueInfoHost ci;
+    NN_TRY(make_cliques_host(sh, beta, &ci));
+    mats = ci.ck;
+  }
+  PlanHost plan;
+  NN_TRY(build_plan(sh, beta, mats, true, &plan));
+  *ntiles = (int64_t)plan.tiles.size();
+  if (tiles_out) {
+    NN_CHECK(max_tiles >= *ntiles, NNSDP_ERR_ARG, "tiles_out too small");
+    static_assert(sizeof(TileDev) == 11 * sizeof(int32_t), "TileDev layout");
+    memcpy(tiles_out, plan.tiles.data(), plan.tiles.size() * sizeof(TileDev));
+  }
+  return NNSDP_OK;
+}
+
 // ---- batch ----------------------------------------------------------------------------------
 int32_t nnsdp_batch_destroy(nnsdp_batch* b) {
   if (!b) return NNSDP_OK;
@@ -785,6 +828,20 @@ int32_t nnsdp_batch_prepare(nnsdp_batch* b) {
   return NNSDP_OK;
 }
 
+// One emitter pass = fill, window and edge kernels back to back, each inside its own CUDA-event span
+// (ST_EMIT_FILL / _WINDOW / _EDGE) so that the per-kernel launch durations can be read back.
+static void emit_pass(nnsdp_batch* b, const GramDev& gd, int q0, int nq, double* dst) {
+  const NetPerDev& nd = *b->nd;
+  int total = 0;
+  for (int which = 0; which < 3; ++which) {
+    b->span_begin(ST_EMIT_FILL + which, b->st);
+    const int l = launch_emit(nd.nd, b->bd, gd, b->pd, q0, nq, dst, b->st, which);
+    b->span_end(b->st, l);
+    total += l;
+  }
+  b->stage_launches[ST_EMIT] += total;
+}
+
 int32_t nnsdp_batch_emit(nnsdp_batch* b, int64_t q0, int64_t nq) {
   NN_CHECK(b != nullptr, NNSDP_ERR_ARG, "batch is NULL");
   NN_CHECK(b->prepared, NNSDP_ERR_STATE, "nnsdp_batch_emit before nnsdp_batch_prepare");
@@ -796,9 +853,7 @@ int32_t nnsdp_batch_emit(nnsdp_batch* b, int64_t q0, int64_t nq) {
   b->span_begin(ST_GRAM, b->st);
   int l = launch_gram(nd.nd, b->bd, b->gd, (int)b->net->max_block, (int)q0, (int)nq, b->st);
   b->span_end(b->st, l);
-  b->span_begin(ST_EMIT, b->st);
-  l = launch_emit(nd.nd, b->bd, b->gd, b->pd, (int)q0, (int)nq, b->ringbuf.as<double>(), b->st);
-  b->span_end(b->st, l);
+  emit_pass(b, b->gd, (int)q0, (int)nq, b->ringbuf.as<double>());
   NN_CUDA(cudaGetLastError());
   return NNSDP_OK;
 }
@@ -836,9 +891,7 @@ int32_t nnsdp_batch_run(nnsdp_batch* b, double* host_out) {
     b->span_begin(ST_GRAM, b->st);
     int l = launch_gram(nd.nd, b->bd, gd, (int)b->net->max_block, (int)q0, (int)nq, b->st);
     b->span_end(b->st, l);
-    b->span_begin(ST_EMIT, b->st);
-    l = launch_emit(nd.nd, b->bd, gd, b->pd, (int)q0, (int)nq, dst, b->st);
-    b->span_end(b->st, l);
+    emit_pass(b, gd, (int)q0, (int)nq, dst);
     if (host_out) {
       NN_CUDA(cudaEventRecord(b->ev_done[h], b->st));
       NN_CUDA(cudaStreamWaitEvent(b->st_copy, b->ev_done[h], 0));

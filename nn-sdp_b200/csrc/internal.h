@@ -226,8 +226,9 @@ int launch_prep(const NetDev& net, const BatchDev& b, int* err_flag, cudaStream_
 int launch_gram(const NetDev& net, const BatchDev& b, const GramDev& g, int max_n, int q0, int nq,
                 cudaStream_t st);
 // K4+K5: emit all tiles of queries [q0, q0+nq) to out + slot * per_query, slot = q - q0.
+// which: -1 = the whole pass (fill, window, edge kernels back to back); 0 / 1 / 2 = one of them.
 int launch_emit(const NetDev& net, const BatchDev& b, const GramDev& g, const PlanDev& plan,
-                int q0, int nq, double* out, cudaStream_t st);
+                int q0, int nq, double* out, cudaStream_t st, int which = -1);
 
 constexpr int PREP_THREADS = 256;
 constexpr int MAX_WINDOW_BETA = 4;  // RC / CR register-window programs are instantiated for beta <= 4

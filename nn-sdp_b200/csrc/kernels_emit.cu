@@ -457,7 +457,11 @@ emit_edge_kernel(NetDev net, BatchDev b, GramDev g, PlanDev plan, int tile0, int
   const MatDev mat = plan.mats[t.mat];
   const int slot0 = blockIdx.y * group;
   const int nslots = min(group, nq - slot0);
-  const int TR = plan.tile_rows;
+  // thread = (row, column group); thin sliver tiles (2 x 32, 128 x 2, ...) spread their few entries over
+  // as many threads as possible: rows per column group = smallest power of two covering the tile's rows
+  int TR = 1;
+  while (TR < t.nrows) TR <<= 1;
+  if (TR > ETHREADS) TR = ETHREADS;
   const int tr = threadIdx.x % TR, cg = threadIdx.x / TR, ncg = ETHREADS / TR;
   const long long tile_off = mat.out_off + (t.row0 + tr) + (long long)t.col0 * mat.ld;
   const bool uniform = (t.flags & TF_UNIFORM) != 0;
@@ -474,16 +478,16 @@ emit_edge_kernel(NetDev net, BatchDev b, GramDev g, PlanDev plan, int tile0, int
 }  // namespace
 
 int launch_emit(const NetDev& net, const BatchDev& b, const GramDev& g, const PlanDev& plan,
-                int q0, int nq, double* out, cudaStream_t st) {
+                int q0, int nq, double* out, cudaStream_t st, int which) {
   if (nq <= 0) return 0;
   static const int wgroup = [] { const char* e = getenv("NNSDP_WINDOW_GROUP"); int v = e ? atoi(e) : SLOT_GROUP; return v < 1 ? 1 : (v > SLOT_GROUP ? SLOT_GROUP : v); }();
   static const int egroup = [] { const char* e = getenv("NNSDP_EDGE_GROUP"); int v = e ? atoi(e) : 1; return v < 1 ? 1 : (v > SLOT_GROUP ? SLOT_GROUP : v); }();
   int launches = 0;
-  if (plan.n_fill > 0) {
+  if (plan.n_fill > 0 && (which < 0 || which == 0)) {
     emit_fill_kernel<<<dim3(plan.n_fill, nq), ETHREADS, 0, st>>>(net, b, g, plan, q0, nq, out);
     ++launches;
   }
-  if (plan.n_window > 0) {
+  if (plan.n_window > 0 && (which < 0 || which == 1)) {
     const dim3 grid(plan.n_window * ((nq + wgroup - 1) / wgroup));
     const int t0 = plan.n_fill;
     switch (b.beta) {
@@ -496,7 +500,7 @@ int launch_emit(const NetDev& net, const BatchDev& b, const GramDev& g, const Pl
     }
     ++launches;
   }
-  if (plan.n_edge > 0) {
+  if (plan.n_edge > 0 && (which < 0 || which == 2)) {
     emit_edge_kernel<<<dim3(plan.n_edge, (nq + egroup - 1) / egroup), ETHREADS, 0, st>>>(
         net, b, g, plan, plan.n_fill + plan.n_window, q0, nq, egroup, out);
     ++launches;

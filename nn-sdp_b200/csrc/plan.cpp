@@ -179,50 +179,90 @@ int32_t build_plan(const Shape& sh, int64_t beta, const std::vector<CliqueRanges
     std::vector<Piece> rows, cols;
     cut(sh, c, split_blocks, plan->tile_rows, &rows);
     cut(sh, c, split_blocks, plan->tile_cols, &cols);
+    // classification of one rectangular tile (global ranges inclusive, l0 = local index of g0)
+    auto make_tile = [&](int64_t rg0, int64_t rg1, int64_t rl0, int64_t cg0, int64_t cg1, int64_t cl0) {
+      TileDev t{};
+      t.mat = (int32_t)ci;
+      t.row0 = (int32_t)rl0;
+      t.nrows = (int32_t)(rg1 - rg0 + 1);
+      t.grow0 = (int32_t)rg0;
+      t.col0 = (int32_t)cl0;
+      t.ncols = (int32_t)(cg1 - cg0 + 1);
+      t.gcol0 = (int32_t)cg0;
+      const int rb0 = sh.block_of(rg0), rb1 = sh.block_of(rg1);
+      const int cb0 = sh.block_of(cg0), cb1 = sh.block_of(cg1);
+      uint32_t f = 0;
+      for (int Bi = rb0; Bi <= rb1; ++Bi) {
+        const int64_t br0 = std::max<int64_t>(rg0, sh.off[Bi]);
+        const int64_t br1 = std::min<int64_t>(rg1, Bi == K ? sh.off[K] : sh.off[Bi + 1] - 1);
+        for (int Bj = cb0; Bj <= cb1; ++Bj) {
+          const int64_t bc0 = std::max<int64_t>(cg0, sh.off[Bj]);
+          const int64_t bc1 = std::min<int64_t>(cg1, Bj == K ? sh.off[K] : sh.off[Bj + 1] - 1);
+          f |= pair_flags(sh, beta, Bi, br0, br1, Bj, bc0, bc1);
+        }
+      }
+      if (!classify) f = TF_ALL;
+      t.rblk = t.cblk = -1;
+      if (rb0 == rb1 && cb0 == cb1 && rb0 < K && cb0 < K && beta <= MAX_FAST_BETA) {
+        f |= TF_UNIFORM;
+        t.rblk = rb0;
+        t.cblk = cb0;
+      }
+      t.flags = f;
+      const uint32_t terms = f & TF_ALL;
+      const bool fast = (f & TF_UNIFORM) && plan->tile_rows == 128 && plan->tile_cols == 32 &&
+                        beta <= MAX_WINDOW_BETA;
+      // SAME tiles of x_1 (Zin / S11) go to the edge kernel
+      const bool aff_only = (rg0 == sh.off[K] && rg1 == sh.off[K]) || (cg0 == sh.off[K] && cg1 == sh.off[K]);
+      if (terms == 0) t.prog = PROG_ZERO;
+      else if (aff_only && classify) t.prog = PROG_AFF;
+      else if (!(f & TF_UNIFORM)) t.prog = PROG_GENERAL;
+      else if (terms == (TF_SAME | TF_BAND) && t.rblk >= 1) t.prog = PROG_DIAG;
+      else if (terms == TF_SAME && t.rblk >= 1) t.prog = PROG_SAME;
+      else if (terms == TF_RC && fast) t.prog = PROG_RC;
+      else if (terms == TF_CR && fast) t.prog = PROG_CR;
+      else t.prog = PROG_MIXED;
+      return t;
+    };
+    // Cut points that isolate the beta-thin slivers of a block: the last beta indices of a hidden block
+    // are the neurons within beta of the next layer (F(r,c) / F(c,r) slivers inside the diagonal block and
+    // the band corner), the first beta those within beta of the previous layer.
+    auto sliver_cuts = [&](int blk, int64_t g0, int64_t g1, std::vector<int64_t>* pts) {
+      pts->clear();
+      pts->push_back(g0);
+      if (blk >= 1 && blk < K && beta > 0) {
+        const int64_t a0 = sh.off[blk] + beta, a1 = sh.off[blk + 1] - beta;  // first index of mid / of tail
+        if (a0 > g0 && a0 <= g1) pts->push_back(a0);
+        if (a1 > g0 && a1 <= g1 && a1 > a0) pts->push_back(a1);
+      }
+      pts->push_back(g1 + 1);
+    };
     for (const Piece& cp : cols) {
       for (const Piece& rp : rows) {
-        TileDev t{};
-        t.mat = (int32_t)ci;
-        t.row0 = (int32_t)rp.l0;
-        t.nrows = (int32_t)(rp.g1 - rp.g0 + 1);
-        t.grow0 = (int32_t)rp.g0;
-        t.col0 = (int32_t)cp.l0;
-        t.ncols = (int32_t)(cp.g1 - cp.g0 + 1);
-        t.gcol0 = (int32_t)cp.g0;
-        const int rb0 = sh.block_of(rp.g0), rb1 = sh.block_of(rp.g1);
-        const int cb0 = sh.block_of(cp.g0), cb1 = sh.block_of(cp.g1);
-        uint32_t f = 0;
-        for (int Bi = rb0; Bi <= rb1; ++Bi) {
-          const int64_t br0 = std::max<int64_t>(rp.g0, sh.off[Bi]);
-          const int64_t br1 = std::min<int64_t>(rp.g1, Bi == K ? sh.off[K] : sh.off[Bi + 1] - 1);
-          for (int Bj = cb0; Bj <= cb1; ++Bj) {
-            const int64_t bc0 = std::max<int64_t>(cp.g0, sh.off[Bj]);
-            const int64_t bc1 = std::min<int64_t>(cp.g1, Bj == K ? sh.off[K] : sh.off[Bj + 1] - 1);
-            f |= pair_flags(sh, beta, Bi, br0, br1, Bj, bc0, bc1);
+        TileDev t = make_tile(rp.g0, rp.g1, rp.l0, cp.g0, cp.g1, cp.l0);
+        if (classify && t.prog == PROG_MIXED && plan->tile_rows == 128) {
+          // A tile is MIXED when several terms meet in it.  Often that is one thin sliver inside a tile
+          // whose bulk is a plain copy / fill / window: split at the sliver boundaries and classify the
+          // pieces separately, so that only the slivers are evaluated entry by entry.
+          std::vector<int64_t> rc, cc;
+          sliver_cuts(t.rblk, rp.g0, rp.g1, &rc);
+          sliver_cuts(t.cblk, cp.g0, cp.g1, &cc);
+          if (rc.size() > 2 || cc.size() > 2) {
+            std::vector<TileDev> sub;
+            bool gain = false;
+            for (size_t j = 0; j + 1 < cc.size(); ++j)
+              for (size_t i = 0; i + 1 < rc.size(); ++i) {
+                TileDev u = make_tile(rc[i], rc[i + 1] - 1, rp.l0 + (rc[i] - rp.g0), cc[j], cc[j + 1] - 1,
+                                      cp.l0 + (cc[j] - cp.g0));
+                gain |= (u.prog != PROG_MIXED);
+                sub.push_back(u);
+              }
+            if (gain) {
+              for (const TileDev& u : sub) plan->tiles.push_back(u);
+              continue;
+            }
           }
         }
-        if (!classify) f = TF_ALL;
-        t.rblk = t.cblk = -1;
-        if (rb0 == rb1 && cb0 == cb1 && rb0 < K && cb0 < K && beta <= MAX_FAST_BETA) {
-          f |= TF_UNIFORM;
-          t.rblk = rb0;
-          t.cblk = cb0;
-        }
-        t.flags = f;
-        const uint32_t terms = f & TF_ALL;
-        const bool fast = (f & TF_UNIFORM) && plan->tile_rows == 128 && plan->tile_cols == 32 &&
-                          beta <= MAX_WINDOW_BETA;
-        // SAME tiles of x_1 (Zin / S11) go to the edge kernel
-        const bool aff_only = (rp.g0 == sh.off[K] && rp.g1 == sh.off[K]) ||
-                              (cp.g0 == sh.off[K] && cp.g1 == sh.off[K]);
-        if (terms == 0) t.prog = PROG_ZERO;
-        else if (aff_only && classify) t.prog = PROG_AFF;
-        else if (!(f & TF_UNIFORM)) t.prog = PROG_GENERAL;
-        else if (terms == (TF_SAME | TF_BAND) && t.rblk >= 1) t.prog = PROG_DIAG;
-        else if (terms == TF_SAME && t.rblk >= 1) t.prog = PROG_SAME;
-        else if (terms == TF_RC && fast) t.prog = PROG_RC;
-        else if (terms == TF_CR && fast) t.prog = PROG_CR;
-        else t.prog = PROG_MIXED;
         plan->tiles.push_back(t);
       }
     }

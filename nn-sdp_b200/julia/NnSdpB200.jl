@@ -1,0 +1,194 @@
+# NnSdpB200.jl -- Julia host side of libnnsdp_b200.so (C ABI: include/nnsdp_b200.h).
+#
+# NOT EXECUTED IN THIS REPOSITORY'S CI: Julia is not installed in the build image.  The file is kept
+# deliberately thin (ccall + array reshapes) so that a reviewer can vouch for it against the header;
+# the same ABI is exercised by the ctypes binding (nn-sdp_b200/nnsdp_b200/_lib.py) in tests/.
+#
+# It plugs into the reference at its three dispatch points without touching solveQuery / runQuery:
+#   * makeIntervalsInfo(x1min, x1max, ffnet, ::IntervalsB200)      src/Intervals/Intervals.jl:38-49
+#   * makeZin / makeZac / makeZout for numeric gamma                src/Qc/input.jl:19, activ.jl:30, output.jl:52,64
+#   * makeCliques (index sets), assembleCliqueBlocks (batched)      src/Methods/chordal_cliques.jl:13-59
+# Usage from the reference's module tree:   include("NnSdpB200.jl"); using .NnSdpB200
+module NnSdpB200
+
+using LinearAlgebra
+using ..MyMath
+using ..MyNeuralNetwork
+using ..Intervals
+using ..Qc
+
+const LIB = get(ENV, "NNSDP_B200_LIB", joinpath(@__DIR__, "..", "lib", "libnnsdp_b200.so"))
+
+const OUT_SAFETY, OUT_HPLANE, OUT_CIRCLE, OUT_ELLIPSOID = Int32(0), Int32(1), Int32(2), Int32(3)
+
+# mirrors `nnsdp_sizes` (14 x int64)
+struct Sizes
+  K::Int64; Zdim::Int64; acdim::Int64; xtot::Int64; lamdim::Int64; secdim::Int64
+  n_in::Int64; n_out::Int64; sdim::Int64; ncliques::Int64; sum_ck::Int64; sum_ck_sq::Int64
+  sum_dk::Int64; max_ck::Int64
+end
+
+# mirrors `nnsdp_query_inputs` (13 (pointer, stride) pairs; out_kind/reserved after the 9th)
+struct QueryInputs
+  x1min::Ptr{Float64}; x1min_stride::Int64
+  x1max::Ptr{Float64}; x1max_stride::Int64
+  ymin::Ptr{Float64}; ymin_stride::Int64
+  ymax::Ptr{Float64}; ymax_stride::Int64
+  smin::Ptr{Float64}; smin_stride::Int64
+  smax::Ptr{Float64}; smax_stride::Int64
+  gamma_in::Ptr{Float64}; gamma_in_stride::Int64
+  gamma_bnd::Ptr{Float64}; gamma_bnd_stride::Int64
+  gamma_sec::Ptr{Float64}; gamma_sec_stride::Int64
+  out_kind::Int32; reserved::Int32
+  out_S::Ptr{Float64}; out_S_stride::Int64
+  out_vec::Ptr{Float64}; out_vec_stride::Int64
+  out_invP::Ptr{Float64}; out_invP_stride::Int64
+  gamma_out::Ptr{Float64}; gamma_out_stride::Int64
+end
+
+lasterror() = unsafe_string(ccall((:nnsdp_last_error, LIB), Cstring, ()))
+check(status::Int32) = status == 0 ? nothing : error("nnsdp_b200 error $(status): $(lasterror())")
+
+# ---- handles --------------------------------------------------------------------------------------
+mutable struct Context
+  h::Ptr{Cvoid}
+  function Context(devices::Vector{Int} = [0])
+    out = Ref{Ptr{Cvoid}}(C_NULL)
+    ids = Int32.(devices)
+    check(ccall((:nnsdp_ctx_create, LIB), Int32, (Int32, Ptr{Int32}, Ptr{Ptr{Cvoid}}), length(ids), ids, out))
+    ctx = new(out[])
+    finalizer(c -> ccall((:nnsdp_ctx_destroy, LIB), Int32, (Ptr{Cvoid},), c.h), ctx)
+  end
+end
+
+mutable struct DeviceNet
+  h::Ptr{Cvoid}
+  ctx::Context
+  ffnet::FeedFwdNet
+  function DeviceNet(ctx::Context, ffnet::FeedFwdNet)
+    # Ms[k] is a dense column-major Matrix{Float64} [W_k b_k]: passed as-is (MyNeuralNetwork.jl:12-27)
+    Ms = [Matrix{Float64}(M) for M in ffnet.Ms]
+    out = Ref{Ptr{Cvoid}}(C_NULL)
+    GC.@preserve Ms begin
+      ptrs = [pointer(M) for M in Ms]
+      check(ccall((:nnsdp_net_upload, LIB), Int32,
+                  (Ptr{Cvoid}, Int64, Ptr{Int64}, Ptr{Ptr{Float64}}, Ptr{Ptr{Cvoid}}),
+                  ctx.h, ffnet.K, Int64.(ffnet.xdims), ptrs, out))
+    end
+    net = new(out[], ctx, ffnet)
+    finalizer(n -> ccall((:nnsdp_net_destroy, LIB), Int32, (Ptr{Cvoid},), n.h), net)
+  end
+end
+
+function sizes(net::DeviceNet, β::Int)
+  s = Ref{Sizes}()
+  check(ccall((:nnsdp_query_sizes, LIB), Int32, (Ptr{Cvoid}, Int64, Ptr{Sizes}), net.h, β, s))
+  return s[]
+end
+
+# ---- dispatch point 1: interval bounds -----------------------------------------------------------
+struct IntervalsB200 <: IntervalsMethod
+  net::DeviceNet
+end
+
+# Same return type as intervalsWorstCase (src/Intervals/intervals_easy.jl:2-37)
+function Intervals.makeIntervalsInfo(x1min::VecReal, x1max::VecReal, ffnet::FeedFwdNet, method::IntervalsB200)
+  sz = sizes(method.net, 0)
+  lo, hi = Vector{Float64}(x1min), Vector{Float64}(x1max)
+  xmin, xmax = zeros(sz.xtot), zeros(sz.xtot)
+  amin, amax = zeros(sz.acdim), zeros(sz.acdim)
+  check(ccall((:nnsdp_bounds_ibp, LIB), Int32,
+              (Ptr{Cvoid}, Ptr{Cvoid}, Int64, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}),
+              method.net.ctx.h, method.net.h, 1, lo, hi, xmin, xmax, amin, amax))
+  xoff = cumsum([0; ffnet.xdims])
+  aoff = cumsum([0; ffnet.xdims[2:end-1]])
+  x_intvs = [(xmin[xoff[k]+1:xoff[k+1]], xmax[xoff[k]+1:xoff[k+1]]) for k in 1:(ffnet.K+1)]
+  acx_intvs = [(amin[aoff[k]+1:aoff[k+1]], amax[aoff[k]+1:aoff[k+1]]) for k in 1:(ffnet.K-1)]
+  return IntervalsInfo(ffnet=ffnet, x_intvs=x_intvs, acx_intvs=acx_intvs)
+end
+
+# ---- clique index sets (bit-exact with makeCliques, src/Methods/chordal_cliques.jl:13-59) ---------
+function makeCliquesB200(net::DeviceNet, β::Int)
+  sz = sizes(net, β)
+  ck_off, ck_idx = zeros(Int64, sz.ncliques + 1), zeros(Int64, sz.sum_ck)
+  ck1_len, d_off, d_idx = zeros(Int64, sz.ncliques), zeros(Int64, 2 * sz.ncliques + 1), zeros(Int64, sz.sum_dk)
+  check(ccall((:nnsdp_cliques, LIB), Int32,
+              (Ptr{Cvoid}, Int64, Ptr{Int64}, Ptr{Int64}, Ptr{Int64}, Ptr{Int64}, Ptr{Int64}),
+              net.h, β, ck_off, ck_idx, ck1_len, d_off, d_idx))
+  cliques = Vector{Tuple{VecInt, Vector{VecInt}, Vector{VecInt}}}()
+  for k in 1:sz.ncliques
+    Ck = ck_idx[ck_off[k]+1:ck_off[k+1]]
+    parts = ck1_len[k] < length(Ck) ? [Ck[1:ck1_len[k]], Ck[ck1_len[k]+1:end]] : [Ck]
+    D1 = d_idx[d_off[2k-1]+1:d_off[2k]]
+    D2 = d_idx[d_off[2k]+1:d_off[2k+1]]
+    push!(cliques, (Ck, parts, isempty(D2) ? [D1] : [D1, D2]))
+  end
+  return cliques
+end
+
+# ---- dispatch point 2/3: numeric-gamma assembly --------------------------------------------------
+# One query = what SafetyQuery / ReachQuery hold (src/Methods/Methods.jl:19-41) plus numeric multipliers.
+# `γacs = [γbounded, γsector]` in the order makeQcActivsIntvs returns the QCs (src/Qc/activ.jl:64).
+function query_inputs(qc_input::QcInputBox, qc_out, qc_bounded::QcActivBounded, qc_sector::QcActivSector,
+                      γin::Vector{Float64}, γacs::Vector{Vector{Float64}}, γout::Vector{Float64}, keep::Vector{Any})
+  p(v) = (push!(keep, v); pointer(v))
+  kind, S, vec, invP = OUT_SAFETY, Float64[], Float64[], Float64[]
+  if qc_out isa QcSafety
+    S = vec_colmajor(Matrix{Float64}(qc_out.S))
+  elseif qc_out isa QcReachHplane
+    kind, vec = OUT_HPLANE, Vector{Float64}(qc_out.normal)
+  elseif qc_out isa QcReachCircle
+    kind, vec = OUT_CIRCLE, Vector{Float64}(qc_out.yc)
+  elseif qc_out isa QcReachEllipsoid
+    kind, vec, invP = OUT_ELLIPSOID, Vector{Float64}(qc_out.yc), vec_colmajor(Matrix{Float64}(qc_out.invP))
+  else
+    error("unrecognized qc: $(qc_out)")   # src/Qc/output.jl:95
+  end
+  n(v) = length(v)
+  return QueryInputs(
+    p(Vector{Float64}(qc_input.x1min)), n(qc_input.x1min), p(Vector{Float64}(qc_input.x1max)), n(qc_input.x1max),
+    p(Vector{Float64}(qc_bounded.acymin)), qc_bounded.acydim, p(Vector{Float64}(qc_bounded.acymax)), qc_bounded.acydim,
+    p(Vector{Float64}(qc_sector.smin)), qc_sector.acxdim, p(Vector{Float64}(qc_sector.smax)), qc_sector.acxdim,
+    p(γin), n(γin), p(γacs[1]), n(γacs[1]), p(γacs[2]), n(γacs[2]),
+    kind, Int32(0),
+    isempty(S) ? Ptr{Float64}(C_NULL) : p(S), n(S), isempty(vec) ? Ptr{Float64}(C_NULL) : p(vec), n(vec),
+    isempty(invP) ? Ptr{Float64}(C_NULL) : p(invP), n(invP), isempty(γout) ? Ptr{Float64}(C_NULL) : p(γout), n(γout))
+end
+vec_colmajor(M::Matrix{Float64}) = vec(copy(M))
+
+# Z[C_k, C_k] for every clique (dense Matrix{Float64}), i.e. Ec(Ck) * (Zin + Zout + sum(Zacs)) * Ec(Ck)'
+# with the numeric multipliers of scripts/test_acas.jl:81-85.
+function assembleCliqueBlocks(net::DeviceNet, β::Int, qc_input, qc_out, qc_bounded, qc_sector,
+                              γin, γacs, γout = Float64[])
+  sz = sizes(net, β)
+  keep = Any[]
+  qi = Ref(query_inputs(qc_input, qc_out, qc_bounded, qc_sector, Vector{Float64}(γin),
+                        [Vector{Float64}(g) for g in γacs], Vector{Float64}(γout), keep))
+  out = Vector{Float64}(undef, sz.sum_ck_sq)
+  GC.@preserve keep check(ccall((:nnsdp_assemble_blocks, LIB), Int32,
+              (Ptr{Cvoid}, Ptr{Cvoid}, Int64, Int64, Ptr{QueryInputs}, Ptr{Float64}), net.ctx.h, net.h, β, 1, qi, out))
+  cliques = makeCliquesB200(net, β)
+  blocks, o = Vector{Matrix{Float64}}(), 0
+  for (Ck, _, _) in cliques
+    n = length(Ck)
+    push!(blocks, reshape(out[o+1:o+n*n], n, n))   # column-major on the wire == Julia layout
+    o += n * n
+  end
+  return cliques, blocks
+end
+
+# The dense Z = Zin + Zout + sum(Zacs) (src/Methods/chordal_sdp.jl:114,145) for numeric multipliers.
+function assembleZ(net::DeviceNet, β::Int, qc_input, qc_out, qc_bounded, qc_sector, γin, γacs, γout = Float64[])
+  sz = sizes(net, β)
+  keep = Any[]
+  qi = Ref(query_inputs(qc_input, qc_out, qc_bounded, qc_sector, Vector{Float64}(γin),
+                        [Vector{Float64}(g) for g in γacs], Vector{Float64}(γout), keep))
+  Z = Matrix{Float64}(undef, sz.Zdim, sz.Zdim)
+  GC.@preserve keep check(ccall((:nnsdp_assemble_dense, LIB), Int32,
+              (Ptr{Cvoid}, Ptr{Cvoid}, Int64, Int64, Ptr{QueryInputs}, Ptr{Float64}), net.ctx.h, net.h, β, 1, qi, Z))
+  return Z
+end
+
+export Context, DeviceNet, IntervalsB200, makeCliquesB200, assembleCliqueBlocks, assembleZ
+
+end # module

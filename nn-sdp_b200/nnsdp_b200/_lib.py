@@ -65,6 +65,7 @@ PROTOTYPES = {
     "nnsdp_sizes_from_xdims": (c_i32, [c_i64, c_i64p, c_i64, C.POINTER(Sizes)]),
     "nnsdp_cliques_from_xdims": (c_i32, [c_i64, c_i64p, c_i64, c_i64p, c_i64p, c_i64p, c_i64p, c_i64p]),
     "nnsdp_plan_stats": (c_i32, [c_i64, c_i64p, c_i64, c_i32, c_i64p, c_i64p, c_i64p, c_i64p]),
+    "nnsdp_plan_tiles": (c_i32, [c_i64, c_i64p, c_i64, c_i32, c_i64, C.POINTER(c_i32), c_i64p]),
     "nnsdp_bounds_ibp": (c_i32, [c_vp, c_vp, c_i64, c_dp, c_dp, c_dp, c_dp, c_dp, c_dp]),
     "nnsdp_preact_from_x": (c_i32, [c_vp, c_vp, c_i64, c_dp, c_dp, c_dp, c_dp]),
     "nnsdp_sector_minmax": (c_i32, [c_vp, c_i64, c_dp, c_dp, c_dp, c_dp]),

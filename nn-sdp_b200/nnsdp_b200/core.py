@@ -14,7 +14,7 @@ import numpy as np
 
 from . import _lib as L
 
-STAGES = {"bounds": 0, "prepare": 1, "gram": 2, "emit": 3, "d2h": 4}
+STAGES = {"bounds": 0, "prepare": 1, "gram": 2, "emit": 3, "d2h": 4, "emit_fill": 5, "emit_window": 6, "emit_edge": 7}
 
 
 def _dp(a: Optional[np.ndarray]):
@@ -123,6 +123,20 @@ def plan_stats(xdims: Sequence[int], beta: int, dense: bool = False) -> dict:
                                    entries.ctypes.data_as(L.c_i64p), C.byref(tr), C.byref(tc)))
     return {"tile_rows": int(tr.value), "tile_cols": int(tc.value),
             "tiles": dict(zip(PROGRAMS, tiles.tolist())), "entries": dict(zip(PROGRAMS, entries.tolist()))}
+
+
+TILE_FIELDS = ("mat", "row0", "nrows", "col0", "ncols", "grow0", "gcol0", "flags", "rblk", "cblk", "prog")
+
+
+def plan_tiles(xdims: Sequence[int], beta: int, dense: bool = False) -> np.ndarray:
+    """The emission plan's tile list as an (ntiles, 11) int32 array (columns: TILE_FIELDS); host only."""
+    K = len(xdims) - 1
+    xd = (L.c_i64 * (K + 1))(*[int(x) for x in xdims])
+    n = L.c_i64(0)
+    L.check(L.lib.nnsdp_plan_tiles(K, xd, beta, int(dense), 0, None, C.byref(n)))
+    out = np.zeros((int(n.value), 11), dtype=np.int32)
+    L.check(L.lib.nnsdp_plan_tiles(K, xd, beta, int(dense), int(n.value), out.ctypes.data_as(C.POINTER(L.c_i32)), C.byref(n)))
+    return out
 
 
 def _cliques_call(fn, sz):
