@@ -118,7 +118,7 @@ struct nnsdp_batch {
   bool dense = false;
   nnsdp_sizes sz{};
   PlanHost plan;
-  DevBuf d_tiles, d_mats, d_goff, d_ldG;
+  DevBuf d_tiles, d_strips, d_mats, d_goff, d_ldG;
   std::vector<long long> goff;
   std::vector<int> ldG;
   long long gram_per_query = 0;
@@ -178,7 +178,7 @@ struct nnsdp_batch {
     spans.clear();
   }
   std::vector<DevBuf*> all_bufs() {
-    return {&d_tiles, &d_mats, &d_goff, &d_ldG, &x1min, &x1max, &ymin, &ymax, &smin, &smax,
+    return {&d_tiles, &d_strips, &d_mats, &d_goff, &d_ldG, &x1min, &x1max, &ymin, &ymax, &smin, &smax,
             &gin, &gbnd, &gsec, &outS, &outvec, &outinvP, &gout, &xmin, &xmax, &acxmin, &acxmax,
             &smin_c, &smax_c, &d11, &Md, &T0, &Bt, &u, &aff, &part, &act, &cnt, &Z11, &Z1K, &U,
             &gram, &ringbuf, &flags};
@@ -628,14 +628,7 @@ int32_t nnsdp_batch_create(nnsdp_ctx* ctx, int32_t dev_index, const nnsdp_net* n
     NN_TRY(b->U.ensure((size_t)sh.n_out() * sh.n[sh.K - 1] * Q * 8));
     b->bd.npart = npart;
     // Gram scratch layout (one slot per ring entry)
-    b->goff.assign(sh.K, 0);
-    b->ldG.assign(sh.K, 0);
-    long long go = 0;
-    for (int blk = 0; blk <= sh.K - 2; ++blk) {
-      b->ldG[blk] = round_up(sh.n[blk], 16);
-      b->goff[blk] = go;
-      go += (long long)b->ldG[blk] * sh.n[blk];
-    }
+    const long long go = gram_layout(sh, &b->goff, &b->ldG);
     b->gram_per_query = go;
     NN_TRY(upload(b->d_goff, b->goff.data(), b->goff.size() * 8, b->st));
     NN_TRY(upload(b->d_ldG, b->ldG.data(), b->ldG.size() * 4, b->st));
@@ -658,6 +651,8 @@ int32_t nnsdp_batch_create(nnsdp_ctx* ctx, int32_t dev_index, const nnsdp_net* n
     NN_TRY(upload(b->d_tiles, b->plan.tiles.data(), b->plan.tiles.size() * sizeof(TileDev), b->st));
     NN_TRY(upload(b->d_mats, b->plan.mats.data(), b->plan.mats.size() * sizeof(MatDev), b->st));
     NN_TRY(b->ringbuf.ensure((size_t)b->plan.per_query_doubles * b->ring * 8));
+    NN_TRY(upload(b->d_strips, b->plan.strips.data(), b->plan.strips.size() * sizeof(StripDev), b->st));
+    b->pd.strips = b->d_strips.as<StripDev>();
     b->pd.tiles = b->d_tiles.as<TileDev>();
     b->pd.mats = b->d_mats.as<MatDev>();
     b->pd.ntiles = (int)b->plan.tiles.size();

@@ -81,6 +81,8 @@ struct CliqueInfoHost {
 
 int32_t make_cliques_host(const Shape& sh, int64_t beta, CliqueInfoHost* out);
 int64_t lambda_dim(int64_t acdim, int64_t beta);
+// Gram scratch layout of one query: block b (b <= K-2) at goff[b], leading dimension ldG[b].
+long long gram_layout(const Shape& sh, std::vector<long long>* goff, std::vector<int>* ldG);
 int32_t fill_sizes(const Shape& sh, int64_t beta, nnsdp_sizes* out);
 
 // ---------------------------------------------------------------------------------
@@ -115,6 +117,16 @@ struct TileDev {
   int32_t prog;         // TileProg
 };
 
+// A strip of the fill kernel, self-contained (one 64 B load, no dependent look-ups at CTA start).
+struct alignas(16) StripDev {
+  long long out_off;  // offset (doubles) of the output matrix inside one query's output
+  long long goff;     // offset of block rblk's Gram inside one query's Gram scratch (SAME / DIAG)
+  int32_t ld, row0, nrows, col0;
+  int32_t ncols, grow0, gcol0, prog;
+  int32_t rblk, rl0, cl0, ldG;  // block-local index of output row r is rl0 + r, of column col0 + c is cl0 + c
+};
+static_assert(sizeof(StripDev) == 64, "StripDev must be 64 bytes");
+
 struct MatDev {
   int64_t out_off;  // offset (doubles) of this matrix inside one query's output
   int32_t n;        // side
@@ -122,6 +134,7 @@ struct MatDev {
 };
 
 struct PlanHost {
+  std::vector<StripDev> strips;  // fill class, built from tiles[0 .. n_fill)
   std::vector<TileDev> tiles;
   std::vector<MatDev> mats;
   int64_t per_query_doubles = 0;
@@ -192,6 +205,7 @@ struct GramDev {
 };
 
 struct PlanDev {
+  const StripDev* strips;    // n_fill entries, parallel to tiles[0 .. n_fill)
   const TileDev* tiles;
   const MatDev* mats;
   int ntiles;                // tiles are sorted: [fill | window | edge]
@@ -231,6 +245,8 @@ int launch_emit(const NetDev& net, const BatchDev& b, const GramDev& g, const Pl
                 int q0, int nq, double* out, cudaStream_t st, int which = -1);
 
 constexpr int PREP_THREADS = 256;
+constexpr int STRIP_ROWS = 512, STRIP_COLS = 8;  // fill-class strips (plan.cpp, emit_fill_kernel)
+constexpr int AFFROW_COLS = 1024;                // columns of one affine-row job
 constexpr int MAX_WINDOW_BETA = 4;  // RC / CR register-window programs are instantiated for beta <= 4
 constexpr int MAX_FAST_BETA = 8;  // uniform-tile fast path of the emitter stages 2*beta+1 <= 17 band taps
 

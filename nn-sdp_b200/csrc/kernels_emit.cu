@@ -370,63 +370,116 @@ __device__ __forceinline__ double s22_entry(const double* WK, const double* U, i
   return acc;
 }
 
-__global__ void __launch_bounds__(ETHREADS)
-emit_fill_kernel(NetDev net, BatchDev b, GramDev g, PlanDev plan, int q0, int nq,
-                 double* __restrict__ out) {
-  const TileDev t = plan.tiles[blockIdx.x];
-  const MatDev mat = plan.mats[t.mat];
-  const int slot = blockIdx.y, q = q0 + slot;
-  const int TR = plan.tile_rows;
-  const int tr = threadIdx.x % TR, cg = threadIdx.x / TR, ncg = ETHREADS / TR;
-  if (tr >= t.nrows) return;
-  const long long ld = mat.ld;
-  double* o = out + (long long)slot * plan.per_query + mat.out_off + (t.row0 + tr) + t.col0 * ld;
-  const int K = net.K, prog = t.prog;
-  if (prog == PROG_ZERO) {
-    for (int c = cg; c < t.ncols; c += ncg) o[c * ld] = 0.0;
+// One strip for one query.  `t` lives in shared memory (broadcast reads keep the register count at 32).
+__device__ __forceinline__ void fill_strip(const NetDev& net, const BatchDev& b, const GramDev& g,
+                                           const StripDev& t, int q, int slot, double* __restrict__ o) {
+  const long long ld = t.ld;
+  const int K = net.K, prog = t.prog, tid = threadIdx.x;
+  const int row0 = t.row0, row_end = t.row0 + t.nrows, ncols = t.ncols;
+  if (prog == PROG_AFF && t.nrows == 1 && t.grow0 == net.Zdim - 1) {  // affine row Z[a, :], thread = column
+    const double* aff = b.aff + (long long)q * net.Zdim;
+    for (int c = tid; c < ncols; c += ETHREADS) o[row0 + (t.col0 + c) * ld] = aff[t.gcol0 + c];
     return;
   }
-  if (prog == PROG_AFF) {
-    const double* aff = b.aff + (long long)q * net.Zdim;
-    const int a = net.Zdim - 1, gr = t.grow0 + tr;
-    for (int c = cg; c < t.ncols; c += ncg) o[c * ld] = aff[gr == a ? t.gcol0 + c : gr];
+  // Strip: thread = row inside a TR-row chunk (x column group when the strip is short).  For every column
+  // the chunks start on a 32 B sector boundary of the output (rows before the strip are masked), so each
+  // warp store covers whole sectors although ld is odd.  TR is a power of two.
+  int lg = 5;
+  while ((1 << lg) < ETHREADS && (1 << lg) < t.nrows + 3) ++lg;
+  const int TR = 1 << lg;
+  const int tr = tid & (TR - 1), cg = tid >> lg, ncg = ETHREADS >> lg;
+  double* col = o + (t.col0 + cg) * ld;  // column cg of the strip; advanced by ncg columns per trip
+  const long long cstep = (long long)ncg * ld;
+#define NNSDP_STRIP_LOOP(VALUE)                                                     \
+  for (int c = cg; c < ncols; c += ncg, col += cstep) {                               \
+    int r = row0 - (int)(((size_t)(col + row0) >> 3) & 3) + tr;                       \
+    if (r >= row0 && r < row_end) col[r] = (VALUE);                                   \
+    for (r += TR; r < row_end; r += TR) col[r] = (VALUE);                             \
+  }
+
+  if (prog == PROG_ZERO) {
+    NNSDP_STRIP_LOOP(0.0)
+    return;
+  }
+  if (prog == PROG_AFF) {  // affine column Z[:, a]
+    const double* aff = b.aff + (long long)q * net.Zdim + (t.grow0 - row0);
+    NNSDP_STRIP_LOOP(aff[r])
     return;
   }
   // SAME / DIAG: rows and columns in block Br, 1 <= Br <= K-1
-  const int Br = t.rblk;
-  const int rl = t.grow0 - net.off[Br] + tr, cl0 = t.gcol0 - net.off[Br];
+  const int Br = t.rblk, rl0 = t.rl0, cl0 = t.cl0;
   const bool copy = Br <= K - 2 && b.cnt[(long long)q * K + Br] > 0;  // Gram of an active layer
   const bool s22 = Br == K - 1 && b.has_s22;                           // W_K' S22 W_K of the output QC
-  const double* G = nullptr;
-  int ldG = 0;
   const double* WK = net.M[K - 1];
   const double* U = b.U + (long long)q * net.n_out * net.n[K - 1];
+  const int ldG = t.ldG;
+  const double* G = g.scratch + (long long)slot * g.per_query + t.goff + rl0;  // G[r + cl*ldG]
   if (copy) {
-    ldG = g.ldG[Br];
-    G = g.scratch + (long long)slot * g.per_query + g.goff[Br] + rl + (long long)cl0 * ldG;
-    for (int c = cg; c < t.ncols; c += ncg) o[c * ld] = G[(long long)c * ldG];
+    const double* Gc = G + (long long)(cl0 + cg) * ldG;
+    const long long gstep = (long long)ncg * ldG;
+    for (int c = cg; c < ncols; c += ncg, col += cstep, Gc += gstep) {
+      int r = row0 - (int)(((size_t)(col + row0) >> 3) & 3) + tr;
+      if (r >= row0 && r < row_end) col[r] = Gc[r];
+      for (r += TR; r < row_end; r += TR) col[r] = Gc[r];
+    }
   } else if (s22) {
-    for (int c = cg; c < t.ncols; c += ncg) o[c * ld] = s22_entry(WK, U, net.n_out, rl, cl0 + c);
+    NNSDP_STRIP_LOOP(s22_entry(WK, U, net.n_out, rl0 + r, cl0 + c))
   } else {
-    for (int c = cg; c < t.ncols; c += ncg) o[c * ld] = 0.0;
+    NNSDP_STRIP_LOOP(0.0)
   }
+#undef NNSDP_STRIP_LOOP
   if (prog == PROG_DIAG) {
-    // band entries of this row: columns jr - beta .. jr + beta; each is re-written by its owner
+    // band entries |jr - jc| <= beta inside the strip: each is re-written by the thread that stored the
+    // bulk value of that entry (same thread, program order), with the formula of the general programs.
+    // A thread owns at most one row of a column's (2 beta + 1 <= TR) band rows.
     const int beta = b.beta, n0 = net.n_in;
     const long long acdim = net.acdim;
-    const int jr = t.grow0 - n0 + tr, jc0 = t.gcol0 - n0;
+    const int jr0 = t.grow0 - n0, jc0 = t.gcol0 - n0;
+    if (jc0 + ncols - 1 + beta < jr0 || jc0 - beta > jr0 + t.nrows - 1) return;  // no band entry in this strip
     const double* T0 = b.T0 + (long long)q * acdim;
     const double* Bt = b.Bt + (long long)q * beta * acdim;
     const double* gbnd = b.gbnd + q * b.s_gbnd;
-    for (int jc = max(jr - beta, jc0); jc <= min(jr + beta, jc0 + t.ncols - 1); ++jc) {
-      const int c = jc - jc0;
-      if (c % ncg != cg) continue;
+    for (int c = cg; c < ncols; c += ncg) {
+      const int jc = jc0 + c;
+      const int lo = max(jc - beta, jr0), hi = min(jc + beta, jr0 + t.nrows - 1);
+      if (lo > hi) continue;
+      double* cp = o + (t.col0 + c) * ld;
+      const int base = row0 - (int)(((size_t)(cp + row0) >> 3) & 3);
+      const int rlo = row0 + (lo - jr0);
+      const int d = (tr - (rlo - base)) & (TR - 1);  // offset of this thread's row inside the band rows
+      if (d > hi - lo) continue;
+      const int r = rlo + d, jr = lo + d;
       double val = 0.0;
-      if (copy) val += G[(long long)c * ldG];
-      if (s22) val += s22_entry(WK, U, net.n_out, rl, cl0 + c);
+      if (copy) val += G[r + (long long)(cl0 + c) * ldG];
+      if (s22) val += s22_entry(WK, U, net.n_out, rl0 + r, cl0 + c);
       val += 0.0;  // the (absent) window terms f1 + f2 of the general formula
-      o[c * ld] = __dadd_rn(val, band_term(T0, gbnd, Bt, acdim, jr, jc));
+      cp[r] = __dadd_rn(val, band_term(T0, gbnd, Bt, acdim, jr, jc));
     }
+  }
+}
+
+// grid = (strip groups, queries).  A CTA walks strips blockIdx.x, blockIdx.x + gridDim.x, ...; the 64 B
+// descriptor of the next strip is fetched into registers of four threads before the stores of the
+// current strip are issued and parked in shared memory afterwards, so no CTA waits on a descriptor load
+// except for its first strip.
+__global__ void __launch_bounds__(ETHREADS, 8)
+emit_fill_kernel(NetDev net, BatchDev b, GramDev g, PlanDev plan, int q0, int nq,
+                 double* __restrict__ out) {
+  __shared__ int4 desc[2][4];
+  const int slot = blockIdx.y, q = q0 + slot, tid = threadIdx.x;
+  const int n = plan.n_fill, stride = gridDim.x;
+  int i = blockIdx.x;
+  if (tid < 4) desc[0][tid] = reinterpret_cast<const int4*>(plan.strips + i)[tid];
+  __syncthreads();
+  double* base = out + (long long)slot * plan.per_query;
+  for (int buf = 0; i < n; i += stride, buf ^= 1) {
+    const int nxt = i + stride;
+    int4 pre = make_int4(0, 0, 0, 0);
+    if (tid < 4 && nxt < n) pre = reinterpret_cast<const int4*>(plan.strips + nxt)[tid];
+    const StripDev& t = *reinterpret_cast<const StripDev*>(desc[buf]);
+    fill_strip(net, b, g, t, q, slot, base + t.out_off);
+    if (tid < 4) desc[buf ^ 1][tid] = pre;
+    __syncthreads();
   }
 }
 
@@ -484,7 +537,9 @@ int launch_emit(const NetDev& net, const BatchDev& b, const GramDev& g, const Pl
   static const int egroup = [] { const char* e = getenv("NNSDP_EDGE_GROUP"); int v = e ? atoi(e) : 1; return v < 1 ? 1 : (v > SLOT_GROUP ? SLOT_GROUP : v); }();
   int launches = 0;
   if (plan.n_fill > 0 && (which < 0 || which == 0)) {
-    emit_fill_kernel<<<dim3(plan.n_fill, nq), ETHREADS, 0, st>>>(net, b, g, plan, q0, nq, out);
+    static const int per_cta = [] { const char* e = getenv("NNSDP_FILL_STRIPS_PER_CTA"); int v = e ? atoi(e) : 1; return v < 1 ? 1 : v; }();
+    const int gx = (plan.n_fill + per_cta - 1) / per_cta;
+    emit_fill_kernel<<<dim3(gx, nq), ETHREADS, 0, st>>>(net, b, g, plan, q0, nq, out);
     ++launches;
   }
   if (plan.n_window > 0 && (which < 0 || which == 1)) {

@@ -59,6 +59,42 @@ __global__ void tile_fill8_slotfast(double* out, int n, int ld, int tiles_r, siz
   double* o = out + (size_t)blockIdx.x * slot_stride;
   for (int c = cg; c < 32; c += 2) if (c0 + c < n) o[r + (size_t)(c0 + c) * ld] = v;
 }
+// tall strips: a CTA owns `h` rows x 8 columns; per column the 256 threads walk 2 KB chunks that start on
+// a 32 B sector boundary (rows before the strip are masked), so every warp store covers 8 whole sectors
+__global__ void strip_fill_aligned(double* out, int n, int ld, int h, int strips_r, double v) {
+  const int r_lo = (blockIdx.x % strips_r) * h, c0 = (blockIdx.x / strips_r) * 8;
+  const int r_hi = min(r_lo + h, n);
+  double* o = out + (size_t)blockIdx.y * (size_t)ld * n;
+  for (int c = c0; c < min(c0 + 8, n); ++c) {
+    double* col = o + (size_t)c * ld;
+    const int mis = (int)(((size_t)(col + r_lo) >> 3) & 3);
+    for (int r = r_lo - mis + threadIdx.x; r < r_hi; r += 256) if (r >= r_lo) col[r] = v;
+  }
+}
+// aligned strips over a subset of the row strips only (mask bit i = row strip i is written): mimics the
+// emitter's fill kernel, which leaves the window regions of every column to another kernel
+__global__ void strip_fill_masked(double* out, int n, int ld, int h, int strips_r, unsigned mask, int nsel, double v) {
+  int k = blockIdx.x % nsel, rs = 0;
+  for (int i = 0; i < strips_r; ++i) if (mask >> i & 1) { if (k == 0) { rs = i; break; } --k; }
+  const int r_lo = rs * h, c0 = (blockIdx.x / nsel) * 8;
+  const int r_hi = min(r_lo + h, n);
+  double* o = out + (size_t)blockIdx.y * (size_t)ld * n;
+  for (int c = c0; c < min(c0 + 8, n); ++c) {
+    double* col = o + (size_t)c * ld;
+    const int mis = (int)(((size_t)(col + r_lo) >> 3) & 3);
+    for (int r = r_lo - mis + threadIdx.x; r < r_hi; r += 256) if (r >= r_lo) col[r] = v;
+  }
+}
+// same strips, no alignment (rows start at r_lo)
+__global__ void strip_fill_plain(double* out, int n, int ld, int h, int strips_r, double v) {
+  const int r_lo = (blockIdx.x % strips_r) * h, c0 = (blockIdx.x / strips_r) * 8;
+  const int r_hi = min(r_lo + h, n);
+  double* o = out + (size_t)blockIdx.y * (size_t)ld * n;
+  for (int c = c0; c < min(c0 + 8, n); ++c) {
+    double* col = o + (size_t)c * ld;
+    for (int r = r_lo + threadIdx.x; r < r_hi; r += 256) col[r] = v;
+  }
+}
 __global__ void linear_fill(double* out, size_t n, double v) {
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) out[i] = v;
 }
@@ -88,6 +124,25 @@ int main() {
   timeit("tile_fill8 ld=3004", [&] { tile_fill8<<<grid, 256>>>(buf, n, 3004, tiles_r, 1.0); }, bytes);
   timeit("tile_fill8 ld=3008", [&] { tile_fill8<<<grid, 256>>>(buf, n, 3008, tiles_r, 1.0); }, bytes);
   timeit("tile_fill8_aligned ld=3003", [&] { tile_fill8_aligned<<<grid, 256>>>(buf, n, 3003, tiles_r, 1.0); }, bytes);
+  for (int h : {1001, 501, 256}) {
+    const int strips_r = (n + h - 1) / h;
+    dim3 g2(strips_r * ((n + 7) / 8), nmat);
+    char nm[96];
+    snprintf(nm, sizeof nm, "strip_fill_aligned ld=3003 h=%d x 8 cols", h);
+    timeit(nm, [&] { strip_fill_aligned<<<g2, 256>>>(buf, n, 3003, h, strips_r, 1.0); }, bytes);
+    snprintf(nm, sizeof nm, "strip_fill_plain   ld=3003 h=%d x 8 cols", h);
+    timeit(nm, [&] { strip_fill_plain<<<g2, 256>>>(buf, n, 3003, h, strips_r, 1.0); }, bytes);
+  }
+  {
+    const int h = 501, strips_r = 6;
+    for (unsigned mask : {0x3Fu, 0x33u, 0x0Fu, 0x15u}) {
+      int nsel = __builtin_popcount(mask);
+      dim3 g2(nsel * ((n + 7) / 8), nmat);
+      char nm[96];
+      snprintf(nm, sizeof nm, "strip_fill_masked h=501 row-strip mask 0x%02x", mask);
+      timeit(nm, [&] { strip_fill_masked<<<g2, 256>>>(buf, n, 3003, h, strips_r, mask, nsel, 1.0); }, bytes * nsel / 6.0);
+    }
+  }
   timeit("tile_fill16 ld=3004", [&] { tile_fill16<<<grid, 256>>>(buf, n, 3004, tiles_r, 1.0); }, bytes);
   timeit("tile_fill16 ld=3008", [&] { tile_fill16<<<grid, 256>>>(buf, n, 3008, tiles_r, 1.0); }, bytes);
   {
