@@ -275,36 +275,61 @@ def run_ours(args):
                                  "achieved": pass_gbs, "frac": pass_gbs / peak, "share_of_step": emit_ms / ms if ms > 0 else None,
                                  "note": "8*sum|Ck|^2 bytes per query over the three kernels of a pass"}}
 
+    # ---- end-to-end through the public API with host buffers (bounded sample of the same workload), on
+    # EVERY rank at the same time: the ranks share the host's memory bandwidth and PCIe root complexes,
+    # so the whole-job figure is world * Qe / (slowest rank's time), not N times a single-GPU number.
+    Qe = min(Q, args.e2e_queries)
+    pin = nb.PinnedBuffer(Qe * sz["sum_ck_sq"])
+    eb = nb.Batch(net, beta, Qcap=Qe, ring=min(ring, Qe))
+    sub = {k: (v[:Qe] if v.shape[0] == Q else v) for k, v in inp.items()}
+    ebatch = nb.NumericBatch(out_kind=nb.OUT_SAFETY, **sub)
+    h2d = sum(int(np.asarray(v).nbytes) for v in sub.values())
+    d2h = Qe * sz["sum_ck_sq"] * 8
+
+    def e2e_step(flags=0):
+        eb.set_inputs(ebatch, Q=Qe)            # host -> device copy of this step's inputs
+        eb.run(pin.array, flags=flags)         # compute + gather of every dense block into host memory
+
+    def time_e2e(flags):
+        e2e_step(flags)
+        nrep = max(1, min(args.steps, 3))
+        if world > 1:
+            dist.barrier()
+        t0 = time.perf_counter()
+        for _ in range(nrep):
+            e2e_step(flags)
+        dt = (time.perf_counter() - t0) / nrep
+        if world > 1:
+            t = torch.tensor([dt], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
+        return dt
+
+    e2e_s = time_e2e(0)
+    gs = eb.gather_stats()
+    e2e = {"value": world * Qe / e2e_s, "unit": "queries/s", "h2d_bytes_per_step": world * h2d,
+           "d2h_bytes_per_step": world * (gs["dma_bytes"] + gs["thin_bytes"]),
+           "queries_per_step": world * Qe, "ms_per_step": 1e3 * e2e_s, "host_result_bytes_per_step": world * d2h,
+           "host_zero_filled_bytes_per_step": world * gs["zeroed_bytes"], "sparse_gather": gs["sparse"],
+           "note": "bounded sample of the workload on every rank concurrently; the complete dense blocks (1.33 GB/query) "
+                   "land in pinned host memory: dense cells by strided DMA, thin entries packed + scattered, "
+                   "structural / value-dependent zeros filled by host threads"}
+    # variants, for the record: caller-zeroed buffers (NNSDP_RUN_HOST_PREZEROED) and the plain dense copy
+    t_pre = time_e2e(nb.RUN_HOST_PREZEROED)
+    gs_pre = eb.gather_stats()
+    t_dense = time_e2e(nb.RUN_DENSE_COPY)
+    e2e["variants"] = {
+        "host_prezeroed": {"value": world * Qe / t_pre, "d2h_bytes_per_step": world * (gs_pre["dma_bytes"] + gs_pre["thin_bytes"]),
+                           "host_zero_filled_bytes_per_step": world * gs_pre["zeroed_bytes"]},
+        "dense_copy": {"value": world * Qe / t_dense, "d2h_bytes_per_step": world * d2h}}
+    eb.close()
+    pin.close()
+
     line = None
     if rank == 0:
-        # ---- end-to-end through the public API with host buffers (bounded sample of the same workload)
-        Qe = min(Q, args.e2e_queries)
-        pin = nb.PinnedBuffer(Qe * sz["sum_ck_sq"])
-        eb = nb.Batch(net, beta, Qcap=Qe, ring=min(ring, Qe))
-        sub = {k: (v[:Qe] if v.shape[0] == Q else v) for k, v in inp.items()}
-        ebatch = nb.NumericBatch(out_kind=nb.OUT_SAFETY, **sub)
-        h2d = sum(int(np.asarray(v).nbytes) for v in sub.values())
-        d2h = Qe * sz["sum_ck_sq"] * 8
-
-        def e2e_step():
-            eb.set_inputs(ebatch, Q=Qe)      # host -> device copy of this step's inputs
-            eb.run(pin.array)                # compute + device -> host gather of every block
-
-        e2e_step()
-        t0 = time.perf_counter()
-        nrep = max(1, min(args.steps, 3))
-        for _ in range(nrep):
-            e2e_step()
-        e2e_s = (time.perf_counter() - t0) / nrep
-        e2e = {"value": Qe / e2e_s, "unit": "queries/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-               "queries_per_step": Qe, "ms_per_step": 1e3 * e2e_s,
-               "note": "bounded sample of the workload: dense blocks are 1.33 GB/query, PCIe-bound"}
-        eb.close()
-        pin.close()
-
         # ---- CPU baseline on this box's host cores (bounded sample)
         cpu = None
-        if not args.no_cpu:
+        if not args.no_cpu and world == 1:
             nq_cpu = 8 if w["W"] >= 500 else 256
             cpu_queries_per_sec(name, 1, 1e9)  # warm-up
             qps, done, dt = cpu_queries_per_sec(name, nq_cpu, 20.0)
@@ -343,7 +368,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
     ap.add_argument("--queries", type=int, default=None, help="override queries per GPU per step")
-    ap.add_argument("--e2e-queries", type=int, default=8)
+    ap.add_argument("--e2e-queries", type=int, default=16)
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup

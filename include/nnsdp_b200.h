@@ -196,6 +196,23 @@ int32_t nnsdp_batch_emit(nnsdp_batch* batch, int64_t q0, int64_t nq);
  * Q queries through the ring, chunk by chunk.  If host_out != NULL every chunk is copied
  * to host_out[q * per_query_doubles] (device -> host inside the call).  Blocking. */
 int32_t nnsdp_batch_run(nnsdp_batch* batch, double* host_out);
+/* The same with flags.  The host gather never moves structural zeros over PCIe when the network is
+ * wide enough: dense cells of every block (the W' M windows, Gram-active diagonal blocks) are copied
+ * by strided DMA, the few other non-zeros (band, slivers, affine row / column) travel packed and are
+ * scattered by host threads, and everything else is zero-filled by host threads -- host_out ends up
+ * holding the complete dense blocks either way.
+ *   NNSDP_RUN_HOST_PREZEROED  the caller guarantees that every entry of host_out that is structurally
+ *                             zero for this (network, beta) -- the ZERO tiles of nnsdp_plan_tiles --
+ *                             already holds 0.0 (a fresh calloc / zeros(), or a buffer a previous run
+ *                             of the same batch filled); those bytes are then not touched at all.
+ *   NNSDP_RUN_DENSE_COPY      copy the dense ring contents (one contiguous DMA per chunk). */
+#define NNSDP_RUN_HOST_PREZEROED 1
+#define NNSDP_RUN_DENSE_COPY 2
+int32_t nnsdp_batch_run_ex(nnsdp_batch* batch, double* host_out, int32_t flags);
+/* Bytes the host gather of the last run moved: DMA (strided cells or dense), packed thin entries, and
+ * bytes zero-filled by host threads; *sparse_usable = 1 if the sparse gather applies to this batch. */
+int32_t nnsdp_batch_gather_stats(nnsdp_batch* batch, int64_t* dma_bytes, int64_t* thin_bytes,
+                                 int64_t* zeroed_bytes, int32_t* sparse_usable);
 int32_t nnsdp_batch_sync(nnsdp_batch* batch);
 /* Copy results back (any pointer may be NULL). Blocking. */
 int32_t nnsdp_batch_get_bounds(nnsdp_batch* batch, double* xmin, double* xmax, double* acxmin,

@@ -7,6 +7,9 @@
 #include <string.h>
 
 #include <algorithm>
+#include <condition_variable>
+#include <deque>
+#include <functional>
 #include <memory>
 #include <mutex>
 #include <thread>
@@ -109,7 +112,89 @@ struct StageSpan {
 
 }  // namespace
 
+namespace {
+
+// Host worker threads of a batch: zero-fill and scatter of the sparse host gather.
+class WorkerPool {
+ public:
+  explicit WorkerPool(int n) {
+    for (int i = 0; i < n; ++i) th_.emplace_back([this] { loop(); });
+  }
+  ~WorkerPool() {
+    {
+      std::lock_guard<std::mutex> l(m_);
+      stop_ = true;
+    }
+    cv_.notify_all();
+    for (auto& t : th_) t.join();
+  }
+  // tasks are tagged with a group id (the chunk); wait_group blocks until that group has drained
+  void submit(int group, std::function<void()> fn) {
+    {
+      std::lock_guard<std::mutex> l(m_);
+      if ((int)pending_.size() <= group) pending_.resize(group + 1, 0);
+      ++pending_[group];
+      q_.emplace_back(group, std::move(fn));
+    }
+    cv_.notify_one();
+  }
+  void wait_group(int group) {
+    std::unique_lock<std::mutex> l(m_);
+    done_cv_.wait(l, [&] { return (int)pending_.size() <= group || pending_[group] == 0; });
+  }
+  void wait_all() {
+    std::unique_lock<std::mutex> l(m_);
+    done_cv_.wait(l, [&] {
+      for (int p : pending_)
+        if (p) return false;
+      return true;
+    });
+    pending_.clear();
+  }
+  int size() const { return (int)th_.size(); }
+
+ private:
+  void loop() {
+    for (;;) {
+      std::pair<int, std::function<void()>> job;
+      {
+        std::unique_lock<std::mutex> l(m_);
+        cv_.wait(l, [&] { return stop_ || !q_.empty(); });
+        if (stop_ && q_.empty()) return;
+        job = std::move(q_.front());
+        q_.pop_front();
+      }
+      job.second();
+      {
+        std::lock_guard<std::mutex> l(m_);
+        --pending_[job.first];
+      }
+      done_cv_.notify_all();
+    }
+  }
+  std::vector<std::thread> th_;
+  std::deque<std::pair<int, std::function<void()>>> q_;
+  std::vector<int> pending_;
+  std::mutex m_;
+  std::condition_variable cv_, done_cv_;
+  bool stop_ = false;
+};
+
+constexpr int GATHER_STAGES = 4;  // packed thin-entry staging buffers in flight
+
+}  // namespace
+
 struct nnsdp_batch {
+  // sparse host gather (DESIGN.md "end to end")
+  GatherPlan gp;
+  std::vector<CliqueRanges> mats_host;
+  DevBuf d_thin_idx, d_packed;
+  double* h_packed = nullptr;  // pinned, GATHER_STAGES * chunk * nthin doubles
+  size_t h_packed_doubles = 0;
+  cudaEvent_t ev_packed[GATHER_STAGES] = {nullptr, nullptr, nullptr, nullptr};
+  std::unique_ptr<WorkerPool> pool;
+  std::vector<int> h_cnt;      // Gram-active neuron counts per (query, block), host copy
+  int64_t gather_bytes_dma = 0, gather_bytes_zeroed = 0, gather_bytes_thin = 0;  // of the last run
   nnsdp_ctx* ctx = nullptr;
   int dev_index = 0, dev = 0;
   const nnsdp_net* net = nullptr;
@@ -555,7 +640,13 @@ int32_t nnsdp_batch_destroy(nnsdp_batch* b) {
   if (b->st) cudaStreamSynchronize(b->st);
   if (b->st_copy) cudaStreamSynchronize(b->st_copy);
   b->resolve_spans();
+  b->pool.reset();
   for (DevBuf* x : b->all_bufs()) x->release();
+  b->d_thin_idx.release();
+  b->d_packed.release();
+  if (b->h_packed) cudaFreeHost(b->h_packed);
+  for (cudaEvent_t e : b->ev_packed)
+    if (e) cudaEventDestroy(e);
   for (cudaEvent_t e : b->ev_pool) cudaEventDestroy(e);
   for (cudaEvent_t e : {b->ev_start, b->ev_stop, b->ev_done[0], b->ev_done[1], b->ev_free[0], b->ev_free[1]})
     if (e) cudaEventDestroy(e);
@@ -648,6 +739,15 @@ int32_t nnsdp_batch_create(nnsdp_ctx* ctx, int32_t dev_index, const nnsdp_net* n
     }
     const char* noclass = getenv("NNSDP_NO_TILE_CLASSES");  // validation aid: evaluate every term everywhere
     NN_TRY(build_plan(sh, beta, mats, !(noclass && noclass[0] == '1'), &b->plan));
+    b->mats_host = mats;
+    NN_TRY(build_gather_plan(sh, beta, mats, b->plan, &b->gp));
+    if (const char* e = getenv("NNSDP_DENSE_GATHER"))  // developer aid: always copy the dense output
+      if (e[0] == '1') b->gp.usable = false;
+    if (b->gp.usable) {
+      NN_TRY(upload(b->d_thin_idx, b->gp.thin_idx.data(), b->gp.thin_idx.size() * 8, b->st));
+      for (int i = 0; i < GATHER_STAGES; ++i)
+        NN_CUDA(cudaEventCreateWithFlags(&b->ev_packed[i], cudaEventDisableTiming));
+    }
     NN_TRY(upload(b->d_tiles, b->plan.tiles.data(), b->plan.tiles.size() * sizeof(TileDev), b->st));
     NN_TRY(upload(b->d_mats, b->plan.mats.data(), b->plan.mats.size() * sizeof(MatDev), b->st));
     NN_TRY(b->ringbuf.ensure((size_t)b->plan.per_query_doubles * b->ring * 8));
@@ -862,7 +962,103 @@ int32_t nnsdp_batch_sync(nnsdp_batch* b) {
   return NNSDP_OK;
 }
 
-int32_t nnsdp_batch_run(nnsdp_batch* b, double* host_out) {
+// Sparse host gather of the queries [q0, q0 + nq) of chunk `ci` whose blocks sit in ring slots starting
+// at `dst`: strided DMA of the dense cells, packed copy of the thin entries, host-side zero fill +
+// scatter on the worker threads.  Everything is asynchronous; the caller drains pool and streams.
+static int32_t gather_chunk(nnsdp_batch* b, int ci, int64_t q0, int64_t nq, int h, const double* dst,
+                            double* host_out, int32_t flags) {
+  const GatherPlan& gp = b->gp;
+  const int64_t per = b->plan.per_query_doubles;
+  const int64_t nthin = (int64_t)gp.thin_idx.size();
+  const int sb = ci % GATHER_STAGES;
+  const int K = b->net->sh.K;
+  const bool prezeroed = (flags & NNSDP_RUN_HOST_PREZEROED) != 0;
+  const int64_t chunk_cap = std::max<int64_t>(1, b->ring / 2);
+  double* d_pk = b->d_packed.as<double>() + (int64_t)sb * chunk_cap * nthin;
+  double* h_pk = b->h_packed + (int64_t)sb * chunk_cap * nthin;
+  launch_pack_thin(dst, per, b->d_thin_idx.as<long long>(), nthin, d_pk, (int)nq, b->st);
+  NN_CUDA(cudaEventRecord(b->ev_done[h], b->st));
+  NN_CUDA(cudaStreamWaitEvent(b->st_copy, b->ev_done[h], 0));
+  b->span_begin(ST_D2H, b->st_copy);
+  if (nthin) NN_CUDA(cudaMemcpyAsync(h_pk, d_pk, (size_t)nq * nthin * 8, cudaMemcpyDeviceToHost, b->st_copy));
+  NN_CUDA(cudaEventRecord(b->ev_packed[sb], b->st_copy));
+  auto active = [&](const GatherCell& c, int64_t q) {
+    return c.kind == GK_ALWAYS || (c.kind == GK_GRAM && b->h_cnt[q * K + c.blk] > 0) ||
+           (c.kind == GK_S22 && b->bd.has_s22);
+  };
+  for (int64_t q = q0; q < q0 + nq; ++q) {
+    const double* src = dst + (q - q0) * per;
+    double* out = host_out + q * per;
+    for (const GatherColSeg& cs : gp.colsegs) {
+      const MatDev& md = b->plan.mats[cs.mat];
+      for (const GatherCell& c : cs.cells) {
+        if (!active(c, q)) continue;
+        const int64_t off = md.out_off + c.row0 + (int64_t)cs.col0 * md.ld;
+        NN_CUDA(cudaMemcpy2DAsync(out + off, (size_t)md.ld * 8, src + off, (size_t)md.ld * 8,
+                                  (size_t)c.nrows * 8, (size_t)cs.ncols, cudaMemcpyDeviceToHost, b->st_copy));
+        b->gather_bytes_dma += (int64_t)c.nrows * cs.ncols * 8;
+      }
+    }
+  }
+  b->span_end(b->st_copy, 0);
+  NN_CUDA(cudaEventRecord(b->ev_free[h], b->st_copy));
+  b->gather_bytes_thin += nq * nthin * 8;
+  // host side: one task per (query, matrix)
+  const int nm = (int)b->plan.mats.size();
+  cudaEvent_t ev = b->ev_packed[sb];
+  const int dev = b->dev;
+  for (int64_t q = q0; q < q0 + nq; ++q) {
+    for (int m = 0; m < nm; ++m) {
+      double* out = host_out + q * per;
+      const double* pk = h_pk + (q - q0) * nthin;
+      // what to zero is decided here (cheap) so the task needs no access to mutable batch state
+      struct Run { int64_t off; int32_t nrows, ncols, ld; };
+      std::vector<Run> runs;
+      const MatDev& md = b->plan.mats[m];
+      for (int s = gp.colseg_begin[m]; s < gp.colseg_begin[m + 1]; ++s) {
+        const GatherColSeg& cs = gp.colsegs[s];
+        int32_t run0 = -1, runlen = 0;
+        auto flush = [&] {
+          if (runlen > 0) {
+            runs.push_back({md.out_off + run0 + (int64_t)cs.col0 * md.ld, runlen, cs.ncols, md.ld});
+            b->gather_bytes_zeroed += (int64_t)runlen * cs.ncols * 8;
+          }
+          run0 = -1;
+          runlen = 0;
+        };
+        for (const GatherCell& c : cs.cells) {
+          const bool skip = active(c, q) || (prezeroed && c.pure_zero);
+          if (skip) {
+            flush();
+            continue;
+          }
+          if (runlen > 0 && run0 + runlen == c.row0) {
+            runlen += c.nrows;
+          } else {
+            flush();
+            run0 = c.row0;
+            runlen = c.nrows;
+          }
+        }
+        flush();
+      }
+      const int64_t t0 = gp.thin_begin[m], t1 = gp.thin_begin[m + 1];
+      const int64_t* idx = gp.thin_idx.data();
+      b->pool->submit(ci, [=, runs = std::move(runs)] {
+        for (const Run& r : runs)
+          for (int32_t c = 0; c < r.ncols; ++c) memset(out + r.off + (int64_t)c * r.ld, 0, (size_t)r.nrows * 8);
+        if (t1 > t0) {
+          cudaSetDevice(dev);
+          cudaEventSynchronize(ev);
+          for (int64_t i = t0; i < t1; ++i) out[idx[i]] = pk[i];
+        }
+      });
+    }
+  }
+  return NNSDP_OK;
+}
+
+int32_t nnsdp_batch_run_ex(nnsdp_batch* b, double* host_out, int32_t flags) {
   NN_CHECK(b != nullptr, NNSDP_ERR_ARG, "batch is NULL");
   NN_CHECK(b->have_inputs, NNSDP_ERR_STATE, "nnsdp_batch_run before nnsdp_batch_set_inputs");
   NN_CHECK(b->ring > 0, NNSDP_ERR_STATE, "batch was created without an output ring");
@@ -875,19 +1071,46 @@ int32_t nnsdp_batch_run(nnsdp_batch* b, double* host_out) {
   // emission of the other
   const int nhalf = (host_out && b->ring >= 2) ? 2 : 1;
   const int64_t chunk = (nhalf == 2) ? b->ring / 2 : b->ring;
+  const bool sparse = host_out && b->gp.usable && !(flags & NNSDP_RUN_DENSE_COPY);
+  b->gather_bytes_dma = b->gather_bytes_zeroed = b->gather_bytes_thin = 0;
+  if (sparse) {
+    const int K = b->net->sh.K;
+    b->h_cnt.resize((size_t)K * b->Q);
+    NN_CUDA(cudaMemcpyAsync(b->h_cnt.data(), b->cnt.p, b->h_cnt.size() * 4, cudaMemcpyDeviceToHost, b->st));
+    NN_CUDA(cudaStreamSynchronize(b->st));
+    const size_t need = (size_t)GATHER_STAGES * chunk * b->gp.thin_idx.size();
+    if (need > b->h_packed_doubles) {
+      if (b->h_packed) cudaFreeHost(b->h_packed);
+      b->h_packed = nullptr;
+      b->h_packed_doubles = 0;
+      NN_CUDA(cudaHostAlloc((void**)&b->h_packed, std::max<size_t>(need, 1) * 8, cudaHostAllocPortable));
+      b->h_packed_doubles = need;
+      NN_TRY(b->d_packed.ensure(std::max<size_t>(need, 1) * 8));
+    }
+    if (!b->pool) {
+      int nt = (int)std::min<unsigned>(16u, std::max(1u, std::thread::hardware_concurrency()));
+      if (const char* e = getenv("NNSDP_HOST_THREADS")) nt = std::max(1, atoi(e));
+      b->pool.reset(new WorkerPool(nt));
+    }
+  }
   bool used[2] = {false, false};
-  int h = 0;
-  for (int64_t q0 = 0; q0 < b->Q; q0 += chunk, h = (h + 1) % nhalf) {
+  int h = 0, ci = 0;
+  int32_t status = NNSDP_OK;
+  for (int64_t q0 = 0; q0 < b->Q && status == NNSDP_OK; q0 += chunk, h = (h + 1) % nhalf, ++ci) {
     const int64_t nq = std::min(chunk, b->Q - q0);
     double* dst = b->ringbuf.as<double>() + (int64_t)h * chunk * per;
     GramDev gd = b->gd;
     gd.scratch += (int64_t)h * chunk * gd.per_query;
+    if (sparse && ci >= GATHER_STAGES) b->pool->wait_group(ci - GATHER_STAGES);  // staging buffer reuse
     if (host_out && used[h]) NN_CUDA(cudaStreamWaitEvent(b->st, b->ev_free[h], 0));
     b->span_begin(ST_GRAM, b->st);
     int l = launch_gram(nd.nd, b->bd, gd, (int)b->net->max_block, (int)q0, (int)nq, b->st);
     b->span_end(b->st, l);
     emit_pass(b, gd, (int)q0, (int)nq, dst);
-    if (host_out) {
+    if (sparse) {
+      status = gather_chunk(b, ci, q0, nq, h, dst, host_out, flags);
+      used[h] = true;
+    } else if (host_out) {
       NN_CUDA(cudaEventRecord(b->ev_done[h], b->st));
       NN_CUDA(cudaStreamWaitEvent(b->st_copy, b->ev_done[h], 0));
       b->span_begin(ST_D2H, b->st_copy);
@@ -896,12 +1119,33 @@ int32_t nnsdp_batch_run(nnsdp_batch* b, double* host_out) {
       b->span_end(b->st_copy, 0);
       NN_CUDA(cudaEventRecord(b->ev_free[h], b->st_copy));
       used[h] = true;
+      b->gather_bytes_dma += nq * per * 8;
     }
+  }
+  if (b->pool) b->pool->wait_all();
+  if (status != NNSDP_OK) {
+    cudaStreamSynchronize(b->st);
+    cudaStreamSynchronize(b->st_copy);
+    return status;
   }
   NN_CUDA(cudaGetLastError());
   NN_CUDA(cudaStreamSynchronize(b->st));
   NN_CUDA(cudaStreamSynchronize(b->st_copy));
   b->resolve_spans();
+  return NNSDP_OK;
+}
+
+int32_t nnsdp_batch_run(nnsdp_batch* b, double* host_out) { return nnsdp_batch_run_ex(b, host_out, 0); }
+
+/* Bytes moved by the host gather of the last nnsdp_batch_run*: strided / dense DMA, packed thin
+ * entries, and bytes zero-filled by host threads. */
+int32_t nnsdp_batch_gather_stats(nnsdp_batch* b, int64_t* dma_bytes, int64_t* thin_bytes,
+                                 int64_t* zeroed_bytes, int32_t* sparse_usable) {
+  NN_CHECK(b != nullptr, NNSDP_ERR_ARG, "batch is NULL");
+  if (dma_bytes) *dma_bytes = b->gather_bytes_dma;
+  if (thin_bytes) *thin_bytes = b->gather_bytes_thin;
+  if (zeroed_bytes) *zeroed_bytes = b->gather_bytes_zeroed;
+  if (sparse_usable) *sparse_usable = b->gp.usable ? 1 : 0;
   return NNSDP_OK;
 }
 

@@ -142,9 +142,42 @@ struct PlanHost {
   int n_fill = 0, n_window = 0, n_edge = 0;  // tiles are sorted by kernel class
 };
 
+// ---------------------------------------------------------------------------------
+// host gather plan: how one query's dense output reaches caller-owned host memory without moving
+// structural zeros over PCIe.  Every output matrix is cut at block boundaries into cells; a cell is
+//   DENSE_ALWAYS  W' M windows (rows of block b against the neurons of layer b+1, and the transpose),
+//   DENSE_GRAM    diagonal block of a layer whose Gram is non-zero for this query (value dependent),
+//   DENSE_S22     the x_K block when the output QC has an S22 part,
+// (copied as one strided DMA each) or it is not dense: then it is zero-filled by host threads and its
+// few possibly non-zero entries (band, slivers, affine row / column: the "thin" list) are packed on the
+// device, copied contiguously and scattered by the host.
+// ---------------------------------------------------------------------------------
+enum GatherKind : int32_t { GK_NONE = 0, GK_ALWAYS = 1, GK_GRAM = 2, GK_S22 = 3 };
+constexpr int GATHER_MIN_RECT = 256;  // smaller cells are never worth a strided DMA of their own
+
+struct GatherCell {
+  int32_t row0, nrows;  // local rows
+  int32_t kind, blk;    // GatherKind; block of a GK_GRAM cell
+  int32_t pure_zero;    // no term of Z can be non-zero in the cell (and no thin entry lies in it)
+};
+struct GatherColSeg {   // a block-aligned range of columns of one matrix and its cells top to bottom
+  int32_t mat, col0, ncols;
+  std::vector<GatherCell> cells;
+};
+struct GatherPlan {
+  bool usable = false;                 // false: copy the dense output (small nets)
+  std::vector<GatherColSeg> colsegs;   // ordered by matrix
+  std::vector<int32_t> colseg_begin;   // per matrix: first colseg (size nmats + 1)
+  std::vector<int64_t> thin_idx;       // offsets (doubles) inside one query's output, ascending per matrix
+  std::vector<int64_t> thin_begin;     // per matrix: first thin entry (size nmats + 1)
+  int64_t dense_always_doubles = 0;    // statistics
+};
+
 // tile_rows in {32, 64, 128}; classify = false marks every tile TF_ALL (validation mode).
 int32_t build_plan(const Shape& sh, int64_t beta, const std::vector<CliqueRanges>& mats,
                    bool classify, PlanHost* plan);
+int32_t build_gather_plan(const Shape& sh, int64_t beta, const std::vector<CliqueRanges>& mats,
+                          const PlanHost& plan, GatherPlan* gp);
 
 // ---------------------------------------------------------------------------------
 // device-side descriptors (passed by value to kernels)
@@ -243,6 +276,10 @@ int launch_gram(const NetDev& net, const BatchDev& b, const GramDev& g, int max_
 // which: -1 = the whole pass (fill, window, edge kernels back to back); 0 / 1 / 2 = one of them.
 int launch_emit(const NetDev& net, const BatchDev& b, const GramDev& g, const PlanDev& plan,
                 int q0, int nq, double* out, cudaStream_t st, int which = -1);
+
+// thin-entry pack: packed[s * nthin + i] = ring[s * per_query + idx[i]] for the nq slots of a chunk
+int launch_pack_thin(const double* ring, long long per_query, const long long* idx, long long nthin,
+                     double* packed, int nq, cudaStream_t st);
 
 constexpr int PREP_THREADS = 256;
 constexpr int STRIP_ROWS = 512, STRIP_COLS = 8;  // fill-class strips (plan.cpp, emit_fill_kernel)

@@ -530,6 +530,28 @@ emit_edge_kernel(NetDev net, BatchDev b, GramDev g, PlanDev plan, int tile0, int
 
 }  // namespace
 
+namespace {
+__global__ void pack_thin_kernel(const double* __restrict__ ring, long long per_query,
+                                 const long long* __restrict__ idx, long long nthin,
+                                 double* __restrict__ packed, int nq) {
+  const long long total = nthin * nq;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long s = i / nthin, k = i - s * nthin;
+    packed[i] = ring[s * per_query + idx[k]];
+  }
+}
+}  // namespace
+
+int launch_pack_thin(const double* ring, long long per_query, const long long* idx, long long nthin,
+                     double* packed, int nq, cudaStream_t st) {
+  if (nthin <= 0 || nq <= 0) return 0;
+  long long blocks = (nthin * nq + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  pack_thin_kernel<<<(int)blocks, 256, 0, st>>>(ring, per_query, idx, nthin, packed, nq);
+  return 1;
+}
+
 int launch_emit(const NetDev& net, const BatchDev& b, const GramDev& g, const PlanDev& plan,
                 int q0, int nq, double* out, cudaStream_t st, int which) {
   if (nq <= 0) return 0;

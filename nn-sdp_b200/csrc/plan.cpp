@@ -404,4 +404,94 @@ int32_t build_plan(const Shape& sh, int64_t beta, const std::vector<CliqueRanges
   return NNSDP_OK;
 }
 
+
+int32_t build_gather_plan(const Shape& sh, int64_t beta, const std::vector<CliqueRanges>& mats,
+                          const PlanHost& plan, GatherPlan* gp) {
+  const int K = sh.K;
+  gp->usable = false;
+  gp->colsegs.clear();
+  gp->thin_idx.clear();
+  gp->colseg_begin.assign(mats.size() + 1, 0);
+  gp->thin_begin.assign(mats.size() + 1, 0);
+  gp->dense_always_doubles = 0;
+  // cells
+  std::vector<std::vector<Piece>> segs(mats.size());
+  for (size_t m = 0; m < mats.size(); ++m) {
+    cut(sh, mats[m], true, int64_t(1) << 40, &segs[m]);
+    gp->colseg_begin[m] = (int32_t)gp->colsegs.size();
+    for (const Piece& sc : segs[m]) {
+      GatherColSeg cs;
+      cs.mat = (int32_t)m;
+      cs.col0 = (int32_t)sc.l0;
+      cs.ncols = (int32_t)(sc.g1 - sc.g0 + 1);
+      const int Bj = sh.block_of(sc.g0);
+      for (const Piece& sr : segs[m]) {
+        GatherCell c{};
+        c.row0 = (int32_t)sr.l0;
+        c.nrows = (int32_t)(sr.g1 - sr.g0 + 1);
+        const int Bi = sh.block_of(sr.g0);
+        c.kind = GK_NONE;
+        c.blk = -1;
+        if (std::min(c.nrows, cs.ncols) >= GATHER_MIN_RECT && Bi < K && Bj < K) {
+          if (Bj == Bi + 1 || Bi == Bj + 1) c.kind = GK_ALWAYS;
+          else if (Bi == Bj && Bi >= 1 && Bi <= K - 2) c.kind = GK_GRAM, c.blk = Bi;
+          else if (Bi == Bj && Bi == K - 1) c.kind = GK_S22;
+        }
+        c.pure_zero = pair_flags(sh, beta, Bi, sr.g0, sr.g1, Bj, sc.g0, sc.g1) == 0;
+        if (c.kind == GK_ALWAYS) gp->dense_always_doubles += (int64_t)c.nrows * cs.ncols;
+        cs.cells.push_back(c);
+      }
+      gp->colsegs.push_back(cs);
+    }
+  }
+  gp->colseg_begin[mats.size()] = (int32_t)gp->colsegs.size();
+  // thin entries, from the tiles of the emission plan
+  auto cell_of = [&](int mat, int row, int col, int nrows, int ncols) -> const GatherCell* {
+    for (int s = gp->colseg_begin[mat]; s < gp->colseg_begin[mat + 1]; ++s) {
+      const GatherColSeg& cs = gp->colsegs[s];
+      if (col < cs.col0 || col + ncols > cs.col0 + cs.ncols) continue;
+      for (const GatherCell& c : cs.cells)
+        if (row >= c.row0 && row + nrows <= c.row0 + c.nrows) return &c;
+    }
+    return nullptr;  // the tile straddles cells
+  };
+  std::vector<std::vector<int64_t>> per_mat(mats.size());
+  const int64_t n0 = sh.n[0];
+  for (const TileDev& t : plan.tiles) {
+    if (t.prog == PROG_ZERO) continue;
+    const MatDev& md = plan.mats[t.mat];
+    std::vector<int64_t>& out = per_mat[t.mat];
+    bool band_only = false;
+    if (t.prog != PROG_AFF) {
+      const GatherCell* c = cell_of(t.mat, t.row0, t.col0, t.nrows, t.ncols);
+      if (c && c->kind == GK_ALWAYS) continue;
+      if (c && (c->kind == GK_GRAM || c->kind == GK_S22)) {
+        if (t.prog == PROG_SAME) continue;
+        band_only = (t.prog == PROG_DIAG);
+      }
+    }
+    for (int c = 0; c < t.ncols; ++c) {
+      int r_lo = 0, r_hi = t.nrows - 1;
+      if (band_only) {
+        const int64_t jc = t.gcol0 - n0 + c, jr0 = t.grow0 - n0;
+        r_lo = (int)std::max<int64_t>(0, jc - beta - jr0);
+        r_hi = (int)std::min<int64_t>(t.nrows - 1, jc + beta - jr0);
+      }
+      for (int r = r_lo; r <= r_hi; ++r)
+        out.push_back(md.out_off + (t.row0 + r) + (int64_t)(t.col0 + c) * md.ld);
+    }
+  }
+  for (size_t m = 0; m < mats.size(); ++m) {
+    std::sort(per_mat[m].begin(), per_mat[m].end());
+    per_mat[m].erase(std::unique(per_mat[m].begin(), per_mat[m].end()), per_mat[m].end());
+    gp->thin_begin[m] = (int64_t)gp->thin_idx.size();
+    gp->thin_idx.insert(gp->thin_idx.end(), per_mat[m].begin(), per_mat[m].end());
+  }
+  gp->thin_begin[mats.size()] = (int64_t)gp->thin_idx.size();
+  // worth it only when most of the output is either dense cells or zeros
+  gp->usable = gp->dense_always_doubles > 0 &&
+               (int64_t)gp->thin_idx.size() * 8 <= plan.per_query_doubles;
+  return NNSDP_OK;
+}
+
 }  // namespace nnsdp

@@ -13,6 +13,7 @@ LIB_PATH = os.environ.get("NNSDP_B200_LIB", os.path.join(_HERE, "..", "lib", "li
 
 OK, ERR_ARG, ERR_CUDA, ERR_NOMEM, ERR_STATE, ERR_ASSERT = 0, -1, -2, -3, -4, -5
 OUT_SAFETY, OUT_HPLANE, OUT_CIRCLE, OUT_ELLIPSOID = 0, 1, 2, 3
+RUN_HOST_PREZEROED, RUN_DENSE_COPY = 1, 2
 
 c_i32, c_i64, c_u64 = C.c_int32, C.c_int64, C.c_uint64
 c_dp = C.POINTER(C.c_double)
@@ -78,6 +79,8 @@ PROTOTYPES = {
     "nnsdp_batch_prepare": (c_i32, [c_vp]),
     "nnsdp_batch_emit": (c_i32, [c_vp, c_i64, c_i64]),
     "nnsdp_batch_run": (c_i32, [c_vp, c_dp]),
+    "nnsdp_batch_run_ex": (c_i32, [c_vp, c_dp, c_i32]),
+    "nnsdp_batch_gather_stats": (c_i32, [c_vp, c_i64p, c_i64p, c_i64p, C.POINTER(c_i32)]),
     "nnsdp_batch_sync": (c_i32, [c_vp]),
     "nnsdp_batch_get_bounds": (c_i32, [c_vp, c_dp, c_dp, c_dp, c_dp, c_dp, c_dp]),
     "nnsdp_batch_get_slot": (c_i32, [c_vp, c_i64, c_dp]),

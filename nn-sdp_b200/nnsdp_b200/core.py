@@ -342,12 +342,18 @@ class Batch:
     def emit(self, q0: int, nq: int):
         L.check(L.lib.nnsdp_batch_emit(self._h, q0, nq))
 
-    def run(self, host_out: Optional[np.ndarray] = None, host_ptr: Optional[int] = None):
+    def run(self, host_out: Optional[np.ndarray] = None, host_ptr: Optional[int] = None, flags: int = 0):
         if host_ptr is not None:
             p = C.cast(C.c_void_p(host_ptr), L.c_dp)
         else:
             p = _dp(host_out)
-        L.check(L.lib.nnsdp_batch_run(self._h, p))
+        L.check(L.lib.nnsdp_batch_run_ex(self._h, p, flags))
+
+    def gather_stats(self) -> dict:
+        a, t, z, u = L.c_i64(0), L.c_i64(0), L.c_i64(0), L.c_i32(0)
+        L.check(L.lib.nnsdp_batch_gather_stats(self._h, C.byref(a), C.byref(t), C.byref(z), C.byref(u)))
+        return {"dma_bytes": int(a.value), "thin_bytes": int(t.value), "zeroed_bytes": int(z.value),
+                "sparse": bool(u.value)}
 
     def sync(self):
         L.check(L.lib.nnsdp_batch_sync(self._h))

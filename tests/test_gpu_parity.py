@@ -492,3 +492,76 @@ def clique_block_oracle(net, beta, q, Ck):
     out[:, la] = aff[Ck]
     out[la, :] = aff[Ck]
     return out
+
+
+# ---------------------------------------------------------------------------------------------
+# sparse host gather (nnsdp_batch_run_ex): wide layers, so dense cells travel by strided DMA, thin
+# entries packed, the rest zero-filled on the host
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("kind", ["hplaneS", "ellipsoid"])
+def test_sparse_host_gather_matches_dense_copy(ctx, kind):
+    import nnsdp_b200 as nb
+
+    xdims, beta, nq = [2, 300, 280, 320, 290, 2], 2, 5
+    net = rand_net(xdims, seed=31, sigma=0.08)
+    rng = np.random.default_rng(4)
+    # radius 0 -> every layer Gram-active; large radius -> none; mixed in one batch
+    qs = [rand_query(net, beta, rng, kind=kind, radius=r) for r in (0.0, 0.4, 1e-4, 0.05, 0.0)]
+    dnet = nb.Net(ctx, net.xdims, net.Ms)
+    b = nb.Batch(dnet, beta, Qcap=nq, ring=3)      # odd ring: chunks of 1 query, staging buffers wrap
+    b.set_inputs(to_numeric_batch(nb, net, qs))
+    dense = np.full((nq, b.per_query), np.nan)
+    b.run(dense, flags=nb.RUN_DENSE_COPY)
+    assert not b.gather_stats()["sparse"] or b.gather_stats()["zeroed_bytes"] == 0
+    sparse = np.full((nq, b.per_query), np.nan)     # garbage everywhere: every entry must be written
+    b.run(sparse)
+    st = b.gather_stats()
+    assert st["sparse"] and st["zeroed_bytes"] > 0 and st["thin_bytes"] > 0
+    assert st["dma_bytes"] < 0.8 * dense.nbytes
+    assert np.array_equal(dense, sparse)
+    pre = np.zeros((nq, b.per_query))               # structural zeros already in place
+    pre[:, :] = 0.0
+    # non-structural entries hold garbage: only ZERO tiles are promised to be zero
+    tiles = nb.plan_tiles(xdims, beta)
+    sz = dnet.sizes(beta)
+    cl = dnet.cliques(beta)
+    offs = np.concatenate([[0], np.cumsum([len(c[0]) ** 2 for c in cl])])
+    mask = np.ones(b.per_query, dtype=bool)         # True = may hold garbage
+    for t in tiles[tiles[:, 10] == 0]:
+        n = len(cl[t[0]][0])
+        blk = mask[offs[t[0]]:offs[t[0] + 1]].reshape(n, n)          # [col, row] view of the column-major block
+        blk[t[3]:t[3] + t[4], t[1]:t[1] + t[2]] = False
+    pre[:, mask] = np.nan
+    b.run(pre, flags=nb.RUN_HOST_PREZEROED)
+    st2 = b.gather_stats()
+    assert st2["zeroed_bytes"] < st["zeroed_bytes"]
+    assert np.array_equal(dense, pre)
+    # and against the oracle
+    cliques = o.make_cliques(net, beta)
+    ref = o.run_query(net, beta, qs[0], form="closed")
+    for blk, rb in zip(nb.split_blocks(sparse[0], cliques), ref["blocks"]):
+        assert relerr(blk, rb) <= TOL
+    assert sz["sum_ck_sq"] == b.per_query
+    b.close()
+
+
+def test_sparse_host_gather_dense_Z(ctx):
+    """The same gather on the whole-Z output (one matrix, every block pair a cell)."""
+    import nnsdp_b200 as nb
+
+    xdims, beta, nq = [3, 270, 300, 260, 3], 1, 3
+    net = rand_net(xdims, seed=8, sigma=0.08)
+    rng = np.random.default_rng(9)
+    qs = [rand_query(net, beta, rng, kind="circle", radius=r) for r in (0.0, 0.3, 1e-3)]
+    dnet = nb.Net(ctx, net.xdims, net.Ms)
+    b = nb.Batch(dnet, beta, Qcap=nq, ring=2, dense=True)
+    b.set_inputs(to_numeric_batch(nb, net, qs))
+    a = np.full((nq, b.per_query), np.nan)
+    c = np.full((nq, b.per_query), np.nan)
+    b.run(a, flags=nb.RUN_DENSE_COPY)
+    b.run(c)
+    assert b.gather_stats()["sparse"]
+    assert np.array_equal(a, c)
+    Z = c[1].reshape(sum(xdims[:-1]) + 1, -1).T
+    assert relerr(Z, o.run_query(net, beta, qs[1], form="closed")["Z"]) <= TOL
+    b.close()
