@@ -1,0 +1,40 @@
+#!/usr/bin/env python
+"""Condense an `ncu --set full` report into the handful of per-launch counters DESIGN.md / bench.py cite.
+
+    python tools/ncu_summary.py gpurun_out/r1_emit_full.ncu-rep > profiles/r1_emit_full.summary.csv
+"""
+import csv
+import subprocess
+import sys
+
+METRICS = [
+    "gpu__time_duration.sum", "launch__grid_size", "launch__block_size", "launch__registers_per_thread",
+    "launch__occupancy_limit_registers", "launch__occupancy_limit_shared_mem",
+    "sm__warps_active.avg.pct_of_peak_sustained_active", "sm__issue_active.avg.pct_of_peak_sustained_elapsed",
+    "smsp__inst_executed.sum", "sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active",
+    "dram__bytes_read.sum", "dram__bytes_write.sum", "dram__throughput.avg.pct_of_peak_sustained_elapsed",
+    "lts__throughput.avg.pct_of_peak_sustained_elapsed", "l1tex__throughput.avg.pct_of_peak_sustained_elapsed",
+    "l1tex__t_sectors_pipe_lsu_mem_global_op_st.sum", "l1tex__t_requests_pipe_lsu_mem_global_op_st.sum",
+    "l1tex__t_sectors_pipe_lsu_mem_global_op_ld.sum", "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum",
+    "smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_lg_throttle_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_drain_per_issue_active.ratio",
+]
+
+
+def main():
+    rep = sys.argv[1]
+    out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True, check=True).stdout
+    rows = list(csv.reader(out.splitlines()))
+    hdr, units = rows[0], rows[1]
+    ki = hdr.index("Kernel Name")
+    w = csv.writer(sys.stdout)
+    cols = [m for m in METRICS if m in hdr]
+    w.writerow(["kernel"] + [f"{m} [{units[hdr.index(m)]}]" for m in cols])
+    for r in rows[2:]:
+        name = r[ki].replace("unnamed>::", "").split("(")[0].replace("void ", "")
+        w.writerow([name] + [r[hdr.index(m)] for m in cols])
+
+
+if __name__ == "__main__":
+    main()
