@@ -370,25 +370,27 @@ __device__ __forceinline__ double s22_entry(const double* WK, const double* U, i
   return acc;
 }
 
-// One strip for one query.  `t` lives in shared memory (broadcast reads keep the register count at 32).
-__device__ __forceinline__ void fill_strip(const NetDev& net, const BatchDev& b, const GramDev& g,
-                                           const StripDev& t, int q, int slot, double* __restrict__ o) {
-  const long long ld = t.ld;
-  const int K = net.K, prog = t.prog, tid = threadIdx.x;
-  const int row0 = t.row0, row_end = t.row0 + t.nrows, ncols = t.ncols;
-  if (prog == PROG_AFF && t.nrows == 1 && t.grow0 == net.Zdim - 1) {  // affine row Z[a, :], thread = column
-    const double* aff = b.aff + (long long)q * net.Zdim;
-    for (int c = tid; c < ncols; c += ETHREADS) o[row0 + (t.col0 + c) * ld] = aff[t.gcol0 + c];
-    return;
-  }
-  // Strip: thread = row inside a TR-row chunk (x column group when the strip is short).  For every column
-  // the chunks start on a 32 B sector boundary of the output (rows before the strip are masked), so each
-  // warp store covers whole sectors although ld is odd.  TR is a power of two.
+// One strip (<= STRIP_ROWS x STRIP_COLS, or one wide affine-row job) for one query: grid = (strips, queries).
+// The 64 B descriptor is fetched with four independent 16 B loads; nothing else is looked up before the
+// first store of a ZERO strip.  Thread = row inside a TR-row chunk (x column group when the strip is
+// short); for every column the chunks start on a 32 B sector boundary of the output (rows before the strip
+// are masked), so each warp store covers whole sectors although ld is odd.  TR is a power of two.
+__global__ void __launch_bounds__(ETHREADS, 8)
+emit_fill_kernel(NetDev net, BatchDev b, GramDev g, PlanDev plan, int q0, int nq,
+                 double* __restrict__ out) {
+  const int4* dp = reinterpret_cast<const int4*>(plan.strips + blockIdx.x);
+  const int4 d0 = __ldg(dp), d1 = __ldg(dp + 1), d2 = __ldg(dp + 2);
+  const int slot = blockIdx.y, tid = threadIdx.x;
+  const long long out_off = ((long long)(unsigned)d0.x) | ((long long)d0.y << 32);
+  const long long ld = d1.x;
+  const int row0 = d1.y, nrows = d1.z, col0 = d1.w, ncols = d2.x, prog = d2.w;
+  const int row_end = row0 + nrows;
+  double* o = out + (long long)slot * plan.per_query + out_off;  // base of the output matrix
   int lg = 5;
-  while ((1 << lg) < ETHREADS && (1 << lg) < t.nrows + 3) ++lg;
+  while ((1 << lg) < ETHREADS && (1 << lg) < nrows + 3) ++lg;
   const int TR = 1 << lg;
   const int tr = tid & (TR - 1), cg = tid >> lg, ncg = ETHREADS >> lg;
-  double* col = o + (t.col0 + cg) * ld;  // column cg of the strip; advanced by ncg columns per trip
+  double* col = o + (col0 + cg) * ld;  // column cg of the strip; advanced by ncg columns per trip
   const long long cstep = (long long)ncg * ld;
 #define NNSDP_STRIP_LOOP(VALUE)                                                     \
   for (int c = cg; c < ncols; c += ncg, col += cstep) {                               \
@@ -396,24 +398,31 @@ __device__ __forceinline__ void fill_strip(const NetDev& net, const BatchDev& b,
     if (r >= row0 && r < row_end) col[r] = (VALUE);                                   \
     for (r += TR; r < row_end; r += TR) col[r] = (VALUE);                             \
   }
-
   if (prog == PROG_ZERO) {
     NNSDP_STRIP_LOOP(0.0)
     return;
   }
-  if (prog == PROG_AFF) {  // affine column Z[:, a]
-    const double* aff = b.aff + (long long)q * net.Zdim + (t.grow0 - row0);
-    NNSDP_STRIP_LOOP(aff[r])
+  const int q = q0 + slot, K = net.K;
+  const int grow0 = d2.y, gcol0 = d2.z;
+  if (prog == PROG_AFF) {
+    const double* aff = b.aff + (long long)q * net.Zdim;
+    if (nrows == 1 && grow0 == net.Zdim - 1) {  // affine row Z[a, :], thread = column
+      for (int c = tid; c < ncols; c += ETHREADS) o[row0 + (col0 + c) * ld] = aff[gcol0 + c];
+    } else {  // affine column Z[:, a]
+      aff += grow0 - row0;
+      NNSDP_STRIP_LOOP(aff[r])
+    }
     return;
   }
   // SAME / DIAG: rows and columns in block Br, 1 <= Br <= K-1
-  const int Br = t.rblk, rl0 = t.rl0, cl0 = t.cl0;
+  const int4 d3 = __ldg(dp + 3);
+  const int Br = d3.x, rl0 = d3.y, cl0 = d3.z, ldG = d3.w;  // block-local index of output row r is rl0 + r
+  const long long goff = ((long long)(unsigned)d0.z) | ((long long)d0.w << 32);
   const bool copy = Br <= K - 2 && b.cnt[(long long)q * K + Br] > 0;  // Gram of an active layer
   const bool s22 = Br == K - 1 && b.has_s22;                           // W_K' S22 W_K of the output QC
   const double* WK = net.M[K - 1];
   const double* U = b.U + (long long)q * net.n_out * net.n[K - 1];
-  const int ldG = t.ldG;
-  const double* G = g.scratch + (long long)slot * g.per_query + t.goff + rl0;  // G[r + cl*ldG]
+  const double* G = g.scratch + (long long)slot * g.per_query + goff + rl0;  // G[r + cl*ldG]
   if (copy) {
     const double* Gc = G + (long long)(cl0 + cg) * ldG;
     const long long gstep = (long long)ncg * ldG;
@@ -434,16 +443,16 @@ __device__ __forceinline__ void fill_strip(const NetDev& net, const BatchDev& b,
     // A thread owns at most one row of a column's (2 beta + 1 <= TR) band rows.
     const int beta = b.beta, n0 = net.n_in;
     const long long acdim = net.acdim;
-    const int jr0 = t.grow0 - n0, jc0 = t.gcol0 - n0;
-    if (jc0 + ncols - 1 + beta < jr0 || jc0 - beta > jr0 + t.nrows - 1) return;  // no band entry in this strip
+    const int jr0 = grow0 - n0, jc0 = gcol0 - n0;
+    if (jc0 + ncols - 1 + beta < jr0 || jc0 - beta > jr0 + nrows - 1) return;  // no band entry in this strip
     const double* T0 = b.T0 + (long long)q * acdim;
     const double* Bt = b.Bt + (long long)q * beta * acdim;
     const double* gbnd = b.gbnd + q * b.s_gbnd;
     for (int c = cg; c < ncols; c += ncg) {
       const int jc = jc0 + c;
-      const int lo = max(jc - beta, jr0), hi = min(jc + beta, jr0 + t.nrows - 1);
+      const int lo = max(jc - beta, jr0), hi = min(jc + beta, jr0 + nrows - 1);
       if (lo > hi) continue;
-      double* cp = o + (t.col0 + c) * ld;
+      double* cp = o + (col0 + c) * ld;
       const int base = row0 - (int)(((size_t)(cp + row0) >> 3) & 3);
       const int rlo = row0 + (lo - jr0);
       const int d = (tr - (rlo - base)) & (TR - 1);  // offset of this thread's row inside the band rows
@@ -455,31 +464,6 @@ __device__ __forceinline__ void fill_strip(const NetDev& net, const BatchDev& b,
       val += 0.0;  // the (absent) window terms f1 + f2 of the general formula
       cp[r] = __dadd_rn(val, band_term(T0, gbnd, Bt, acdim, jr, jc));
     }
-  }
-}
-
-// grid = (strip groups, queries).  A CTA walks strips blockIdx.x, blockIdx.x + gridDim.x, ...; the 64 B
-// descriptor of the next strip is fetched into registers of four threads before the stores of the
-// current strip are issued and parked in shared memory afterwards, so no CTA waits on a descriptor load
-// except for its first strip.
-__global__ void __launch_bounds__(ETHREADS, 8)
-emit_fill_kernel(NetDev net, BatchDev b, GramDev g, PlanDev plan, int q0, int nq,
-                 double* __restrict__ out) {
-  __shared__ int4 desc[2][4];
-  const int slot = blockIdx.y, q = q0 + slot, tid = threadIdx.x;
-  const int n = plan.n_fill, stride = gridDim.x;
-  int i = blockIdx.x;
-  if (tid < 4) desc[0][tid] = reinterpret_cast<const int4*>(plan.strips + i)[tid];
-  __syncthreads();
-  double* base = out + (long long)slot * plan.per_query;
-  for (int buf = 0; i < n; i += stride, buf ^= 1) {
-    const int nxt = i + stride;
-    int4 pre = make_int4(0, 0, 0, 0);
-    if (tid < 4 && nxt < n) pre = reinterpret_cast<const int4*>(plan.strips + nxt)[tid];
-    const StripDev& t = *reinterpret_cast<const StripDev*>(desc[buf]);
-    fill_strip(net, b, g, t, q, slot, base + t.out_off);
-    if (tid < 4) desc[buf ^ 1][tid] = pre;
-    __syncthreads();
   }
 }
 
@@ -559,9 +543,7 @@ int launch_emit(const NetDev& net, const BatchDev& b, const GramDev& g, const Pl
   static const int egroup = [] { const char* e = getenv("NNSDP_EDGE_GROUP"); int v = e ? atoi(e) : 1; return v < 1 ? 1 : (v > SLOT_GROUP ? SLOT_GROUP : v); }();
   int launches = 0;
   if (plan.n_fill > 0 && (which < 0 || which == 0)) {
-    static const int per_cta = [] { const char* e = getenv("NNSDP_FILL_STRIPS_PER_CTA"); int v = e ? atoi(e) : 1; return v < 1 ? 1 : v; }();
-    const int gx = (plan.n_fill + per_cta - 1) / per_cta;
-    emit_fill_kernel<<<dim3(gx, nq), ETHREADS, 0, st>>>(net, b, g, plan, q0, nq, out);
+    emit_fill_kernel<<<dim3(plan.n_fill, nq), ETHREADS, 0, st>>>(net, b, g, plan, q0, nq, out);
     ++launches;
   }
   if (plan.n_window > 0 && (which < 0 || which == 1)) {

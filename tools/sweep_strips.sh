@@ -1,5 +1,5 @@
 # usage: bash tools/sweep_strips.sh  -- bench the emitter for a few strip geometries (developer aid)
-for cfg in "512 8 1" "512 8 4" "512 8 8" "512 8 16" "1024 8 8" "512 16 8" "256 8 8"; do set -- $cfg; echo "== rows $1 cols $2 strips/CTA $3"; NNSDP_STRIP_ROWS=$1 NNSDP_STRIP_COLS=$2 NNSDP_FILL_STRIPS_PER_CTA=$3 python bench.py --no-cpu --queries 256 --steps 3 --e2e-queries 1 | python -c "
+for cfg in "512 8" "1024 8" "512 4" "256 8" "512 16"; do set -- $cfg; echo "== rows $1 cols $2"; NNSDP_STRIP_ROWS=$1 NNSDP_STRIP_COLS=$2 python bench.py --no-cpu --queries 256 --steps 3 --e2e-queries 1 | python -c "
 import json,sys
 for l in sys.stdin:
     if l.startswith('{'):
