@@ -279,6 +279,8 @@ def run_ours(args):
     # EVERY rank at the same time: the ranks share the host's memory bandwidth and PCIe root complexes,
     # so the whole-job figure is world * Qe / (slowest rank's time), not N times a single-GPU number.
     Qe = min(Q, args.e2e_queries)
+    # host worker threads of the gather: share the box's cores between the ranks of this node
+    os.environ.setdefault("NNSDP_HOST_THREADS", str(max(2, min(16, (os.cpu_count() or 16) // max(world, 1)))))
     pin = nb.PinnedBuffer(Qe * sz["sum_ck_sq"])
     eb = nb.Batch(net, beta, Qcap=Qe, ring=min(ring, Qe))
     sub = {k: (v[:Qe] if v.shape[0] == Q else v) for k, v in inp.items()}
@@ -368,7 +370,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
     ap.add_argument("--queries", type=int, default=None, help="override queries per GPU per step")
-    ap.add_argument("--e2e-queries", type=int, default=16)
+    ap.add_argument("--e2e-queries", type=int, default=8)
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
