@@ -234,6 +234,34 @@ int32_t nnsdp_batch_stage_reset(nnsdp_batch* batch);
  * non-empty active set and the sum over them of |active|. */
 int32_t nnsdp_batch_gram_stats(nnsdp_batch* batch, int64_t* n_contractions, int64_t* sum_active);
 
+/* ---- affine-coefficient mode ---------------------------------------------
+ * Z(gamma) = Z0 + sum_v gamma_v Z_v for ONE query, restricted to the upper triangle of the clique
+ * cover, as COO triplets -- the data from which `@constraint(model, Z .== Zksum)`
+ * (src/Methods/chordal_sdp.jl:119,150) can be added without building AffExpr matrices
+ * (src/Methods/Methods.jl:69-78, chordal_sdp.jl:96-153).  No multipliers are read from `in`.
+ *   variables (1-based, the reference's creation order):
+ *     [gamma_in (n_in); gamma_out (reach kinds only: 1); gamma_ac1 = bounded (acdim); gamma_ac2 = sector (secdim)]
+ *     -- var_in / var_out / var_bnd / var_sec are the 0-based offsets of the four groups
+ *   entries e = 1..nent: the positions (ent_row[e] <= ent_col[e]) of the cover's upper triangle,
+ *     column-major; Z is structurally zero outside the cover (and Zksum has no variable there)
+ *   Z[ent_row[e], ent_col[e]](gamma) = z0[e] + sum over triplets t with coo_ent[t] = e of
+ *     coo_val[t] * gamma[coo_var[t]].   Duplicate (entry, variable) pairs occur and are to be summed
+ *     (Julia: sparse(coo_ent, coo_var, coo_val, nent, nvar)).
+ * nnsdp_affine_create computes everything on the device and reports the sizes; it fails with
+ * NNSDP_ERR_NOMEM if max_nnz > 0 and nnz > max_nnz (the Gram term costs n_k(n_k+1)/2 coefficients per
+ * stably-active neuron).  nnsdp_affine_get copies into caller buffers (any pointer may be NULL). */
+typedef struct nnsdp_affine nnsdp_affine;
+typedef struct {
+  int64_t nvar, nent, nnz;
+  int64_t var_in, var_out, var_bnd, var_sec;
+} nnsdp_affine_sizes;
+int32_t nnsdp_affine_create(nnsdp_ctx* ctx, const nnsdp_net* net, int64_t beta,
+                            const nnsdp_query_inputs* in, int64_t max_nnz, nnsdp_affine** affine,
+                            nnsdp_affine_sizes* sizes);
+int32_t nnsdp_affine_get(nnsdp_affine* affine, int64_t* ent_row, int64_t* ent_col, double* z0,
+                         int64_t* coo_ent, int64_t* coo_var, double* coo_val);
+int32_t nnsdp_affine_destroy(nnsdp_affine* affine);
+
 #ifdef __cplusplus
 }
 #endif

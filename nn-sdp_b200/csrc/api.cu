@@ -1417,3 +1417,152 @@ int32_t nnsdp_assemble_dense(nnsdp_ctx* ctx, const nnsdp_net* net, int64_t beta,
 }
 
 }  // extern "C"
+
+// -----------------------------------------------------------------------------------------
+// affine-coefficient mode: Z(gamma) = Z0 + sum_v gamma_v Z_v over the cover
+// -----------------------------------------------------------------------------------------
+struct nnsdp_affine {
+  nnsdp_batch* batch = nullptr;  // Q = 1, all multipliers zero: bounds, slopes, constant part
+  nnsdp_affine_sizes sz{};
+  std::vector<int> lo;           // first cover row of every column (0-based)
+  std::vector<long long> col_ptr;
+  DevBuf d_lo, d_colptr, d_counts, d_offs, d_ent, d_var, d_val, d_z0;
+};
+
+extern "C" {
+
+int32_t nnsdp_affine_destroy(nnsdp_affine* h) {
+  if (!h) return NNSDP_OK;
+  if (h->batch) cudaSetDevice(h->batch->dev);
+  for (DevBuf* x : {&h->d_lo, &h->d_colptr, &h->d_counts, &h->d_offs, &h->d_ent, &h->d_var, &h->d_val, &h->d_z0})
+    x->release();
+  nnsdp_batch_destroy(h->batch);
+  delete h;
+  return NNSDP_OK;
+}
+
+int32_t nnsdp_affine_create(nnsdp_ctx* ctx, const nnsdp_net* net, int64_t beta,
+                            const nnsdp_query_inputs* in, int64_t max_nnz, nnsdp_affine** out,
+                            nnsdp_affine_sizes* sizes) {
+  NN_CHECK(out != nullptr, NNSDP_ERR_ARG, "affine output pointer is NULL");
+  *out = nullptr;
+  NN_CHECK(ctx && net && in && sizes, NNSDP_ERR_ARG, "NULL argument");
+  const Shape& sh = net->sh;
+  nnsdp_affine* h = new nnsdp_affine();
+  struct Guard {
+    nnsdp_affine* h;
+    ~Guard() { if (h) nnsdp_affine_destroy(h); }
+  } guard{h};
+  NN_TRY(nnsdp_batch_create(ctx, 0, net, beta, 1, 1, 0, &h->batch));
+  nnsdp_batch* b = h->batch;
+  // one query with every multiplier zero: the prepared vectors then hold the constant part of Z
+  nnsdp_query_inputs q = *in;
+  std::vector<double> zeros((size_t)std::max<int64_t>(b->sz.secdim, 1), 0.0);
+  const double zero1 = 0.0;
+  q.gamma_in = zeros.data();
+  q.gamma_bnd = zeros.data();
+  q.gamma_sec = zeros.data();
+  q.gamma_in_stride = q.gamma_bnd_stride = q.gamma_sec_stride = 0;
+  if (q.out_kind != NNSDP_OUT_SAFETY) {
+    q.gamma_out = &zero1;
+    q.gamma_out_stride = 0;
+  }
+  NN_TRY(nnsdp_batch_set_inputs(b, 1, &q));
+  if (!b->bounds_supplied) NN_TRY(nnsdp_batch_bounds(b));
+  NN_TRY(nnsdp_batch_prepare(b));
+  NN_CUDA(cudaSetDevice(b->dev));
+  // cover: column c holds rows [lo(c), c]; lo(c) = smallest index sharing a clique with c
+  CliqueInfoHost ci;
+  NN_TRY(make_cliques_host(sh, beta, &ci));
+  h->lo.assign((size_t)sh.Zdim, 0);
+  for (int64_t c = 0; c < sh.Zdim; ++c) {
+    int64_t lo = c;
+    for (const CliqueRanges& ck : ci.ck) {
+      bool has = false;
+      for (int s = 0; s < ck.nseg; ++s) has |= (c >= ck.lo[s] && c <= ck.hi[s]);
+      if (has) lo = std::min(lo, ck.lo[0]);
+    }
+    h->lo[c] = (int)lo;
+  }
+  h->col_ptr.assign((size_t)sh.Zdim + 1, 0);
+  for (int64_t c = 0; c < sh.Zdim; ++c) h->col_ptr[c + 1] = h->col_ptr[c] + (c - h->lo[c] + 1);
+  nnsdp_affine_sizes& sz = h->sz;
+  sz.var_in = 0;
+  sz.var_out = sh.n_in();
+  sz.var_bnd = sz.var_out + (in->out_kind == NNSDP_OUT_SAFETY ? 0 : 1);
+  sz.var_sec = sz.var_bnd + sh.acdim;
+  sz.nvar = sz.var_sec + b->sz.secdim;
+  sz.nent = h->col_ptr[sh.Zdim];
+  NN_TRY(upload(h->d_lo, h->lo.data(), h->lo.size() * 4, b->st));
+  NN_TRY(upload(h->d_colptr, h->col_ptr.data(), h->col_ptr.size() * 8, b->st));
+  AffineDev A{};
+  A.nvar = sz.nvar;
+  A.var_out = sz.var_out;
+  A.var_bnd = sz.var_bnd;
+  A.var_sec = sz.var_sec;
+  A.acdim = sh.acdim;
+  A.lamdim = b->sz.lamdim;
+  A.beta = beta;
+  A.out_kind = in->out_kind;
+  A.x1min = b->bd.x1min;
+  A.x1max = b->bd.x1max;
+  A.ymin = b->bd.ymin;
+  A.ymax = b->bd.ymax;
+  A.smin = b->bd.smin;
+  A.smax = b->bd.smax;
+  A.col_ptr = h->d_colptr.as<long long>();
+  A.lo = h->d_lo.as<int>();
+  const NetDev& nd = b->nd->nd;
+  NN_TRY(h->d_counts.ensure((size_t)sz.nvar * 8));
+  launch_affine_count(nd, A, h->d_counts.as<long long>(), b->st);
+  std::vector<long long> counts((size_t)sz.nvar), offs((size_t)sz.nvar + 1, 0);
+  NN_CUDA(cudaMemcpyAsync(counts.data(), h->d_counts.p, counts.size() * 8, cudaMemcpyDeviceToHost, b->st));
+  NN_CUDA(cudaStreamSynchronize(b->st));
+  for (int64_t v = 0; v < sz.nvar; ++v) offs[v + 1] = offs[v] + counts[v];
+  sz.nnz = offs[sz.nvar];
+  *sizes = sz;
+  NN_CHECK(max_nnz <= 0 || sz.nnz <= max_nnz, NNSDP_ERR_NOMEM,
+           "affine form has %lld coefficients, more than max_nnz = %lld (the Gram term is n_k^2 per "
+           "stably-active neuron: wide layers need the factored form)", (long long)sz.nnz, (long long)max_nnz);
+  NN_TRY(upload(h->d_offs, offs.data(), offs.size() * 8, b->st));
+  NN_TRY(h->d_ent.ensure((size_t)std::max<int64_t>(sz.nnz, 1) * 8));
+  NN_TRY(h->d_var.ensure((size_t)std::max<int64_t>(sz.nnz, 1) * 8));
+  NN_TRY(h->d_val.ensure((size_t)std::max<int64_t>(sz.nnz, 1) * 8));
+  NN_TRY(h->d_z0.ensure((size_t)std::max<int64_t>(sz.nent, 1) * 8));
+  launch_affine_fill(nd, A, h->d_offs.as<long long>(), h->d_ent.as<long long>(), h->d_var.as<long long>(),
+                     h->d_val.as<double>(), b->st);
+  launch_affine_z0(nd, b->bd, A, h->d_z0.as<double>(), b->st);
+  NN_CUDA(cudaGetLastError());
+  NN_CUDA(cudaStreamSynchronize(b->st));
+  guard.h = nullptr;
+  *out = h;
+  return NNSDP_OK;
+}
+
+int32_t nnsdp_affine_get(nnsdp_affine* h, int64_t* ent_row, int64_t* ent_col, double* z0,
+                         int64_t* coo_ent, int64_t* coo_var, double* coo_val) {
+  NN_CHECK(h != nullptr, NNSDP_ERR_ARG, "affine handle is NULL");
+  nnsdp_batch* b = h->batch;
+  NN_CUDA(cudaSetDevice(b->dev));
+  const int64_t Zdim = b->net->sh.Zdim, nnz = h->sz.nnz;
+  if (ent_row || ent_col)
+    for (int64_t c = 0; c < Zdim; ++c)
+      for (int64_t r = h->lo[c]; r <= c; ++r) {
+        const int64_t e = h->col_ptr[c] + (r - h->lo[c]);
+        if (ent_row) ent_row[e] = r + 1;  // 1-based on the wire
+        if (ent_col) ent_col[e] = c + 1;
+      }
+  if (z0) NN_CUDA(cudaMemcpyAsync(z0, h->d_z0.p, (size_t)h->sz.nent * 8, cudaMemcpyDeviceToHost, b->st));
+  if (coo_ent && nnz) NN_CUDA(cudaMemcpyAsync(coo_ent, h->d_ent.p, (size_t)nnz * 8, cudaMemcpyDeviceToHost, b->st));
+  if (coo_var && nnz) NN_CUDA(cudaMemcpyAsync(coo_var, h->d_var.p, (size_t)nnz * 8, cudaMemcpyDeviceToHost, b->st));
+  if (coo_val && nnz) NN_CUDA(cudaMemcpyAsync(coo_val, h->d_val.p, (size_t)nnz * 8, cudaMemcpyDeviceToHost, b->st));
+  NN_CUDA(cudaStreamSynchronize(b->st));
+  if (coo_ent)
+    for (int64_t i = 0; i < nnz; ++i) coo_ent[i] += 1;
+  if (coo_var)
+    for (int64_t i = 0; i < nnz; ++i) coo_var[i] += 1;
+  return NNSDP_OK;
+}
+
+}  // extern "C"
+

@@ -277,6 +277,21 @@ int launch_gram(const NetDev& net, const BatchDev& b, const GramDev& g, int max_
 int launch_emit(const NetDev& net, const BatchDev& b, const GramDev& g, const PlanDev& plan,
                 int q0, int nq, double* out, cudaStream_t st, int which = -1);
 
+// affine-coefficient mode (kernels_affine.cu): device view of one query's QC data and of the cover
+struct AffineDev {
+  long long nvar, var_out, var_bnd, var_sec;  // variable layout: [gin | gout | gbnd | gsec]
+  long long acdim, lamdim, beta;
+  int out_kind;
+  const double *x1min, *x1max, *ymin, *ymax, *smin, *smax;  // one query
+  const long long* col_ptr;  // Zdim + 1 : first cover entry of every column (upper triangle, column-major)
+  const int* lo;             // Zdim     : first row of column c inside the cover
+};
+int launch_affine_count(const NetDev& net, const AffineDev& A, long long* counts, cudaStream_t st);
+int launch_affine_fill(const NetDev& net, const AffineDev& A, const long long* offs, long long* ent,
+                       long long* var, double* val, cudaStream_t st);
+int launch_affine_z0(const NetDev& net, const BatchDev& b, const AffineDev& A, double* z0,
+                     cudaStream_t st);
+
 // thin-entry pack: packed[s * nthin + i] = ring[s * per_query + idx[i]] for the nq slots of a chunk
 int launch_pack_thin(const double* ring, long long per_query, const long long* idx, long long nthin,
                      double* packed, int nq, cudaStream_t st);

@@ -30,6 +30,13 @@ class Sizes(C.Structure):
         return {n: int(getattr(self, n)) for n, _ in self._fields_}
 
 
+class AffineSizes(C.Structure):
+    _fields_ = [(n, c_i64) for n in ("nvar", "nent", "nnz", "var_in", "var_out", "var_bnd", "var_sec")]
+
+    def as_dict(self):
+        return {n: int(getattr(self, n)) for n, _ in self._fields_}
+
+
 class QueryInputs(C.Structure):
     _fields_ = [
         ("x1min", c_dp), ("x1min_stride", c_i64),
@@ -72,6 +79,9 @@ PROTOTYPES = {
     "nnsdp_sector_minmax": (c_i32, [c_vp, c_i64, c_dp, c_dp, c_dp, c_dp]),
     "nnsdp_assemble_blocks": (c_i32, [c_vp, c_vp, c_i64, c_i64, C.POINTER(QueryInputs), c_dp]),
     "nnsdp_assemble_dense": (c_i32, [c_vp, c_vp, c_i64, c_i64, C.POINTER(QueryInputs), c_dp]),
+    "nnsdp_affine_create": (c_i32, [c_vp, c_vp, c_i64, C.POINTER(QueryInputs), c_i64, C.POINTER(c_vp), C.POINTER(AffineSizes)]),
+    "nnsdp_affine_get": (c_i32, [c_vp, c_i64p, c_i64p, c_dp, c_i64p, c_i64p, c_dp]),
+    "nnsdp_affine_destroy": (c_i32, [c_vp]),
     "nnsdp_batch_create": (c_i32, [c_vp, c_i32, c_vp, c_i64, c_i64, c_i64, c_i32, C.POINTER(c_vp)]),
     "nnsdp_batch_destroy": (c_i32, [c_vp]),
     "nnsdp_batch_set_inputs": (c_i32, [c_vp, c_i64, C.POINTER(QueryInputs)]),

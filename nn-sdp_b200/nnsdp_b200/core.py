@@ -276,6 +276,27 @@ def assemble_dense(net: Net, beta: int, batch: NumericBatch, Q: Optional[int] = 
     return np.transpose(out, (0, 2, 1))  # per-query column-major -> [q, r, c]
 
 
+def affine_form(net: Net, beta: int, batch: NumericBatch, max_nnz: int = 0) -> dict:
+    """Z(gamma) = Z0 + sum_v gamma_v Z_v of ONE query over the upper triangle of the clique cover
+    (nnsdp_affine_create / nnsdp_affine_get).  Multipliers in `batch` are ignored.  Returns the sizes,
+    the 1-based entry positions, z0 and the COO triplets (1-based entry / variable indices)."""
+    qi, keep = batch.pack(1)
+    h, sz = L.c_vp(), L.AffineSizes()
+    L.check(L.lib.nnsdp_affine_create(net.ctx._h, net._h, beta, C.byref(qi), max_nnz, C.byref(h), C.byref(sz)))
+    try:
+        d = sz.as_dict()
+        out = {"ent_row": np.zeros(d["nent"], dtype=np.int64), "ent_col": np.zeros(d["nent"], dtype=np.int64),
+               "z0": np.zeros(d["nent"]), "coo_ent": np.zeros(d["nnz"], dtype=np.int64),
+               "coo_var": np.zeros(d["nnz"], dtype=np.int64), "coo_val": np.zeros(d["nnz"])}
+        ip = lambda a: a.ctypes.data_as(L.c_i64p)
+        L.check(L.lib.nnsdp_affine_get(h, ip(out["ent_row"]), ip(out["ent_col"]), _dp(out["z0"]), ip(out["coo_ent"]),
+                                       ip(out["coo_var"]), _dp(out["coo_val"])))
+        out.update(d)
+        return out
+    finally:
+        L.lib.nnsdp_affine_destroy(h)
+
+
 def split_blocks(flat: np.ndarray, cliques) -> List[np.ndarray]:
     """One query's flat output -> list of |Ck| x |Ck| matrices ([r, c] indexing)."""
     out, o = [], 0

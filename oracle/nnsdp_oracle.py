@@ -865,3 +865,55 @@ def run_query(ffnet: FeedFwdNet, beta: int, query: NumericQuery, form: str = "cl
         "cliques": cliques,
         "blocks": clique_blocks(Z, cliques),
     }
+
+
+# --------------------------------------------------------------------------
+# Affine structure of Z in the multipliers (what JuMP holds as AffExpr entries,
+# src/Methods/chordal_sdp.jl:96-153): Z(gamma) = Z0 + sum_v gamma_v Z_v
+# --------------------------------------------------------------------------
+
+
+def affine_structure(ffnet: FeedFwdNet, beta: int, x1min, x1max, qc_out, intv_info=None):
+    """Z0 and the per-variable coefficient matrices Z_v, obtained by evaluating the LITERAL assembly at
+    gamma = 0 and at the unit vectors (Z is affine, so Z_v = Z(e_v) - Z(0) exactly up to rounding).
+    Variable order = creation order of setupSafety!/setupReach!: [gamma_in; (gamma_out); gamma_ac1; gamma_ac2].
+    Small nets only (nvar literal assemblies)."""
+    if intv_info is None:
+        intv_info = intervals_worst_case(x1min, x1max, ffnet)
+    qcs = make_qc_activs_intvs(ffnet, x1min, x1max, beta, intv_info)
+    qc_in = QcInputBox(x1min, x1max)
+    n1, ac = ffnet.xdims[0], ffnet.acdim
+    nsec = qcs[1].vardim
+    has_out = not isinstance(qc_out, QcSafety)
+    nvar = n1 + (1 if has_out else 0) + ac + nsec
+
+    def Z(g):
+        o = 0
+        gin = g[o:o + n1]; o += n1
+        gout = g[o:o + 1] if has_out else None
+        o += 1 if has_out else 0
+        gb = g[o:o + ac]; o += ac
+        gs = g[o:o + nsec]
+        return assemble_Z_literal(ffnet, qc_in, qc_out, qcs, gin, [gb, gs], gout)
+
+    Z0 = Z(np.zeros(nvar))
+    Zv = []
+    for v in range(nvar):
+        e_v = np.zeros(nvar)
+        e_v[v] = 1.0
+        Zv.append(Z(e_v) - Z0)
+    return Z0, Zv
+
+
+def cover_upper_entries(ffnet: FeedFwdNet, cliques):
+    """1-based (row, col) of the upper triangle of the clique cover, column-major."""
+    Zdim = ffnet.Zdim
+    cover = np.zeros((Zdim, Zdim), dtype=bool)
+    for Ck, _, _ in cliques:
+        cover[np.ix_(Ck - 1, Ck - 1)] = True
+    rows, cols = [], []
+    for c in range(Zdim):
+        r = np.nonzero(cover[: c + 1, c])[0]
+        rows.append(r + 1)
+        cols.append(np.full(len(r), c + 1))
+    return np.concatenate(rows), np.concatenate(cols)

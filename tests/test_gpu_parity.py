@@ -565,3 +565,73 @@ def test_sparse_host_gather_dense_Z(ctx):
     Z = c[1].reshape(sum(xdims[:-1]) + 1, -1).T
     assert relerr(Z, o.run_query(net, beta, qs[1], form="closed")["Z"]) <= TOL
     b.close()
+
+
+# ---------------------------------------------------------------------------------------------
+# affine-coefficient mode: Z(gamma) = Z0 + sum_v gamma_v Z_v as COO over the cover
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("kind", ["safety", "hplane", "ellipsoid"])
+@pytest.mark.parametrize("xdims,beta", [([2, 3, 2], 0), ([2, 3, 3, 2], 1), ([3, 3, 3, 3, 4, 3, 3], 2), ([2, 4, 7, 3, 5, 2], 5),
+                                        ([2, 6, 5, 7, 4, 2], 2)])
+def test_affine_form_against_oracle(ctx, xdims, beta, kind):
+    import nnsdp_b200 as nb
+
+    net = rand_net(xdims, seed=5, sigma=0.5)
+    rng = np.random.default_rng(12)
+    for radius in (0.0, 0.3):
+        q = rand_query(net, beta, rng, kind=kind, radius=radius)
+        dnet = nb.Net(ctx, net.xdims, net.Ms)
+        batch = to_numeric_batch(nb, net, [q])
+        A = nb.affine_form(dnet, beta, batch)
+        Z0, Zv = o.affine_structure(net, beta, q.x1min, q.x1max, q.qc_out)
+        cliques = o.make_cliques(net, beta)
+        er, ec = o.cover_upper_entries(net, cliques)
+        assert A["nent"] == len(er) and np.array_equal(A["ent_row"], er) and np.array_equal(A["ent_col"], ec)
+        assert A["nvar"] == len(Zv)
+        n1, ac = net.xdims[0], net.acdim
+        assert A["var_out"] == n1 and A["var_sec"] - A["var_bnd"] == ac
+        assert A["var_bnd"] - A["var_out"] == (0 if kind == "safety" else 1)
+        scale = max(np.abs(Z0).max(), max(np.abs(z).max() for z in Zv), 1.0)
+        # constant part
+        assert np.abs(A["z0"] - Z0[er - 1, ec - 1]).max() <= TOL * scale
+        # per-variable coefficient matrices (duplicates summed)
+        dense = np.zeros((A["nvar"], A["nent"]))
+        np.add.at(dense, (A["coo_var"] - 1, A["coo_ent"] - 1), A["coo_val"])
+        for v in range(A["nvar"]):
+            ref = Zv[v][er - 1, ec - 1]
+            assert np.abs(dense[v] - ref).max() <= TOL * scale, (v, np.abs(dense[v] - ref).max())
+            # nothing of Z_v lives outside the cover
+            mask = np.zeros_like(Zv[v], dtype=bool)
+            mask[er - 1, ec - 1] = True
+            mask |= mask.T
+            assert not np.any((Zv[v] != 0) & ~mask)
+        # Z(gamma) from the affine form == the numeric device path at a random gamma
+        g = np.concatenate([q.gin, q.gout if kind != "safety" else [], q.gbnd, q.gsec])
+        zg = A["z0"] + g @ dense
+        Znum = nb.assemble_dense(dnet, beta, batch)[0]
+        assert np.abs(zg - Znum[er - 1, ec - 1]).max() <= TOL * max(np.abs(Znum).max(), 1.0)
+
+
+def test_affine_form_mid_size_and_limit(ctx):
+    """W = 40, D = 6: the Gram term dominates nnz; max_nnz is enforced."""
+    import nnsdp_b200 as nb
+
+    xdims, beta = [2] + [40] * 6 + [2], 2
+    net = rand_net(xdims, seed=2, sigma=0.3)
+    rng = np.random.default_rng(1)
+    q = rand_query(net, beta, rng, kind="hplane", radius=0.0)   # every neuron stable: p_j in {0, 1}
+    dnet = nb.Net(ctx, net.xdims, net.Ms)
+    batch = to_numeric_batch(nb, net, [q])
+    A = nb.affine_form(dnet, beta, batch)
+    info = o.intervals_worst_case(q.x1min, q.x1max, net)
+    smin, smax = o.make_sector_min_max(np.concatenate([p[0] for p in info.acx_intvs]), np.concatenate([p[1] for p in info.acx_intvs]))
+    nact = int((smin * smax != 0).sum())
+    assert A["nnz"] >= nact * (40 * 41 // 2) or nact == 0
+    g = np.concatenate([q.gin, q.gout, q.gbnd, q.gsec])
+    zg = A["z0"].copy()
+    np.add.at(zg, A["coo_ent"] - 1, A["coo_val"] * g[A["coo_var"] - 1])
+    Znum = nb.assemble_dense(dnet, beta, batch)[0]
+    assert np.abs(zg - Znum[A["ent_row"] - 1, A["ent_col"] - 1]).max() <= TOL * max(np.abs(Znum).max(), 1.0)
+    with pytest.raises(nb.NnsdpError) as e:
+        nb.affine_form(dnet, beta, batch, max_nnz=10)
+    assert e.value.code == -3
