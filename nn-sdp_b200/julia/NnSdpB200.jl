@@ -12,10 +12,12 @@
 module NnSdpB200
 
 using LinearAlgebra
+using SparseArrays
 using ..MyMath
 using ..MyNeuralNetwork
 using ..Intervals
 using ..Qc
+using ..Methods
 
 const LIB = get(ENV, "NNSDP_B200_LIB", joinpath(@__DIR__, "..", "lib", "libnnsdp_b200.so"))
 
@@ -189,6 +191,109 @@ function assembleZ(net::DeviceNet, β::Int, qc_input, qc_out, qc_bounded, qc_sec
   return Z
 end
 
+# ---- dispatch point 3: the symbolic hand-off -----------------------------------------------------
+# Z(γ) = Z0 + Σ_v γ_v Z_v over the upper triangle of the clique cover, as a sparse matrix A (nent × nvar)
+# and a constant vector z0: what `Z = Zin + Zout + sum(Zacs)` holds entry by entry as AffExpr
+# (src/Methods/chordal_sdp.jl:114,145) without ever forming the AffExpr matrices.
+struct AffineSizes
+  nvar::Int64; nent::Int64; nnz::Int64
+  var_in::Int64; var_out::Int64; var_bnd::Int64; var_sec::Int64
+end
+
+function affineForm(net::DeviceNet, β::Int, qc_input, qc_out, qc_bounded, qc_sector; max_nnz::Int = 0)
+  keep = Any[]
+  nsec = qc_sector.vardim
+  qi = Ref(query_inputs(qc_input, qc_out, qc_bounded, qc_sector, zeros(length(qc_input.x1min)),
+                        [zeros(qc_bounded.acydim), zeros(nsec)], qc_out isa QcSafety ? Float64[] : [0.0], keep))
+  h, sz = Ref{Ptr{Cvoid}}(C_NULL), Ref{AffineSizes}()
+  GC.@preserve keep check(ccall((:nnsdp_affine_create, LIB), Int32,
+      (Ptr{Cvoid}, Ptr{Cvoid}, Int64, Ptr{QueryInputs}, Int64, Ptr{Ptr{Cvoid}}, Ptr{AffineSizes}),
+      net.ctx.h, net.h, β, qi, max_nnz, h, sz))
+  s = sz[]
+  ent_row, ent_col, z0 = zeros(Int64, s.nent), zeros(Int64, s.nent), zeros(s.nent)
+  coo_ent, coo_var, coo_val = zeros(Int64, s.nnz), zeros(Int64, s.nnz), zeros(s.nnz)
+  try
+    check(ccall((:nnsdp_affine_get, LIB), Int32,
+        (Ptr{Cvoid}, Ptr{Int64}, Ptr{Int64}, Ptr{Float64}, Ptr{Int64}, Ptr{Int64}, Ptr{Float64}),
+        h[], ent_row, ent_col, z0, coo_ent, coo_var, coo_val))
+  finally
+    ccall((:nnsdp_affine_destroy, LIB), Int32, (Ptr{Cvoid},), h[])
+  end
+  A = sparse(coo_ent, coo_var, coo_val, s.nent, s.nvar)   # duplicates are summed
+  return s, ent_row, ent_col, z0, A
+end
+
+# Options type that selects the GPU-assembled constraints in runQuery (src/Methods/Methods.jl:97-103);
+# same five fields as ChordalSdpOptions (src/Methods/chordal_sdp.jl:10-16) plus the device network.
+Base.@kwdef struct ChordalB200Options <: Methods.QueryOptions
+  include_default_mosek_opts::Bool = true
+  mosek_opts::Dict{String, Any} = Dict()
+  decomp_mode::Methods.DecompMode = Methods.SingleDecomp()
+  use_dual::Bool = false
+  verbose::Bool = false
+  net::DeviceNet
+end
+
+# Common part of setupSafety!/setupReach! (src/Methods/chordal_sdp.jl:96-153): variables in the reference's
+# creation order, clique PSD variables through the reference's own setupZs!, and the equality
+# Z[r,c](γ) == Zksum[r,c] on the upper triangle of the cover (both sides are symmetric and identically zero
+# outside the cover, so this is the same feasible set as the reference's Zdim^2 scalar equalities).
+function setupB200!(model, query, qc_out, opts::ChordalB200Options)
+  ffnet = query.ffnet
+  qc_bounded, qc_sector = query.qc_activs[1], query.qc_activs[2]   # order of makeQcActivsIntvs (activ.jl:64)
+  β = qc_sector.β
+  s, ent_row, ent_col, z0, A = affineForm(opts.net, β, query.qc_input, qc_out, qc_bounded, qc_sector)
+  vars = Dict()
+  γin = Methods.JuMP.@variable(model, [1:query.qc_input.vardim])
+  Methods.JuMP.@constraint(model, γin .>= 0)
+  vars[:γin] = γin
+  γ = Vector{Methods.JuMP.VariableRef}(γin)
+  if !(qc_out isa QcSafety)
+    γout = Methods.JuMP.@variable(model, [1:qc_out.vardim])
+    Methods.JuMP.@constraint(model, γout .>= 0)
+    vars[:γout] = γout
+    append!(γ, γout)
+  end
+  for (i, qc) in enumerate(query.qc_activs)
+    γac = Methods.JuMP.@variable(model, [1:qc.vardim])
+    Methods.JuMP.@constraint(model, γac .>= 0)
+    vars[Symbol(:γac, i)] = γac
+    append!(γ, γac)
+  end
+  @assert length(γ) == s.nvar
+  Zvec = A * γ .+ z0                                   # nent affine expressions, built by one sparse product
+  # Zksum on the same entries: sum of the clique variables that contain (r, c)
+  cliques = Methods.makeCliques(query.qcs, ffnet)
+  ref_opts = Methods.ChordalSdpOptions(decomp_mode = opts.decomp_mode)
+  Zs, _ = Methods.setupZs!(model, cliques, query, ref_opts)
+  col_first = Dict{Int64, Int64}()                      # column -> index of its first entry
+  for e in length(ent_col):-1:1; col_first[ent_col[e]] = e end
+  entry(r, c) = col_first[c] + (r - ent_row[col_first[c]])
+  Zksum = zeros(Methods.JuMP.AffExpr, s.nent)
+  for (k, (Ck, _, _)) in enumerate(cliques)
+    for j in 1:length(Ck), i in 1:j
+      Methods.JuMP.add_to_expression!(Zksum[entry(Ck[i], Ck[j])], Zs[k][i, j])
+    end
+  end
+  Methods.JuMP.@constraint(model, Zvec .== Zksum)
+  vars[:Z] = sparse(ent_row, ent_col, Zvec, sum(ffnet.zdims), sum(ffnet.zdims))   # upper triangle of Z(γ)
+  return vars
+end
+
+function Methods.setupSafety!(model, query::Methods.SafetyQuery, opts::ChordalB200Options)
+  vars = setupB200!(model, query, query.qc_safety, opts)
+  γacs = [vars[Symbol(:γac, i)] for i in 1:length(query.qc_activs)]
+  Methods.JuMP.@objective(model, Min, sum(vars[:γin]) + sum(sum(γac) for γac in γacs))   # chordal_sdp.jl:111
+  return model, vars
+end
+
+function Methods.setupReach!(model, query::Methods.ReachQuery, opts::ChordalB200Options)
+  vars = setupB200!(model, query, query.qc_reach, opts)
+  Methods.JuMP.@objective(model, Min, query.obj_func(vars[:γout]))                        # chordal_sdp.jl:136
+  return model, vars
+end
+
 export Context, DeviceNet, IntervalsB200, makeCliquesB200, assembleCliqueBlocks, assembleZ
+export affineForm, ChordalB200Options
 
 end # module
