@@ -635,3 +635,55 @@ def test_affine_form_mid_size_and_limit(ctx):
     with pytest.raises(nb.NnsdpError) as e:
         nb.affine_form(dnet, beta, batch, max_nnz=10)
     assert e.value.code == -3
+
+
+# ---------------------------------------------------------------------------------------------
+# wide layers (128-row tiles, strips, RC / CR window programs, sliver sub-tiles) x output kinds x beta
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("kind", ["safety", "hplane", "ellipsoid"])
+@pytest.mark.parametrize("xdims,beta", [
+    ([3, 150, 260, 140, 2], 0), ([3, 150, 260, 140, 2], 1), ([3, 150, 260, 140, 2], 4),
+    ([3, 150, 260, 140, 2], 6),            # beta > MAX_WINDOW_BETA: no register-window programs
+    ([2, 129, 128, 127, 300, 4], 3),       # widths around the tile size, last block wide
+    ([6, 520, 33, 520, 3], 2),             # a narrow layer between wide ones: slivers dominate
+])
+def test_wide_nets_all_programs(ctx, xdims, beta, kind):
+    import nnsdp_b200 as nb
+
+    net = rand_net(xdims, seed=17, sigma=0.1)
+    rng = np.random.default_rng(23)
+    qs = [rand_query(net, beta, rng, kind=kind, radius=r) for r in (0.0, 0.2)]
+    dnet = nb.Net(ctx, net.xdims, net.Ms)
+    batch = to_numeric_batch(nb, net, qs)
+    Z = nb.assemble_dense(dnet, beta, batch)
+    flat = nb.assemble_blocks(dnet, beta, batch)
+    cliques = dnet.cliques(beta)
+    for i, q in enumerate(qs):
+        ref = o.run_query(net, beta, q, form="closed")
+        assert relerr(Z[i], ref["Z"]) <= TOL
+        assert np.array_equal(Z[i], Z[i].T)
+        for blk, (Ck, _, _), rb in zip(nb.split_blocks(flat[i], cliques), cliques, ref["blocks"]):
+            assert np.array_equal(blk, Z[i][np.ix_(Ck - 1, Ck - 1)])
+            assert relerr(blk, rb) <= TOL
+
+
+def test_ragged_batches_and_rings(ctx):
+    """Q not a multiple of the ring, ring of 1, Q = 1, more ring slots than queries."""
+    import nnsdp_b200 as nb
+
+    xdims, beta = [2, 300, 270, 2], 2
+    net = rand_net(xdims, seed=3, sigma=0.1)
+    rng = np.random.default_rng(5)
+    qs = [rand_query(net, beta, rng, kind="circle", radius=0.01 * i) for i in range(7)]
+    dnet = nb.Net(ctx, net.xdims, net.Ms)
+    cliques = o.make_cliques(net, beta)
+    refs = [o.run_query(net, beta, q)["blocks"] for q in qs]
+    for nq, ring in ((7, 3), (7, 1), (1, 4), (5, 8), (7, 2)):
+        b = nb.Batch(dnet, beta, Qcap=nq, ring=ring)
+        b.set_inputs(to_numeric_batch(nb, net, qs[:nq]))
+        out = np.full((nq, b.per_query), np.nan)
+        b.run(out)
+        for i in range(nq):
+            for blk, rb in zip(nb.split_blocks(out[i], cliques), refs[i]):
+                assert relerr(blk, rb) <= TOL
+        b.close()
