@@ -85,6 +85,53 @@ __global__ void strip_fill_masked(double* out, int n, int ld, int h, int strips_
     for (int r = r_lo - mis + threadIdx.x; r < r_hi; r += 256) if (r >= r_lo) col[r] = v;
   }
 }
+// ---- does interleaving the fill strips and the window tiles of one column panel pay? ----------------
+// rows [0, 1002) and [2004, 3003) of every column are "fill" (aligned 501-row strips x 8 cols), rows
+// [1002, 2004) are "window" (128 x 32 tiles, 8 B stores, like emit_window_kernel).  Variant `panel` runs
+// both in ONE kernel with CTAs ordered by 32-column panel; the baseline runs two kernels back to back.
+__device__ __forceinline__ void fill_strip_dev(double* o, int ld, int r_lo, int r_hi, int c0, int n, double v) {
+  for (int c = c0; c < min(c0 + 8, n); ++c) {
+    double* col = o + (size_t)c * ld;
+    const int mis = (int)(((size_t)(col + r_lo) >> 3) & 3);
+    for (int r = r_lo - mis + threadIdx.x; r < r_hi; r += 256) if (r >= r_lo) col[r] = v;
+  }
+}
+__device__ __forceinline__ void window_tile_dev(double* o, int ld, int r0, int r_hi, int c0, int n, double v) {
+  const int tr = threadIdx.x & 127, cg = threadIdx.x >> 7;
+  const int r = r0 + tr;
+  if (r >= r_hi) return;
+  for (int c = cg; c < 32; c += 2) if (c0 + c < n) o[r + (size_t)(c0 + c) * ld] = v;
+}
+// items of one panel: 4 column strips x 4 row strips (0,1,4,5) = 16 fill items, then 8 window tiles
+__global__ void panel_unified(double* out, int n, int ld, double v) {
+  const int panel = blockIdx.x / 24, it = blockIdx.x % 24;
+  double* o = out + (size_t)blockIdx.y * (size_t)ld * n;
+  const int c0 = panel * 32;
+  if (it < 16) {
+    const int cs = it / 4, k = it % 4, rs = (k < 2) ? k : k + 2;
+    fill_strip_dev(o, ld, rs * 501, min(rs * 501 + 501, n), c0 + cs * 8, n, v);
+  } else {
+    window_tile_dev(o, ld, 1002 + (it - 16) * 128, 2004, c0, n, v);
+  }
+}
+__global__ void panel_fill_only(double* out, int n, int ld, double v) {
+  const int panel = blockIdx.x / 16, it = blockIdx.x % 16;
+  double* o = out + (size_t)blockIdx.y * (size_t)ld * n;
+  const int cs = it / 4, k = it % 4, rs = (k < 2) ? k : k + 2;
+  fill_strip_dev(o, ld, rs * 501, min(rs * 501 + 501, n), panel * 32 + cs * 8, n, v);
+}
+__global__ void panel_window_only(double* out, int n, int ld, double v) {
+  const int panel = blockIdx.x / 8, it = blockIdx.x % 8;
+  double* o = out + (size_t)blockIdx.y * (size_t)ld * n;
+  window_tile_dev(o, ld, 1002 + it * 128, 2004, panel * 32, n, v);
+}
+// window part as tall strips too (what a unified kernel could do if the window program allowed it)
+__global__ void panel_unified_strips(double* out, int n, int ld, double v) {
+  const int panel = blockIdx.x / 24, it = blockIdx.x % 24;
+  double* o = out + (size_t)blockIdx.y * (size_t)ld * n;
+  const int cs = it / 6, rs = it % 6;
+  fill_strip_dev(o, ld, rs * 501, min(rs * 501 + 501, n), panel * 32 + cs * 8, n, v);
+}
 // same strips, no alignment (rows start at r_lo)
 __global__ void strip_fill_plain(double* out, int n, int ld, int h, int strips_r, double v) {
   const int r_lo = (blockIdx.x % strips_r) * h, c0 = (blockIdx.x / strips_r) * 8;
@@ -142,6 +189,17 @@ int main() {
       snprintf(nm, sizeof nm, "strip_fill_masked h=501 row-strip mask 0x%02x", mask);
       timeit(nm, [&] { strip_fill_masked<<<g2, 256>>>(buf, n, 3003, h, strips_r, mask, nsel, 1.0); }, bytes * nsel / 6.0);
     }
+  }
+  {
+    const int panels = (n + 31) / 32;
+    timeit("panel: fill kernel then window kernel (2 launches)", [&] {
+      panel_fill_only<<<dim3(panels * 16, nmat), 256>>>(buf, n, 3003, 1.0);
+      panel_window_only<<<dim3(panels * 8, nmat), 256>>>(buf, n, 3003, 1.0);
+    }, bytes);
+    timeit("panel: fill kernel alone", [&] { panel_fill_only<<<dim3(panels * 16, nmat), 256>>>(buf, n, 3003, 1.0); }, bytes * 2 / 3);
+    timeit("panel: window kernel alone", [&] { panel_window_only<<<dim3(panels * 8, nmat), 256>>>(buf, n, 3003, 1.0); }, bytes / 3);
+    timeit("panel: ONE kernel, items ordered by panel", [&] { panel_unified<<<dim3(panels * 24, nmat), 256>>>(buf, n, 3003, 1.0); }, bytes);
+    timeit("panel: ONE kernel, all strips (upper bound)", [&] { panel_unified_strips<<<dim3(panels * 24, nmat), 256>>>(buf, n, 3003, 1.0); }, bytes);
   }
   timeit("tile_fill16 ld=3004", [&] { tile_fill16<<<grid, 256>>>(buf, n, 3004, tiles_r, 1.0); }, bytes);
   timeit("tile_fill16 ld=3008", [&] { tile_fill16<<<grid, 256>>>(buf, n, 3008, tiles_r, 1.0); }, bytes);
