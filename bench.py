@@ -38,7 +38,11 @@ WORKLOADS = {
 DEFAULT_WORKLOAD = "stress-W1000-D20-beta2-Q1024"
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the `ncu --set full` capture of the same
 # command (profiles/): filled in when a capture exists for the current kernels, else null.
-NCU_TRAFFIC = {}
+NCU_TRAFFIC = {  # bytes per launch (8-query pass), profiles/r1_emit_full.summary.csv
+    "emit_fill_kernel": 8.272976e9 + 141.445632e6,     # algorithmic 8.17 GB
+    "emit_window_kernel": 2.419744e9 + 342.088960e6,   # algorithmic 2.46 GB (+ the W tiles it reads)
+    "emit_edge_kernel": 0.006930e9 + 11.059200e6,
+}
 
 
 def make_workload(name: str, rank: int, Q: int | None = None):

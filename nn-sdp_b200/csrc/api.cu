@@ -982,9 +982,25 @@ static int32_t gather_chunk(nnsdp_batch* b, int ci, int64_t q0, int64_t nq, int 
   b->span_begin(ST_D2H, b->st_copy);
   if (nthin) NN_CUDA(cudaMemcpyAsync(h_pk, d_pk, (size_t)nq * nthin * 8, cudaMemcpyDeviceToHost, b->st_copy));
   NN_CUDA(cudaEventRecord(b->ev_packed[sb], b->st_copy));
-  auto active = [&](const GatherCell& c, int64_t q) {
+  // Large cells that are NOT dense for this query hold zeros in the ring (plus thin entries, which are
+  // scattered afterwards in any case).  The copy engine idles most of the time while the host threads
+  // zero-fill, so a share of those cells is copied as well: both then finish at about the same time.
+  static const int dma_zero_pct = [] {
+    const char* e = getenv("NNSDP_GATHER_DMA_ZERO_PCT");
+    const int v = e ? atoi(e) : 20;
+    return v < 0 ? 0 : (v > 100 ? 100 : v);
+  }();
+  auto dense_now = [&](const GatherCell& c, int64_t q) {
     return c.kind == GK_ALWAYS || (c.kind == GK_GRAM && b->h_cnt[q * K + c.blk] > 0) ||
            (c.kind == GK_S22 && b->bd.has_s22);
+  };
+  auto active = [&](const GatherCell& c, int64_t q) {
+    if (dense_now(c, q)) return true;
+    if (std::min<int64_t>(c.nrows, c.ncols_hint) < GATHER_MIN_RECT) return false;
+    if (prezeroed && c.pure_zero) return false;
+    // deterministic pseudo-random share, independent of the order of evaluation
+    const uint64_t hsh = ((uint64_t)q * 1315423911u) ^ ((uint64_t)c.row0 * 2654435761u) ^ ((uint64_t)c.col0_hint * 97u);
+    return (int)((hsh >> 7) % 100) < dma_zero_pct;
   };
   for (int64_t q = q0; q < q0 + nq; ++q) {
     const double* src = dst + (q - q0) * per;

@@ -159,6 +159,7 @@ struct GatherCell {
   int32_t row0, nrows;  // local rows
   int32_t kind, blk;    // GatherKind; block of a GK_GRAM cell
   int32_t pure_zero;    // no term of Z can be non-zero in the cell (and no thin entry lies in it)
+  int32_t ncols_hint, col0_hint;  // copy of the owning column segment's extent
 };
 struct GatherColSeg {   // a block-aligned range of columns of one matrix and its cells top to bottom
   int32_t mat, col0, ncols;

@@ -429,6 +429,8 @@ int32_t build_gather_plan(const Shape& sh, int64_t beta, const std::vector<Cliqu
         GatherCell c{};
         c.row0 = (int32_t)sr.l0;
         c.nrows = (int32_t)(sr.g1 - sr.g0 + 1);
+        c.ncols_hint = cs.ncols;
+        c.col0_hint = cs.col0;
         const int Bi = sh.block_of(sr.g0);
         c.kind = GK_NONE;
         c.blk = -1;
