@@ -234,6 +234,16 @@ int32_t nnsdp_batch_stage_reset(nnsdp_batch* batch);
  * non-empty active set and the sum over them of |active|. */
 int32_t nnsdp_batch_gram_stats(nnsdp_batch* batch, int64_t* n_contractions, int64_t* sum_active);
 
+/* ---- certificate check -----------------------------------------------------
+ * lambda_max of Z(gamma) for every query of a prepared batch, without forming Z: Z x is evaluated from the
+ * factored form R' Q R + Zin + Zout (one GEMM per layer over the batch) inside a Lanczos iteration with full
+ * re-orthogonalisation, at most max_iters steps; a query stops when its largest Ritz value has moved by less
+ * than tol (relative) over the last three steps.  Replaces eigmax(Symmetric(Matrix(value.(Z))))
+ * (src/Methods/Methods.jl:116-117; acceptance test experiments/acas.jl:71-79, scale.jl:76).
+ * lam_max[Q]; iters[Q] may be NULL.  The Ritz value converges to lambda_max from below. */
+int32_t nnsdp_batch_lambda_max(nnsdp_batch* batch, int32_t max_iters, double tol, double* lam_max,
+                               int32_t* iters);
+
 /* ---- affine-coefficient mode ---------------------------------------------
  * Z(gamma) = Z0 + sum_v gamma_v Z_v for ONE query, restricted to the upper triangle of the clique
  * cover, as COO triplets -- the data from which `@constraint(model, Z .== Zksum)`

@@ -1,6 +1,7 @@
 // Host runtime behind the C ABI of include/nnsdp_b200.h: contexts (devices + streams), uploaded
 // networks, device-resident batches of queries, and the one-shot entry points that shard queries
 // over the devices of a context (one host thread per device, no collective).
+#include <math.h>
 #include <stdarg.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -1433,6 +1434,134 @@ int32_t nnsdp_assemble_dense(nnsdp_ctx* ctx, const nnsdp_net* net, int64_t beta,
 }
 
 }  // extern "C"
+
+// -----------------------------------------------------------------------------------------
+// lambda_max of Z(gamma), matrix-free
+// -----------------------------------------------------------------------------------------
+namespace {
+
+// largest eigenvalue of the symmetric tridiagonal (alpha[0..m), beta[0..m-1)) by Sturm bisection
+double tridiag_lambda_max(const double* alpha, const double* beta, int m) {
+  if (m <= 0) return 0.0;
+  double lo = alpha[0], hi = alpha[0];
+  for (int i = 0; i < m; ++i) {
+    const double r = (i > 0 ? fabs(beta[i - 1]) : 0.0) + (i + 1 < m ? fabs(beta[i]) : 0.0);
+    lo = std::min(lo, alpha[i] - r);
+    hi = std::max(hi, alpha[i] + r);
+  }
+  auto count_below = [&](double x) {  // number of eigenvalues < x
+    int cnt = 0;
+    double d = 1.0;
+    for (int i = 0; i < m; ++i) {
+      const double b2 = i > 0 ? beta[i - 1] * beta[i - 1] : 0.0;
+      d = (alpha[i] - x) - (i > 0 ? b2 / d : 0.0);
+      if (d == 0.0) d = -1e-300;
+      if (d < 0.0) ++cnt;
+    }
+    return cnt;
+  };
+  for (int it = 0; it < 200 && hi - lo > 4e-16 * std::max(fabs(lo), fabs(hi)); ++it) {
+    const double mid = 0.5 * (lo + hi);
+    if (count_below(mid) >= m) hi = mid; else lo = mid;
+  }
+  return 0.5 * (lo + hi);
+}
+
+}  // namespace
+
+extern "C" int32_t nnsdp_batch_lambda_max(nnsdp_batch* b, int32_t max_iters, double tol, double* lam_max,
+                                          int32_t* iters_out) {
+  NN_CHECK(b && lam_max, NNSDP_ERR_ARG, "NULL argument");
+  NN_CHECK(b->prepared, NNSDP_ERR_STATE, "nnsdp_batch_lambda_max before nnsdp_batch_prepare");
+  NN_CHECK(max_iters >= 1, NNSDP_ERR_ARG, "max_iters must be >= 1");
+  NN_CUDA(cudaSetDevice(b->dev));
+  const Shape& sh = b->net->sh;
+  const NetPerDev& npd = *b->nd;
+  const NetDev& nd = npd.nd;
+  const int n = (int)sh.Zdim, ac = (int)sh.acdim, K = sh.K;
+  const int m = (int)std::min<int64_t>(max_iters, sh.Zdim);
+  // queries per chunk: the Krylov basis is (m + 1) x Qc x Zdim doubles; keep it under ~2 GiB
+  int Qc = (int)std::max<int64_t>(1, std::min<int64_t>(b->Q, (int64_t(1) << 28) / ((int64_t)(m + 1) * n)));
+  Qc = std::min(Qc, 64);
+  DevBuf dV, dw, dt, ds1, dc, dnrm, dalpha, dbeta;
+  struct Rel {
+    std::vector<DevBuf*> v;
+    ~Rel() { for (DevBuf* x : v) x->release(); }
+  } rel{{&dV, &dw, &dt, &ds1, &dc, &dnrm, &dalpha, &dbeta}};
+  NN_TRY(dV.ensure((size_t)(m + 1) * Qc * n * 8));
+  NN_TRY(dw.ensure((size_t)Qc * n * 8));
+  NN_TRY(dt.ensure((size_t)Qc * ac * 8));
+  NN_TRY(ds1.ensure((size_t)Qc * ac * 8));
+  NN_TRY(dc.ensure((size_t)Qc * (m + 1) * 8));
+  NN_TRY(dnrm.ensure((size_t)Qc * 8));
+  cudaStream_t st = b->st;
+  std::vector<double> hc((size_t)Qc * (m + 1)), hn((size_t)Qc);
+  for (int64_t q0 = 0; q0 < b->Q; q0 += Qc) {
+    const int nq = (int)std::min<int64_t>(Qc, b->Q - q0);
+    double* V = dV.as<double>();
+    double* w = dw.as<double>();
+    auto Vj = [&](int j) { return V + (size_t)j * Qc * n; };
+    launch_eig_init(w, n, nq, (int)q0, st);
+    launch_eig_normalize(w, Vj(0), n, nq, dnrm.as<double>(), st);
+    std::vector<std::vector<double>> alpha(nq), beta(nq);
+    std::vector<double> theta(nq, 0.0);
+    std::vector<std::vector<double>> hist(nq);
+    std::vector<int> done(nq, 0), its(nq, 0);
+    int j = 0;
+    for (; j < m; ++j) {
+      // ---- w = Z v_j ----
+      const double* x = Vj(j);
+      NN_CUDA(cudaMemsetAsync(dt.p, 0, (size_t)nq * ac * 8, st));
+      for (int k = 0; k <= K - 2; ++k)  // t_{k+1} = W_k x_k
+        gemm_acc_launch(npd.M[k].as<double>(), (int)sh.n[k + 1], (int)sh.n[k + 1], (int)sh.n[k], x + sh.off[k], n,
+                        dt.as<double>() + sh.noff(k + 1), ac, nq, st);
+      launch_eig_mid(nd, b->bd, (int)q0, nq, x, dt.as<double>(), ds1.as<double>(), w, st);
+      launch_eig_io(nd, b->bd, (int)q0, nq, x, w, st);
+      for (int k = 0; k <= K - 2; ++k)  // y_k += W_k' s1_{k+1}
+        gemm_acc_launch(npd.Wt[k].as<double>(), b->net->ldT[k], (int)sh.n[k], (int)sh.n[k + 1],
+                        ds1.as<double>() + sh.noff(k + 1), ac, w + sh.off[k], n, nq, st);
+      // ---- alpha_j and full re-orthogonalisation against v_0..v_j (classical Gram-Schmidt, twice) ----
+      launch_eig_multidot(V, w, n, Qc, j + 1, dc.as<double>(), m + 1, st);
+      launch_eig_project(V, w, n, Qc, j + 1, dc.as<double>(), m + 1, st);
+      NN_CUDA(cudaMemcpyAsync(hc.data(), dc.p, (size_t)nq * (m + 1) * 8, cudaMemcpyDeviceToHost, st));
+      NN_CUDA(cudaStreamSynchronize(st));
+      for (int q = 0; q < nq; ++q) alpha[q].push_back(hc[(size_t)q * (m + 1) + j]);
+      launch_eig_multidot(V, w, n, Qc, j + 1, dc.as<double>(), m + 1, st);
+      launch_eig_project(V, w, n, Qc, j + 1, dc.as<double>(), m + 1, st);
+      NN_CUDA(cudaMemcpyAsync(hc.data(), dc.p, (size_t)nq * (m + 1) * 8, cudaMemcpyDeviceToHost, st));
+      launch_eig_normalize(w, Vj(j + 1), n, nq, dnrm.as<double>(), st);
+      NN_CUDA(cudaMemcpyAsync(hn.data(), dnrm.p, (size_t)nq * 8, cudaMemcpyDeviceToHost, st));
+      NN_CUDA(cudaStreamSynchronize(st));
+      bool all_done = true;
+      for (int q = 0; q < nq; ++q) {
+        alpha[q][j] += hc[(size_t)q * (m + 1) + j];  // second-pass correction of alpha_j
+        if (done[q]) continue;
+        its[q] = j + 1;
+        theta[q] = tridiag_lambda_max(alpha[q].data(), beta[q].data(), j + 1);
+        hist[q].push_back(theta[q]);
+        const double scale = std::max(fabs(theta[q]), 1e-300);
+        // stop on an invariant subspace (beta_j ~ 0) or when the largest Ritz value has not moved by more
+        // than tol (relative) over the last three steps
+        bool stable = (int)hist[q].size() >= 10;
+        for (int back = 2; stable && back <= 4; ++back)
+          stable = fabs(hist[q][hist[q].size() - back] - theta[q]) <= tol * scale;
+        if (hn[q] <= 1e-13 * std::max(scale, fabs(alpha[q][j])) || stable) done[q] = 1;
+        beta[q].push_back(hn[q]);
+        if (!done[q]) all_done = false;
+      }
+      if (all_done) {
+        ++j;
+        break;
+      }
+    }
+    for (int q = 0; q < nq; ++q) {
+      lam_max[q0 + q] = theta[q];
+      if (iters_out) iters_out[q0 + q] = its[q];
+    }
+  }
+  NN_CUDA(cudaGetLastError());
+  return NNSDP_OK;
+}
 
 // -----------------------------------------------------------------------------------------
 // affine-coefficient mode: Z(gamma) = Z0 + sum_v gamma_v Z_v over the cover

@@ -293,6 +293,21 @@ int launch_affine_fill(const NetDev& net, const AffineDev& A, const long long* o
 int launch_affine_z0(const NetDev& net, const BatchDev& b, const AffineDev& A, double* z0,
                      cudaStream_t st);
 
+// matrix-free lambda_max (kernels_eig.cu); Qc = queries of the current chunk, first one is q_first
+int launch_eig_init(double* v, int Zdim, int Qc, int q_first, cudaStream_t st);
+int launch_eig_mid(const NetDev& net, const BatchDev& b, int q_first, int Qc, const double* x,
+                   const double* t, double* s1, double* y, cudaStream_t st);
+int launch_eig_io(const NetDev& net, const BatchDev& b, int q_first, int Qc, const double* x, double* y,
+                  cudaStream_t st);
+int launch_eig_multidot(const double* V, const double* w, int n, int Qc, int nv, double* c, int c_ld,
+                        cudaStream_t st);
+int launch_eig_project(const double* V, double* w, int n, int Qc, int nv, const double* c, int c_ld,
+                       cudaStream_t st);
+int launch_eig_normalize(const double* w, double* dst, int n, int Qc, double* nrm, cudaStream_t st);
+// C (M x N, column q at C + q * ldc) += A (M x Kdim, column-major, lda) * B (column q at B + q * ldb)
+int gemm_acc_launch(const double* A, int lda, int M, int Kdim, const double* B, long long ldb,
+                    double* C, long long ldc, int N, cudaStream_t st);
+
 // thin-entry pack: packed[s * nthin + i] = ring[s * per_query + idx[i]] for the nq slots of a chunk
 int launch_pack_thin(const double* ring, long long per_query, const long long* idx, long long nthin,
                      double* packed, int nq, cudaStream_t st);

@@ -191,6 +191,29 @@ function assembleZ(net::DeviceNet, β::Int, qc_input, qc_out, qc_bounded, qc_sec
   return Z
 end
 
+# ---- certificate check: eigmax(Z) without forming Z (src/Methods/Methods.jl:116-117, experiments/acas.jl:71-79) ----
+# λmax of Z(γ) for numeric multipliers, matrix-free Lanczos on the device (nnsdp_batch_lambda_max).
+function eigmaxZ(net::DeviceNet, β::Int, qc_input, qc_out, qc_bounded, qc_sector, γin, γacs, γout = Float64[];
+                 max_iters::Int = 300, tol::Float64 = 1e-10)
+  keep = Any[]
+  qi = Ref(query_inputs(qc_input, qc_out, qc_bounded, qc_sector, Vector{Float64}(γin),
+                        [Vector{Float64}(g) for g in γacs], Vector{Float64}(γout), keep))
+  h = Ref{Ptr{Cvoid}}(C_NULL)
+  check(ccall((:nnsdp_batch_create, LIB), Int32,
+              (Ptr{Cvoid}, Int32, Ptr{Cvoid}, Int64, Int64, Int64, Int32, Ptr{Ptr{Cvoid}}),
+              net.ctx.h, 0, net.h, β, 1, 1, 0, h))
+  lam, its = zeros(1), zeros(Int32, 1)
+  try
+    GC.@preserve keep check(ccall((:nnsdp_batch_set_inputs, LIB), Int32, (Ptr{Cvoid}, Int64, Ptr{QueryInputs}), h[], 1, qi))
+    check(ccall((:nnsdp_batch_prepare, LIB), Int32, (Ptr{Cvoid},), h[]))
+    check(ccall((:nnsdp_batch_lambda_max, LIB), Int32, (Ptr{Cvoid}, Int32, Float64, Ptr{Float64}, Ptr{Int32}),
+                h[], max_iters, tol, lam, its))
+  finally
+    ccall((:nnsdp_batch_destroy, LIB), Int32, (Ptr{Cvoid},), h[])
+  end
+  return lam[1]
+end
+
 # ---- dispatch point 3: the symbolic hand-off -----------------------------------------------------
 # Z(γ) = Z0 + Σ_v γ_v Z_v over the upper triangle of the clique cover, as a sparse matrix A (nent × nvar)
 # and a constant vector z0: what `Z = Zin + Zout + sum(Zacs)` holds entry by entry as AffExpr
@@ -294,6 +317,6 @@ function Methods.setupReach!(model, query::Methods.ReachQuery, opts::ChordalB200
 end
 
 export Context, DeviceNet, IntervalsB200, makeCliquesB200, assembleCliqueBlocks, assembleZ
-export affineForm, ChordalB200Options
+export affineForm, ChordalB200Options, eigmaxZ
 
 end # module

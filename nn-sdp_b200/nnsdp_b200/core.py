@@ -370,6 +370,13 @@ class Batch:
             p = _dp(host_out)
         L.check(L.lib.nnsdp_batch_run_ex(self._h, p, flags))
 
+    def lambda_max(self, max_iters: int = 200, tol: float = 1e-10):
+        """lambda_max(Z(gamma)) of every query (matrix-free Lanczos on the device); needs bounds + prepare."""
+        lam = np.zeros(self.Q)
+        its = np.zeros(self.Q, dtype=np.int32)
+        L.check(L.lib.nnsdp_batch_lambda_max(self._h, max_iters, tol, _dp(lam), its.ctypes.data_as(C.POINTER(L.c_i32))))
+        return lam, its
+
     def gather_stats(self) -> dict:
         a, t, z, u = L.c_i64(0), L.c_i64(0), L.c_i64(0), L.c_i32(0)
         L.check(L.lib.nnsdp_batch_gather_stats(self._h, C.byref(a), C.byref(t), C.byref(z), C.byref(u)))

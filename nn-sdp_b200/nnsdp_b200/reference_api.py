@@ -383,3 +383,20 @@ def assembleCliqueBlocks(query, gin, gacs: Sequence[np.ndarray], gout=None):
     flat = core.assemble_blocks(query.ffnet.device(), beta, b, Q=1)[0]
     cliques = makeCliques(query.qcs, query.ffnet)
     return cliques, core.split_blocks(flat, cliques)
+
+
+def eigmaxZ(query, gin, gacs: Sequence[np.ndarray], gout=None, max_iters: int = 300, tol: float = 1e-10) -> float:
+    """eigmax(Symmetric(Matrix(Z))) of src/Methods/Methods.jl:116-117 for numeric multipliers, computed
+    matrix-free on the device (nnsdp_batch_lambda_max): the acceptance quantity of experiments/acas.jl:71-79."""
+    qc_out, bnd, sec = _query_parts(query)
+    g = {type(q): ga for q, ga in zip(query.qc_activs, gacs)}
+    beta = sec.beta if sec else 0
+    batch = _batch_for(query.ffnet, query.qc_input, qc_out, bnd, sec, gin, g.get(QcActivBounded), g.get(QcActivSector), gout, beta)
+    b = core.Batch(query.ffnet.device(), beta, Qcap=1, ring=1)
+    try:
+        b.set_inputs(batch, Q=1)
+        b.prepare()
+        lam, _ = b.lambda_max(max_iters=max_iters, tol=tol)
+        return float(lam[0])
+    finally:
+        b.close()

@@ -250,6 +250,8 @@ def test_reference_api_mirror(ctx):
     cl2, blocks = R.assembleCliqueBlocks(query, gin, [gb, gs])
     for blk, (Ck, _, _) in zip(blocks, cl2):
         assert relerr(blk, Zr[np.ix_(Ck - 1, Ck - 1)]) <= TOL
+    ev = np.linalg.eigvalsh(Zr)
+    assert abs(R.eigmaxZ(query, gin, [gb, gs]) - ev[-1]) <= 1e-9 * max(abs(ev[0]), abs(ev[-1]))
 
 
 def test_error_paths(ctx):
@@ -687,3 +689,54 @@ def test_ragged_batches_and_rings(ctx):
             for blk, rb in zip(nb.split_blocks(out[i], cliques), refs[i]):
                 assert relerr(blk, rb) <= TOL
         b.close()
+
+
+# ---------------------------------------------------------------------------------------------
+# certificate check: lambda_max(Z) matrix-free against numpy's dense eigvalsh
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("kind", ["safety", "hplane", "ellipsoid"])
+@pytest.mark.parametrize("xdims,beta", [([2, 3, 2], 0), ([3, 3, 3, 3, 4, 3, 3], 2), ([2, 4, 7, 3, 5, 2], 5), ([2] + [20] * 6 + [2], 2),
+                                        ([5, 50, 50, 50, 5], 2), ([3, 150, 260, 140, 2], 3)])
+def test_lambda_max_matrix_free(ctx, xdims, beta, kind):
+    import nnsdp_b200 as nb
+
+    net = rand_net(xdims, seed=4, sigma=0.2)
+    rng = np.random.default_rng(6)
+    qs = [rand_query(net, beta, rng, kind=kind, radius=r) for r in (0.0, 0.05, 0.4)]
+    dnet = nb.Net(ctx, net.xdims, net.Ms)
+    b = nb.Batch(dnet, beta, Qcap=3, ring=1)
+    b.set_inputs(to_numeric_batch(nb, net, qs))
+    b.bounds()
+    b.prepare()
+    lam, its = b.lambda_max(max_iters=400, tol=1e-12)
+    for i, q in enumerate(qs):
+        Z = o.run_query(net, beta, q, form="closed")["Z"]
+        ev = np.linalg.eigvalsh(Z)
+        scale = max(abs(ev[0]), abs(ev[-1]))
+        assert abs(lam[i] - ev[-1]) <= 1e-9 * scale, (lam[i], ev[-1], its[i])
+        assert lam[i] <= ev[-1] + 1e-12 * scale           # a Ritz value never exceeds lambda_max
+        assert 1 <= its[i] <= min(400, Z.shape[0])
+    b.close()
+
+
+def test_lambda_max_negative_definite_certificate(ctx):
+    """A Z that is negative definite by construction (only the -2 gamma diagonals): the check returns its
+    largest (negative) eigenvalue, i.e. the certificate eigmax(Z) <= 0 of experiments/acas.jl:71-79."""
+    import nnsdp_b200 as nb
+
+    xdims, beta = [2, 30, 30, 2], 1
+    net = rand_net(xdims, seed=1, sigma=0.0)       # zero weights and biases: no coupling at all
+    rng = np.random.default_rng(0)
+    q = rand_query(net, beta, rng, kind="hplane", radius=0.1)
+    q.gsec[:] = 0.0
+    q.qc_out = o.QcReachHplane(np.zeros(2))
+    dnet = nb.Net(ctx, net.xdims, net.Ms)
+    b = nb.Batch(dnet, beta, Qcap=1, ring=1)
+    b.set_inputs(to_numeric_batch(nb, net, [q]))
+    b.bounds()
+    b.prepare()
+    lam, _ = b.lambda_max(max_iters=100, tol=1e-12)
+    Z = o.run_query(net, beta, q, form="closed")["Z"]
+    ev = np.linalg.eigvalsh(Z)
+    assert ev[-1] < 0 and abs(lam[0] - ev[-1]) <= 1e-9 * abs(ev[0])
+    b.close()
