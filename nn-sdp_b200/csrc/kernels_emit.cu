@@ -501,14 +501,27 @@ emit_edge_kernel(NetDev net, BatchDev b, GramDev g, PlanDev plan, int tile0, int
   if (TR > ETHREADS) TR = ETHREADS;
   const int tr = threadIdx.x % TR, cg = threadIdx.x / TR, ncg = ETHREADS / TR;
   const long long tile_off = mat.out_off + (t.row0 + tr) + (long long)t.col0 * mat.ld;
-  const bool uniform = (t.flags & TF_UNIFORM) != 0;
-  for (int s = 0; s < nslots; ++s) {
+  // thin sliver tiles (a few hundred entries) skip the shared-memory staging and its barriers: the per-entry
+  // evaluator with direct loads is cheaper there (same bits), and since it has no barrier the threads a thin
+  // tile leaves idle work on other queries of the group at the same time
+  const bool uniform = (t.flags & TF_UNIFORM) != 0 && t.nrows * t.ncols > 512;
+  if (uniform) {
+    for (int s = 0; s < nslots; ++s) {
+      const QView v = make_view(net, b, g, q0 + slot0 + s, slot0 + s);
+      double* o = out + (long long)(slot0 + s) * plan.per_query + tile_off;
+      emit_mixed(net, b, g, t, mat, v, o, tr, cg, ncg, smem);
+    }
+    return;
+  }
+  int TC = 1;
+  while (TC < t.ncols && TC < ncg) TC <<= 1;  // column groups one query needs
+  const int per = TR * TC;                     // threads per query
+  const int spar = ETHREADS / per;             // queries in flight
+  const int sub = threadIdx.x / per, cg2 = (threadIdx.x % per) / TR;
+  for (int s = sub; s < nslots; s += spar) {
     const QView v = make_view(net, b, g, q0 + slot0 + s, slot0 + s);
     double* o = out + (long long)(slot0 + s) * plan.per_query + tile_off;
-    if (uniform)
-      emit_mixed(net, b, g, t, mat, v, o, tr, cg, ncg, smem);
-    else
-      emit_general(net, b, g, t, mat, v, o, tr, cg, ncg);
+    emit_general(net, b, g, t, mat, v, o, tr, cg2, TC);
   }
 }
 
@@ -540,7 +553,9 @@ int launch_emit(const NetDev& net, const BatchDev& b, const GramDev& g, const Pl
                 int q0, int nq, double* out, cudaStream_t st, int which) {
   if (nq <= 0) return 0;
   static const int wgroup = [] { const char* e = getenv("NNSDP_WINDOW_GROUP"); int v = e ? atoi(e) : SLOT_GROUP; return v < 1 ? 1 : (v > SLOT_GROUP ? SLOT_GROUP : v); }();
-  static const int egroup = [] { const char* e = getenv("NNSDP_EDGE_GROUP"); int v = e ? atoi(e) : 1; return v < 1 ? 1 : (v > SLOT_GROUP ? SLOT_GROUP : v); }();
+  // queries per edge CTA: one when a pass holds few queries (wide nets, 8 ring slots), eight when it holds many
+  static const int egroup_env = [] { const char* e = getenv("NNSDP_EDGE_GROUP"); int v = e ? atoi(e) : 0; return v < 0 ? 0 : (v > SLOT_GROUP ? SLOT_GROUP : v); }();
+  const int egroup = egroup_env > 0 ? egroup_env : (nq >= 64 ? SLOT_GROUP : (nq >= 16 ? 2 : 1));
   int launches = 0;
   if (plan.n_fill > 0 && (which < 0 || which == 0)) {
     emit_fill_kernel<<<dim3(plan.n_fill, nq), ETHREADS, 0, st>>>(net, b, g, plan, q0, nq, out);

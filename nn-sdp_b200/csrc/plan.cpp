@@ -182,9 +182,11 @@ int32_t build_plan(const Shape& sh, int64_t beta, const std::vector<CliqueRanges
   for (auto& c : mats) max_n = std::max(max_n, c.size());
   int64_t min_hidden = sh.n[1];
   for (int b = 1; b <= K - 1; ++b) min_hidden = std::min(min_hidden, sh.n[b]);
-  plan->tile_rows = max_n >= 512 ? 128 : (max_n >= 48 ? 64 : 32);
-  plan->tile_cols = 32;
   const bool split_blocks = min_hidden >= 48;
+  // 128-row tiles whenever rows are cut at block boundaries (a block of 50..127 rows is then one row piece and
+  // the register-window programs apply); small nets get smaller tiles evaluated entry by entry
+  plan->tile_rows = (split_blocks || max_n >= 512) ? 128 : (max_n >= 48 ? 64 : 32);
+  plan->tile_cols = 32;
   int64_t out_off = 0;
   for (size_t ci = 0; ci < mats.size(); ++ci) {
     const CliqueRanges& c = mats[ci];
@@ -319,10 +321,12 @@ int32_t build_plan(const Shape& sh, int64_t beta, const std::vector<CliqueRanges
     });
     std::vector<TileDev> strips;
     static const int strip_rows = [] { const char* e = getenv("NNSDP_STRIP_ROWS"); int v = e ? atoi(e) : STRIP_ROWS; return v < 32 ? 32 : v; }();
-    static const int strip_cols = [] { const char* e = getenv("NNSDP_STRIP_COLS"); int v = e ? atoi(e) : STRIP_COLS; return v < 1 ? 1 : v; }();
+    static const int strip_cols_min = [] { const char* e = getenv("NNSDP_STRIP_COLS"); int v = e ? atoi(e) : STRIP_COLS; return v < 1 ? 1 : v; }();
     auto flush = [&](const TileDev& m) {
       const int nchunk = (m.nrows + strip_rows - 1) / strip_rows;
       const int h = (m.nrows + nchunk - 1) / nchunk;
+      // short strips are made wider so that a CTA still has ~32 KB to write (at most a tile's 32 columns)
+      const int strip_cols = std::max(strip_cols_min, std::min(32, 4096 / std::max(h, 1)));
       for (int c0 = 0; c0 < m.ncols; c0 += strip_cols)
         for (int r0 = 0; r0 < m.nrows; r0 += h) {
           TileDev u = m;

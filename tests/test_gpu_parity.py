@@ -740,3 +740,25 @@ def test_lambda_max_negative_definite_certificate(ctx):
     ev = np.linalg.eigvalsh(Z)
     assert ev[-1] < 0 and abs(lam[0] - ev[-1]) <= 1e-9 * abs(ev[0])
     b.close()
+
+
+def test_multi_device_context_shards_queries(ctx):
+    """One nnsdp_ctx over two devices: queries are split in contiguous ranges, one host thread per device, and
+    gathered into the caller's buffer (second form).  Needs >= 2 GPUs."""
+    import nnsdp_b200 as nb
+
+    if nb.device_count() < 2:
+        pytest.skip("needs two CUDA devices")
+    xdims, beta, nq = [2, 300, 270, 2], 2, 7
+    net = rand_net(xdims, seed=3, sigma=0.1)
+    rng = np.random.default_rng(5)
+    qs = [rand_query(net, beta, rng, kind="ellipsoid", radius=0.02 * i) for i in range(nq)]
+    batch = to_numeric_batch(nb, net, qs)
+    one = nb.assemble_blocks(nb.Net(ctx, net.xdims, net.Ms), beta, batch)
+    ctx2 = nb.Context([0, 1])
+    dnet2 = nb.Net(ctx2, net.xdims, net.Ms)
+    two = nb.assemble_blocks(dnet2, beta, batch)
+    assert np.array_equal(one, two)
+    r1 = nb.bounds_ibp(nb.Net(ctx, net.xdims, net.Ms), np.stack([q.x1min for q in qs]), np.stack([q.x1max for q in qs]))
+    r2 = nb.bounds_ibp(dnet2, np.stack([q.x1min for q in qs]), np.stack([q.x1max for q in qs]))
+    assert all(np.array_equal(r1[k], r2[k]) for k in r1)
