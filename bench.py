@@ -45,7 +45,7 @@ NCU_TRAFFIC = {  # bytes per launch (8-query pass), profiles/r1_emit_full.summar
 }
 
 
-def make_workload(name: str, rank: int, Q: int | None = None):
+def make_workload(name: str, rank: int, Q: int | None = None, radius_scale: float = 1.0):
     """Seeded synthetic inputs.  Returns (xdims, Ms, inputs)."""
     w = WORKLOADS[name]
     W, D, beta = w["W"], w["D"], w["beta"]
@@ -60,7 +60,7 @@ def make_workload(name: str, rank: int, Q: int | None = None):
     acdim = W * D
     lamdim = sum(range(acdim - beta, acdim + 1))
     centre = rq.uniform(0.5, 1.5, (Q, 2))
-    radius = rq.uniform(0.01, 0.5, (Q, 1))
+    radius = rq.uniform(0.01, 0.5, (Q, 1)) * radius_scale   # radius_scale << 1: stable ReLUs, Gram-heavy
     normal = np.array([1.0, 0.0])
     S = np.zeros((5, 5))
     S[2:4, 4] = normal
@@ -237,7 +237,7 @@ def run_ours(args):
     name = args.workload
     w = WORKLOADS[name]
     Q = args.queries or w["Q"]
-    xdims, Ms, beta, inp = make_workload(name, rank, Q=Q)
+    xdims, Ms, beta, inp = make_workload(name, rank, Q=Q, radius_scale=args.radius_scale)
     ctx = nb.Context([local])
     net = nb.Net(ctx, xdims, Ms)
     sz = net.sizes(beta)
@@ -394,6 +394,7 @@ def run_ours(args):
                        "dense_block_bytes_per_query": 8 * sz["sum_ck_sq"], "ring_slots": ring,
                        "l2": "outputs (ring) and inputs are far larger than the 126 MB L2",
                        "gram_contractions_per_step": ncon, "gram_active_rows_per_step": nact,
+                       "radius_scale": args.radius_scale,
                        "parallelism": f"queries sharded over {world} GPU(s), no collective"},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks,
             "gpu_launches": int(round(launches_per_step * args.steps)),
@@ -417,6 +418,8 @@ def main():
     ap.add_argument("--queries", type=int, default=None, help="override queries per GPU per step")
     ap.add_argument("--e2e-queries", type=int, default=8)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--radius-scale", type=float, default=1.0,
+                    help="scale of the input-box radii (default 1 = BASELINE config 5); small values make every ReLU stable (Gram-heavy)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":
