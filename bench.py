@@ -31,14 +31,14 @@ sys.path.insert(0, os.path.join(ROOT, "nn-sdp_b200"))
 
 WORKLOADS = {
     # name: (width, depth, beta, queries, ring slots)
-    "stress-W1000-D20-beta2-Q1024": dict(W=1000, D=20, beta=2, Q=1024, ring=8),
+    "stress-W1000-D20-beta2-Q1024": dict(W=1000, D=20, beta=2, Q=1024, ring=32),   # 32 slots = 42.6 GB of blocks in HBM
     "mid-W100-D50-beta2-Q1024": dict(W=100, D=50, beta=2, Q=1024, ring=256),
     "tiny-W10-D10-beta1-Q64": dict(W=10, D=10, beta=1, Q=64, ring=64),
 }
 DEFAULT_WORKLOAD = "stress-W1000-D20-beta2-Q1024"
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the `ncu --set full` capture of the same
 # command (profiles/): filled in when a capture exists for the current kernels, else null.
-NCU_TRAFFIC = {  # bytes per launch (8-query pass), profiles/r1_emit_full.summary.csv
+NCU_TRAFFIC = {  # DRAM bytes of one launch over 8 queries (scaled to the pass size), profiles/r1_emit_full.summary.csv
     "emit_fill_kernel": 8.272976e9 + 141.445632e6,     # algorithmic 8.17 GB
     "emit_window_kernel": 2.419744e9 + 342.088960e6,   # algorithmic 2.46 GB (+ the W tiles it reads)
     "emit_edge_kernel": 0.006930e9 + 11.059200e6,
@@ -241,7 +241,7 @@ def run_ours(args):
     ctx = nb.Context([local])
     net = nb.Net(ctx, xdims, Ms)
     sz = net.sizes(beta)
-    ring = min(w["ring"], Q)
+    ring = min(args.ring or w["ring"], Q)
     batch = nb.Batch(net, beta, Qcap=Q, ring=ring)
     nbatch = nb.NumericBatch(out_kind=nb.OUT_SAFETY, **inp)
     batch.set_inputs(nbatch, Q=Q)
@@ -311,7 +311,9 @@ def run_ours(args):
     pass_bytes = 8.0 * sz["sum_ck_sq"] * q_per_pass
     pass_gbs = pass_bytes / (emit_ms / passes * 1e-3) / 1e9
     roofline = {"bound": "hbm", "kernel": dom["kernel"], "achieved": dom["achieved"], "peak": peak, "unit": "GB/s",
-                "frac": dom["achieved"] / peak, "traffic": NCU_TRAFFIC.get(dom["kernel"]), "peak_source": peak_src,
+                "frac": dom["achieved"] / peak,
+                "traffic": (NCU_TRAFFIC[dom["kernel"]] * q_per_pass / 8.0) if dom["kernel"] in NCU_TRAFFIC and name == DEFAULT_WORKLOAD else None,
+                "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": dom["algorithmic_bytes_per_launch"], "avg_launch_ms": dom["avg_launch_ms"],
                 "share_of_step": dom["share_of_step"],
                 "emitter_pass": {"kernels": kernels, "algorithmic_bytes": pass_bytes, "ms": emit_ms / passes,
@@ -418,6 +420,7 @@ def main():
     ap.add_argument("--queries", type=int, default=None, help="override queries per GPU per step")
     ap.add_argument("--e2e-queries", type=int, default=8)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--ring", type=int, default=None, help="override the number of device-resident output slots")
     ap.add_argument("--radius-scale", type=float, default=1.0,
                     help="scale of the input-box radii (default 1 = BASELINE config 5); small values make every ReLU stable (Gram-heavy)")
     args = ap.parse_args()
