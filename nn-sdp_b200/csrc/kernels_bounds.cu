@@ -6,10 +6,11 @@
 //   one-step pre-activation IBP   src/Intervals/intervals_auto_lirpa.jl:55-62
 //   makeSectorMinMax (ReLU)       src/Qc/activ_sector.jl:63-72
 //
-// The IBP of one layer for Q boxes is a GEMM-shaped contraction
-//   ymin = W+ xmin + W- xmax + b,   ymax = W+ xmax + W- xmin + b
-// with M = n_{k+1}, N = Q, K = n_k; W+ = max(W,0), W- = min(W,0) are formed in registers
-// (the reference re-materialises both matrices on every call).
+// The IBP of one layer for Q boxes is a GEMM-shaped contraction.  The reference computes
+//   ymin = W+ xmin + W- xmax + b,   ymax = W+ xmax + W- xmin + b        (intervals_easy.jl:23-24)
+// with W+ = max(W,0), W- = min(W,0) re-materialised on every call; the same interval in centre / radius
+// form is  y = W c + b -/+ |W| r,  c = (xmin + xmax)/2, r = (xmax - xmin)/2 : two products instead of four
+// (|W| formed in registers), M = n_{k+1}, N = Q, K = n_k.  A degenerate box (r = 0) gives ymin == ymax.
 #include "internal.h"
 
 namespace nnsdp {
@@ -58,8 +59,13 @@ gemm_nn_kernel(const double* __restrict__ A, int lda, int M, int Kdim,
       const int k = idx % BK, n = idx / BK;
       const int gn = n0 + n, gk = k0 + k;
       const bool ok = (gn < N && gk < Kdim);
-      Bs0[k][n] = ok ? B0[(long long)gn * ldb + gk] : 0.0;
-      if (MODE == 0) Bs1[k][n] = ok ? B1[(long long)gn * ldb + gk] : 0.0;
+      if (MODE == 0) {  // centre and radius of the input box: y = W c -/+ |W| r + b
+        const double lo = ok ? B0[(long long)gn * ldb + gk] : 0.0, hi = ok ? B1[(long long)gn * ldb + gk] : 0.0;
+        Bs0[k][n] = 0.5 * (lo + hi);
+        Bs1[k][n] = 0.5 * (hi - lo);
+      } else {
+        Bs0[k][n] = ok ? B0[(long long)gn * ldb + gk] : 0.0;
+      }
     }
     __syncthreads();
 #pragma unroll
@@ -70,19 +76,17 @@ gemm_nn_kernel(const double* __restrict__ A, int lda, int M, int Kdim,
 #pragma unroll
       for (int j = 0; j < 4; ++j) b0[j] = Bs0[k][ty * 4 + j];
       if (MODE == 0) {
-        double b1[4], ap[4], an[4];
+        double b1[4], aa[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) b1[j] = Bs1[k][ty * 4 + j];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) ap[i] = fmax(a[i], 0.0), an[i] = fmin(a[i], 0.0);
+        for (int i = 0; i < 4; ++i) aa[i] = fabs(a[i]);
 #pragma unroll
         for (int i = 0; i < 4; ++i)
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
-            acc0[i][j] = fma(ap[i], b0[j], acc0[i][j]);
-            acc0[i][j] = fma(an[i], b1[j], acc0[i][j]);
-            acc1[i][j] = fma(ap[i], b1[j], acc1[i][j]);
-            acc1[i][j] = fma(an[i], b0[j], acc1[i][j]);
+            acc0[i][j] = fma(a[i], b0[j], acc0[i][j]);    // W c
+            acc1[i][j] = fma(aa[i], b1[j], acc1[i][j]);   // |W| r
           }
       } else {
 #pragma unroll
@@ -104,7 +108,8 @@ gemm_nn_kernel(const double* __restrict__ A, int lda, int M, int Kdim,
       if (gm >= M) continue;
       if (MODE == 0) {
         const double bb = bias[gm];
-        const double ymin = acc0[i][j] + bb, ymax = acc1[i][j] + bb;
+        const double mid = acc0[i][j] + bb;
+        const double ymin = mid - acc1[i][j], ymax = mid + acc1[i][j];
         if (!(ymin <= ymax) && flag_bad) atomicOr(flag_bad, 1);
         if (D0) {
           D0[(long long)gn * ldd + gm] = ymin;
