@@ -96,6 +96,16 @@ struct nnsdp_net {
   std::vector<int> ldT;
   std::vector<NetPerDev> per;
   int64_t max_block = 0;  // max_b n[b], b <= K-2 (Gram side)
+  // batches kept alive between one-shot calls (plan, buffers, streams): creating and destroying a batch
+  // costs milliseconds to a hundred milliseconds (cudaMalloc / cudaFree), more than the work of a small query
+  struct Cached {
+    int dev_index;
+    int64_t beta, Qcap, ring;
+    int dense;
+    nnsdp_batch* b;
+  };
+  mutable std::mutex cache_mu;
+  mutable std::vector<Cached> cache;
 };
 
 namespace {
@@ -502,8 +512,12 @@ int32_t nnsdp_net_upload(nnsdp_ctx* ctx, int64_t K, const int64_t* xdims, const 
   return NNSDP_OK;
 }
 
+int32_t nnsdp_batch_destroy(nnsdp_batch* b);
+
 int32_t nnsdp_net_destroy(nnsdp_net* net) {
   if (!net) return NNSDP_OK;
+  for (auto& c : net->cache) nnsdp_batch_destroy(c.b);
+  net->cache.clear();
   for (auto& pd : net->per) {
     cudaSetDevice(pd.dev);
     pd.release();
@@ -1298,9 +1312,50 @@ int32_t shard_queries(nnsdp_ctx* ctx, int64_t Q, F fn) {
   return NNSDP_OK;
 }
 
+// A batch for a one-shot call: taken from the network's cache when one with the same (device, beta, kind)
+// and enough capacity is idle, created otherwise; handed back on release if it is small enough to keep.
 struct BatchHolder {
   nnsdp_batch* b = nullptr;
-  ~BatchHolder() { nnsdp_batch_destroy(b); }
+  const nnsdp_net* net = nullptr;
+  nnsdp_net::Cached key{};
+  bool keep = false;
+  int32_t acquire(nnsdp_ctx* ctx, int d, const nnsdp_net* n, int64_t beta, int64_t Q, int64_t ring, int dense) {
+    net = n;
+    key = {d, beta, Q, ring, dense, nullptr};
+    {
+      std::lock_guard<std::mutex> l(n->cache_mu);
+      for (size_t i = 0; i < n->cache.size(); ++i) {
+        const auto& c = n->cache[i];
+        if (c.dev_index == d && c.beta == beta && c.dense == dense && c.Qcap >= Q && c.ring >= std::min(ring, Q) &&
+            (ring > 0) == (c.ring > 0)) {
+          b = c.b;
+          key = c;
+          n->cache.erase(n->cache.begin() + i);
+          keep = true;
+          return NNSDP_OK;
+        }
+      }
+    }
+    NN_TRY(nnsdp_batch_create(ctx, d, n, beta, Q, ring, dense, &b));
+    key.b = b;
+    // keep only batches whose device footprint is modest (the ring of a wide net is gigabytes)
+    keep = (b->plan.per_query_doubles * std::max<int64_t>(b->ring, 1) + (int64_t)n->sh.Zdim * Q * 16) * 8 <= (int64_t(512) << 20);
+    return NNSDP_OK;
+  }
+  ~BatchHolder() {
+    if (!b) return;
+    if (keep) {
+      std::lock_guard<std::mutex> l(net->cache_mu);
+      if (net->cache.size() >= 6) {  // drop the oldest
+        nnsdp_batch_destroy(net->cache.front().b);
+        net->cache.erase(net->cache.begin());
+      }
+      key.b = b;
+      net->cache.push_back(key);
+    } else {
+      nnsdp_batch_destroy(b);
+    }
+  }
 };
 
 const double* col(const double* p, int64_t stride, int64_t q0) { return p ? p + stride * q0 : p; }
@@ -1335,7 +1390,7 @@ int32_t assemble_impl(nnsdp_ctx* ctx, const nnsdp_net* net, int64_t beta, int64_
     int64_t ring = std::max<int64_t>(2, (int64_t)((4ll << 30) / (per * 8)));
     ring = std::min<int64_t>(std::min<int64_t>(ring, nq), 4096);
     BatchHolder h;
-    NN_TRY(nnsdp_batch_create(ctx, d, net, beta, nq, ring, dense, &h.b));
+    NN_TRY(h.acquire(ctx, d, net, beta, nq, ring, dense));
     nnsdp_query_inputs sub = shift_inputs(*in, q0);
     NN_TRY(nnsdp_batch_set_inputs(h.b, nq, &sub));
     return nnsdp_batch_run(h.b, out + q0 * per);
@@ -1354,7 +1409,7 @@ int32_t nnsdp_bounds_ibp(nnsdp_ctx* ctx, const nnsdp_net* net, int64_t Q, const 
   const Shape& sh = net->sh;
   return shard_queries(ctx, Q, [&](int d, int64_t q0, int64_t nq) -> int32_t {
     BatchHolder h;
-    NN_TRY(nnsdp_batch_create(ctx, d, net, 0, nq, 0, 0, &h.b));
+    NN_TRY(h.acquire(ctx, d, net, 0, nq, 0, 0));
     nnsdp_query_inputs in;
     memset(&in, 0, sizeof(in));
     in.x1min = x1min + q0 * sh.n_in();
@@ -1376,7 +1431,7 @@ int32_t nnsdp_preact_from_x(nnsdp_ctx* ctx, const nnsdp_net* net, int64_t Q, con
   const Shape& sh = net->sh;
   return shard_queries(ctx, Q, [&](int d, int64_t q0, int64_t nq) -> int32_t {
     BatchHolder h;
-    NN_TRY(nnsdp_batch_create(ctx, d, net, 0, nq, 0, 0, &h.b));
+    NN_TRY(h.acquire(ctx, d, net, 0, nq, 0, 0));
     nnsdp_batch* b = h.b;
     NN_CUDA(cudaSetDevice(b->dev));
     const NetPerDev& nd = *b->nd;
