@@ -155,6 +155,16 @@ int32_t nnsdp_plan_tiles(int64_t K, const int64_t* xdims, int64_t beta, int32_t 
 int32_t nnsdp_bounds_ibp(nnsdp_ctx* ctx, const nnsdp_net* net, int64_t Q, const double* x1min,
                          const double* x1max, double* xmin, double* xmax, double* acxmin,
                          double* acxmax);
+/* CROWN bounds, the reference's DEFAULT interval method: makeIntervalsInfo(x1min, x1max, ffnet,
+ * IntervalsAutoLirpa()) -> intervalsAutoLirpaSliced (src/Intervals/Intervals.jl:38,44-45;
+ * src/Intervals/intervals_auto_lirpa.jl:44-63; exts/auto_lirpa_bridge.py:97-112 -> vendored auto_LiRPA,
+ * compute_bounds(method="CROWN"), float32, one ONNX file + Python call per layer).  Same layout as
+ * nnsdp_bounds_ibp: xmin/xmax are the x_intvs of the sliced method (x_{k+1} bounded as the output of the
+ * k-layer prefix followed by an identity layer, then lb = min(lb, ub), ub = max(lb, ub)); acxmin/acxmax the
+ * one-step IBP of intervals_auto_lirpa.jl:55-62.  FP64 on the device; the reference's values carry float32
+ * precision.  Fails with NNSDP_ERR_ASSERT where the reference asserts ykmin <= ykmax (:60). */
+int32_t nnsdp_bounds_crown(nnsdp_ctx* ctx, const nnsdp_net* net, int64_t Q, const double* x1min,
+                           const double* x1max, double* xmin, double* xmax, double* acxmin, double* acxmax);
 /* One-step pre-activation IBP from given x_intvs
  * (src/Intervals/intervals_auto_lirpa.jl:55-62): reads xmin/xmax (xtot x Q), writes
  * acxmin/acxmax (acdim x Q).  Fails with NNSDP_ERR_ASSERT if some ymin > ymax (:60). */
@@ -187,6 +197,12 @@ int32_t nnsdp_batch_destroy(nnsdp_batch* batch);
 int32_t nnsdp_batch_set_inputs(nnsdp_batch* batch, int64_t Q, const nnsdp_query_inputs* in);
 /* K1 + K2: IBP from the boxes and sector slopes, all on the device. */
 int32_t nnsdp_batch_bounds(nnsdp_batch* batch);
+/* The same with CROWN bounds (see nnsdp_bounds_crown), and the choice nnsdp_batch_run makes when the batch
+ * carries no caller-supplied bounds (default NNSDP_BOUNDS_IBP). */
+#define NNSDP_BOUNDS_IBP 0
+#define NNSDP_BOUNDS_CROWN 1
+int32_t nnsdp_batch_bounds_crown(nnsdp_batch* batch);
+int32_t nnsdp_batch_set_bounds_method(nnsdp_batch* batch, int32_t method);
 /* QC diagonals, band multipliers, affine column (all queries of the batch). */
 int32_t nnsdp_batch_prepare(nnsdp_batch* batch);
 /* Gram contractions + block emission of queries [q0, q0+nq) into ring slots

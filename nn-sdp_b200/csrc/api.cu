@@ -229,6 +229,7 @@ struct nnsdp_batch {
   GramDev gd{};
   PlanDev pd{};
   bool have_inputs = false, bounds_supplied = false, bounds_done = false, prepared = false;
+  int bounds_method = 0;  // 0 = IBP (intervalsWorstCase), 1 = CROWN (the reference's default, IntervalsAutoLirpa)
   cudaStream_t st = nullptr, st_copy = nullptr;
   cudaEvent_t ev_start = nullptr, ev_stop = nullptr;
   cudaEvent_t ev_done[2] = {nullptr, nullptr}, ev_free[2] = {nullptr, nullptr};
@@ -1089,12 +1090,14 @@ static int32_t gather_chunk(nnsdp_batch* b, int ci, int64_t q0, int64_t nq, int 
   return NNSDP_OK;
 }
 
+extern "C" int32_t nnsdp_batch_bounds_crown(nnsdp_batch* b);
+
 int32_t nnsdp_batch_run_ex(nnsdp_batch* b, double* host_out, int32_t flags) {
   NN_CHECK(b != nullptr, NNSDP_ERR_ARG, "batch is NULL");
   NN_CHECK(b->have_inputs, NNSDP_ERR_STATE, "nnsdp_batch_run before nnsdp_batch_set_inputs");
   NN_CHECK(b->ring > 0, NNSDP_ERR_STATE, "batch was created without an output ring");
   NN_CUDA(cudaSetDevice(b->dev));
-  if (!b->bounds_supplied) NN_TRY(nnsdp_batch_bounds(b));
+  if (!b->bounds_supplied) NN_TRY(b->bounds_method == 1 ? nnsdp_batch_bounds_crown(b) : nnsdp_batch_bounds(b));
   NN_TRY(nnsdp_batch_prepare(b));
   const NetPerDev& nd = *b->nd;
   const int64_t per = b->plan.per_query_doubles;
@@ -1491,6 +1494,138 @@ int32_t nnsdp_assemble_dense(nnsdp_ctx* ctx, const nnsdp_net* net, int64_t beta,
 }  // extern "C"
 
 // -----------------------------------------------------------------------------------------
+// CROWN bounds, see kernels_crown.cu
+// -----------------------------------------------------------------------------------------
+namespace {
+
+// x_intvs of intervalsAutoLirpaSliced (post-activation bounds through the relaxation of relu_k, min/max
+// post-processed) into b->xmin / b->xmax, then acx_intvs by one IBP step and the sector slopes.
+int32_t crown_bounds_device(nnsdp_batch* b) {
+  NN_CUDA(cudaSetDevice(b->dev));
+  const Shape& sh = b->net->sh;
+  const NetPerDev& npd = *b->nd;
+  const int K = sh.K, n0 = (int)sh.n_in();
+  const int64_t P = sh.xtot - n0;  // stacked pre-activations y_0 .. y_{K-1}
+  int64_t maxn = 0;
+  for (int k = 0; k <= K; ++k) maxn = std::max(maxn, sh.n[k]);
+  const int64_t ld = maxn;
+  // queries per chunk: two row buffers of 2 * Qc * maxn * ld doubles, kept under ~1.5 GiB together
+  int Qc = (int)std::max<int64_t>(1, std::min<int64_t>(b->Q, (int64_t(3) << 26) / std::max<int64_t>(1, 4 * maxn * ld)));
+  Qc = std::min(Qc, 256);
+  DevBuf rowsA, rowsB, bias, prel, preu, du, bu, dl;
+  struct Rel {
+    std::vector<DevBuf*> v;
+    ~Rel() { for (DevBuf* x : v) x->release(); }
+  } rel{{&rowsA, &rowsB, &bias, &prel, &preu, &du, &bu, &dl}};
+  NN_TRY(rowsA.ensure((size_t)2 * Qc * maxn * ld * 8));
+  NN_TRY(rowsB.ensure((size_t)2 * Qc * maxn * ld * 8));
+  NN_TRY(bias.ensure((size_t)2 * Qc * maxn * 8));
+  for (DevBuf* x : {&prel, &preu, &du, &bu, &dl}) NN_TRY(x->ensure((size_t)Qc * P * 8));
+  cudaStream_t st = b->st;
+  double* xmin = b->xmin.as<double>();
+  double* xmax = b->xmax.as<double>();
+  auto poff = [&](int k) { return sh.xoff[k + 1] - n0; };  // offset of y_k inside the stacked pre-activations
+  auto bias_of = [&](int k) { return npd.M[k].as<double>() + (size_t)sh.n[k] * sh.n[k + 1]; };
+  b->span_begin(ST_BOUNDS, st);
+  int launches = 0;
+  launches += launch_place_x1(b->bd.x1min, b->bd.s_x1min, b->bd.x1max, b->bd.s_x1max, xmin, xmax, sh.xtot, n0,
+                              (int)b->Q, st);
+  for (int64_t q0 = 0; q0 < b->Q; q0 += Qc) {
+    const int nq = (int)std::min<int64_t>(Qc, b->Q - q0);
+    // pushes the current rows (in `cur`, nrows x n[k+1], functions of x_{k+1}) back through relu_k, W_k, ...,
+    // relu_0, W_0 and concretises on the input box
+    auto chain = [&](const double* srcL, const double* srcU, long long src_row_stride, long long src_q_stride,
+                     int k_first, int nrows, double* out_lo, double* out_hi, long long out_stride, int post) {
+      double* cur = rowsA.as<double>();
+      double* nxt = rowsB.as<double>();
+      for (int k = k_first; k >= 0; --k) {
+        const int n = (int)sh.n[k + 1];
+        launches += launch_crown_row(srcL, srcU, src_row_stride, src_q_stride, cur, ld, nrows, nq, n,
+                                     du.as<double>() + poff(k), bu.as<double>() + poff(k), dl.as<double>() + poff(k),
+                                     P, bias_of(k), bias.as<double>(), st);
+        cudaMemsetAsync(nxt, 0, (size_t)2 * nq * nrows * ld * 8, st);
+        launches += gemm_acc_launch(npd.Wt[k].as<double>(), b->net->ldT[k], (int)sh.n[k], n, cur, ld, nxt, ld,
+                                    2 * nq * nrows, st);
+        srcL = nxt;
+        srcU = nxt + (size_t)nq * nrows * ld;
+        src_row_stride = ld;
+        src_q_stride = (long long)nrows * ld;
+        std::swap(cur, nxt);
+      }
+      launches += launch_crown_concretize(srcL, srcU, src_row_stride, src_q_stride, nrows, nq, n0, b->bd.x1min,
+                                          b->bd.s_x1min, b->bd.x1max, b->bd.s_x1max, (int)q0, bias.as<double>(),
+                                          out_lo, out_hi, out_stride, post, st);
+    };
+    // y_0 by interval arithmetic (exact for the first layer; auto_LiRPA bound_general.py:1257-1262)
+    launches += ibp_layer_launch(npd.M[0].as<double>(), (int)sh.n[1], n0, xmin + q0 * sh.xtot, xmax + q0 * sh.xtot,
+                                 sh.xtot, nullptr, nullptr, prel.as<double>(), preu.as<double>(), P, nq, 0, 0, nullptr,
+                                 st);
+    launches += launch_crown_params(prel.as<double>(), preu.as<double>(), P, (int)sh.n[1], nq, du.as<double>(),
+                                    bu.as<double>(), dl.as<double>(), st);
+    // y_t, t = 1 .. K-1: backward from A = W_t
+    for (int t = 1; t <= K - 1; ++t) {
+      const int nrows = (int)sh.n[t + 1];
+      launches += launch_crown_init_bias(bias_of(t), nrows, nq, bias.as<double>(), st);
+      const double* wrows = npd.Wt[t].as<double>();  // row r of W_t = column r of Wt_t
+      chain(wrows, wrows, b->net->ldT[t], 0, t - 1, nrows, prel.as<double>() + poff(t), preu.as<double>() + poff(t),
+            P, 0);
+      if (t <= K - 2)
+        launches += launch_crown_params(prel.as<double>() + poff(t), preu.as<double>() + poff(t), P, nrows, nq,
+                                        du.as<double>() + poff(t), bu.as<double>() + poff(t),
+                                        dl.as<double>() + poff(t), st);
+    }
+    // x_{k+1} = relu(y_k), k = 0 .. K-2: the output of the (k+1)-layer prefix followed by an identity layer
+    for (int k = 0; k <= K - 2; ++k) {
+      const int nrows = (int)sh.n[k + 1];
+      double* src = rowsB.as<double>();  // chain() writes its first step into rowsA
+      launches += launch_crown_init_post(npd.Wt[k].as<double>(), b->net->ldT[k], (int)sh.n[k], bias_of(k),
+                                         du.as<double>() + poff(k), bu.as<double>() + poff(k),
+                                         dl.as<double>() + poff(k), P, src, ld, nrows, nq, bias.as<double>(), st);
+      // rows are now functions of x_k: continue with relu_{k-1}, W_{k-1}, ... (k = 0: concretise at once)
+      chain(src, src + (size_t)nq * nrows * ld, ld, (long long)nrows * ld, k - 1, nrows,
+            xmin + q0 * sh.xtot + sh.xoff[k + 1], xmax + q0 * sh.xtot + sh.xoff[k + 1], sh.xtot, 1);
+    }
+    // x_K = y_{K-1} with the same post-processing: copy through a concretisation-free path
+    {
+      const int nrows = (int)sh.n[K];
+      // rows = identity is not needed: min/max of the already computed bounds
+      launches += launch_crown_init_bias(nullptr, nrows, nq, bias.as<double>(), st);
+      // reuse the concretize kernel with zero-length rows: L = lbias, U = ubias -- so load the bounds as biases
+      cudaMemcpy2DAsync(bias.as<double>(), (size_t)nrows * 8, prel.as<double>() + poff(K - 1), (size_t)P * 8,
+                        (size_t)nrows * 8, nq, cudaMemcpyDeviceToDevice, st);
+      cudaMemcpy2DAsync(bias.as<double>() + (size_t)nq * nrows, (size_t)nrows * 8, preu.as<double>() + poff(K - 1),
+                        (size_t)P * 8, (size_t)nrows * 8, nq, cudaMemcpyDeviceToDevice, st);
+      launches += launch_crown_concretize(rowsA.as<double>(), rowsA.as<double>(), ld, 0, nrows, nq, 0, b->bd.x1min,
+                                          b->bd.s_x1min, b->bd.x1max, b->bd.s_x1max, (int)q0, bias.as<double>(),
+                                          xmin + q0 * sh.xtot + sh.xoff[K], xmax + q0 * sh.xtot + sh.xoff[K], sh.xtot,
+                                          1, st);
+    }
+  }
+  // acx_intvs: one IBP step from x_intvs (intervals_auto_lirpa.jl:55-62), then makeSectorMinMax
+  for (int k = 0; k <= K - 2; ++k)
+    launches += ibp_layer_launch(npd.M[k].as<double>(), (int)sh.n[k + 1], (int)sh.n[k], xmin + sh.xoff[k],
+                                 xmax + sh.xoff[k], sh.xtot, nullptr, nullptr, b->acxmin.as<double>() + sh.noff(k + 1),
+                                 b->acxmax.as<double>() + sh.noff(k + 1), sh.acdim, (int)b->Q, 0, 0,
+                                 b->flags.as<int>() + 1, st);
+  launches += launch_sector_minmax(sh.acdim * (long long)b->Q, b->acxmin.as<double>(), b->acxmax.as<double>(),
+                                   b->smin_c.as<double>(), b->smax_c.as<double>(), st);
+  b->span_end(st, launches);
+  NN_CUDA(cudaGetLastError());
+  NN_CUDA(cudaStreamSynchronize(st));  // the temporary buffers are released on return
+  b->bounds_done = true;
+  return NNSDP_OK;
+}
+
+}  // namespace
+
+extern "C" int32_t nnsdp_batch_bounds_crown(nnsdp_batch* b) {
+  NN_CHECK(b != nullptr, NNSDP_ERR_ARG, "batch is NULL");
+  NN_CHECK(b->have_inputs, NNSDP_ERR_STATE, "nnsdp_batch_bounds_crown before nnsdp_batch_set_inputs");
+  NN_TRY(crown_bounds_device(b));
+  return check_flags(b, "nnsdp_batch_bounds_crown");
+}
+
+// -----------------------------------------------------------------------------------------
 // lambda_max of Z(gamma), matrix-free
 // -----------------------------------------------------------------------------------------
 namespace {
@@ -1762,6 +1897,38 @@ int32_t nnsdp_affine_get(nnsdp_affine* h, int64_t* ent_row, int64_t* ent_col, do
   if (coo_var)
     for (int64_t i = 0; i < nnz; ++i) coo_var[i] += 1;
   return NNSDP_OK;
+}
+
+}  // extern "C"
+
+extern "C" {
+
+int32_t nnsdp_batch_set_bounds_method(nnsdp_batch* b, int32_t method) {
+  NN_CHECK(b != nullptr, NNSDP_ERR_ARG, "batch is NULL");
+  NN_CHECK(method == NNSDP_BOUNDS_IBP || method == NNSDP_BOUNDS_CROWN, NNSDP_ERR_ARG, "unrecognized method: %d", method);
+  b->bounds_method = method;
+  return NNSDP_OK;
+}
+
+int32_t nnsdp_bounds_crown(nnsdp_ctx* ctx, const nnsdp_net* net, int64_t Q, const double* x1min,
+                           const double* x1max, double* xmin, double* xmax, double* acxmin, double* acxmax) {
+  NN_CHECK(ctx && net && x1min && x1max, NNSDP_ERR_ARG, "NULL argument");
+  NN_CHECK(Q >= 1, NNSDP_ERR_ARG, "Q must be >= 1");
+  const Shape& sh = net->sh;
+  return shard_queries(ctx, Q, [&](int d, int64_t q0, int64_t nq) -> int32_t {
+    BatchHolder h;
+    NN_TRY(h.acquire(ctx, d, net, 0, nq, 0, 0));
+    nnsdp_query_inputs in;
+    memset(&in, 0, sizeof(in));
+    in.x1min = x1min + q0 * sh.n_in();
+    in.x1max = x1max + q0 * sh.n_in();
+    in.x1min_stride = in.x1max_stride = sh.n_in();
+    NN_TRY(nnsdp_batch_set_inputs(h.b, nq, &in));
+    NN_TRY(nnsdp_batch_bounds_crown(h.b));
+    return nnsdp_batch_get_bounds(h.b, xmin ? xmin + q0 * sh.xtot : nullptr, xmax ? xmax + q0 * sh.xtot : nullptr,
+                                  acxmin ? acxmin + q0 * sh.acdim : nullptr,
+                                  acxmax ? acxmax + q0 * sh.acdim : nullptr, nullptr, nullptr);
+  });
 }
 
 }  // extern "C"

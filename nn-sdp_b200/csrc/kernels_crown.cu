@@ -1,0 +1,200 @@
+// CROWN bounds for ReLU MLPs on the device: the reference's DEFAULT interval method
+//   makeIntervalsInfo(..., IntervalsAutoLirpa())             src/Intervals/Intervals.jl:38,44-45
+//   intervalsAutoLirpaSliced                                 src/Intervals/intervals_auto_lirpa.jl:44-63
+//   exts/auto_lirpa_bridge.py:97-112 -> auto_LiRPA compute_bounds(method="CROWN")  (vendored, float32)
+// which costs K Julia->Python round trips through temporary ONNX files.  Algorithm (backward linear
+// relaxation, see oracle/nnsdp_oracle.py "CROWN bounds" for the citations into the vendored auto_LiRPA):
+// a target (the pre-activation y_t, or the post-activation x_{k+1} of a prefix) is kept as two affine
+// functions  lA x + lb <= target <= uA x + ub  of an earlier activation vector and pushed back layer by layer
+//   through relu_k :  uA <- uA+ d_u + uA- d_l,  ub += uA+ . b_u ;   lA <- lA+ d_l + lA- d_u,  lb += lA- . b_u
+//   through W_k, b_k:  b += A b_k ;  A <- A W_k                          (one FP64 GEMM for the whole batch)
+// down to the input box, where  lower = lA c - |lA| r + lb,  upper = uA c + |uA| r + ub.
+// FP64 throughout (the reference's values carry float32 precision).  Rows of lA / uA of all queries of a chunk
+// are stacked, so the linear step is one GEMM against the shared W_k'.
+#include <algorithm>
+
+#include "internal.h"
+
+namespace nnsdp {
+
+namespace {
+
+constexpr int CR_THREADS = 128;
+
+__device__ __forceinline__ double cr_block_sum(double v, double* sh) {
+  sh[threadIdx.x] = v;
+  __syncthreads();
+  for (int s = CR_THREADS / 2; s > 0; s >>= 1) {
+    if (threadIdx.x < s) sh[threadIdx.x] += sh[threadIdx.x + s];
+    __syncthreads();
+  }
+  const double r = sh[0];
+  __syncthreads();
+  return r;
+}
+
+// ReLU relaxation of one layer from its pre-activation bounds (auto_LiRPA operators/activation.py:306-323,387-388)
+__global__ void crown_params_kernel(const double* __restrict__ l, const double* __restrict__ u, long long stride,
+                                    int n, double* __restrict__ d_u, double* __restrict__ b_u,
+                                    double* __restrict__ d_l) {
+  const int q = blockIdx.y;
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= n) return;
+  const long long o = (long long)q * stride + c;
+  const double lb_r = fmin(l[o], 0.0);
+  double ub_r = fmax(u[o], 0.0);
+  ub_r = fmax(ub_r, lb_r + 1e-8);
+  const double ud = ub_r / (ub_r - lb_r);
+  d_u[o] = ud;
+  b_u[o] = -lb_r * ud;
+  d_l[o] = ud > 0.5 ? 1.0 : 0.0;
+}
+
+// One chain step for one row of one query: relaxation through relu_k (params of y_k) and the bias part of
+// the linear layer k.  src rows may be shared by all queries (q_stride_src = 0: the target's own W rows).
+//   rows: [2][Qc][nrows][ld]  (0 = lower, 1 = upper);  bias: [2][Qc][nrows]
+__global__ void __launch_bounds__(CR_THREADS)
+crown_row_kernel(const double* __restrict__ srcL, const double* __restrict__ srcU, long long src_row_stride,
+                 long long src_q_stride, double* __restrict__ dst, long long dst_row_stride, int nrows, int Qc,
+                 int n, const double* __restrict__ d_u, const double* __restrict__ b_u,
+                 const double* __restrict__ d_l, long long par_stride, const double* __restrict__ bias_k,
+                 double* __restrict__ bias) {
+  __shared__ double red[CR_THREADS];
+  const int r = blockIdx.x, q = blockIdx.y;
+  const double* sl = srcL + (long long)q * src_q_stride + (long long)r * src_row_stride;
+  const double* su = srcU + (long long)q * src_q_stride + (long long)r * src_row_stride;
+  double* dl = dst + ((long long)q * nrows + r) * dst_row_stride;
+  double* du = dst + ((long long)(Qc + q) * nrows + r) * dst_row_stride;
+  const double* pu = d_u + (long long)q * par_stride;
+  const double* pb = b_u + (long long)q * par_stride;
+  const double* pl = d_l + (long long)q * par_stride;
+  double accl = 0.0, accu = 0.0;
+  for (int c = threadIdx.x; c < n; c += CR_THREADS) {
+    double al = sl[c], au = su[c];
+    if (au > 0.0) {
+      accu = fma(au, pb[c], accu);
+      au *= pu[c];
+    } else {
+      au *= pl[c];
+    }
+    if (al < 0.0) {
+      accl = fma(al, pb[c], accl);
+      al *= pu[c];
+    } else {
+      al *= pl[c];
+    }
+    accl = fma(al, bias_k[c], accl);
+    accu = fma(au, bias_k[c], accu);
+    dl[c] = al;
+    du[c] = au;
+  }
+  const double tl = cr_block_sum(accl, red), tu = cr_block_sum(accu, red);
+  if (threadIdx.x == 0) {
+    bias[(long long)q * nrows + r] += tl;
+    bias[((long long)Qc + q) * nrows + r] += tu;
+  }
+}
+
+// bias[.][q][r] = b_t[r]  (start of a pre-activation target)
+__global__ void crown_init_bias_kernel(const double* __restrict__ bt, int nrows, int Qc, double* __restrict__ bias) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= 2 * Qc * nrows) return;
+  bias[i] = bt ? bt[i % nrows] : 0.0;
+}
+
+// start of a post-activation target x_{k+1} = relu(y_k): A = I through relu_k and W_k at once:
+//   uA row r = d_u[r] W_k[r, :], ub[r] = b_u[r] + d_u[r] b_k[r];   lA row r = d_l[r] W_k[r, :], lb[r] = d_l[r] b_k[r]
+__global__ void __launch_bounds__(CR_THREADS)
+crown_init_post_kernel(const double* __restrict__ Wt, int ldT, int n_in_k, const double* __restrict__ bias_k,
+                       const double* __restrict__ d_u, const double* __restrict__ b_u,
+                       const double* __restrict__ d_l, long long par_stride, double* __restrict__ dst,
+                       long long dst_row_stride, int nrows, int Qc, double* __restrict__ bias) {
+  const int r = blockIdx.x, q = blockIdx.y;
+  const double du = d_u[(long long)q * par_stride + r], dl = d_l[(long long)q * par_stride + r];
+  const double* w = Wt + (long long)r * ldT;  // row r of W_k
+  double* ol = dst + ((long long)q * nrows + r) * dst_row_stride;
+  double* ou = dst + ((long long)(Qc + q) * nrows + r) * dst_row_stride;
+  for (int c = threadIdx.x; c < n_in_k; c += CR_THREADS) {
+    ol[c] = dl * w[c];
+    ou[c] = du * w[c];
+  }
+  if (threadIdx.x == 0) {
+    bias[(long long)q * nrows + r] = dl * bias_k[r];
+    bias[((long long)Qc + q) * nrows + r] = b_u[(long long)q * par_stride + r] + du * bias_k[r];
+  }
+}
+
+// concretisation on the input box; optional min/max post-processing of intervals_auto_lirpa.jl:37-39
+__global__ void __launch_bounds__(CR_THREADS)
+crown_concretize_kernel(const double* __restrict__ rowsL, const double* __restrict__ rowsU, long long row_stride,
+                        long long q_stride, int nrows, int Qc, int n0, const double* __restrict__ x1min,
+                        long long s_min, const double* __restrict__ x1max, long long s_max, int q_first,
+                        const double* __restrict__ bias, double* __restrict__ out_lo, double* __restrict__ out_hi,
+                        long long out_stride, int postprocess) {
+  __shared__ double red[CR_THREADS];
+  const int r = blockIdx.x, q = blockIdx.y;
+  const double* al = rowsL + (long long)q * q_stride + (long long)r * row_stride;
+  const double* au = rowsU + (long long)q * q_stride + (long long)r * row_stride;
+  const double* lo = x1min + (long long)(q_first + q) * s_min;
+  const double* hi = x1max + (long long)(q_first + q) * s_max;
+  double sl = 0.0, su = 0.0;
+  for (int c = threadIdx.x; c < n0; c += CR_THREADS) {
+    const double cc = 0.5 * (lo[c] + hi[c]), rr = 0.5 * (hi[c] - lo[c]);
+    sl += al[c] * cc - fabs(al[c]) * rr;
+    su += au[c] * cc + fabs(au[c]) * rr;
+  }
+  const double tl = cr_block_sum(sl, red), tu = cr_block_sum(su, red);
+  if (threadIdx.x == 0) {
+    double L = tl + bias[(long long)q * nrows + r], U = tu + bias[((long long)Qc + q) * nrows + r];
+    if (postprocess) {
+      L = fmin(L, U);
+      U = fmax(L, U);
+    }
+    out_lo[(long long)q * out_stride + r] = L;
+    out_hi[(long long)q * out_stride + r] = U;
+  }
+}
+
+}  // namespace
+
+int launch_crown_params(const double* l, const double* u, long long stride, int n, int Qc, double* d_u,
+                        double* b_u, double* d_l, cudaStream_t st) {
+  crown_params_kernel<<<dim3((n + 127) / 128, Qc), 128, 0, st>>>(l, u, stride, n, d_u, b_u, d_l);
+  return 1;
+}
+
+int launch_crown_row(const double* srcL, const double* srcU, long long src_row_stride, long long src_q_stride,
+                     double* dst, long long dst_row_stride, int nrows, int Qc, int n, const double* d_u,
+                     const double* b_u, const double* d_l, long long par_stride, const double* bias_k,
+                     double* bias, cudaStream_t st) {
+  crown_row_kernel<<<dim3(nrows, Qc), CR_THREADS, 0, st>>>(srcL, srcU, src_row_stride, src_q_stride, dst,
+                                                          dst_row_stride, nrows, Qc, n, d_u, b_u, d_l, par_stride,
+                                                          bias_k, bias);
+  return 1;
+}
+
+int launch_crown_init_bias(const double* bt, int nrows, int Qc, double* bias, cudaStream_t st) {
+  const int n = 2 * Qc * nrows;
+  crown_init_bias_kernel<<<(n + 255) / 256, 256, 0, st>>>(bt, nrows, Qc, bias);
+  return 1;
+}
+
+int launch_crown_init_post(const double* Wt, int ldT, int n_in_k, const double* bias_k, const double* d_u,
+                           const double* b_u, const double* d_l, long long par_stride, double* dst,
+                           long long dst_row_stride, int nrows, int Qc, double* bias, cudaStream_t st) {
+  crown_init_post_kernel<<<dim3(nrows, Qc), CR_THREADS, 0, st>>>(Wt, ldT, n_in_k, bias_k, d_u, b_u, d_l, par_stride,
+                                                                dst, dst_row_stride, nrows, Qc, bias);
+  return 1;
+}
+
+int launch_crown_concretize(const double* rowsL, const double* rowsU, long long row_stride, long long q_stride,
+                            int nrows, int Qc, int n0, const double* x1min, long long s_min, const double* x1max,
+                            long long s_max, int q_first, const double* bias, double* out_lo, double* out_hi,
+                            long long out_stride, int postprocess, cudaStream_t st) {
+  crown_concretize_kernel<<<dim3(nrows, Qc), CR_THREADS, 0, st>>>(rowsL, rowsU, row_stride, q_stride, nrows, Qc, n0,
+                                                                 x1min, s_min, x1max, s_max, q_first, bias, out_lo,
+                                                                 out_hi, out_stride, postprocess);
+  return 1;
+}
+
+}  // namespace nnsdp

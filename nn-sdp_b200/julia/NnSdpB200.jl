@@ -109,6 +109,27 @@ function Intervals.makeIntervalsInfo(x1min::VecReal, x1max::VecReal, ffnet::Feed
   return IntervalsInfo(ffnet=ffnet, x_intvs=x_intvs, acx_intvs=acx_intvs)
 end
 
+# CROWN bounds: the reference's default method (IntervalsAutoLirpa -> intervalsAutoLirpaSliced,
+# src/Intervals/intervals_auto_lirpa.jl:44-63) without the K ONNX / Python round trips, FP64 on the device.
+struct IntervalsCrownB200 <: IntervalsMethod
+  net::DeviceNet
+end
+
+function Intervals.makeIntervalsInfo(x1min::VecReal, x1max::VecReal, ffnet::FeedFwdNet, method::IntervalsCrownB200)
+  sz = sizes(method.net, 0)
+  lo, hi = Vector{Float64}(x1min), Vector{Float64}(x1max)
+  xmin, xmax = zeros(sz.xtot), zeros(sz.xtot)
+  amin, amax = zeros(sz.acdim), zeros(sz.acdim)
+  check(ccall((:nnsdp_bounds_crown, LIB), Int32,
+              (Ptr{Cvoid}, Ptr{Cvoid}, Int64, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}),
+              method.net.ctx.h, method.net.h, 1, lo, hi, xmin, xmax, amin, amax))
+  xoff = cumsum([0; ffnet.xdims])
+  aoff = cumsum([0; ffnet.xdims[2:end-1]])
+  x_intvs = [(xmin[xoff[k]+1:xoff[k+1]], xmax[xoff[k]+1:xoff[k+1]]) for k in 1:(ffnet.K+1)]
+  acx_intvs = [(amin[aoff[k]+1:aoff[k+1]], amax[aoff[k]+1:aoff[k+1]]) for k in 1:(ffnet.K-1)]
+  return IntervalsInfo(ffnet=ffnet, x_intvs=x_intvs, acx_intvs=acx_intvs)
+end
+
 # ---- clique index sets (bit-exact with makeCliques, src/Methods/chordal_cliques.jl:13-59) ---------
 function makeCliquesB200(net::DeviceNet, β::Int)
   sz = sizes(net, β)
@@ -316,7 +337,7 @@ function Methods.setupReach!(model, query::Methods.ReachQuery, opts::ChordalB200
   return model, vars
 end
 
-export Context, DeviceNet, IntervalsB200, makeCliquesB200, assembleCliqueBlocks, assembleZ
+export Context, DeviceNet, IntervalsB200, IntervalsCrownB200, makeCliquesB200, assembleCliqueBlocks, assembleZ
 export affineForm, ChordalB200Options, eigmaxZ
 
 end # module

@@ -75,6 +75,9 @@ PROTOTYPES = {
     "nnsdp_plan_stats": (c_i32, [c_i64, c_i64p, c_i64, c_i32, c_i64p, c_i64p, c_i64p, c_i64p]),
     "nnsdp_plan_tiles": (c_i32, [c_i64, c_i64p, c_i64, c_i32, c_i64, C.POINTER(c_i32), c_i64p]),
     "nnsdp_bounds_ibp": (c_i32, [c_vp, c_vp, c_i64, c_dp, c_dp, c_dp, c_dp, c_dp, c_dp]),
+    "nnsdp_bounds_crown": (c_i32, [c_vp, c_vp, c_i64, c_dp, c_dp, c_dp, c_dp, c_dp, c_dp]),
+    "nnsdp_batch_bounds_crown": (c_i32, [c_vp]),
+    "nnsdp_batch_set_bounds_method": (c_i32, [c_vp, c_i32]),
     "nnsdp_preact_from_x": (c_i32, [c_vp, c_vp, c_i64, c_dp, c_dp, c_dp, c_dp]),
     "nnsdp_sector_minmax": (c_i32, [c_vp, c_i64, c_dp, c_dp, c_dp, c_dp]),
     "nnsdp_assemble_blocks": (c_i32, [c_vp, c_vp, c_i64, c_i64, C.POINTER(QueryInputs), c_dp]),

@@ -235,6 +235,18 @@ def bounds_ibp(net: Net, x1min, x1max):
     return {"xmin": xmin, "xmax": xmax, "acxmin": acxmin, "acxmax": acxmax}
 
 
+def bounds_crown(net: Net, x1min, x1max):
+    """CROWN bounds (the reference's default IntervalsAutoLirpa, sliced variant) for Q boxes on the device."""
+    x1min = np.atleast_2d(_f64(x1min))
+    x1max = np.atleast_2d(_f64(x1max))
+    Q = x1min.shape[0]
+    sz = net.sizes(0)
+    out = {k: np.empty((Q, sz[d])) for k, d in (("xmin", "xtot"), ("xmax", "xtot"), ("acxmin", "acdim"), ("acxmax", "acdim"))}
+    L.check(L.lib.nnsdp_bounds_crown(net.ctx._h, net._h, Q, _dp(x1min), _dp(x1max), _dp(out["xmin"]), _dp(out["xmax"]),
+                                     _dp(out["acxmin"]), _dp(out["acxmax"])))
+    return out
+
+
 def preact_from_x(net: Net, xmin, xmax):
     xmin = np.atleast_2d(_f64(xmin))
     xmax = np.atleast_2d(_f64(xmax))
@@ -356,6 +368,12 @@ class Batch:
 
     def bounds(self):
         L.check(L.lib.nnsdp_batch_bounds(self._h))
+
+    def bounds_crown(self):
+        L.check(L.lib.nnsdp_batch_bounds_crown(self._h))
+
+    def set_bounds_method(self, method: str):
+        L.check(L.lib.nnsdp_batch_set_bounds_method(self._h, {"ibp": 0, "crown": 1}[method]))
 
     def prepare(self):
         L.check(L.lib.nnsdp_batch_prepare(self._h))

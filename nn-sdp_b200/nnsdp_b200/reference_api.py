@@ -91,6 +91,10 @@ class IntervalsB200(IntervalsMethod):
     """IntervalsWorstCase (IBP) evaluated on the GPU."""
 
 
+class IntervalsCrownB200(IntervalsMethod):
+    """IntervalsAutoLirpa (CROWN, sliced variant: the reference's default) evaluated on the GPU in FP64."""
+
+
 @dataclass
 class IntervalsInfo:
     ffnet: FeedFwdNet
@@ -115,12 +119,13 @@ def _split(v: np.ndarray, dims: Sequence[int]):
 
 def makeIntervalsInfo(x1min, x1max, ffnet: FeedFwdNet, method: IntervalsMethod = None) -> IntervalsInfo:
     method = method or IntervalsB200()
-    if not isinstance(method, IntervalsB200):
+    if not isinstance(method, (IntervalsB200, IntervalsCrownB200)):
         raise ValueError(f"unrecognized method: {method}")
     x1min = np.asarray(x1min, dtype=np.float64)
     x1max = np.asarray(x1max, dtype=np.float64)
     assert len(x1min) == len(x1max) == ffnet.xdims[0]
-    r = core.bounds_ibp(ffnet.device(), x1min[None, :], x1max[None, :])
+    fn = core.bounds_crown if isinstance(method, IntervalsCrownB200) else core.bounds_ibp
+    r = fn(ffnet.device(), x1min[None, :], x1max[None, :])
     xs_min, xs_max = _split(r["xmin"][0], ffnet.xdims), _split(r["xmax"][0], ffnet.xdims)
     ac_min, ac_max = _split(r["acxmin"][0], ffnet.xdims[1:-1]), _split(r["acxmax"][0], ffnet.xdims[1:-1])
     return IntervalsInfo(ffnet=ffnet, x_intvs=list(zip(xs_min, xs_max)), acx_intvs=list(zip(ac_min, ac_max)))

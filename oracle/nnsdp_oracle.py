@@ -917,3 +917,80 @@ def cover_upper_entries(ffnet: FeedFwdNet, cliques):
         rows.append(r + 1)
         cols.append(np.full(len(r), c + 1))
     return np.concatenate(rows), np.concatenate(cols)
+
+
+# --------------------------------------------------------------------------
+# CROWN bounds: the reference's DEFAULT interval method (IntervalsAutoLirpa, Intervals.jl:38,44-45 ->
+# intervalsAutoLirpaSliced, intervals_auto_lirpa.jl:44-63 -> exts/auto_lirpa_bridge.py:97-112 ->
+# auto_LiRPA BoundedModule.compute_bounds(method="CROWN")).
+#
+# PARITY UNPINNED, twice over: auto_LiRPA (vendored, 2021) does not import under this interpreter, and it
+# computes in float32.  This is a float64 restatement of the algorithm for ReLU MLPs as read from the
+# vendored sources:
+#   * bound_general.py:1212-1366  every pre-activation node gets bounds by backward LiRPA with C = I,
+#     except the first linear layer, which is bounded by interval arithmetic (:1257-1262);
+#   * operators/activation.py:306-323  ReLU relaxation from (l, u): lb_r = min(l, 0), ub_r = max(u, 0),
+#     ub_r = max(ub_r, lb_r + 1e-8), upper_d = ub_r / (ub_r - lb_r), upper_b = -lb_r * upper_d;
+#     :387-388 "adaptive" lower slope lower_d = (upper_d > 0.5);
+#     :440-455  uA <- uA+ * upper_d + uA- * lower_d, ubias += uA+ . upper_b ; lA <- lA+ * lower_d + lA- * upper_d,
+#               lbias += lA- . upper_b;
+#   * linear layer: A <- A W, bias += A b;  concretisation on the box: A c -/+ |A| r + bias.
+# intervalsAutoLirpaSliced bounds x_{k+1} as the OUTPUT of the k-layer prefix followed by an identity layer,
+# i.e. through the relaxation of relu_k (so a lower bound may be negative), then lb = min(lb, ub),
+# ub = max(lb, ub) (intervals_auto_lirpa.jl:37-39), and finally one IBP step for acx_intvs (:55-62).
+# --------------------------------------------------------------------------
+
+
+def _relu_relaxation(l, u):
+    lb_r = np.minimum(l, 0.0)
+    ub_r = np.maximum(u, 0.0)
+    ub_r = np.maximum(ub_r, lb_r + 1e-8)
+    upper_d = ub_r / (ub_r - lb_r)
+    upper_b = -lb_r * upper_d
+    lower_d = (upper_d > 0.5).astype(np.float64)
+    return upper_d, upper_b, lower_d
+
+
+def _crown_backward(ffnet: FeedFwdNet, pre, lA, uA, lb, ub, j_start, x1min, x1max):
+    """Propagate (lA, lb), (uA, ub), linear in x_{j_start+1} (the output of relu_{j_start}), back to the input.
+    pre[j] = (l, u) bounds of y_j, j = 1..; j_start = 0 means the functions are already linear in x_1."""
+    for j in range(j_start, 0, -1):
+        d_u, b_u, d_l = _relu_relaxation(*pre[j])
+        up, un = np.maximum(uA, 0.0), np.minimum(uA, 0.0)
+        lp, ln = np.maximum(lA, 0.0), np.minimum(lA, 0.0)
+        ub = ub + up @ b_u
+        lb = lb + ln @ b_u
+        uA = up * d_u + un * d_l
+        lA = lp * d_l + ln * d_u
+        W, b = ffnet.Ms[j - 1][:, :-1], ffnet.Ms[j - 1][:, -1]
+        ub = ub + uA @ b
+        lb = lb + lA @ b
+        uA = uA @ W
+        lA = lA @ W
+    c, r = 0.5 * (x1min + x1max), 0.5 * (x1max - x1min)
+    return lA @ c - np.abs(lA) @ r + lb, uA @ c + np.abs(uA) @ r + ub
+
+
+def intervals_crown(x1min, x1max, ffnet: FeedFwdNet) -> IntervalsInfo:
+    x1min = np.asarray(x1min, dtype=np.float64)
+    x1max = np.asarray(x1max, dtype=np.float64)
+    K = ffnet.K
+    pre = {}  # pre[j] = bounds of y_j = W_j x_j + b_j, j = 1..K
+    pre[1] = _ibp_layer(ffnet.Ms[0], x1min, x1max)
+    for i in range(2, K + 1):
+        W, b = ffnet.Ms[i - 1][:, :-1], ffnet.Ms[i - 1][:, -1]
+        pre[i] = _crown_backward(ffnet, pre, W.copy(), W.copy(), b.copy(), b.copy(), i - 1, x1min, x1max)
+    x_intvs = [(x1min, x1max)]
+    for k in range(1, K):  # slice k: identity o relu_k o (layers 1..k)
+        n = ffnet.xdims[k]
+        eye = np.eye(n)
+        lo, hi = _crown_backward(ffnet, pre, eye.copy(), eye.copy(), np.zeros(n), np.zeros(n), k, x1min, x1max)
+        lo = np.minimum(lo, hi)  # intervals_auto_lirpa.jl:37-38
+        hi = np.maximum(lo, hi)
+        x_intvs.append((lo, hi))
+    lo, hi = pre[K]
+    lo = np.minimum(lo, hi)
+    hi = np.maximum(lo, hi)
+    x_intvs.append((lo, hi))
+    acx = preact_from_x(x_intvs, ffnet)  # :55-62
+    return IntervalsInfo(ffnet=ffnet, x_intvs=x_intvs, acx_intvs=acx)

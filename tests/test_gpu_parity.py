@@ -762,3 +762,72 @@ def test_multi_device_context_shards_queries(ctx):
     r1 = nb.bounds_ibp(nb.Net(ctx, net.xdims, net.Ms), np.stack([q.x1min for q in qs]), np.stack([q.x1max for q in qs]))
     r2 = nb.bounds_ibp(dnet2, np.stack([q.x1min for q in qs]), np.stack([q.x1max for q in qs]))
     assert all(np.array_equal(r1[k], r2[k]) for k in r1)
+
+
+# ---------------------------------------------------------------------------------------------
+# CROWN bounds: the reference's default IntervalsAutoLirpa, sliced variant
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("xdims", [[2, 3, 2], [2, 6, 5, 7, 2], [2] + [10] * 10 + [2], [5, 50, 50, 50, 50, 50, 50, 5],
+                                   [2] + [20] * 10 + [2], [3, 150, 260, 140, 2], [2, 4, 7, 3, 5, 2]])
+def test_crown_bounds_against_oracle(ctx, xdims):
+    import nnsdp_b200 as nb
+
+    net = rand_net(xdims, seed=8)
+    rng = np.random.default_rng(3)
+    n1 = xdims[0]
+    centres = rng.uniform(0.5, 1.5, (5, n1))
+    radii = np.array([0.0, 1e-3, 0.05, 0.2, 0.5])[:, None]
+    lo, hi = centres - radii, centres + radii
+    dnet = nb.Net(ctx, net.xdims, net.Ms)
+    r = nb.bounds_crown(dnet, lo, hi)
+    ibp = nb.bounds_ibp(dnet, lo, hi)
+    for i in range(5):
+        ref = o.intervals_crown(lo[i], hi[i], net)
+        xmin = np.concatenate([p[0] for p in ref.x_intvs])
+        xmax = np.concatenate([p[1] for p in ref.x_intvs])
+        amin = np.concatenate([p[0] for p in ref.acx_intvs])
+        amax = np.concatenate([p[1] for p in ref.acx_intvs])
+        scale = max(np.abs(xmin).max(), np.abs(xmax).max(), 1.0)
+        for got, want in ((r["xmin"][i], xmin), (r["xmax"][i], xmax), (r["acxmin"][i], amin), (r["acxmax"][i], amax)):
+            assert np.abs(got - want).max() <= 1e-11 * scale
+        assert np.all(r["xmin"][i] <= r["xmax"][i]) and np.all(r["acxmin"][i] <= r["acxmax"][i])
+        # the first hidden layer is interval arithmetic in both methods
+        n2 = xdims[1]
+        assert np.abs(r["acxmin"][i][:n2] - ibp["acxmin"][i][:n2]).max() <= TOL * scale
+        # soundness: sampled activations lie inside the bounds
+        for _ in range(50):
+            x = rng.uniform(lo[i], hi[i])
+            xs = [x]
+            for k, M in enumerate(net.Ms):
+                y = M @ np.append(xs[-1], 1.0)
+                xs.append(np.maximum(y, 0.0) if k < net.K - 1 else y)
+            allx = np.concatenate(xs)
+            assert np.all(allx >= r["xmin"][i] - 1e-9 * scale) and np.all(allx <= r["xmax"][i] + 1e-9 * scale)
+
+
+def test_crown_in_the_batch_pipeline(ctx):
+    """Blocks assembled with CROWN bounds computed on the device == blocks from the oracle with the oracle's
+    CROWN intervals (makeQcActivsIntvs with the default method, src/Qc/activ.jl:45-67)."""
+    import nnsdp_b200 as nb
+
+    xdims, beta = [2] + [12] * 8 + [2], 2
+    net = rand_net(xdims, seed=6)
+    rng = np.random.default_rng(2)
+    qs = [rand_query(net, beta, rng, kind="hplane", radius=r) for r in (0.02, 0.3)]
+    dnet = nb.Net(ctx, net.xdims, net.Ms)
+    b = nb.Batch(dnet, beta, Qcap=2, ring=2)
+    b.set_inputs(to_numeric_batch(nb, net, qs))
+    b.set_bounds_method("crown")
+    out = np.empty((2, b.per_query))
+    b.run(out)
+    cliques = o.make_cliques(net, beta)
+    tighter = 0
+    for i, q in enumerate(qs):
+        info = o.intervals_crown(q.x1min, q.x1max, net)
+        ref = o.run_query(net, beta, q, intv_info=info)
+        for blk, rb in zip(nb.split_blocks(out[i], cliques), ref["blocks"]):
+            assert relerr(blk, rb) <= 1e-11
+        ibp = o.intervals_worst_case(q.x1min, q.x1max, net)
+        tighter += sum((p[1] - p[0]).sum() for p in ibp.x_intvs) > sum((p[1] - p[0]).sum() for p in info.x_intvs)
+    assert tighter == 2
+    b.close()

@@ -169,6 +169,39 @@ def test_sector_thresholds():
     assert np.array_equal(smin, [0, 1, 0, 0]) and np.array_equal(smax, [1, 1, 1, 0])  # strict, activ_sector.jl:67-68
 
 
+def test_crown_restatement_sound_and_tighter_than_ibp():
+    """The CROWN restatement (parity unpinned, oracle header) at least has the properties a bound method must
+    have: sampled activations lie inside, the first layer equals interval arithmetic, a point box gives the
+    forward pass, and on deep nets it is far tighter than IBP (why it is the reference's default)."""
+    for xdims in ([2, 6, 5, 7, 2], [2] + [10] * 10 + [2], [3, 20, 20, 20, 3]):
+        net = rand_net(xdims, seed=3)
+        lo = np.full(xdims[0], 0.5)
+        hi = lo + 0.4
+        ci = o.intervals_crown(lo, hi, net)
+        ib = o.intervals_worst_case(lo, hi, net)
+        assert np.allclose(ci.acx_intvs[0][0], ib.acx_intvs[0][0]) and np.allclose(ci.acx_intvs[0][1], ib.acx_intvs[0][1])
+        rng = np.random.default_rng(0)
+        for _ in range(300):
+            x = rng.uniform(lo, hi)
+            xs = [x]
+            for k, M in enumerate(net.Ms):
+                y = M @ np.append(xs[-1], 1.0)
+                xs.append(np.maximum(y, 0.0) if k < net.K - 1 else y)
+            for k in range(net.K + 1):
+                assert np.all(xs[k] >= ci.x_intvs[k][0] - 1e-9) and np.all(xs[k] <= ci.x_intvs[k][1] + 1e-9)
+        wc = sum((p[1] - p[0]).sum() for p in ci.x_intvs[1:])
+        wi = sum((p[1] - p[0]).sum() for p in ib.x_intvs[1:])
+        assert wc <= wi * (1 + 1e-12)
+        pt = o.intervals_crown(lo, lo, net)
+        y = o.eval_feed_fwd_net(net, lo)
+        assert np.abs(pt.x_intvs[-1][0] - y).max() <= 1e-6 * max(np.abs(y).max(), 1.0)   # 1e-8 guard in the relaxation
+    deep = rand_net([2] + [10] * 10 + [2], seed=3)
+    lo, hi = np.full(2, 0.5), np.full(2, 0.9)
+    wc = sum((p[1] - p[0]).sum() for p in o.intervals_crown(lo, hi, deep).x_intvs[1:])
+    wi = sum((p[1] - p[0]).sum() for p in o.intervals_worst_case(lo, hi, deep).x_intvs[1:])
+    assert wc < 0.1 * wi
+
+
 # ---------------------------------------------------------------------------------------------
 # golden fixtures (tests/golden/make_golden.py)
 # ---------------------------------------------------------------------------------------------
