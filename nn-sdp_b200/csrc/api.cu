@@ -1543,8 +1543,7 @@ int32_t crown_bounds_device(nnsdp_batch* b) {
         launches += launch_crown_row(srcL, srcU, src_row_stride, src_q_stride, cur, ld, nrows, nq, n,
                                      du.as<double>() + poff(k), bu.as<double>() + poff(k), dl.as<double>() + poff(k),
                                      P, bias_of(k), bias.as<double>(), st);
-        cudaMemsetAsync(nxt, 0, (size_t)2 * nq * nrows * ld * 8, st);
-        launches += gemm_acc_launch(npd.Wt[k].as<double>(), b->net->ldT[k], (int)sh.n[k], n, cur, ld, nxt, ld,
+        launches += gemm_set_launch(npd.Wt[k].as<double>(), b->net->ldT[k], (int)sh.n[k], n, cur, ld, nxt, ld,
                                     2 * nq * nrows, st);
         srcL = nxt;
         srcU = nxt + (size_t)nq * nrows * ld;

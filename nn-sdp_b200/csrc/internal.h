@@ -307,6 +307,9 @@ int launch_eig_normalize(const double* w, double* dst, int n, int Qc, double* nr
 // C (M x N, column q at C + q * ldc) += A (M x Kdim, column-major, lda) * B (column q at B + q * ldb)
 int gemm_acc_launch(const double* A, int lda, int M, int Kdim, const double* B, long long ldb,
                     double* C, long long ldc, int N, cudaStream_t st);
+// the same with C = A * B
+int gemm_set_launch(const double* A, int lda, int M, int Kdim, const double* B, long long ldb,
+                    double* C, long long ldc, int N, cudaStream_t st);
 
 // CROWN bounds (kernels_crown.cu): rows of lA / uA of a chunk of Qc queries are stacked [2][Qc][nrows][ld]
 int launch_crown_params(const double* l, const double* u, long long stride, int n, int Qc, double* d_u,

@@ -20,7 +20,7 @@ namespace {
 constexpr int BM = 64, BN = 64, BK = 16;
 constexpr int GEMM_THREADS = 256;
 
-// MODE 0: IBP layer.  MODE 1: C += A * B (affine column).
+// MODE 0: IBP layer.  MODE 1: C += A * B (affine column).  MODE 2: C = A * B.
 template <int MODE>
 __global__ void __launch_bounds__(GEMM_THREADS)
 gemm_nn_kernel(const double* __restrict__ A, int lda, int M, int Kdim,
@@ -120,7 +120,8 @@ gemm_nn_kernel(const double* __restrict__ A, int lda, int M, int Kdim,
           C1[(long long)gn * ldc + gm] = relu ? fmax(ymax, 0.0) : ymax;
         }
       } else {
-        C0[(long long)gn * ldc + gm] += acc0[i][j];
+        if (MODE == 2) C0[(long long)gn * ldc + gm] = acc0[i][j];
+        else C0[(long long)gn * ldc + gm] += acc0[i][j];
       }
     }
   }
@@ -200,6 +201,14 @@ int affine_layer_launch(const double* Wt, int ldT, int n_rows, int n_neurons, co
   gemm_nn_kernel<1><<<grid, GEMM_THREADS, 0, st>>>(Wt, ldT, n_rows, n_neurons, u, nullptr, u_stride,
                                                   Q, nullptr, aff, nullptr, aff_stride, nullptr,
                                                   nullptr, 0, 0, 0, nullptr);
+  return 1;
+}
+
+int gemm_set_launch(const double* A, int lda, int M, int Kdim, const double* B, long long ldb,
+                    double* C, long long ldc, int N, cudaStream_t st) {
+  dim3 grid((M + BM - 1) / BM, (N + BN - 1) / BN);
+  gemm_nn_kernel<2><<<grid, GEMM_THREADS, 0, st>>>(A, lda, M, Kdim, B, nullptr, ldb, N, nullptr, C, nullptr,
+                                                  ldc, nullptr, nullptr, 0, 0, 0, nullptr);
   return 1;
 }
 
