@@ -148,6 +148,15 @@ int32_t nnsdp_plan_stats(int64_t K, const int64_t* xdims, int64_t beta, int32_t 
 int32_t nnsdp_plan_tiles(int64_t K, const int64_t* xdims, int64_t beta, int32_t dense_Z,
                          int64_t max_tiles, int32_t* tiles_out, int64_t* ntiles);
 
+/* The host-gather plan of nnsdp_batch_run_ex (host only, for inspection and tests): every output matrix cut at
+ * block boundaries into cells, 8 int32 each {mat, row0, nrows, col0, ncols, kind, blk, pure_zero} with kind
+ * 0 = never copied as a whole, 1 = always dense, 2 = dense when layer blk has a stably-active neuron,
+ * 3 = dense when the output QC has an S22 part; and the offsets (doubles inside one query's output) of the thin
+ * entries that travel packed.  *usable = 0 means the dense copy is used for this network. */
+int32_t nnsdp_gather_plan(int64_t K, const int64_t* xdims, int64_t beta, int32_t dense_Z, int64_t max_cells,
+                          int32_t* cells_out, int64_t* ncells, int64_t max_thin, int64_t* thin_out,
+                          int64_t* nthin, int32_t* usable);
+
 /* ---- one-shot entry points with HOST buffers ------------------------------------------
  * intervalsWorstCase (src/Intervals/intervals_easy.jl:2-37), batched over Q boxes.
  *   x1min,x1max : n_in x Q;  xmin,xmax : xtot x Q (x_intvs stacked, x_1 first);

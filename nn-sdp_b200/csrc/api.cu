@@ -649,6 +649,55 @@ int32_t nnsdp_plan_tiles(int64_t K, const int64_t* xdims, int64_t beta, int32_t 
   return NNSDP_OK;
 }
 
+/* The host-gather plan (host only): cells {mat, row0, nrows, col0, ncols, kind, blk, pure_zero} (8 int32 each;
+ * kind 0 = never dense, 1 = always, 2 = Gram-active layers only, 3 = S22 only) and the thin-entry offsets
+ * (doubles inside one query's output).  Either output may be NULL to query the counts. */
+int32_t nnsdp_gather_plan(int64_t K, const int64_t* xdims, int64_t beta, int32_t dense_Z, int64_t max_cells,
+                          int32_t* cells_out, int64_t* ncells, int64_t max_thin, int64_t* thin_out,
+                          int64_t* nthin, int32_t* usable) {
+  NN_CHECK(ncells && nthin, NNSDP_ERR_ARG, "NULL argument");
+  Shape sh;
+  NN_TRY(shape_from_xdims(K, xdims, &sh));
+  nnsdp_sizes sz;
+  NN_TRY(fill_sizes(sh, beta, &sz));
+  std::vector<CliqueRanges> mats;
+  if (dense_Z) {
+    CliqueRanges c;
+    c.nseg = 1;
+    c.lo[0] = 0;
+    c.hi[0] = sh.Zdim - 1;
+    mats.push_back(c);
+  } else {
+    CliqueInfoHost ci;
+    NN_TRY(make_cliques_host(sh, beta, &ci));
+    mats = ci.ck;
+  }
+  PlanHost plan;
+  NN_TRY(build_plan(sh, beta, mats, true, &plan));
+  GatherPlan gp;
+  NN_TRY(build_gather_plan(sh, beta, mats, plan, &gp));
+  int64_t nc = 0;
+  for (const GatherColSeg& cs : gp.colsegs) nc += (int64_t)cs.cells.size();
+  *ncells = nc;
+  *nthin = (int64_t)gp.thin_idx.size();
+  if (usable) *usable = gp.usable ? 1 : 0;
+  if (cells_out) {
+    NN_CHECK(max_cells >= nc, NNSDP_ERR_ARG, "cells_out too small");
+    int64_t i = 0;
+    for (const GatherColSeg& cs : gp.colsegs)
+      for (const GatherCell& c : cs.cells) {
+        int32_t* o = cells_out + 8 * i++;
+        o[0] = cs.mat; o[1] = c.row0; o[2] = c.nrows; o[3] = cs.col0; o[4] = cs.ncols;
+        o[5] = c.kind; o[6] = c.blk; o[7] = c.pure_zero;
+      }
+  }
+  if (thin_out) {
+    NN_CHECK(max_thin >= *nthin, NNSDP_ERR_ARG, "thin_out too small");
+    memcpy(thin_out, gp.thin_idx.data(), gp.thin_idx.size() * 8);
+  }
+  return NNSDP_OK;
+}
+
 // ---- batch ----------------------------------------------------------------------------------
 int32_t nnsdp_batch_destroy(nnsdp_batch* b) {
   if (!b) return NNSDP_OK;

@@ -139,6 +139,20 @@ def plan_tiles(xdims: Sequence[int], beta: int, dense: bool = False) -> np.ndarr
     return out
 
 
+def gather_plan(xdims: Sequence[int], beta: int, dense: bool = False) -> dict:
+    """Cells (ncells, 8) [mat, row0, nrows, col0, ncols, kind, blk, pure_zero] and thin-entry offsets of the
+    host-gather plan (host only)."""
+    K = len(xdims) - 1
+    xd = (L.c_i64 * (K + 1))(*[int(x) for x in xdims])
+    nc, nt, us = L.c_i64(0), L.c_i64(0), L.c_i32(0)
+    L.check(L.lib.nnsdp_gather_plan(K, xd, beta, int(dense), 0, None, C.byref(nc), 0, None, C.byref(nt), C.byref(us)))
+    cells = np.zeros((int(nc.value), 8), dtype=np.int32)
+    thin = np.zeros(int(nt.value), dtype=np.int64)
+    L.check(L.lib.nnsdp_gather_plan(K, xd, beta, int(dense), int(nc.value), cells.ctypes.data_as(C.POINTER(L.c_i32)),
+                                    C.byref(nc), int(nt.value), thin.ctypes.data_as(L.c_i64p), C.byref(nt), C.byref(us)))
+    return {"cells": cells, "thin": thin, "usable": bool(us.value)}
+
+
 def _cliques_call(fn, sz):
     p = sz["ncliques"]
     ck_off = np.zeros(p + 1, dtype=np.int64)

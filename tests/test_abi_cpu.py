@@ -140,3 +140,55 @@ def test_shard_ranges_partition():
             assert max(n for _, n in rs) - min(n for _, n in rs) <= 1
     with pytest.raises(ValueError):
         shard_range(4, 2, 2)
+
+
+@pytest.mark.parametrize("xdims,beta,dense", [([2, 300, 280, 320, 290, 2], 2, False), ([3, 270, 300, 260, 3], 1, True),
+                                              ([2] + [1000] * 20 + [2], 2, False), ([2] + [10] * 10 + [2], 1, False)])
+def test_gather_plan_accounts_for_every_possible_nonzero(xdims, beta, dense):
+    """Host-gather invariant: an output entry that the emission plan does not classify as structurally zero is
+    covered by a dense cell (copied whole, always or conditionally) or is in the thin list; cells partition
+    every matrix; thin entries never lie inside always-dense cells (they would travel twice)."""
+    import nnsdp_b200 as nb
+
+    gp = nb.gather_plan(xdims, beta, dense=dense)
+    tiles = nb.plan_tiles(xdims, beta, dense=dense)
+    sz = nb.sizes_from_xdims(xdims, beta)
+    if dense:
+        ns = [sz["Zdim"]]
+    else:
+        ns = [len(c[0]) for c in nb.cliques_from_xdims(xdims, beta)]
+    offs = np.concatenate([[0], np.cumsum([n * n for n in ns])])
+    cells = gp["cells"]
+    # cells partition every matrix
+    for m, n in enumerate(ns):
+        cm = cells[cells[:, 0] == m]
+        assert int((cm[:, 2].astype(np.int64) * cm[:, 4]).sum()) == n * n
+    if not gp["usable"]:
+        assert max(xdims) < 256 or len(gp["thin"]) * 8 > offs[-1]
+        return
+    if sum(n * n for n in ns) > 5e7:   # the stress config: check counts only
+        assert 400_000 < len(gp["thin"]) < 1_500_000 and np.all(np.diff(gp["thin"]) != 0)
+        always = cells[cells[:, 5] == 1]
+        assert 8 * int((always[:, 2].astype(np.int64) * always[:, 4]).sum()) > 0.2 * 8 * offs[-1]
+        return
+    covered = np.zeros(offs[-1], dtype=np.int8)       # 1 = always dense, 2 = conditionally dense
+    for m, r0, nr, c0, nc, kind, blk, pure in cells:
+        if kind == 0:
+            continue
+        blkv = covered[offs[m]:offs[m + 1]].reshape(ns[m], ns[m])   # [col, row]
+        blkv[c0:c0 + nc, r0:r0 + nr] = 1 if kind == 1 else 2
+    thin = np.zeros(offs[-1], dtype=bool)
+    thin[gp["thin"]] = True
+    assert not np.any(thin & (covered == 1))
+    for t in tiles:
+        m, r0, nr, c0, nc, prog = t[0], t[1], t[2], t[3], t[4], t[10]
+        if prog == 0:      # ZERO
+            continue
+        sl = np.zeros((ns[m], ns[m]), dtype=bool)
+        sl[c0:c0 + nc, r0:r0 + nr] = True
+        idx = offs[m] + np.flatnonzero(sl.ravel())
+        if prog in (1, 6):   # SAME / DIAG: Gram / S22 values live in conditional cells; only the band must be thin
+            ok = (covered[idx] > 0) | thin[idx]
+        else:
+            ok = (covered[idx] == 1) | thin[idx]
+        assert np.all(ok), (t, int((~ok).sum()))
