@@ -38,10 +38,10 @@ WORKLOADS = {
 DEFAULT_WORKLOAD = "stress-W1000-D20-beta2-Q1024"
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the `ncu --set full` capture of the same
 # command (profiles/): filled in when a capture exists for the current kernels, else null.
-NCU_TRAFFIC = {  # DRAM bytes of one launch over 8 queries (scaled to the pass size), profiles/r1_emit_full.summary.csv
-    "emit_fill_kernel": 8.272976e9 + 141.445632e6,     # algorithmic 8.17 GB
-    "emit_window_kernel": 2.419744e9 + 342.088960e6,   # algorithmic 2.46 GB (+ the W tiles it reads)
-    "emit_edge_kernel": 0.006930e9 + 11.059200e6,
+NCU_TRAFFIC = {  # DRAM bytes (write + read) of one 32-query launch / 4, profiles/r1_emit_full.summary.csv
+    "emit_fill_kernel": (33.256634e9 + 480.637184e6) / 4,    # algorithmic 8.17 GB per 8 queries
+    "emit_window_kernel": (9.852402e9 + 476.953344e6) / 4,   # algorithmic 2.46 GB (+ the W tiles it reads)
+    "emit_edge_kernel": (0.055518e9 + 49.865472e6) / 4,
 }
 
 
