@@ -122,6 +122,14 @@ int32_t nnsdp_net_upload(nnsdp_ctx* ctx, int64_t K, const int64_t* xdims, const 
                          nnsdp_net** net);
 int32_t nnsdp_net_destroy(nnsdp_net* net);
 
+/* .nnet reader, host only: the format of the reference's fixtures bench/rand/*.nnet as read
+ * by exts/nnet_parser.jl:35-131 and loadFromNnet (src/MyNeuralNetwork/network_files.jl).  Two calls: the first
+ * with Ms_out == NULL returns K, xdims (K+1 entries, if xdims_out != NULL and max_layers >= K) and the number
+ * of doubles needed; the second fills Ms_out with the matrices [W_k b_k] back to back, each column-major
+ * xdims[k+1] x (xdims[k]+1) -- what nnsdp_net_upload takes (Ms[k] = Ms_out + sum_{k'<k} xdims[k'+1](xdims[k']+1)). */
+int32_t nnsdp_nnet_read(const char* path, int64_t max_layers, int64_t* K, int64_t* xdims_out,
+                        int64_t max_doubles, double* Ms_out, int64_t* doubles_needed);
+
 /* ---- integer work on the host, bit-exact --------------------------------------------- */
 int32_t nnsdp_query_sizes(const nnsdp_net* net, int64_t beta, nnsdp_sizes* sizes);
 /* makeCliques (src/Methods/chordal_cliques.jl:13-59).  Outputs (1-based):

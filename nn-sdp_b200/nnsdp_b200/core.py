@@ -92,6 +92,22 @@ class Net:
         return _cliques_call(lambda *a: L.lib.nnsdp_cliques(self._h, beta, *a), self.sizes(beta))
 
 
+def read_nnet(path: str):
+    """(xdims, Ms) of a .nnet file through the library's reader (host only); Ms[k] = [W_k b_k]."""
+    K, need = L.c_i64(0), L.c_i64(0)
+    L.check(L.lib.nnsdp_nnet_read(path.encode(), 0, C.byref(K), None, 0, None, C.byref(need)))
+    xd = np.zeros(K.value + 1, dtype=np.int64)
+    buf = np.zeros(need.value)
+    L.check(L.lib.nnsdp_nnet_read(path.encode(), K.value, C.byref(K), xd.ctypes.data_as(L.c_i64p), need.value, _dp(buf),
+                                  C.byref(need)))
+    Ms, o = [], 0
+    for k in range(K.value):
+        n = int(xd[k + 1] * (xd[k] + 1))
+        Ms.append(buf[o:o + n].reshape(int(xd[k] + 1), int(xd[k + 1])).T.copy())
+        o += n
+    return xd.tolist(), Ms
+
+
 def sizes_from_xdims(xdims: Sequence[int], beta: int) -> dict:
     """nnsdp_sizes_from_xdims: host-only (no device needed)."""
     K = len(xdims) - 1

@@ -192,3 +192,20 @@ def test_gather_plan_accounts_for_every_possible_nonzero(xdims, beta, dense):
         else:
             ok = (covered[idx] == 1) | thin[idx]
         assert np.all(ok), (t, int((~ok).sum()))
+
+
+def test_nnet_reader_against_the_references_reader():
+    """nnsdp_nnet_read on the shipped fixture == the weights the reference's own exts/NNet/utils/readNNet.py
+    produced (tests/golden/scale_W5_D5_weights.npz) == the oracle's reader."""
+    import nnsdp_b200 as nb
+
+    gold = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    xd, Ms = nb.read_nnet(os.path.join(gold, "scale-I2-O2-W5-D5.nnet"))
+    d = np.load(os.path.join(gold, "scale_W5_D5_weights.npz"))
+    assert xd == d["xdims"].tolist()
+    for k, M in enumerate(Ms):
+        assert np.array_equal(M, d[f"M{k}"])
+    ref = o.load_nnet(os.path.join(gold, "scale-I2-O2-W5-D5.nnet"))
+    assert all(np.array_equal(a, b) for a, b in zip(Ms, ref.Ms))
+    with pytest.raises(nb.NnsdpError):
+        nb.read_nnet(os.path.join(gold, "does-not-exist.nnet"))
