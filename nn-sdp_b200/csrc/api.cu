@@ -205,6 +205,9 @@ struct nnsdp_batch {
   cudaEvent_t ev_packed[GATHER_STAGES] = {nullptr, nullptr, nullptr, nullptr};
   std::unique_ptr<WorkerPool> pool;
   std::vector<int> h_cnt;      // Gram-active neuron counts per (query, block), host copy
+  std::vector<int> h_pairs;    // active (query, block) pairs (two ints each) in query order; pair_begin[q] = first pair of query q
+  std::vector<int64_t> pair_begin;
+  DevBuf d_pairs;
   int64_t gather_bytes_dma = 0, gather_bytes_zeroed = 0, gather_bytes_thin = 0;  // of the last run
   nnsdp_ctx* ctx = nullptr;
   int dev_index = 0, dev = 0;
@@ -709,6 +712,7 @@ int32_t nnsdp_batch_destroy(nnsdp_batch* b) {
   for (DevBuf* x : b->all_bufs()) x->release();
   b->d_thin_idx.release();
   b->d_packed.release();
+  b->d_pairs.release();
   if (b->h_packed) cudaFreeHost(b->h_packed);
   for (cudaEvent_t e : b->ev_packed)
     if (e) cudaEventDestroy(e);
@@ -983,7 +987,22 @@ int32_t nnsdp_batch_prepare(nnsdp_batch* b) {
                                     b->bd.aff + sh.off[blk], sh.Zdim, (int)b->Q, b->st);
   b->span_end(b->st, launches);
   NN_CUDA(cudaGetLastError());
-  NN_TRY(check_flags(b, "nnsdp_batch_prepare"));
+  // Gram-active neuron counts per (query, block): the host builds the work list of the Gram kernel from them
+  // (most (query, layer) pairs have no stably-active neuron) and the host gather needs them as well
+  b->h_cnt.resize((size_t)sh.K * b->Q);
+  NN_CUDA(cudaMemcpyAsync(b->h_cnt.data(), b->cnt.p, b->h_cnt.size() * 4, cudaMemcpyDeviceToHost, b->st));
+  NN_TRY(check_flags(b, "nnsdp_batch_prepare"));  // synchronises the stream
+  b->h_pairs.clear();
+  b->pair_begin.assign((size_t)b->Q + 1, 0);
+  for (int64_t q = 0; q < b->Q; ++q) {
+    for (int blk = 0; blk <= sh.K - 2; ++blk)
+      if (b->h_cnt[(size_t)q * sh.K + blk] > 0) {
+        b->h_pairs.push_back((int)q);
+        b->h_pairs.push_back(blk);
+      }
+    b->pair_begin[q + 1] = (int64_t)b->h_pairs.size() / 2;
+  }
+  NN_TRY(upload(b->d_pairs, b->h_pairs.data(), b->h_pairs.size() * 4, b->st));
   b->prepared = true;
   return NNSDP_OK;
 }
@@ -1011,7 +1030,8 @@ int32_t nnsdp_batch_emit(nnsdp_batch* b, int64_t q0, int64_t nq) {
   NN_CUDA(cudaSetDevice(b->dev));
   const NetPerDev& nd = *b->nd;
   b->span_begin(ST_GRAM, b->st);
-  int l = launch_gram(nd.nd, b->bd, b->gd, (int)b->net->max_block, (int)q0, (int)nq, b->st);
+  int l = launch_gram(nd.nd, b->bd, b->gd, (int)b->net->max_block, (int)q0, b->d_pairs.as<int>() + 2 * b->pair_begin[q0],
+                      (int)(b->pair_begin[q0 + nq] - b->pair_begin[q0]), b->st);
   b->span_end(b->st, l);
   emit_pass(b, b->gd, (int)q0, (int)nq, b->ringbuf.as<double>());
   NN_CUDA(cudaGetLastError());
@@ -1157,10 +1177,6 @@ int32_t nnsdp_batch_run_ex(nnsdp_batch* b, double* host_out, int32_t flags) {
   const bool sparse = host_out && b->gp.usable && !(flags & NNSDP_RUN_DENSE_COPY);
   b->gather_bytes_dma = b->gather_bytes_zeroed = b->gather_bytes_thin = 0;
   if (sparse) {
-    const int K = b->net->sh.K;
-    b->h_cnt.resize((size_t)K * b->Q);
-    NN_CUDA(cudaMemcpyAsync(b->h_cnt.data(), b->cnt.p, b->h_cnt.size() * 4, cudaMemcpyDeviceToHost, b->st));
-    NN_CUDA(cudaStreamSynchronize(b->st));
     const size_t need = (size_t)GATHER_STAGES * chunk * b->gp.thin_idx.size();
     if (need > b->h_packed_doubles) {
       if (b->h_packed) cudaFreeHost(b->h_packed);
@@ -1187,7 +1203,8 @@ int32_t nnsdp_batch_run_ex(nnsdp_batch* b, double* host_out, int32_t flags) {
     if (sparse && ci >= GATHER_STAGES) b->pool->wait_group(ci - GATHER_STAGES);  // staging buffer reuse
     if (host_out && used[h]) NN_CUDA(cudaStreamWaitEvent(b->st, b->ev_free[h], 0));
     b->span_begin(ST_GRAM, b->st);
-    int l = launch_gram(nd.nd, b->bd, gd, (int)b->net->max_block, (int)q0, (int)nq, b->st);
+    int l = launch_gram(nd.nd, b->bd, gd, (int)b->net->max_block, (int)q0, b->d_pairs.as<int>() + 2 * b->pair_begin[q0],
+                        (int)(b->pair_begin[q0 + nq] - b->pair_begin[q0]), b->st);
     b->span_end(b->st, l);
     emit_pass(b, gd, (int)q0, (int)nq, dst);
     if (sparse) {

@@ -271,8 +271,9 @@ int launch_transpose_w(const double* Mk, int n_out_k, int n_in_k, double* Wt, in
 // K2b: per-query QC diagonals, band multipliers, affine column, Gram active sets.
 int launch_prep(const NetDev& net, const BatchDev& b, int* err_flag, cudaStream_t st);
 // K3: Gram contractions (DMMA) for queries [q0, q0+nq) into scratch slots 0..nq-1.
-int launch_gram(const NetDev& net, const BatchDev& b, const GramDev& g, int max_n, int q0, int nq,
-                cudaStream_t st);
+// pairs: npairs active (query, block) pairs (two ints each) with q0 <= query < q0 + ring slots; scratch slot = query - q0
+int launch_gram(const NetDev& net, const BatchDev& b, const GramDev& g, int max_n, int q0, const int* pairs,
+                int npairs, cudaStream_t st);
 // K4+K5: emit all tiles of queries [q0, q0+nq) to out + slot * per_query, slot = q - q0.
 // which: -1 = the whole pass (fill, window, edge kernels back to back); 0 / 1 / 2 = one of them.
 int launch_emit(const NetDev& net, const BatchDev& b, const GramDev& g, const PlanDev& plan,

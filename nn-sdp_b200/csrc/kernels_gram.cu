@@ -44,12 +44,12 @@ __device__ __forceinline__ void dmma_m8n8k4(double& c0, double& c1, double a, do
 }
 
 __global__ void __launch_bounds__(GTHREADS, 1)
-gram_kernel(NetDev net, BatchDev b, GramDev g, int q0) {
+gram_kernel(NetDev net, BatchDev b, GramDev g, int q0, const int* __restrict__ pairs) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   GramSmem& sm = *reinterpret_cast<GramSmem*>(smem_raw);
 
-  const int blk = blockIdx.y;                 // Gram of block blk uses layer matrix M[blk]
-  const int slot = blockIdx.z, q = q0 + slot;
+  // work list: only (query, block) pairs with active neurons; Gram of block blk uses layer matrix M[blk]
+  const int q = pairs[2 * blockIdx.y], blk = pairs[2 * blockIdx.y + 1], slot = q - q0;
   const int cnt = b.cnt[(long long)q * net.K + blk];
   if (cnt == 0) return;
   const int nb = net.n[blk];
@@ -151,16 +151,16 @@ gram_kernel(NetDev net, BatchDev b, GramDev g, int q0) {
 
 }  // namespace
 
-int launch_gram(const NetDev& net, const BatchDev& b, const GramDev& g, int max_n, int q0, int nq,
-                cudaStream_t st) {
-  if (net.K < 2 || nq <= 0) return 0;
+int launch_gram(const NetDev& net, const BatchDev& b, const GramDev& g, int max_n, int q0, const int* pairs,
+                int npairs, cudaStream_t st) {
+  if (net.K < 2 || npairs <= 0) return 0;
   static bool attr_set = false;  // per process; harmless if repeated per device
   (void)attr_set;
   cudaFuncSetAttribute(gram_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                        (int)sizeof(GramSmem));
   const int ntile = (max_n + GT - 1) / GT;
-  dim3 grid(ntile * (ntile + 1) / 2, net.K - 1, nq);
-  gram_kernel<<<grid, GTHREADS, sizeof(GramSmem), st>>>(net, b, g, q0);
+  dim3 grid(ntile * (ntile + 1) / 2, npairs);
+  gram_kernel<<<grid, GTHREADS, sizeof(GramSmem), st>>>(net, b, g, q0, pairs);
   return 1;
 }
 
