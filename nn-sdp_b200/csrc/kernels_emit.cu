@@ -469,7 +469,7 @@ emit_fill_kernel(NetDev net, BatchDev b, GramDev g, PlanDev plan, int q0, int nq
 
 // ---- kernel 2: RC / CR window sums (128 x 32 tiles, beta <= 4) ------------------------------------
 template <int BETA>
-__global__ void __launch_bounds__(ETHREADS)
+__global__ void __launch_bounds__(ETHREADS, 4)
 emit_window_kernel(NetDev net, BatchDev b, PlanDev plan, int tile0, int q0, int nq, int group,
                    double* __restrict__ out) {
   __shared__ double smem[SMEM_DOUBLES];
