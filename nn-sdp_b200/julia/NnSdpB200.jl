@@ -313,7 +313,7 @@ function setupB200!(model, query, qc_out, opts::ChordalB200Options)
   col_first = Dict{Int64, Int64}()                      # column -> index of its first entry
   for e in length(ent_col):-1:1; col_first[ent_col[e]] = e end
   entry(r, c) = col_first[c] + (r - ent_row[col_first[c]])
-  Zksum = zeros(Methods.JuMP.AffExpr, s.nent)
+  Zksum = [zero(Methods.JuMP.AffExpr) for _ in 1:s.nent]   # distinct objects: add_to_expression! mutates in place
   for (k, (Ck, _, _)) in enumerate(cliques)
     for j in 1:length(Ck), i in 1:j
       Methods.JuMP.add_to_expression!(Zksum[entry(Ck[i], Ck[j])], Zs[k][i, j])
