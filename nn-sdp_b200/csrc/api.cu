@@ -232,6 +232,7 @@ struct nnsdp_batch {
   GramDev gd{};
   PlanDev pd{};
   bool have_inputs = false, bounds_supplied = false, bounds_done = false, prepared = false;
+  bool shared_gram = false;  // all queries of the batch have the same Gram blocks (set by prepare)
   int bounds_method = 0;  // 0 = IBP (intervalsWorstCase), 1 = CROWN (the reference's default, IntervalsAutoLirpa)
   cudaStream_t st = nullptr, st_copy = nullptr;
   cudaEvent_t ev_start = nullptr, ev_stop = nullptr;
@@ -1003,6 +1004,11 @@ int32_t nnsdp_batch_prepare(nnsdp_batch* b) {
     b->pair_begin[q + 1] = (int64_t)b->h_pairs.size() / 2;
   }
   NN_TRY(upload(b->d_pairs, b->h_pairs.data(), b->h_pairs.size() * 4, b->st));
+  // A reach batch (src/NnSdp.jl:73-95) shares the box, the bounds and every multiplier but gamma_out between
+  // its queries: the Gram blocks are then the same for all of them and are contracted once, into slot 0.
+  const BatchDev& bd = b->bd;
+  b->shared_gram = b->Q > 1 && bd.s_gsec == 0 &&
+                   (b->bounds_supplied ? (bd.s_smin == 0 && bd.s_smax == 0) : (bd.s_x1min == 0 && bd.s_x1max == 0));
   b->prepared = true;
   return NNSDP_OK;
 }
@@ -1029,11 +1035,18 @@ int32_t nnsdp_batch_emit(nnsdp_batch* b, int64_t q0, int64_t nq) {
            (long long)(q0 + nq), (long long)b->Q, (long long)b->ring);
   NN_CUDA(cudaSetDevice(b->dev));
   const NetPerDev& nd = *b->nd;
+  GramDev gd = b->gd;
   b->span_begin(ST_GRAM, b->st);
-  int l = launch_gram(nd.nd, b->bd, b->gd, (int)b->net->max_block, (int)q0, b->d_pairs.as<int>() + 2 * b->pair_begin[q0],
-                      (int)(b->pair_begin[q0 + nq] - b->pair_begin[q0]), b->st);
+  int l;
+  if (b->shared_gram) {  // query 0's Gram blocks serve every query: every slot reads slot 0
+    l = launch_gram(nd.nd, b->bd, gd, (int)b->net->max_block, 0, b->d_pairs.as<int>(), (int)b->pair_begin[1], b->st);
+    gd.per_query = 0;
+  } else {
+    l = launch_gram(nd.nd, b->bd, gd, (int)b->net->max_block, (int)q0, b->d_pairs.as<int>() + 2 * b->pair_begin[q0],
+                    (int)(b->pair_begin[q0 + nq] - b->pair_begin[q0]), b->st);
+  }
   b->span_end(b->st, l);
-  emit_pass(b, b->gd, (int)q0, (int)nq, b->ringbuf.as<double>());
+  emit_pass(b, gd, (int)q0, (int)nq, b->ringbuf.as<double>());
   NN_CUDA(cudaGetLastError());
   return NNSDP_OK;
 }
@@ -1199,13 +1212,18 @@ int32_t nnsdp_batch_run_ex(nnsdp_batch* b, double* host_out, int32_t flags) {
     const int64_t nq = std::min(chunk, b->Q - q0);
     double* dst = b->ringbuf.as<double>() + (int64_t)h * chunk * per;
     GramDev gd = b->gd;
-    gd.scratch += (int64_t)h * chunk * gd.per_query;
+    if (b->shared_gram) gd.per_query = 0;  // every slot reads the Gram blocks of query 0 (contracted once, below)
+    else gd.scratch += (int64_t)h * chunk * gd.per_query;
     if (sparse && ci >= GATHER_STAGES) b->pool->wait_group(ci - GATHER_STAGES);  // staging buffer reuse
     if (host_out && used[h]) NN_CUDA(cudaStreamWaitEvent(b->st, b->ev_free[h], 0));
-    b->span_begin(ST_GRAM, b->st);
-    int l = launch_gram(nd.nd, b->bd, gd, (int)b->net->max_block, (int)q0, b->d_pairs.as<int>() + 2 * b->pair_begin[q0],
-                        (int)(b->pair_begin[q0 + nq] - b->pair_begin[q0]), b->st);
-    b->span_end(b->st, l);
+    if (!b->shared_gram || ci == 0) {
+      b->span_begin(ST_GRAM, b->st);
+      int l = b->shared_gram
+                  ? launch_gram(nd.nd, b->bd, b->gd, (int)b->net->max_block, 0, b->d_pairs.as<int>(), (int)b->pair_begin[1], b->st)
+                  : launch_gram(nd.nd, b->bd, gd, (int)b->net->max_block, (int)q0, b->d_pairs.as<int>() + 2 * b->pair_begin[q0],
+                                (int)(b->pair_begin[q0 + nq] - b->pair_begin[q0]), b->st);
+      b->span_end(b->st, l);
+    }
     emit_pass(b, gd, (int)q0, (int)nq, dst);
     if (sparse) {
       status = gather_chunk(b, ci, q0, nq, h, dst, host_out, flags);

@@ -831,3 +831,35 @@ def test_crown_in_the_batch_pipeline(ctx):
         tighter += sum((p[1] - p[0]).sum() for p in ibp.x_intvs) > sum((p[1] - p[0]).sum() for p in info.x_intvs)
     assert tighter == 2
     b.close()
+
+
+def test_reach_batch_shares_the_gram_blocks(ctx):
+    """A reach batch on a wide net (shared box and multipliers, per-direction normal and gamma_out): the Gram
+    contraction runs once for the whole batch (src/NnSdp.jl:73-95 builds qc_input / qc_activs once)."""
+    import nnsdp_b200 as nb
+
+    xdims, beta, nq = [2, 150, 260, 140, 2], 2, 6
+    net = rand_net(xdims, seed=9, sigma=0.3)
+    rng = np.random.default_rng(2)
+    base = rand_query(net, beta, rng, kind="hplane", radius=0.0)     # degenerate box: every layer Gram-active
+    th = 2 * np.pi * np.arange(nq) / nq
+    normals = np.stack([np.cos(th), np.sin(th)], axis=1)
+    gouts = rng.random((nq, 1))
+    batch = nb.NumericBatch(x1min=base.x1min, x1max=base.x1max, gamma_in=base.gin, gamma_bnd=base.gbnd,
+                            gamma_sec=base.gsec, out_kind=nb.OUT_HPLANE, out_vec=normals, gamma_out=gouts)
+    dnet = nb.Net(ctx, net.xdims, net.Ms)
+    b = nb.Batch(dnet, beta, Qcap=nq, ring=4)
+    b.set_inputs(batch, Q=nq)
+    out = np.full((nq, b.per_query), np.nan)
+    b.run(out)
+    ms, launches = b.stage_ms("gram")
+    assert launches == 1                      # one contraction for 6 queries in 3 chunks
+    ncon, nact = b.gram_stats()
+    assert ncon == nq * (len(xdims) - 2)
+    cliques = o.make_cliques(net, beta)
+    for i in range(nq):
+        q = o.NumericQuery(base.x1min, base.x1max, base.gin, base.gbnd, base.gsec, o.QcReachHplane(normals[i]), gouts[i])
+        ref = o.run_query(net, beta, q)
+        for blk, rb in zip(nb.split_blocks(out[i], cliques), ref["blocks"]):
+            assert relerr(blk, rb) <= TOL
+    b.close()
