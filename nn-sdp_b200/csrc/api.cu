@@ -1095,7 +1095,7 @@ static int32_t gather_chunk(nnsdp_batch* b, int ci, int64_t q0, int64_t nq, int 
   auto active = [&](const GatherCell& c, int64_t q) {
     if (dense_now(c, q)) return true;
     if (std::min<int64_t>(c.nrows, c.ncols_hint) < GATHER_MIN_RECT) return false;
-    if (prezeroed && c.pure_zero) return false;
+    if (prezeroed) return false;  // little is left to zero-fill: the host threads keep up without help
     // deterministic pseudo-random share, independent of the order of evaluation
     const uint64_t hsh = ((uint64_t)q * 1315423911u) ^ ((uint64_t)c.row0 * 2654435761u) ^ ((uint64_t)c.col0_hint * 97u);
     return (int)((hsh >> 7) % 100) < dma_zero_pct;
