@@ -863,3 +863,32 @@ def test_reach_batch_shares_the_gram_blocks(ctx):
         for blk, rb in zip(nb.split_blocks(out[i], cliques), ref["blocks"]):
             assert relerr(blk, rb) <= TOL
     b.close()
+
+
+def test_crown_and_lambda_max_over_several_chunks(ctx):
+    """More queries than one internal chunk holds (CROWN: 256, lambda_max: 64)."""
+    import nnsdp_b200 as nb
+
+    xdims, beta, Q = [2, 8, 9, 7, 2], 1, 300
+    net = rand_net(xdims, seed=12)
+    rng = np.random.default_rng(1)
+    c = rng.uniform(0.5, 1.5, (Q, 2))
+    rad = rng.uniform(0.0, 0.3, (Q, 1))
+    dnet = nb.Net(ctx, net.xdims, net.Ms)
+    r = nb.bounds_crown(dnet, c - rad, c + rad)
+    for i in (0, 127, 255, 256, 257, 299):
+        ref = o.intervals_crown(c[i] - rad[i], c[i] + rad[i], net)
+        xmin = np.concatenate([p[0] for p in ref.x_intvs])
+        xmax = np.concatenate([p[1] for p in ref.x_intvs])
+        scale = max(np.abs(xmax).max(), 1.0)
+        assert np.abs(r["xmin"][i] - xmin).max() <= 1e-11 * scale and np.abs(r["xmax"][i] - xmax).max() <= 1e-11 * scale
+    qs = [rand_query(net, beta, rng, kind="circle", radius=0.1) for _ in range(70)]
+    b = nb.Batch(dnet, beta, Qcap=70, ring=1)
+    b.set_inputs(to_numeric_batch(nb, net, qs))
+    b.bounds()
+    b.prepare()
+    lam, its = b.lambda_max(max_iters=100, tol=1e-12)
+    for i in (0, 63, 64, 69):
+        ev = np.linalg.eigvalsh(o.run_query(net, beta, qs[i])["Z"])
+        assert abs(lam[i] - ev[-1]) <= 1e-9 * max(abs(ev[0]), abs(ev[-1]))
+    b.close()
