@@ -10,6 +10,19 @@ for p in (os.path.join(ROOT, "nn-sdp_b200"), os.path.join(ROOT, "oracle"), ROOT)
         sys.path.insert(0, p)
 
 
+def _ensure_library():
+    """The tests go through the C ABI: build the shared library if a fresh checkout has none yet
+    (same command as __graft_entry__.build(); nvcc cross-compiles without a GPU)."""
+    lib = os.path.join(ROOT, "nn-sdp_b200", "lib", "libnnsdp_b200.so")
+    if not os.path.exists(lib):
+        import subprocess
+
+        subprocess.run(["make", "-C", os.path.join(ROOT, "nn-sdp_b200"), "-j8"], check=True)
+
+
+_ensure_library()
+
+
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
 
