@@ -892,3 +892,53 @@ def test_crown_and_lambda_max_over_several_chunks(ctx):
         ev = np.linalg.eigvalsh(o.run_query(net, beta, qs[i])["Z"])
         assert abs(lam[i] - ev[-1]) <= 1e-9 * max(abs(ev[0]), abs(ev[-1]))
     b.close()
+
+
+# ---------------------------------------------------------------------------------------------
+# randomised shapes around every threshold of the planner (block split at 48, tiles of 128 x 32, strips of 512,
+# gather cells of 256, window programs up to beta = 4, fast band up to beta = 8)
+# ---------------------------------------------------------------------------------------------
+def _random_shapes():
+    rng = np.random.default_rng(20241018)
+    pool = [3, 7, 31, 33, 47, 48, 49, 63, 64, 65, 127, 128, 129, 200, 255, 256, 257, 300, 511, 513]
+    shapes = []
+    for i in range(24):
+        depth = int(rng.integers(1, 5))
+        hidden = [int(rng.choice(pool if i % 3 else pool[:12])) for _ in range(depth)]
+        if sum(h * h for h in hidden) > 600_000:      # keep the oracle's dense Z small
+            hidden = [min(h, 300) for h in hidden]
+        xd = [int(rng.integers(1, 7))] + hidden + [int(rng.integers(1, 6))]
+        beta = int(rng.choice([0, 1, 2, 3, 4, 5, 8, 9]))
+        beta = min(beta, sum(hidden))
+        kind = ["safety", "hplane", "circle", "ellipsoid", "hplaneS"][i % 5]
+        shapes.append((xd, beta, kind))
+    return shapes
+
+
+@pytest.mark.parametrize("xdims,beta,kind", _random_shapes())
+def test_random_shapes_around_planner_thresholds(ctx, xdims, beta, kind):
+    import nnsdp_b200 as nb
+
+    net = rand_net(xdims, seed=sum(xdims) + beta, sigma=0.15)
+    rng = np.random.default_rng(beta + 7)
+    qs = [rand_query(net, beta, rng, kind=kind, radius=r) for r in (0.0, 0.25)]
+    dnet = nb.Net(ctx, net.xdims, net.Ms)
+    batch = to_numeric_batch(nb, net, qs)
+    b = nb.Batch(dnet, beta, Qcap=2, ring=2)
+    b.set_inputs(batch)
+    out = np.full((2, b.per_query), np.nan)
+    b.run(out)                                   # sparse gather where the net is wide enough
+    Zd = nb.assemble_dense(dnet, beta, batch)
+    cliques = dnet.cliques(beta)
+    refc = o.make_cliques(net, beta)
+    assert len(cliques) == len(refc) and all(np.array_equal(a[0], r[0]) for a, r in zip(cliques, refc))
+    for i, q in enumerate(qs):
+        ref = o.run_query(net, beta, q, form="closed")
+        assert relerr(Zd[i], ref["Z"]) <= TOL
+        assert np.array_equal(Zd[i], Zd[i].T)
+        for blk, (Ck, _, _) in zip(nb.split_blocks(out[i], cliques), cliques):
+            assert np.array_equal(blk, Zd[i][np.ix_(Ck - 1, Ck - 1)])
+    lam, _ = b.lambda_max(max_iters=300, tol=1e-12)
+    ev = np.linalg.eigvalsh(o.run_query(net, beta, qs[1], form="closed")["Z"])
+    assert abs(lam[1] - ev[-1]) <= 1e-8 * max(abs(ev[0]), abs(ev[-1]))
+    b.close()
