@@ -942,3 +942,31 @@ def test_random_shapes_around_planner_thresholds(ctx, xdims, beta, kind):
     ev = np.linalg.eigvalsh(o.run_query(net, beta, qs[1], form="closed")["Z"])
     assert abs(lam[1] - ev[-1]) <= 1e-8 * max(abs(ev[0]), abs(ev[-1]))
     b.close()
+
+
+@pytest.mark.parametrize("xdims,beta", [([3, 65, 49, 2], 2), ([4, 127, 48, 3], 3), ([2, 63, 63, 64, 4], 4), ([5, 47, 3, 3, 4], 3)])
+def test_affine_form_and_crown_on_mid_shapes(ctx, xdims, beta):
+    """Affine form: Z(gamma) rebuilt from the COO triplets == the numeric device path at a random gamma (no
+    oracle needed at these sizes); CROWN == the oracle's restatement."""
+    import nnsdp_b200 as nb
+
+    net = rand_net(xdims, seed=3, sigma=0.2)
+    rng = np.random.default_rng(4)
+    dnet = nb.Net(ctx, net.xdims, net.Ms)
+    for kind, radius in (("ellipsoid", 0.0), ("safety", 0.2)):
+        q = rand_query(net, beta, rng, kind=kind, radius=radius)
+        batch = to_numeric_batch(nb, net, [q])
+        A = nb.affine_form(dnet, beta, batch)
+        g = np.concatenate([q.gin, q.gout if kind != "safety" else [], q.gbnd, q.gsec])
+        zg = A["z0"].copy()
+        np.add.at(zg, A["coo_ent"] - 1, A["coo_val"] * g[A["coo_var"] - 1])
+        Z = nb.assemble_dense(dnet, beta, batch)[0]
+        assert np.abs(zg - Z[A["ent_row"] - 1, A["ent_col"] - 1]).max() <= TOL * max(np.abs(Z).max(), 1.0)
+        # nothing of Z lies outside the entries the affine form lists
+        mask = np.zeros_like(Z, dtype=bool)
+        mask[A["ent_row"] - 1, A["ent_col"] - 1] = True
+        assert not np.any((Z != 0) & ~(mask | mask.T))
+        r = nb.bounds_crown(dnet, q.x1min[None], q.x1max[None])
+        ref = o.intervals_crown(q.x1min, q.x1max, net)
+        xmax = np.concatenate([p[1] for p in ref.x_intvs])
+        assert np.abs(r["xmax"][0] - xmax).max() <= 1e-11 * max(np.abs(xmax).max(), 1.0)
