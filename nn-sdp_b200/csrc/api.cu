@@ -1620,20 +1620,37 @@ int32_t crown_bounds_device(nnsdp_batch* b) {
     // relu_0, W_0 and concretises on the input box
     auto chain = [&](const double* srcL, const double* srcU, long long src_row_stride, long long src_q_stride,
                      int k_first, int nrows, double* out_lo, double* out_hi, long long out_stride, int post) {
-      double* cur = rowsA.as<double>();
-      double* nxt = rowsB.as<double>();
+      // Per step either one fused launch (relaxation + biases + product; fewer launches) or a row kernel followed
+      // by a plain GEMM (less work per GEMM tile: the relaxation parameters are read once per row, not once per
+      // row and GEMM row-tile).  The output alternates between the two row buffers; the source of the first step
+      // is either the shared W rows or rowsB, so the first output goes to rowsA.
+      static const int fused_env = [] { const char* e = getenv("NNSDP_CROWN_FUSED"); return e ? atoi(e) : -1; }();
+      double* nxt = rowsA.as<double>();
+      double* other = rowsB.as<double>();
       for (int k = k_first; k >= 0; --k) {
         const int n = (int)sh.n[k + 1];
-        launches += launch_crown_row(srcL, srcU, src_row_stride, src_q_stride, cur, ld, nrows, nq, n,
-                                     du.as<double>() + poff(k), bu.as<double>() + poff(k), dl.as<double>() + poff(k),
-                                     P, bias_of(k), bias.as<double>(), st);
-        launches += gemm_set_launch(npd.Wt[k].as<double>(), b->net->ldT[k], (int)sh.n[k], n, cur, ld, nxt, ld,
-                                    2 * nq * nrows, st);
+        const bool fused = fused_env >= 0 ? fused_env != 0 : (sh.n[k] <= 64);  // one GEMM row-tile: nothing is re-read
+        if (fused) {
+          launches += launch_crown_step(npd.Wt[k].as<double>(), b->net->ldT[k], (int)sh.n[k], n, srcL, srcU,
+                                        src_row_stride, src_q_stride, nxt, ld, nrows, nq, du.as<double>() + poff(k),
+                                        bu.as<double>() + poff(k), dl.as<double>() + poff(k), P, bias_of(k),
+                                        bias.as<double>(), st);
+        } else {
+          // the row kernel may work in place when its source is one of the two row buffers
+          double* scaled = (srcL == other) ? other : nxt;
+          double* prod = (scaled == nxt) ? other : nxt;
+          launches += launch_crown_row(srcL, srcU, src_row_stride, src_q_stride, scaled, ld, nrows, nq, n,
+                                       du.as<double>() + poff(k), bu.as<double>() + poff(k), dl.as<double>() + poff(k),
+                                       P, bias_of(k), bias.as<double>(), st);
+          launches += gemm_set_launch(npd.Wt[k].as<double>(), b->net->ldT[k], (int)sh.n[k], n, scaled, ld, prod, ld,
+                                      2 * nq * nrows, st);
+          if (prod != nxt) std::swap(nxt, other);
+        }
         srcL = nxt;
         srcU = nxt + (size_t)nq * nrows * ld;
         src_row_stride = ld;
         src_q_stride = (long long)nrows * ld;
-        std::swap(cur, nxt);
+        std::swap(nxt, other);
       }
       launches += launch_crown_concretize(srcL, srcU, src_row_stride, src_q_stride, nrows, nq, n0, b->bd.x1min,
                                           b->bd.s_x1min, b->bd.x1max, b->bd.s_x1max, (int)q0, bias.as<double>(),

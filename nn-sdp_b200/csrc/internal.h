@@ -319,6 +319,11 @@ int launch_crown_row(const double* srcL, const double* srcU, long long src_row_s
                      double* dst, long long dst_row_stride, int nrows, int Qc, int n, const double* d_u,
                      const double* b_u, const double* d_l, long long par_stride, const double* bias_k,
                      double* bias, cudaStream_t st);
+// relaxation through relu_k + bias updates + product with W_k in one launch (replaces launch_crown_row + GEMM)
+int launch_crown_step(const double* Wt, int ldT, int M, int Kdim, const double* srcL, const double* srcU,
+                      long long src_row_stride, long long src_q_stride, double* dst, long long ld, int nrows, int Qc,
+                      const double* d_u, const double* b_u, const double* d_l, long long par_stride,
+                      const double* bias_k, double* bias, cudaStream_t st);
 int launch_crown_init_bias(const double* bt, int nrows, int Qc, double* bias, cudaStream_t st);
 int launch_crown_init_post(const double* Wt, int ldT, int n_in_k, const double* bias_k, const double* d_u,
                            const double* b_u, const double* d_l, long long par_stride, double* dst,

@@ -95,6 +95,110 @@ crown_row_kernel(const double* __restrict__ srcL, const double* __restrict__ src
   }
 }
 
+// One chain step in ONE launch: relaxation through relu_k, the two bias updates and the product with W_k.
+//   dst[col] (n_k entries) = W_k' * relax(src[col])          col = (half, q, r): half 0 = lower, 1 = upper
+//   bias[col] += sum_c [sign rule] src[col][c] b_u[c] + relax(src[col])[c] b_k[c]
+// A SIMT FP64 GEMM (64 x 64 x 16 tiles, 4 x 4 register blocks) whose B operand -- the rows of lA / uA -- is
+// relaxed while it is staged into shared memory; the CTAs of the first row-tile also reduce the bias sums of
+// their 64 columns (16 threads share a column of the staged tile: half-warp shuffle).  Replaces a row kernel
+// plus a GEMM: the chain is launch-bound on deep narrow nets and this halves the launches.
+constexpr int SB_M = 64, SB_N = 64, SB_K = 16, SB_THREADS = 256;
+
+__global__ void __launch_bounds__(SB_THREADS)
+crown_step_kernel(const double* __restrict__ Wt, int ldT, int M, int Kdim,          // W_k' : M = n_k rows, Kdim = n_{k+1}
+                  const double* __restrict__ srcL, const double* __restrict__ srcU, long long src_row_stride,
+                  long long src_q_stride, double* __restrict__ dst, long long ld, int nrows, int Qc,
+                  const double* __restrict__ d_u, const double* __restrict__ b_u, const double* __restrict__ d_l,
+                  long long par_stride, const double* __restrict__ bias_k, double* __restrict__ bias) {
+  __shared__ double As[SB_K][SB_M];
+  __shared__ double Bs[SB_K][SB_N + 1];
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  const int m0 = blockIdx.x * SB_M, n0 = blockIdx.y * SB_N;
+  const int N = 2 * Qc * nrows;
+  const bool do_bias = (blockIdx.x == 0);
+  // the four columns of the staged B tile this thread loads (k = tid % 16, n = tid / 16 + 16 i)
+  const int kk = tid & 15;
+  const double* colp[4];
+  const double *pu[4], *pb[4], *pl[4];
+  bool upper[4], valid[4];
+  double bsum[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int gn = n0 + (tid >> 4) + 16 * i;
+    valid[i] = gn < N;
+    const int g = valid[i] ? gn : 0;
+    const int half = g / (Qc * nrows), rem = g - half * (Qc * nrows);
+    const int q = rem / nrows, r = rem - q * nrows;
+    upper[i] = half == 1;
+    colp[i] = (half ? srcU : srcL) + (long long)q * src_q_stride + (long long)r * src_row_stride;
+    pu[i] = d_u + (long long)q * par_stride;
+    pb[i] = b_u + (long long)q * par_stride;
+    pl[i] = d_l + (long long)q * par_stride;
+  }
+  double acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.0;
+
+  for (int k0 = 0; k0 < Kdim; k0 += SB_K) {
+#pragma unroll
+    for (int i = 0; i < (SB_K * SB_M) / SB_THREADS; ++i) {
+      const int idx = tid + i * SB_THREADS;
+      const int m = idx % SB_M, k = idx / SB_M;
+      const int gm = m0 + m, gk = k0 + k;
+      As[k][m] = (gm < M && gk < Kdim) ? Wt[gm + (long long)gk * ldT] : 0.0;
+    }
+    const int gk = k0 + kk;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      double t = 0.0;
+      if (valid[i] && gk < Kdim) {
+        const double v = colp[i][gk];
+        const bool use_u = upper[i] ? (v > 0.0) : (v < 0.0);  // the entries that take the upper line of the relaxation
+        t = v * (use_u ? pu[i][gk] : pl[i][gk]);
+        if (do_bias) {
+          if (use_u) bsum[i] = fma(v, pb[i][gk], bsum[i]);
+          bsum[i] = fma(t, bias_k[gk], bsum[i]);
+        }
+      }
+      Bs[kk][(tid >> 4) + 16 * i] = t;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < SB_K; ++k) {
+      double a[4], bb[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) a[i] = As[k][tx * 4 + i];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) bb[j] = Bs[k][ty * 4 + j];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fma(a[i], bb[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int gn = n0 + ty * 4 + j;
+    if (gn >= N) continue;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int gm = m0 + tx * 4 + i;
+      if (gm < M) dst[(long long)gn * ld + gm] = acc[i][j];
+    }
+  }
+  if (do_bias) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      double v = bsum[i];
+      for (int o = 8; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o, 16);
+      if (kk == 0 && valid[i]) bias[n0 + (tid >> 4) + 16 * i] += v;
+    }
+  }
+}
+
 // bias[.][q][r] = b_t[r]  (start of a pre-activation target)
 __global__ void crown_init_bias_kernel(const double* __restrict__ bt, int nrows, int Qc, double* __restrict__ bias) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -170,6 +274,17 @@ int launch_crown_row(const double* srcL, const double* srcU, long long src_row_s
   crown_row_kernel<<<dim3(nrows, Qc), CR_THREADS, 0, st>>>(srcL, srcU, src_row_stride, src_q_stride, dst,
                                                           dst_row_stride, nrows, Qc, n, d_u, b_u, d_l, par_stride,
                                                           bias_k, bias);
+  return 1;
+}
+
+int launch_crown_step(const double* Wt, int ldT, int M, int Kdim, const double* srcL, const double* srcU,
+                      long long src_row_stride, long long src_q_stride, double* dst, long long ld, int nrows, int Qc,
+                      const double* d_u, const double* b_u, const double* d_l, long long par_stride,
+                      const double* bias_k, double* bias, cudaStream_t st) {
+  const int N = 2 * Qc * nrows;
+  dim3 grid((M + SB_M - 1) / SB_M, (N + SB_N - 1) / SB_N);
+  crown_step_kernel<<<grid, SB_THREADS, 0, st>>>(Wt, ldT, M, Kdim, srcL, srcU, src_row_stride, src_q_stride, dst, ld,
+                                                 nrows, Qc, d_u, b_u, d_l, par_stride, bias_k, bias);
   return 1;
 }
 
