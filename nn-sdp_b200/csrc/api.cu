@@ -1593,17 +1593,23 @@ int32_t crown_bounds_device(nnsdp_batch* b) {
   int64_t maxn = 0;
   for (int k = 0; k <= K; ++k) maxn = std::max(maxn, sh.n[k]);
   const int64_t ld = maxn;
-  // queries per chunk: two row buffers of 2 * Qc * maxn * ld doubles, kept under ~1.5 GiB together
-  int Qc = (int)std::max<int64_t>(1, std::min<int64_t>(b->Q, (int64_t(3) << 26) / std::max<int64_t>(1, 4 * maxn * ld)));
+  // narrow nets (every step is the fused kernel): the post-activation targets walk back together, stacked
+  static const bool no_wave = [] { const char* e = getenv("NNSDP_CROWN_NO_WAVEFRONT"); return e && e[0] == '1'; }();
+  int64_t max_hidden_in = 0;
+  for (int k = 0; k <= K - 2; ++k) max_hidden_in = std::max(max_hidden_in, sh.n[k]);
+  const bool wavefront = !no_wave && K >= 16 && max_hidden_in <= 64;  // shallow nets: too few steps to save
+  const int64_t rows_cap = wavefront ? std::max<int64_t>(maxn, sh.acdim) : maxn;  // row slots per (half, query)
+  // queries per chunk: two row buffers of 2 * Qc * rows_cap * ld doubles, kept under ~1.5 GiB together
+  int Qc = (int)std::max<int64_t>(1, std::min<int64_t>(b->Q, (int64_t(3) << 26) / std::max<int64_t>(1, 4 * rows_cap * ld)));
   Qc = std::min(Qc, 256);
   DevBuf rowsA, rowsB, bias, prel, preu, du, bu, dl;
   struct Rel {
     std::vector<DevBuf*> v;
     ~Rel() { for (DevBuf* x : v) x->release(); }
   } rel{{&rowsA, &rowsB, &bias, &prel, &preu, &du, &bu, &dl}};
-  NN_TRY(rowsA.ensure((size_t)2 * Qc * maxn * ld * 8));
-  NN_TRY(rowsB.ensure((size_t)2 * Qc * maxn * ld * 8));
-  NN_TRY(bias.ensure((size_t)2 * Qc * maxn * 8));
+  NN_TRY(rowsA.ensure((size_t)2 * Qc * rows_cap * ld * 8));
+  NN_TRY(rowsB.ensure((size_t)2 * Qc * rows_cap * ld * 8));
+  NN_TRY(bias.ensure((size_t)2 * Qc * rows_cap * 8));
   for (DevBuf* x : {&prel, &preu, &du, &bu, &dl}) NN_TRY(x->ensure((size_t)Qc * P * 8));
   cudaStream_t st = b->st;
   double* xmin = b->xmin.as<double>();
@@ -1632,7 +1638,7 @@ int32_t crown_bounds_device(nnsdp_batch* b) {
         const bool fused = fused_env >= 0 ? fused_env != 0 : (sh.n[k] <= 64);  // one GEMM row-tile: nothing is re-read
         if (fused) {
           launches += launch_crown_step(npd.Wt[k].as<double>(), b->net->ldT[k], (int)sh.n[k], n, srcL, srcU,
-                                        src_row_stride, src_q_stride, nxt, ld, nrows, nq, du.as<double>() + poff(k),
+                                        src_row_stride, src_q_stride, nxt, ld, nrows, nrows, nq, du.as<double>() + poff(k),
                                         bu.as<double>() + poff(k), dl.as<double>() + poff(k), P, bias_of(k),
                                         bias.as<double>(), st);
         } else {
@@ -1652,7 +1658,7 @@ int32_t crown_bounds_device(nnsdp_batch* b) {
         src_q_stride = (long long)nrows * ld;
         std::swap(nxt, other);
       }
-      launches += launch_crown_concretize(srcL, srcU, src_row_stride, src_q_stride, nrows, nq, n0, b->bd.x1min,
+      launches += launch_crown_concretize(srcL, srcU, src_row_stride, src_q_stride, nrows, nrows, 0, nq, n0, b->bd.x1min,
                                           b->bd.s_x1min, b->bd.x1max, b->bd.s_x1max, (int)q0, bias.as<double>(),
                                           out_lo, out_hi, out_stride, post, st);
     };
@@ -1675,15 +1681,48 @@ int32_t crown_bounds_device(nnsdp_batch* b) {
                                         dl.as<double>() + poff(t), st);
     }
     // x_{k+1} = relu(y_k), k = 0 .. K-2: the output of the (k+1)-layer prefix followed by an identity layer
-    for (int k = 0; k <= K - 2; ++k) {
-      const int nrows = (int)sh.n[k + 1];
-      double* src = rowsB.as<double>();  // chain() writes its first step into rowsA
-      launches += launch_crown_init_post(npd.Wt[k].as<double>(), b->net->ldT[k], (int)sh.n[k], bias_of(k),
-                                         du.as<double>() + poff(k), bu.as<double>() + poff(k),
-                                         dl.as<double>() + poff(k), P, src, ld, nrows, nq, bias.as<double>(), st);
-      // rows are now functions of x_k: continue with relu_{k-1}, W_{k-1}, ... (k = 0: concretise at once)
-      chain(src, src + (size_t)nq * nrows * ld, ld, (long long)nrows * ld, k - 1, nrows,
-            xmin + q0 * sh.xtot + sh.xoff[k + 1], xmax + q0 * sh.xtot + sh.xoff[k + 1], sh.xtot, 1);
+    if (wavefront) {
+      // Narrow nets: all K-1 targets walk back together.  Their rows are stacked (target K-2 first); the step
+      // through (relu_j, W_j) handles the rows of every target k > j in one fused launch, after which target j
+      // joins the stack: 2 (K-1) launches instead of (K-1)(K-2)/2 chain steps.
+      const int Rs = (int)sh.acdim;
+      std::vector<int> roff(K, 0);
+      for (int k = K - 3; k >= 0; --k) roff[k] = roff[k + 1] + (int)sh.n[k + 2];
+      double* cur = rowsA.as<double>();
+      double* nxt = rowsB.as<double>();
+      auto join = [&](int k) {  // rows of target k, functions of x_k, into `cur`
+        launches += launch_crown_init_post(npd.Wt[k].as<double>(), b->net->ldT[k], (int)sh.n[k], bias_of(k),
+                                           du.as<double>() + poff(k), bu.as<double>() + poff(k),
+                                           dl.as<double>() + poff(k), P, cur, ld, (int)sh.n[k + 1], Rs, roff[k], nq,
+                                           bias.as<double>(), st);
+      };
+      join(K - 2);
+      for (int j = K - 3; j >= 0; --j) {
+        launches += launch_crown_step(npd.Wt[j].as<double>(), b->net->ldT[j], (int)sh.n[j], (int)sh.n[j + 1], cur,
+                                      cur + (size_t)nq * Rs * ld, ld, (long long)Rs * ld, nxt, ld, roff[j], Rs, nq,
+                                      du.as<double>() + poff(j), bu.as<double>() + poff(j), dl.as<double>() + poff(j),
+                                      P, bias_of(j), bias.as<double>(), st);
+        std::swap(cur, nxt);
+        join(j);
+      }
+      for (int k = 0; k <= K - 2; ++k)
+        launches += launch_crown_concretize(cur + (size_t)roff[k] * ld, cur + ((size_t)nq * Rs + roff[k]) * ld, ld,
+                                            (long long)Rs * ld, (int)sh.n[k + 1], Rs, roff[k], nq, n0, b->bd.x1min,
+                                            b->bd.s_x1min, b->bd.x1max, b->bd.s_x1max, (int)q0, bias.as<double>(),
+                                            xmin + q0 * sh.xtot + sh.xoff[k + 1], xmax + q0 * sh.xtot + sh.xoff[k + 1],
+                                            sh.xtot, 1, st);
+    } else {
+      for (int k = 0; k <= K - 2; ++k) {
+        const int nrows = (int)sh.n[k + 1];
+        double* src = rowsB.as<double>();  // chain() writes its first step into rowsA
+        launches += launch_crown_init_post(npd.Wt[k].as<double>(), b->net->ldT[k], (int)sh.n[k], bias_of(k),
+                                           du.as<double>() + poff(k), bu.as<double>() + poff(k),
+                                           dl.as<double>() + poff(k), P, src, ld, nrows, nrows, 0, nq,
+                                           bias.as<double>(), st);
+        // rows are now functions of x_k: continue with relu_{k-1}, W_{k-1}, ... (k = 0: concretise at once)
+        chain(src, src + (size_t)nq * nrows * ld, ld, (long long)nrows * ld, k - 1, nrows,
+              xmin + q0 * sh.xtot + sh.xoff[k + 1], xmax + q0 * sh.xtot + sh.xoff[k + 1], sh.xtot, 1);
+      }
     }
     // x_K = y_{K-1} with the same post-processing: copy through a concretisation-free path
     {
@@ -1695,7 +1734,7 @@ int32_t crown_bounds_device(nnsdp_batch* b) {
                         (size_t)nrows * 8, nq, cudaMemcpyDeviceToDevice, st);
       cudaMemcpy2DAsync(bias.as<double>() + (size_t)nq * nrows, (size_t)nrows * 8, preu.as<double>() + poff(K - 1),
                         (size_t)P * 8, (size_t)nrows * 8, nq, cudaMemcpyDeviceToDevice, st);
-      launches += launch_crown_concretize(rowsA.as<double>(), rowsA.as<double>(), ld, 0, nrows, nq, 0, b->bd.x1min,
+      launches += launch_crown_concretize(rowsA.as<double>(), rowsA.as<double>(), ld, 0, nrows, nrows, 0, nq, 0, b->bd.x1min,
                                           b->bd.s_x1min, b->bd.x1max, b->bd.s_x1max, (int)q0, bias.as<double>(),
                                           xmin + q0 * sh.xtot + sh.xoff[K], xmax + q0 * sh.xtot + sh.xoff[K], sh.xtot,
                                           1, st);

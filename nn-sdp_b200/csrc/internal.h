@@ -312,7 +312,8 @@ int gemm_acc_launch(const double* A, int lda, int M, int Kdim, const double* B, 
 int gemm_set_launch(const double* A, int lda, int M, int Kdim, const double* B, long long ldb,
                     double* C, long long ldc, int N, cudaStream_t st);
 
-// CROWN bounds (kernels_crown.cu): rows of lA / uA of a chunk of Qc queries are stacked [2][Qc][nrows][ld]
+// CROWN bounds (kernels_crown.cu): rows of lA / uA of a chunk of Qc queries are stacked [2][Qc][Rs][ld]; a kernel
+// works on nrows rows starting at row slot row0 of every (half, query) group (Rs = nrows, row0 = 0 for one target)
 int launch_crown_params(const double* l, const double* u, long long stride, int n, int Qc, double* d_u,
                         double* b_u, double* d_l, cudaStream_t st);
 int launch_crown_row(const double* srcL, const double* srcU, long long src_row_stride, long long src_q_stride,
@@ -321,17 +322,18 @@ int launch_crown_row(const double* srcL, const double* srcU, long long src_row_s
                      double* bias, cudaStream_t st);
 // relaxation through relu_k + bias updates + product with W_k in one launch (replaces launch_crown_row + GEMM)
 int launch_crown_step(const double* Wt, int ldT, int M, int Kdim, const double* srcL, const double* srcU,
-                      long long src_row_stride, long long src_q_stride, double* dst, long long ld, int nrows, int Qc,
-                      const double* d_u, const double* b_u, const double* d_l, long long par_stride,
+                      long long src_row_stride, long long src_q_stride, double* dst, long long ld, int nrows, int Rs,
+                      int Qc, const double* d_u, const double* b_u, const double* d_l, long long par_stride,
                       const double* bias_k, double* bias, cudaStream_t st);
 int launch_crown_init_bias(const double* bt, int nrows, int Qc, double* bias, cudaStream_t st);
 int launch_crown_init_post(const double* Wt, int ldT, int n_in_k, const double* bias_k, const double* d_u,
                            const double* b_u, const double* d_l, long long par_stride, double* dst,
-                           long long dst_row_stride, int nrows, int Qc, double* bias, cudaStream_t st);
+                           long long dst_row_stride, int nrows, int Rs, int row0, int Qc, double* bias,
+                           cudaStream_t st);
 int launch_crown_concretize(const double* rowsL, const double* rowsU, long long row_stride, long long q_stride,
-                            int nrows, int Qc, int n0, const double* x1min, long long s_min, const double* x1max,
-                            long long s_max, int q_first, const double* bias, double* out_lo, double* out_hi,
-                            long long out_stride, int postprocess, cudaStream_t st);
+                            int nrows, int Rs, int row0, int Qc, int n0, const double* x1min, long long s_min,
+                            const double* x1max, long long s_max, int q_first, const double* bias, double* out_lo,
+                            double* out_hi, long long out_stride, int postprocess, cudaStream_t st);
 
 // thin-entry pack: packed[s * nthin + i] = ring[s * per_query + idx[i]] for the nq slots of a chunk
 int launch_pack_thin(const double* ring, long long per_query, const long long* idx, long long nthin,

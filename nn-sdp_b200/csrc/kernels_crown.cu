@@ -107,9 +107,10 @@ constexpr int SB_M = 64, SB_N = 64, SB_K = 16, SB_THREADS = 256;
 __global__ void __launch_bounds__(SB_THREADS)
 crown_step_kernel(const double* __restrict__ Wt, int ldT, int M, int Kdim,          // W_k' : M = n_k rows, Kdim = n_{k+1}
                   const double* __restrict__ srcL, const double* __restrict__ srcU, long long src_row_stride,
-                  long long src_q_stride, double* __restrict__ dst, long long ld, int nrows, int Qc,
+                  long long src_q_stride, double* __restrict__ dst, long long ld, int nrows, int Rs, int Qc,
                   const double* __restrict__ d_u, const double* __restrict__ b_u, const double* __restrict__ d_l,
                   long long par_stride, const double* __restrict__ bias_k, double* __restrict__ bias) {
+  // nrows active rows per (half, query), stored with Rs row slots per (half, query) in dst and bias
   __shared__ double As[SB_K][SB_M];
   __shared__ double Bs[SB_K][SB_N + 1];
   const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
@@ -120,6 +121,7 @@ crown_step_kernel(const double* __restrict__ Wt, int ldT, int M, int Kdim,      
   const int kk = tid & 15;
   const double* colp[4];
   const double *pu[4], *pb[4], *pl[4];
+  long long slot[4];  // (half * Qc + q) * Rs + r : row slot of the column in dst / bias
   bool upper[4], valid[4];
   double bsum[4] = {0.0, 0.0, 0.0, 0.0};
 #pragma unroll
@@ -130,6 +132,7 @@ crown_step_kernel(const double* __restrict__ Wt, int ldT, int M, int Kdim,      
     const int half = g / (Qc * nrows), rem = g - half * (Qc * nrows);
     const int q = rem / nrows, r = rem - q * nrows;
     upper[i] = half == 1;
+    slot[i] = ((long long)half * Qc + q) * Rs + r;
     colp[i] = (half ? srcU : srcL) + (long long)q * src_q_stride + (long long)r * src_row_stride;
     pu[i] = d_u + (long long)q * par_stride;
     pb[i] = b_u + (long long)q * par_stride;
@@ -183,10 +186,13 @@ crown_step_kernel(const double* __restrict__ Wt, int ldT, int M, int Kdim,      
   for (int j = 0; j < 4; ++j) {
     const int gn = n0 + ty * 4 + j;
     if (gn >= N) continue;
+    const int half = gn / (Qc * nrows), rem = gn - half * (Qc * nrows);
+    const int q = rem / nrows, r = rem - q * nrows;
+    double* out = dst + (((long long)half * Qc + q) * Rs + r) * ld;
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const int gm = m0 + tx * 4 + i;
-      if (gm < M) dst[(long long)gn * ld + gm] = acc[i][j];
+      if (gm < M) out[gm] = acc[i][j];
     }
   }
   if (do_bias) {
@@ -194,7 +200,7 @@ crown_step_kernel(const double* __restrict__ Wt, int ldT, int M, int Kdim,      
     for (int i = 0; i < 4; ++i) {
       double v = bsum[i];
       for (int o = 8; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o, 16);
-      if (kk == 0 && valid[i]) bias[n0 + (tid >> 4) + 16 * i] += v;
+      if (kk == 0 && valid[i]) bias[slot[i]] += v;
     }
   }
 }
@@ -212,26 +218,27 @@ __global__ void __launch_bounds__(CR_THREADS)
 crown_init_post_kernel(const double* __restrict__ Wt, int ldT, int n_in_k, const double* __restrict__ bias_k,
                        const double* __restrict__ d_u, const double* __restrict__ b_u,
                        const double* __restrict__ d_l, long long par_stride, double* __restrict__ dst,
-                       long long dst_row_stride, int nrows, int Qc, double* __restrict__ bias) {
+                       long long dst_row_stride, int Rs, int row0, int Qc, double* __restrict__ bias) {
+  // rows [row0, row0 + gridDim.x) of a stack with Rs row slots per (half, query)
   const int r = blockIdx.x, q = blockIdx.y;
   const double du = d_u[(long long)q * par_stride + r], dl = d_l[(long long)q * par_stride + r];
   const double* w = Wt + (long long)r * ldT;  // row r of W_k
-  double* ol = dst + ((long long)q * nrows + r) * dst_row_stride;
-  double* ou = dst + ((long long)(Qc + q) * nrows + r) * dst_row_stride;
+  double* ol = dst + ((long long)q * Rs + row0 + r) * dst_row_stride;
+  double* ou = dst + ((long long)(Qc + q) * Rs + row0 + r) * dst_row_stride;
   for (int c = threadIdx.x; c < n_in_k; c += CR_THREADS) {
     ol[c] = dl * w[c];
     ou[c] = du * w[c];
   }
   if (threadIdx.x == 0) {
-    bias[(long long)q * nrows + r] = dl * bias_k[r];
-    bias[((long long)Qc + q) * nrows + r] = b_u[(long long)q * par_stride + r] + du * bias_k[r];
+    bias[(long long)q * Rs + row0 + r] = dl * bias_k[r];
+    bias[((long long)Qc + q) * Rs + row0 + r] = b_u[(long long)q * par_stride + r] + du * bias_k[r];
   }
 }
 
 // concretisation on the input box; optional min/max post-processing of intervals_auto_lirpa.jl:37-39
 __global__ void __launch_bounds__(CR_THREADS)
 crown_concretize_kernel(const double* __restrict__ rowsL, const double* __restrict__ rowsU, long long row_stride,
-                        long long q_stride, int nrows, int Qc, int n0, const double* __restrict__ x1min,
+                        long long q_stride, int Rs, int row0, int Qc, int n0, const double* __restrict__ x1min,
                         long long s_min, const double* __restrict__ x1max, long long s_max, int q_first,
                         const double* __restrict__ bias, double* __restrict__ out_lo, double* __restrict__ out_hi,
                         long long out_stride, int postprocess) {
@@ -249,7 +256,7 @@ crown_concretize_kernel(const double* __restrict__ rowsL, const double* __restri
   }
   const double tl = cr_block_sum(sl, red), tu = cr_block_sum(su, red);
   if (threadIdx.x == 0) {
-    double L = tl + bias[(long long)q * nrows + r], U = tu + bias[((long long)Qc + q) * nrows + r];
+    double L = tl + bias[(long long)q * Rs + row0 + r], U = tu + bias[((long long)Qc + q) * Rs + row0 + r];
     if (postprocess) {
       L = fmin(L, U);
       U = fmax(L, U);
@@ -278,13 +285,13 @@ int launch_crown_row(const double* srcL, const double* srcU, long long src_row_s
 }
 
 int launch_crown_step(const double* Wt, int ldT, int M, int Kdim, const double* srcL, const double* srcU,
-                      long long src_row_stride, long long src_q_stride, double* dst, long long ld, int nrows, int Qc,
-                      const double* d_u, const double* b_u, const double* d_l, long long par_stride,
+                      long long src_row_stride, long long src_q_stride, double* dst, long long ld, int nrows, int Rs,
+                      int Qc, const double* d_u, const double* b_u, const double* d_l, long long par_stride,
                       const double* bias_k, double* bias, cudaStream_t st) {
   const int N = 2 * Qc * nrows;
   dim3 grid((M + SB_M - 1) / SB_M, (N + SB_N - 1) / SB_N);
   crown_step_kernel<<<grid, SB_THREADS, 0, st>>>(Wt, ldT, M, Kdim, srcL, srcU, src_row_stride, src_q_stride, dst, ld,
-                                                 nrows, Qc, d_u, b_u, d_l, par_stride, bias_k, bias);
+                                                 nrows, Rs, Qc, d_u, b_u, d_l, par_stride, bias_k, bias);
   return 1;
 }
 
@@ -296,17 +303,18 @@ int launch_crown_init_bias(const double* bt, int nrows, int Qc, double* bias, cu
 
 int launch_crown_init_post(const double* Wt, int ldT, int n_in_k, const double* bias_k, const double* d_u,
                            const double* b_u, const double* d_l, long long par_stride, double* dst,
-                           long long dst_row_stride, int nrows, int Qc, double* bias, cudaStream_t st) {
+                           long long dst_row_stride, int nrows, int Rs, int row0, int Qc, double* bias,
+                           cudaStream_t st) {
   crown_init_post_kernel<<<dim3(nrows, Qc), CR_THREADS, 0, st>>>(Wt, ldT, n_in_k, bias_k, d_u, b_u, d_l, par_stride,
-                                                                dst, dst_row_stride, nrows, Qc, bias);
+                                                                dst, dst_row_stride, Rs, row0, Qc, bias);
   return 1;
 }
 
 int launch_crown_concretize(const double* rowsL, const double* rowsU, long long row_stride, long long q_stride,
-                            int nrows, int Qc, int n0, const double* x1min, long long s_min, const double* x1max,
-                            long long s_max, int q_first, const double* bias, double* out_lo, double* out_hi,
-                            long long out_stride, int postprocess, cudaStream_t st) {
-  crown_concretize_kernel<<<dim3(nrows, Qc), CR_THREADS, 0, st>>>(rowsL, rowsU, row_stride, q_stride, nrows, Qc, n0,
+                            int nrows, int Rs, int row0, int Qc, int n0, const double* x1min, long long s_min,
+                            const double* x1max, long long s_max, int q_first, const double* bias, double* out_lo,
+                            double* out_hi, long long out_stride, int postprocess, cudaStream_t st) {
+  crown_concretize_kernel<<<dim3(nrows, Qc), CR_THREADS, 0, st>>>(rowsL, rowsU, row_stride, q_stride, Rs, row0, Qc, n0,
                                                                  x1min, s_min, x1max, s_max, q_first, bias, out_lo,
                                                                  out_hi, out_stride, postprocess);
   return 1;

@@ -970,3 +970,26 @@ def test_affine_form_and_crown_on_mid_shapes(ctx, xdims, beta):
         ref = o.intervals_crown(q.x1min, q.x1max, net)
         xmax = np.concatenate([p[1] for p in ref.x_intvs])
         assert np.abs(r["xmax"][0] - xmax).max() <= 1e-11 * max(np.abs(xmax).max(), 1.0)
+
+
+def test_crown_wavefront_deep_narrow_net(ctx):
+    """K >= 16 and widths <= 64: the post-activation targets are bounded as one stack (wavefront); same numbers
+    as the oracle's one-target-at-a-time restatement."""
+    import nnsdp_b200 as nb
+
+    xdims = [3] + [9, 12, 7, 10] * 5 + [2]      # K = 21, ragged widths
+    net = rand_net(xdims, seed=21)
+    rng = np.random.default_rng(5)
+    c = rng.uniform(0.5, 1.5, (3, 3))
+    rad = np.array([[0.0], [0.02], [0.3]])
+    dnet = nb.Net(ctx, net.xdims, net.Ms)
+    r = nb.bounds_crown(dnet, c - rad, c + rad)
+    for i in range(3):
+        ref = o.intervals_crown(c[i] - rad[i], c[i] + rad[i], net)
+        xmin = np.concatenate([p[0] for p in ref.x_intvs])
+        xmax = np.concatenate([p[1] for p in ref.x_intvs])
+        amax = np.concatenate([p[1] for p in ref.acx_intvs])
+        scale = max(np.abs(xmax).max(), np.abs(xmin).max(), 1.0)
+        assert np.abs(r["xmin"][i] - xmin).max() <= 1e-11 * scale
+        assert np.abs(r["xmax"][i] - xmax).max() <= 1e-11 * scale
+        assert np.abs(r["acxmax"][i] - amax).max() <= 1e-11 * scale

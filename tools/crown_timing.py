@@ -18,9 +18,11 @@ for xdims, Q in (([2] + [10] * 10 + [2], 64), ([2] + [20] * 100 + [2], 16), ([2]
     dnet = nb.Net(ctx, net.xdims, net.Ms)
     for name, fn in (("ibp", nb.bounds_ibp), ("crown", nb.bounds_crown)):
         fn(dnet, lo, hi)
-        t0 = time.perf_counter()
-        r = fn(dnet, lo, hi)
-        dt = time.perf_counter() - t0
+        dt = 1e9
+        for _ in range(5):   # best of 5: the launch-bound cases are sensitive to host noise
+            t0 = time.perf_counter()
+            r = fn(dnet, lo, hi)
+            dt = min(dt, time.perf_counter() - t0)
         w = float(np.mean(r["xmax"] - r["xmin"]))
         print(f"W{xdims[1]}-D{len(xdims) - 2} Q={Q:3d} {name:5s} {1e3 * dt:9.2f} ms per call ({1e3 * dt / Q:8.3f} ms/query)  mean interval width {w:.4g}")
     if xdims[1] <= 20:
