@@ -951,20 +951,30 @@ int32_t nnsdp_batch_bounds(nnsdp_batch* b) {
   double* xmax = b->xmax.as<double>();
   b->span_begin(ST_BOUNDS, b->st);
   int launches = 0;
-  launches += launch_place_x1(b->bd.x1min, b->bd.s_x1min, b->bd.x1max, b->bd.s_x1max, xmin, xmax,
-                              sh.xtot, (int)sh.n_in(), Q, b->st);
-  for (int k = 0; k < sh.K; ++k) {
-    const bool last = (k == sh.K - 1);
-    launches += ibp_layer_launch(
-        nd.M[k].as<double>(), (int)sh.n[k + 1], (int)sh.n[k], xmin + sh.xoff[k], xmax + sh.xoff[k],
-        sh.xtot, xmin + sh.xoff[k + 1], xmax + sh.xoff[k + 1],
-        last ? nullptr : b->acxmin.as<double>() + sh.noff(k + 1),
-        last ? nullptr : b->acxmax.as<double>() + sh.noff(k + 1), sh.acdim, Q, last ? 0 : 1, 1,
-        nullptr, b->st);
+  int max_out = 0;
+  for (int k = 1; k <= sh.K; ++k) max_out = std::max(max_out, (int)sh.n[k]);
+  const int whole = ibp_all_launch(nd.nd, max_out, b->bd.x1min, b->bd.s_x1min, b->bd.x1max, b->bd.s_x1max, xmin, xmax,
+                                   sh.xtot, b->acxmin.as<double>(), b->acxmax.as<double>(), b->smin_c.as<double>(),
+                                   b->smax_c.as<double>(), sh.acdim, Q, nullptr, b->st);
+  NN_CHECK(whole >= 0, NNSDP_ERR_CUDA, "cooperative launch of the interval propagation failed: %s",
+           cudaGetErrorString(cudaGetLastError()));
+  launches += whole;
+  if (whole == 0) {
+    launches += launch_place_x1(b->bd.x1min, b->bd.s_x1min, b->bd.x1max, b->bd.s_x1max, xmin, xmax,
+                                sh.xtot, (int)sh.n_in(), Q, b->st);
+    for (int k = 0; k < sh.K; ++k) {
+      const bool last = (k == sh.K - 1);
+      launches += ibp_layer_launch(
+          nd.M[k].as<double>(), (int)sh.n[k + 1], (int)sh.n[k], xmin + sh.xoff[k], xmax + sh.xoff[k],
+          sh.xtot, xmin + sh.xoff[k + 1], xmax + sh.xoff[k + 1],
+          last ? nullptr : b->acxmin.as<double>() + sh.noff(k + 1),
+          last ? nullptr : b->acxmax.as<double>() + sh.noff(k + 1), sh.acdim, Q, last ? 0 : 1, 1,
+          nullptr, b->st);
+    }
+    launches += launch_sector_minmax(sh.acdim * (long long)Q, b->acxmin.as<double>(),
+                                     b->acxmax.as<double>(), b->smin_c.as<double>(),
+                                     b->smax_c.as<double>(), b->st);
   }
-  launches += launch_sector_minmax(sh.acdim * (long long)Q, b->acxmin.as<double>(),
-                                   b->acxmax.as<double>(), b->smin_c.as<double>(),
-                                   b->smax_c.as<double>(), b->st);
   b->span_end(b->st, launches);
   NN_CUDA(cudaGetLastError());
   b->bounds_done = true;
@@ -982,10 +992,15 @@ int32_t nnsdp_batch_prepare(nnsdp_batch* b) {
   const NetPerDev& nd = *b->nd;
   b->span_begin(ST_PREP, b->st);
   int launches = launch_prep(nd.nd, b->bd, b->flags.as<int>(), b->st);
-  for (int blk = 0; blk <= sh.K - 2; ++blk)
-    launches += affine_layer_launch(nd.Wt[blk].as<double>(), b->net->ldT[blk], (int)sh.n[blk],
-                                    (int)sh.n[blk + 1], b->bd.u + sh.noff(blk + 1), sh.acdim,
-                                    b->bd.aff + sh.off[blk], sh.Zdim, (int)b->Q, b->st);
+  int max_rows = 0;
+  for (int blk = 0; blk <= sh.K - 2; ++blk) max_rows = std::max(max_rows, (int)sh.n[blk]);
+  const int all = affine_all_launch(nd.nd, sh.K, max_rows, b->bd.u, sh.acdim, b->bd.aff, sh.Zdim, (int)b->Q, b->st);
+  launches += all;
+  if (all == 0)
+    for (int blk = 0; blk <= sh.K - 2; ++blk)
+      launches += affine_layer_launch(nd.Wt[blk].as<double>(), b->net->ldT[blk], (int)sh.n[blk],
+                                      (int)sh.n[blk + 1], b->bd.u + sh.noff(blk + 1), sh.acdim,
+                                      b->bd.aff + sh.off[blk], sh.Zdim, (int)b->Q, b->st);
   b->span_end(b->st, launches);
   NN_CUDA(cudaGetLastError());
   // Gram-active neuron counts per (query, block): the host builds the work list of the Gram kernel from them

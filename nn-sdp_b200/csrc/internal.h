@@ -260,6 +260,13 @@ int ibp_layer_launch(const double* Mk, int n_out_k, int n_in_k, const double* xi
 int affine_layer_launch(const double* Wt, int ldT, int n_rows, int n_neurons, const double* u,
                         long long u_stride, double* aff, long long aff_stride, int Q,
                         cudaStream_t st);
+// Few queries: every affine-column GEMV of the net in one launch / the whole interval propagation (+ sector
+// slopes) as one cooperative kernel.  Return 0 when not applicable (the caller falls back to per-layer launches).
+int affine_all_launch(const NetDev& nd, int K, int max_rows, const double* u, long long u_stride, double* aff,
+                      long long aff_stride, int Q, cudaStream_t st);
+int ibp_all_launch(const NetDev& nd, int max_out, const double* x1min, long long s_min, const double* x1max,
+                   long long s_max, double* xmin, double* xmax, long long x_stride, double* acxmin, double* acxmax,
+                   double* smin, double* smax, long long acx_stride, int Q, int* flag_bad, cudaStream_t st);
 // K2: smin/smax from acx bounds.
 int launch_sector_minmax(long long n, const double* acxmin, const double* acxmax, double* smin,
                          double* smax, cudaStream_t st);

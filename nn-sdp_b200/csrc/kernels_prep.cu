@@ -99,8 +99,6 @@ prep_final_kernel(NetDev net, BatchDev b) {
   const int nK = net.n[K - 1];
   double* S = sh;                 // sdim * sdim, column-major, full symmetric
   double* t2 = S + sdim * sdim;   // n_out : S22 b_K + S23
-  __shared__ int wsum[PREP_THREADS / 32];
-  __shared__ int base_sh;
 
   // ---- S of the output QC (src/Qc/output.jl:52-98) ---------------------------------
   for (int i = tid; i < sdim * sdim; i += PREP_THREADS) S[i] = 0.0;
@@ -212,35 +210,40 @@ prep_final_kernel(NetDev net, BatchDev b) {
     aff[net.Zdim - 1] = s - 2.0 * zin + so;
   }
 
-  // ---- ordered compaction of the Gram-active neurons (d11 != 0) per layer ------------
+}
+
+// Ordered compaction of the Gram-active neurons (d11 != 0) of one layer of one query: grid (K - 1, Q).
+__global__ void __launch_bounds__(PREP_THREADS)
+prep_compact_kernel(NetDev net, BatchDev b) {
+  __shared__ int wsum[PREP_THREADS / 32];
+  __shared__ int base_sh;
+  const int blk = blockIdx.x, q = blockIdx.y, tid = threadIdx.x;
+  const int K = net.K, n_in = net.n_in;
   const double* d11 = b.d11 + (long long)q * net.acdim;
   int* act = b.act + (long long)q * net.acdim;
   const int lane = tid & 31, wid = tid >> 5;
-  for (int blk = 0; blk <= K - 2; ++blk) {
-    const int L0 = net.off[blk + 1] - n_in, nl = net.n[blk + 1];
-    if (tid == 0) base_sh = 0;
+  const int L0 = net.off[blk + 1] - n_in, nl = net.n[blk + 1];
+  if (tid == 0) base_sh = 0;
+  __syncthreads();
+  for (int i0 = 0; i0 < nl; i0 += PREP_THREADS) {
+    const int i = i0 + tid;
+    const bool on = (i < nl) && (d11[L0 + i] != 0.0);
+    const unsigned m = __ballot_sync(0xffffffffu, on);
+    if (lane == 0) wsum[wid] = __popc(m);
     __syncthreads();
-    for (int i0 = 0; i0 < nl; i0 += PREP_THREADS) {
-      const int i = i0 + tid;
-      const bool on = (i < nl) && (d11[L0 + i] != 0.0);
-      const unsigned m = __ballot_sync(0xffffffffu, on);
-      if (lane == 0) wsum[wid] = __popc(m);
-      __syncthreads();
-      int woff = 0;
-      for (int w = 0; w < wid; ++w) woff += wsum[w];
-      const int base = base_sh;
-      if (on) act[L0 + base + woff + __popc(m & ((1u << lane) - 1u))] = i;
-      __syncthreads();
-      if (tid == 0) {
-        int tot = 0;
-        for (int w = 0; w < PREP_THREADS / 32; ++w) tot += wsum[w];
-        base_sh = base + tot;
-      }
-      __syncthreads();
+    int woff = 0;
+    for (int w = 0; w < wid; ++w) woff += wsum[w];
+    const int base = base_sh;
+    if (on) act[L0 + base + woff + __popc(m & ((1u << lane) - 1u))] = i;
+    __syncthreads();
+    if (tid == 0) {
+      int tot = 0;
+      for (int w = 0; w < PREP_THREADS / 32; ++w) tot += wsum[w];
+      base_sh = base + tot;
     }
-    if (tid == 0) b.cnt[(long long)q * K + blk] = base_sh;
     __syncthreads();
   }
+  if (tid == 0) b.cnt[(long long)q * K + blk] = base_sh;
 }
 
 }  // namespace
@@ -250,7 +253,8 @@ int launch_prep(const NetDev& net, const BatchDev& b, int* err_flag, cudaStream_
   prep_neuron_kernel<<<grid, PREP_THREADS, 0, st>>>(net, b, err_flag);
   const size_t shbytes = (size_t)(b.sdim * b.sdim + net.n_out) * sizeof(double);
   prep_final_kernel<<<b.Q, PREP_THREADS, shbytes, st>>>(net, b);
-  return 2;
+  if (net.K >= 2) prep_compact_kernel<<<dim3(net.K - 1, b.Q), PREP_THREADS, 0, st>>>(net, b);
+  return net.K >= 2 ? 3 : 2;
 }
 
 }  // namespace nnsdp

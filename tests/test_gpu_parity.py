@@ -993,3 +993,47 @@ def test_crown_wavefront_deep_narrow_net(ctx):
         assert np.abs(r["xmin"][i] - xmin).max() <= 1e-11 * scale
         assert np.abs(r["xmax"][i] - xmax).max() <= 1e-11 * scale
         assert np.abs(r["acxmax"][i] - amax).max() <= 1e-11 * scale
+
+
+# ---------------------------------------------------------------------------------------------
+# Few-query paths: one cooperative kernel for the interval propagation (Q <= 8), cluster split-K GEMVs per layer
+# (Q <= 32), every affine-column GEMV in one launch, and the tiled GEMM beyond.  Same numbers on every path.
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("nq", [1, 2, 3, 4, 5, 8, 9, 17, 32, 33])
+def test_query_count_thresholds_of_the_bounds_and_affine_kernels(ctx, nq):
+    import nnsdp_b200 as nb
+
+    xdims, beta = [3, 70, 131, 9, 64, 257, 4], 2    # widths around the 8/16/64-row tiles, one narrow layer
+    net = rand_net(xdims, seed=21, sigma=0.3)
+    rng = np.random.default_rng(nq)
+    qs = [rand_query(net, beta, rng, kind="hplane", radius=0.02 * (1 + i % 4)) for i in range(nq)]
+    dnet = nb.Net(ctx, net.xdims, net.Ms)
+    b = nb.Batch(dnet, beta, Qcap=nq, ring=min(nq, 4))
+    b.set_inputs(to_numeric_batch(nb, net, qs))
+    out = np.full((nq, b.per_query), np.nan)
+    b.run(out)
+    bd = b.get_bounds()
+    aff = b.get_affine()
+    cliques = o.make_cliques(net, beta)
+    for i in (0, nq // 2, nq - 1):
+        _, xmin, xmax, amin, amax = _oracle_bounds(net, qs[i])
+        scale = max(np.abs(xmax).max(), np.abs(xmin).max(), 1.0)
+        assert np.abs(bd["xmin"][i] - xmin).max() <= TOL * scale
+        assert np.abs(bd["xmax"][i] - xmax).max() <= TOL * scale
+        assert np.abs(bd["acxmin"][i] - amin).max() <= TOL * scale
+        assert np.abs(bd["acxmax"][i] - amax).max() <= TOL * scale
+        rmin, rmax = o.make_sector_min_max(bd["acxmin"][i], bd["acxmax"][i])
+        assert np.array_equal(bd["smin"][i], rmin) and np.array_equal(bd["smax"][i], rmax)
+        ref = o.run_query(net, beta, qs[i])
+        assert relerr(aff[i], ref["Z"][:, -1]) <= TOL
+        for blk, rb in zip(nb.split_blocks(out[i], cliques), ref["blocks"]):
+            assert relerr(blk, rb) <= TOL
+    # a query's numbers do not depend on how many share the launch (within one path)
+    if nq in (2, 5, 8):
+        b1 = nb.Batch(dnet, beta, Qcap=1, ring=1)
+        b1.set_inputs(to_numeric_batch(nb, net, qs[nq - 1:nq]))
+        o1 = np.empty((1, b.per_query))
+        b1.run(o1)
+        assert np.array_equal(o1[0], out[nq - 1])
+        b1.close()
+    b.close()
