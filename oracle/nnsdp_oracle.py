@@ -11,7 +11,8 @@ or fixtures for this path.  This restatement
 follows the Julia sources line by line (citations below, relative to
 /root/reference) and is cross-checked by (1) a second, independent closed-form
 derivation in this file, (2) the structural sparsity statement in the reference's
-``experiments/plot_sparsity.ipynb`` cell 5, (3) the reference's constructor
+``experiments/plot_sparsity.ipynb`` cell 5 (nnz(Z) lies inside quickRawZ, and the clique
+cover equals quickRawZ + quickEK exactly: index sets and sparsity ARE pinned by it), (3) the reference's constructor
 ``@assert``s, which are reproduced here as assertions, and (4) hand-worked
 examples in ``tests/``.
 
@@ -668,6 +669,18 @@ def structural_pattern_notebook(xdims: Sequence[int], beta: int) -> np.ndarray:
     pat[:N, :N] |= np.outer(a, b) | np.outer(b, a)
     pat[N, :] = True  # quickEa
     pat[:, N] = True
+    return pat
+
+
+def chordal_extension_pattern_notebook(xdims: Sequence[int], beta: int) -> np.ndarray:
+    """quickRawZ(beta) overlaid with quickEK of experiments/plot_sparsity.ipynb cells 5, 16-22 (the figures
+    Zbeta*.png): the x_K rows and columns are filled in.  The union of Ck x Ck over makeCliques equals it."""
+    xdims = [int(x) for x in xdims]
+    K = len(xdims) - 1
+    N = sum(xdims[:-1])
+    pat = structural_pattern_notebook(xdims, beta)
+    lastblk = np.arange(1, N + 1) >= sum(xdims[:K - 1]) + 1   # quickEK
+    pat[:N, :N] |= lastblk[:, None] | lastblk[None, :]
     return pat
 
 

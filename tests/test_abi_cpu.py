@@ -114,6 +114,21 @@ def test_cliques_bit_exact_random_shapes(xdims, beta):
     _check_cliques(xdims, beta)
 
 
+@pytest.mark.parametrize("xdims", [[3, 3, 3, 3, 4, 3, 3], [2, 4, 7, 3, 5, 2], [2] + [10] * 10 + [2], [5] + [50] * 6 + [5]])
+@pytest.mark.parametrize("beta", [0, 1, 2, 4])
+def test_clique_cover_is_the_pattern_the_reference_draws(xdims, beta):
+    """Pin against a statement by the reference's authors that is not makeCliques itself: the figures of
+    experiments/plot_sparsity.ipynb (xdims [3,3,3,3,4,3,3], beta 0/2/4) draw quickRawZ(beta) with the x_K rows
+    and columns filled in; the union of Ck x Ck over nnsdp_cliques must be exactly that set."""
+    import nnsdp_b200 as nb
+
+    want = o.chordal_extension_pattern_notebook(xdims, beta)
+    cover = np.zeros_like(want)
+    for Ck, _, _ in nb.cliques_from_xdims(xdims, beta):
+        cover[np.ix_(Ck - 1, Ck - 1)] = True
+    assert np.array_equal(cover, want)
+
+
 @pytest.mark.parametrize("xdims,beta", [([2, 3, 2], 1), ([2] + [10] * 10 + [2], 1), ([5] + [50] * 6 + [5], 2),
                                         ([2, 70, 130, 64, 3], 2), ([2] + [1000] * 20 + [2], 2), ([2] + [100] * 50 + [2], 3)])
 @pytest.mark.parametrize("dense", [False, True])

@@ -107,6 +107,8 @@ def test_sparsity_inside_notebook_pattern_and_clique_cover(xdims, beta):
         assert np.array_equal(Ck, np.unique(Ck))  # MyMath.jl:46
     assert not np.any((Z != 0) & ~cover)
     assert np.array_equal(o.zksum_pattern(net, r["cliques"]), cover)
+    # ... and it is exactly the filled-in pattern the reference draws (plot_sparsity.ipynb, Zbeta*.png)
+    assert np.array_equal(cover, o.chordal_extension_pattern_notebook(net.xdims, beta))
     # Ec(Ck) Z Ec(Ck)' is the block (MyMath.jl:45-52)
     for (Ck, _, _), blk in zip(r["cliques"], r["blocks"]):
         EcK = o.Ec(Ck, net.Zdim)
