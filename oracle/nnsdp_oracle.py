@@ -5,9 +5,12 @@ THIS FILE IS TEST INFRASTRUCTURE, NOT PRODUCT CODE.  Only ``tests/``,
 legs may import it.  The product path (``nn-sdp_b200/``) never calls it and has no
 CPU fallback.
 
-PARITY UNPINNED: the reference (AntonXue/nn-sdp) is Julia + JuMP + MOSEK, none of
-which exist in this environment, and the reference ships no tests, golden vectors
-or fixtures for this path.  This restatement
+PARITY UNPINNED for the Julia part: the reference (AntonXue/nn-sdp) is Julia + JuMP +
+MOSEK, none of which exist in this environment, and the reference ships no tests,
+golden vectors or fixtures for this path.  Two pieces
+ARE pinned against reference artefacts: the CROWN bounds (the reference's Python
+dependency auto_LiRPA runs here; see intervals_crown below) and the clique cover /
+sparsity pattern (the reference's plot_sparsity notebook).  This restatement
 follows the Julia sources line by line (citations below, relative to
 /root/reference) and is cross-checked by (1) a second, independent closed-form
 derivation in this file, (2) the structural sparsity statement in the reference's
@@ -937,9 +940,13 @@ def cover_upper_entries(ffnet: FeedFwdNet, cliques):
 # intervalsAutoLirpaSliced, intervals_auto_lirpa.jl:44-63 -> exts/auto_lirpa_bridge.py:97-112 ->
 # auto_LiRPA BoundedModule.compute_bounds(method="CROWN")).
 #
-# PARITY UNPINNED, twice over: auto_LiRPA (vendored, 2021) does not import under this interpreter, and it
-# computes in float32.  This is a float64 restatement of the algorithm for ReLU MLPs as read from the
-# vendored sources:
+# PINNED against the reference's own dependency: the vendored auto_LiRPA (2021) is imported from
+# /root/reference/exts (with four name shims for numpy 2 / Python 3.12 / torch 2.11, no numerics) and driven as
+# intervalsAutoLirpaSliced drives it by tests/golden/make_crown_golden.py; this restatement equals its float64
+# run to 1e-15 and its float32 run (what the reference executes) to float32 rounding on the reference's shipped
+# W10-D10 / W5-D5 nets and two seeded random nets (tests/golden/crown_autolirpa.npz,
+# tests/test_oracle_cpu.py::test_crown_restatement_equals_the_vendored_auto_lirpa).  It is a float64
+# restatement of the algorithm for ReLU MLPs as read from the vendored sources:
 #   * bound_general.py:1212-1366  every pre-activation node gets bounds by backward LiRPA with C = I,
 #     except the first linear layer, which is bounded by interval arithmetic (:1257-1262);
 #   * operators/activation.py:306-323  ReLU relaxation from (l, u): lb_r = min(l, 0), ub_r = max(u, 0),

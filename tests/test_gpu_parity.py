@@ -805,6 +805,25 @@ def test_crown_bounds_against_oracle(ctx, xdims):
             assert np.all(allx >= r["xmin"][i] - 1e-9 * scale) and np.all(allx <= r["xmax"][i] + 1e-9 * scale)
 
 
+@pytest.mark.parametrize("name", ["scale_W10_D10", "scale_W5_D5", "rand_acas_5x50", "rand_ragged"])
+def test_crown_bounds_against_the_vendored_auto_lirpa(ctx, name):
+    """The device CROWN against x_intvs computed by the reference's vendored auto_LiRPA itself
+    (tests/golden/crown_autolirpa.npz, generator tests/golden/make_crown_golden.py): float64 run to 1e-11, float32
+    run (what the reference executes) to float32 rounding."""
+    import nnsdp_b200 as nb
+
+    d = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "crown_autolirpa.npz"))
+    xd = d[f"{name}.xdims"].tolist()
+    Ms = [d[f"{name}.M{k}"] for k in range(len(xd) - 1)]
+    dnet = nb.Net(ctx, xd, Ms)
+    r = nb.bounds_crown(dnet, d[f"{name}.x1min"][None, :], d[f"{name}.x1max"][None, :])
+    scale = max(np.abs(d[f"{name}.f64.lo"]).max(), np.abs(d[f"{name}.f64.hi"]).max())
+    assert np.abs(r["xmin"][0] - d[f"{name}.f64.lo"]).max() <= 1e-11 * scale
+    assert np.abs(r["xmax"][0] - d[f"{name}.f64.hi"]).max() <= 1e-11 * scale
+    assert np.abs(r["xmin"][0] - d[f"{name}.f32.lo"]).max() <= 2e-6 * scale
+    assert np.abs(r["xmax"][0] - d[f"{name}.f32.hi"]).max() <= 2e-6 * scale
+
+
 def test_crown_in_the_batch_pipeline(ctx):
     """Blocks assembled with CROWN bounds computed on the device == blocks from the oracle with the oracle's
     CROWN intervals (makeQcActivsIntvs with the default method, src/Qc/activ.jl:45-67)."""

@@ -171,8 +171,35 @@ def test_sector_thresholds():
     assert np.array_equal(smin, [0, 1, 0, 0]) and np.array_equal(smax, [1, 1, 1, 0])  # strict, activ_sector.jl:67-68
 
 
+CROWN_CASES = ["scale_W10_D10", "scale_W5_D5", "rand_acas_5x50", "rand_ragged"]
+
+
+def _crown_golden(name):
+    d = np.load(os.path.join(GOLD, "crown_autolirpa.npz"))
+    xd = d[f"{name}.xdims"].tolist()
+    net = o.FeedFwdNet(xdims=xd, Ms=[d[f"{name}.M{k}"] for k in range(len(xd) - 1)])
+    return d, net
+
+
+@pytest.mark.parametrize("name", CROWN_CASES)
+def test_crown_restatement_equals_the_vendored_auto_lirpa(name):
+    """PIN: tests/golden/crown_autolirpa.npz holds x_intvs computed by the reference's own vendored auto_LiRPA
+    (imported from /root/reference/exts and driven as intervalsAutoLirpaSliced drives it; generator
+    tests/golden/make_crown_golden.py).  The float64 restatement must equal the float64 run to rounding and the
+    float32 run -- what the reference executes -- to float32 rounding."""
+    d, net = _crown_golden(name)
+    info = o.intervals_crown(d[f"{name}.x1min"], d[f"{name}.x1max"], net)
+    lo = np.concatenate([p[0] for p in info.x_intvs])
+    hi = np.concatenate([p[1] for p in info.x_intvs])
+    scale = max(np.abs(lo).max(), np.abs(hi).max())
+    assert np.abs(lo - d[f"{name}.f64.lo"]).max() <= 1e-13 * scale
+    assert np.abs(hi - d[f"{name}.f64.hi"]).max() <= 1e-13 * scale
+    assert np.abs(lo - d[f"{name}.f32.lo"]).max() <= 2e-6 * scale
+    assert np.abs(hi - d[f"{name}.f32.hi"]).max() <= 2e-6 * scale
+
+
 def test_crown_restatement_sound_and_tighter_than_ibp():
-    """The CROWN restatement (parity unpinned, oracle header) at least has the properties a bound method must
+    """The CROWN restatement at least has the properties a bound method must
     have: sampled activations lie inside, the first layer equals interval arithmetic, a point box gives the
     forward pass, and on deep nets it is far tighter than IBP (why it is the reference's default)."""
     for xdims in ([2, 6, 5, 7, 2], [2] + [10] * 10 + [2], [3, 20, 20, 20, 3]):
