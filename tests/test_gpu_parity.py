@@ -1056,3 +1056,43 @@ def test_query_count_thresholds_of_the_bounds_and_affine_kernels(ctx, nq):
         assert np.array_equal(o1[0], out[nq - 1])
         b1.close()
     b.close()
+
+
+def test_recorded_optimum_minimiser_through_the_device_pipeline(ctx):
+    """The reference's scale experiment on its shipped W10-D10 net (experiments/scale.jl: box [0.5, 1.5]^2,
+    findEllipsoid), at the minimiser gamma* stored by oracle/sdp_crosscheck.py: the device pipeline -- CROWN bounds,
+    QC data, blocks, matrix-free lambda_max -- must give the oracle's Z(gamma*) and its certificate value
+    lambda_max(Z(gamma*)) ~ 0^- (the LMI is active at an optimum), for beta = 0, 2, 5."""
+    import json
+    import sys
+
+    import nnsdp_b200 as nb
+
+    gold = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    sys.path.insert(0, os.path.join(os.path.dirname(gold), "..", "oracle"))
+    res = json.load(open(os.path.join(gold, "scale_W10_D10_optimum.json")))
+    net = o.load_nnet(os.path.join(gold, "scale-I2-O2-W10-D10.nnet"))
+    x1min, x1max = np.full(2, 0.5), np.full(2, 1.5)
+    P, yc = np.asarray(res["P"]), np.asarray(res["yc"])
+    invP = np.linalg.inv(P)
+    invP = 0.5 * (invP + invP.T)
+    info = o.intervals_crown(x1min, x1max, net)
+    dnet = nb.Net(ctx, net.xdims, net.Ms)
+    n1, ac = net.xdims[0], net.acdim
+    for beta in (0, 2, 5):
+        g = np.asarray(res["oracle_optimum"][str(beta)]["gamma"])
+        q = o.NumericQuery(x1min=x1min, x1max=x1max, qc_out=o.QcReachEllipsoid(invP=invP, yc=yc), gin=g[:n1],
+                           gout=g[n1:n1 + 1], gbnd=g[n1 + 1:n1 + 1 + ac], gsec=g[n1 + 1 + ac:])
+        ref = o.run_query(net, beta, q, intv_info=info)
+        b = nb.Batch(dnet, beta, Qcap=1, ring=1)
+        b.set_inputs(to_numeric_batch(nb, net, [q]))
+        b.set_bounds_method("crown")
+        out = np.empty((1, b.per_query))
+        b.run(out)
+        for blk, rb in zip(nb.split_blocks(out[0], ref["cliques"]), ref["blocks"]):
+            assert relerr(blk, rb) <= 1e-10        # multipliers span 1e-9 .. 1e4: normwise per block
+        lam, its = b.lambda_max(max_iters=400, tol=1e-12)
+        want = np.linalg.eigvalsh(0.5 * (ref["Z"] + ref["Z"].T)).max()
+        scale = np.abs(ref["Z"]).max()
+        assert abs(lam[0] - want) <= 1e-8 * scale and lam[0] <= 1e-7 * scale
+        b.close()
