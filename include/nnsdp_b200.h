@@ -130,6 +130,18 @@ int32_t nnsdp_net_destroy(nnsdp_net* net);
 int32_t nnsdp_nnet_read(const char* path, int64_t max_layers, int64_t* K, int64_t* xdims_out,
                         int64_t max_doubles, double* Ms_out, int64_t* doubles_needed);
 
+/* vnnlib reader, host only: the "simple" vnnlib subset of read_vnnlib_simple
+ * (exts/vnnlib_parser.jl:99-216), flattened the way loadVnnlibCnf does (experiments/vnnlib_utils.jl:18-56) into
+ * safety queries that nnsdp_assemble_blocks takes directly: the file states NOT phi as
+ * OR_box OR_(A,b) (x in box AND A y <= b); every (box, (A, b)) is one disjunctive clause whose members are, per row
+ * i, the query (box, S = hplaneS(-A_i, -b_i - 1e-4)).  Two calls: with x1min == NULL only nqueries / nclauses are
+ * returned; then x1min, x1max (nqueries x n_in), out_S (nqueries x sdim x sdim, sdim = n_in + n_out + 1) and
+ * clause_of (nqueries, 0-based clause index) are filled.  Boxes keep their order of first appearance (the
+ * reference iterates a Dict there).  Unsupported statements are NNSDP_ERR_ARG, the reader's asserts
+ * NNSDP_ERR_ASSERT. */
+int32_t nnsdp_vnnlib_read(const char* path, int64_t n_in, int64_t n_out, int64_t max_queries, int64_t* nqueries,
+                          int64_t* nclauses, double* x1min, double* x1max, double* out_S, int64_t* clause_of);
+
 /* ---- integer work on the host, bit-exact --------------------------------------------- */
 int32_t nnsdp_query_sizes(const nnsdp_net* net, int64_t beta, nnsdp_sizes* sizes);
 /* makeCliques (src/Methods/chordal_cliques.jl:13-59).  Outputs (1-based):

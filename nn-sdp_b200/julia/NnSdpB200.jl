@@ -235,6 +235,31 @@ function eigmaxZ(net::DeviceNet, β::Int, qc_input, qc_out, qc_bounded, qc_secto
   return lam[1]
 end
 
+# ---- vnnlib property -> batched safety queries (experiments/vnnlib_utils.jl:18-56) -------------------
+# Returns what loadVnnlibCnf returns -- a Vector of disjunctive clauses, each a Vector of
+# (QcInputBox, QcSafety) -- but parsed and flattened by the library in one call; x1min / x1max / S come back
+# as Q-column arrays that assembleCliqueBlocks can take as one batch.
+function loadVnnlibCnfB200(spec_file::String, ffnet)
+  n_in, n_out = ffnet.xdims[1], ffnet.xdims[end]
+  nq, nc = Ref{Int64}(0), Ref{Int64}(0)
+  check(ccall((:nnsdp_vnnlib_read, LIB), Int32,
+              (Cstring, Int64, Int64, Int64, Ptr{Int64}, Ptr{Int64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Int64}),
+              spec_file, n_in, n_out, 0, nq, nc, C_NULL, C_NULL, C_NULL, C_NULL))
+  sdim = n_in + n_out + 1
+  x1min, x1max = zeros(n_in, nq[]), zeros(n_in, nq[])
+  S = zeros(sdim, sdim, nq[])
+  clause = zeros(Int64, nq[])
+  check(ccall((:nnsdp_vnnlib_read, LIB), Int32,
+              (Cstring, Int64, Int64, Int64, Ptr{Int64}, Ptr{Int64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Int64}),
+              spec_file, n_in, n_out, nq[], nq, nc, x1min, x1max, S, clause))
+  cnf = [Vector{Tuple{Any, Any}}() for _ in 1:nc[]]
+  for q in 1:nq[]
+    push!(cnf[clause[q] + 1], (QcInputBox(x1min=x1min[:, q], x1max=x1max[:, q]),
+                               QcSafety(S=Symmetric(S[:, :, q]))))
+  end
+  return cnf, x1min, x1max, S, clause
+end
+
 # ---- dispatch point 3: the symbolic hand-off -----------------------------------------------------
 # Z(γ) = Z0 + Σ_v γ_v Z_v over the upper triangle of the clique cover, as a sparse matrix A (nent × nvar)
 # and a constant vector z0: what `Z = Zin + Zout + sum(Zacs)` holds entry by entry as AffExpr

@@ -69,6 +69,7 @@ PROTOTYPES = {
     "nnsdp_net_upload": (c_i32, [c_vp, c_i64, c_i64p, C.POINTER(c_dp), C.POINTER(c_vp)]),
     "nnsdp_net_destroy": (c_i32, [c_vp]),
     "nnsdp_nnet_read": (c_i32, [C.c_char_p, c_i64, c_i64p, c_i64p, c_i64, c_dp, c_i64p]),
+    "nnsdp_vnnlib_read": (c_i32, [C.c_char_p, c_i64, c_i64, c_i64, c_i64p, c_i64p, c_dp, c_dp, c_dp, c_i64p]),
     "nnsdp_query_sizes": (c_i32, [c_vp, c_i64, C.POINTER(Sizes)]),
     "nnsdp_cliques": (c_i32, [c_vp, c_i64, c_i64p, c_i64p, c_i64p, c_i64p, c_i64p]),
     "nnsdp_sizes_from_xdims": (c_i32, [c_i64, c_i64p, c_i64, C.POINTER(Sizes)]),

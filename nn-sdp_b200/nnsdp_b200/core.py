@@ -92,6 +92,22 @@ class Net:
         return _cliques_call(lambda *a: L.lib.nnsdp_cliques(self._h, beta, *a), self.sizes(beta))
 
 
+def read_vnnlib(path: str, n_in: int, n_out: int) -> dict:
+    """Safety queries of a vnnlib property file (host only): x1min / x1max (nq x n_in), S (nq x sdim x sdim, each
+    symmetric: hplaneS(-A_i, -b_i - 1e-4)) and clause (nq,), the disjunctive clause of the CNF each query belongs
+    to -- read_vnnlib_simple + loadVnnlibCnf of the reference.  The arrays feed NumericBatch(out_S=...) as is."""
+    nq, nc = L.c_i64(0), L.c_i64(0)
+    L.check(L.lib.nnsdp_vnnlib_read(path.encode(), n_in, n_out, 0, C.byref(nq), C.byref(nc), None, None, None, None))
+    sdim = n_in + n_out + 1
+    lo, hi = np.zeros((nq.value, n_in)), np.zeros((nq.value, n_in))
+    S = np.zeros((nq.value, sdim, sdim))
+    cl = np.zeros(nq.value, dtype=np.int64)
+    if nq.value:
+        L.check(L.lib.nnsdp_vnnlib_read(path.encode(), n_in, n_out, nq.value, C.byref(nq), C.byref(nc), _dp(lo), _dp(hi),
+                                        _dp(S), cl.ctypes.data_as(L.c_i64p)))
+    return {"x1min": lo, "x1max": hi, "S": S, "clause": cl, "nclauses": int(nc.value)}
+
+
 def read_nnet(path: str):
     """(xdims, Ms) of a .nnet file through the library's reader (host only); Ms[k] = [W_k b_k]."""
     K, need = L.c_i64(0), L.c_i64(0)

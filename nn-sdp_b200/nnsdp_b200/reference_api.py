@@ -233,6 +233,16 @@ def hplaneS(normal, h, ffnet: FeedFwdNet) -> np.ndarray:
     return S
 
 
+def loadVnnlibCnf(spec_file: str, ffnet: FeedFwdNet):
+    """experiments/vnnlib_utils.jl:18-56: the CNF of a vnnlib property as a list of disjunctive clauses, each a list
+    of (QcInputBox, QcSafety); parsed and flattened by the library (nnsdp_vnnlib_read)."""
+    r = core.read_vnnlib(spec_file, ffnet.xdims[0], ffnet.xdims[-1])
+    cnf = [[] for _ in range(r["nclauses"])]
+    for i, c in enumerate(r["clause"]):
+        cnf[int(c)].append((QcInputBox(x1min=r["x1min"][i], x1max=r["x1max"][i]), QcSafety(S=r["S"][i])))
+    return cnf
+
+
 def makeQcActivs(ffnet: FeedFwdNet, x1min=None, x1max=None, beta: int = None, intv_info: IntervalsInfo = None):
     """makeQcActivsIntvs (src/Qc/activ.jl:45-67) with bounds from the GPU IBP."""
     assert x1min is not None and x1max is not None and isinstance(beta, int)

@@ -884,6 +884,118 @@ def run_query(ffnet: FeedFwdNet, beta: int, query: NumericQuery, form: str = "cl
 
 
 # --------------------------------------------------------------------------
+# vnnlib -> CNF of (QcInputBox, QcSafety) pairs: exts/vnnlib_parser.jl:3-216 (read_statements,
+# update_rv_tuple!, read_vnnlib_simple) and experiments/vnnlib_utils.jl:18-56 (loadVnnlibCnf).
+# PARITY UNPINNED (Julia; the ACAS property files bench/acas/*.vnnlib are not shipped).  One deliberate
+# difference: the reference merges alternatives with equal boxes in a Dict and iterates its values (hash order);
+# here boxes keep the order of first appearance.
+# --------------------------------------------------------------------------
+import re as _re
+
+
+def vnnlib_statements(path: str) -> List[str]:
+    lines = [ln.strip() for ln in open(path).read().split("\n")]
+    assert len(lines) > 0
+    depth, out, cur = 0, [], ""
+    for line in lines:
+        if ";" in line:
+            line = line[: line.index(";")].strip()
+        if not line:
+            continue
+        depth += line.count("(") - line.count(")")
+        assert depth >= 0
+        cur += ("" if not cur else " ") + line
+        if depth == 0:
+            out.append(cur)
+            cur = ""
+    if cur:
+        out.append(cur)
+    out = [" ".join(s.split()) for s in out]
+    return [s.replace("( ", "(").replace(") ", ")") for s in out]
+
+
+def _vnnlib_update(rv, op, first, second, n_in, n_out):
+    box, mat, rhs = rv
+    if first.startswith("X_"):
+        idx = int(first[2:])
+        assert not second.startswith("X") and not second.startswith("Y")
+        assert 0 <= idx < n_in
+        if op == "<=":
+            box[idx][1] = min(float(second), box[idx][1])
+        else:
+            box[idx][0] = max(float(second), box[idx][0])
+        assert box[idx][0] <= box[idx][1]
+        return
+    if op == ">=":
+        first, second = second, first
+    row, b = np.zeros(n_out), 0.0
+    if first.startswith("Y_") and second.startswith("Y_"):
+        row[int(first[2:])] = 1
+        row[int(second[2:])] = -1
+    elif first.startswith("Y_"):
+        row[int(first[2:])] = 1
+        b = float(second)
+    else:
+        assert second.startswith("Y_")
+        row[int(second[2:])] = -1
+        b = -1 * float(first)
+    mat.append(row)
+    rhs.append(b)
+
+
+def read_vnnlib_simple(path: str, n_in: int, n_out: int):
+    """[(box, [(mat, rhs), ...]), ...] with box = [[lo, hi]] * n_in."""
+    import copy
+
+    simple = _re.compile(r"^\(assert \((<=|>=) (\S+) (\S+)\)\)$")
+    declare = _re.compile(r"^\(declare-const (X|Y)_(\S+) Real\)$")
+    rv = [([[-np.inf, np.inf] for _ in range(n_in)], [], [])]
+    for line in vnnlib_statements(path):
+        if declare.match(line):
+            continue
+        m = simple.match(line)
+        if m:
+            for t in rv:
+                _vnnlib_update(t, *m.groups(), n_in, n_out)
+            continue
+        tokens = line.replace("(", " ").replace(")", " ").split()[2:]   # skip 'assert' and 'or'
+        conjuncts = " ".join(tokens).split("and")[1:]
+        old, rv = rv, []
+        for t in old:
+            for c in conjuncts:
+                cp = copy.deepcopy(t)
+                rv.append(cp)
+                ct = c.split()
+                for i in range(len(ct) // 3):
+                    _vnnlib_update(cp, ct[3 * i], ct[3 * i + 1], ct[3 * i + 2], n_in, n_out)
+    merged = {}
+    for box, mat, rhs in rv:
+        key = str(box)
+        merged.setdefault(key, (box, []))[1].append((mat, rhs))
+    final = []
+    for box, specs in merged.values():          # insertion order (the reference: Dict hash order)
+        assert all(np.isfinite(r[0]) and np.isfinite(r[1]) for r in box)
+        final.append((box, specs))
+    return final
+
+
+def load_vnnlib_cnf(path: str, ffnet: FeedFwdNet):
+    """CnfSpec: list of disjunctive clauses, each a list of (QcInputBox, QcSafety)."""
+    n_in, n_out = ffnet.xdims[0], ffnet.xdims[-1]
+    cnf = []
+    for box, specs in read_vnnlib_simple(path, n_in, n_out):
+        qc_in = QcInputBox(np.array([b[0] for b in box]), np.array([b[1] for b in box]))
+        for mat, rhs in specs:
+            A = np.stack(mat)
+            clause = []
+            for i in range(len(rhs)):
+                eps = 1e-4
+                clause.append((qc_in, QcSafety(S=hplaneS(-A[i, :], -rhs[i] - eps, ffnet))))
+            cnf.append(clause)
+    return cnf
+
+
+# --------------------------------------------------------------------------
 # Affine structure of Z in the multipliers (what JuMP holds as AffExpr entries,
 # src/Methods/chordal_sdp.jl:96-153): Z(gamma) = Z0 + sum_v gamma_v Z_v
 # --------------------------------------------------------------------------

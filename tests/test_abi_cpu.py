@@ -224,3 +224,103 @@ def test_nnet_reader_against_the_references_reader():
     assert all(np.array_equal(a, b) for a, b in zip(Ms, ref.Ms))
     with pytest.raises(nb.NnsdpError):
         nb.read_nnet(os.path.join(gold, "does-not-exist.nnet"))
+
+
+# ---------------------------------------------------------------------------------------------
+# vnnlib -> batched safety queries (SURVEY.md 8f-4)
+# ---------------------------------------------------------------------------------------------
+VNNLIB_CASES = {
+    # shape of ACAS Xu property 1: a box and one output threshold
+    "threshold": (5, 5, """; unsafe if COC >= 1500
+(declare-const X_0 Real)
+(declare-const X_1 Real)
+(declare-const X_2 Real)
+(declare-const X_3 Real)
+(declare-const X_4 Real)
+(declare-const Y_0 Real)
+(assert (<= X_0 0.679857769))
+(assert (>= X_0 0.6))
+(assert (<= X_1 0.5))
+(assert (>= X_1 -0.5))
+(assert (<= X_2 0.5))
+(assert (>= X_2 -0.5))
+(assert (<= X_3 0.5))
+(assert (>= X_3 0.45))
+(assert (<= X_4 -0.45))
+(assert (>= X_4 -0.5))
+(assert (>= Y_0 3.991125645861615))
+"""),
+    # shape of property 3 / 4: "COC is minimal" as one conjunction, written over several lines
+    "minimal": (2, 3, """(declare-const X_0 Real)
+(declare-const X_1 Real)
+(declare-const Y_0 Real)
+(assert (<= X_0 0.6798))  ; upper
+(assert (>= X_0 0.6))
+(assert (<= X_1
+   0.5))
+(assert (>= X_1 -0.5))
+(assert (or
+  (and (<= Y_0 Y_1) (<= Y_0 Y_2))
+  (and (>= Y_1 3.25)(<= 1.5 Y_2))
+))
+"""),
+    # disjunction over input boxes times a disjunction over outputs (shape of property 6 / 7), repeated box
+    "boxes": (2, 2, """(assert (>= X_1 -1e-1))
+(assert (<= X_1 2.5E-1))
+(assert (or (and (<= X_0 0.2)(>= X_0 0.0)) (and (<= X_0 0.9)(>= X_0 0.7)) (and (>= X_0 0.0)(<= X_0 0.2))))
+(assert (or (and (<= Y_0 Y_1)) (and (<= Y_1 -0.75)(>= Y_0 0.125)(<= Y_0 Y_0))))
+"""),
+}
+
+
+@pytest.mark.parametrize("name", sorted(VNNLIB_CASES))
+def test_vnnlib_reader_against_the_restated_reference_parser(name, tmp_path):
+    import nnsdp_b200 as nb
+
+    n_in, n_out, text = VNNLIB_CASES[name]
+    path = str(tmp_path / f"{name}.vnnlib")
+    open(path, "w").write(text)
+    net = o.FeedFwdNet(xdims=[n_in, 4, n_out], Ms=[np.zeros((4, n_in + 1)), np.zeros((n_out, 5))])
+    cnf = o.load_vnnlib_cnf(path, net)
+    got = nb.read_vnnlib(path, n_in, n_out)
+    assert got["nclauses"] == len(cnf)
+    flat = [(c, qi, qs) for c, clause in enumerate(cnf) for qi, qs in clause]
+    assert len(flat) == len(got["clause"])
+    for i, (c, qi, qs) in enumerate(flat):
+        assert got["clause"][i] == c
+        assert np.array_equal(got["x1min"][i], qi.x1min) and np.array_equal(got["x1max"][i], qi.x1max)
+        S = np.asarray(qs.S)
+        assert np.array_equal(got["S"][i], S) and np.array_equal(np.signbit(got["S"][i]), np.signbit(S))
+        assert np.array_equal(got["S"][i], got["S"][i].T)
+    if name == "boxes":     # 3 input alternatives, two of them the same box, x 2 output alternatives
+        assert got["nclauses"] == 6 and len(flat) == 2 * (1 + 3) + (1 + 3)
+        assert np.array_equal(got["x1min"][0], [0.0, -0.1]) and np.array_equal(got["x1max"][-1], [0.9, 0.25])
+
+
+def test_vnnlib_reader_errors(tmp_path):
+    import nnsdp_b200 as nb
+
+    def run(text, n_in=1, n_out=1):
+        p = str(tmp_path / "e.vnnlib")
+        open(p, "w").write(text)
+        return nb.read_vnnlib(p, n_in, n_out)
+
+    with pytest.raises(nb.NnsdpError) as e:      # vnnlib_parser.jl:200: every input needs both bounds
+        run("(assert (<= X_0 1.0))\n(assert (<= Y_0 0.0))\n")
+    assert e.value.code == -5
+    with pytest.raises(nb.NnsdpError) as e:      # :60 empty interval
+        run("(assert (<= X_0 1.0))\n(assert (>= X_0 2.0))\n")
+    assert e.value.code == -5
+    with pytest.raises(nb.NnsdpError) as e:      # :52 index range
+        run("(assert (<= X_3 1.0))\n")
+    assert e.value.code == -5
+    with pytest.raises(nb.NnsdpError) as e:
+        run("(check-sat)\n")
+    assert e.value.code == -1
+    with pytest.raises(nb.NnsdpError) as e:
+        run("(assert (and (<= Y_0 1.0)))\n")
+    assert e.value.code == -1
+    with pytest.raises(nb.NnsdpError):
+        nb.read_vnnlib(str(tmp_path / "missing.vnnlib"), 1, 1)
+    ok = run("(assert (<= X_0 1.0))\n(assert (>= X_0 0.0)) ; both\n(assert (<= Y_0 0.5))\n")
+    assert ok["nclauses"] == 1 and ok["S"].shape == (1, 3, 3) and ok["S"][0, 2, 2] == -2 * (-0.5 - 1e-4)

@@ -1096,3 +1096,45 @@ def test_recorded_optimum_minimiser_through_the_device_pipeline(ctx):
         scale = np.abs(ref["Z"]).max()
         assert abs(lam[0] - want) <= 1e-8 * scale and lam[0] <= 1e-7 * scale
         b.close()
+
+
+def test_vnnlib_property_as_one_batch(ctx, tmp_path):
+    """a vnnlib property read by the library (boxes x output half-spaces, the CNF of
+    experiments/vnnlib_utils.jl:18-56) goes through nnsdp_assemble_blocks as ONE batch; every member equals the
+    oracle's blocks for the (QcInputBox, QcSafety) pair of the restated reference parser."""
+    import nnsdp_b200 as nb
+
+    xdims, beta = [5] + [50] * 6 + [5], 2               # ACAS-shaped (the real nets are not shipped)
+    net = rand_net(xdims, seed=12)
+    text = "\n".join(f"(declare-const X_{i} Real)" for i in range(5)) + """
+(assert (<= X_0 0.68))
+(assert (>= X_0 0.6))
+(assert (<= X_1 0.05))
+(assert (>= X_1 -0.05))
+(assert (<= X_2 0.05))
+(assert (>= X_2 -0.05))
+(assert (<= X_4 -0.45))
+(assert (>= X_4 -0.5))
+(assert (or (and (<= X_3 0.5)(>= X_3 0.45)) (and (<= X_3 0.3)(>= X_3 0.25))))
+(assert (or (and (<= Y_0 Y_1)(<= Y_0 Y_2)(<= Y_0 Y_3)(<= Y_0 Y_4)) (and (>= Y_2 0.75))))
+"""
+    path = str(tmp_path / "prop.vnnlib")
+    open(path, "w").write(text)
+    r = nb.read_vnnlib(path, 5, 5)
+    cnf = o.load_vnnlib_cnf(path, net)
+    flat = [pair for clause in cnf for pair in clause]
+    nq = len(flat)
+    assert nq == 10 and r["nclauses"] == 4 and np.array_equal(r["clause"], [0, 0, 0, 0, 1, 2, 2, 2, 2, 3])
+    rng = np.random.default_rng(4)
+    sz = nb.sizes_from_xdims(xdims, beta)
+    gin, gbnd, gsec = rng.random((nq, 5)), rng.random((nq, sz["acdim"])), rng.random((nq, sz["secdim"]))
+    dnet = nb.Net(ctx, net.xdims, net.Ms)
+    batch = nb.NumericBatch(x1min=r["x1min"], x1max=r["x1max"], gamma_in=gin, gamma_bnd=gbnd, gamma_sec=gsec,
+                            out_kind=nb.OUT_SAFETY, out_S=r["S"])
+    out = nb.assemble_blocks(dnet, beta, batch)
+    cliques = o.make_cliques(net, beta)
+    for i, (qi, qs) in enumerate(flat):
+        q = o.NumericQuery(x1min=qi.x1min, x1max=qi.x1max, qc_out=qs, gin=gin[i], gbnd=gbnd[i], gsec=gsec[i])
+        ref = o.run_query(net, beta, q)
+        for blk, rb in zip(nb.split_blocks(out[i], cliques), ref["blocks"]):
+            assert relerr(blk, rb) <= TOL
