@@ -1607,7 +1607,7 @@ int32_t crown_bounds_device(nnsdp_batch* b) {
   const int64_t P = sh.xtot - n0;  // stacked pre-activations y_0 .. y_{K-1}
   int64_t maxn = 0;
   for (int k = 0; k <= K; ++k) maxn = std::max(maxn, sh.n[k]);
-  const int64_t ld = maxn;
+  const int64_t ld = (maxn + 1) & ~(int64_t)1;   // even: 16 B copies in the tensor-core GEMM
   // narrow nets (every step is the fused kernel): the post-activation targets walk back together, stacked
   static const bool no_wave = [] { const char* e = getenv("NNSDP_CROWN_NO_WAVEFRONT"); return e && e[0] == '1'; }();
   int64_t max_hidden_in = 0;

@@ -525,6 +525,7 @@ int affine_layer_launch(const double* Wt, int ldT, int n_rows, int n_neurons, co
         nullptr, st);
     return 1;
   }
+  if (dgemm_dmma_launch(Wt, ldT, n_rows, n_neurons, u, u_stride, aff, aff_stride, Q, 1, st)) return 1;
   dim3 grid((n_rows + BM - 1) / BM, (Q + BN - 1) / BN);
   gemm_nn_kernel<1><<<grid, GEMM_THREADS, 0, st>>>(Wt, ldT, n_rows, n_neurons, u, nullptr, u_stride,
                                                   Q, nullptr, aff, nullptr, aff_stride, nullptr,
@@ -539,6 +540,7 @@ int gemm_set_launch(const double* A, int lda, int M, int Kdim, const double* B, 
                    st);
     return 1;
   }
+  if (dgemm_dmma_launch(A, lda, M, Kdim, B, ldb, C, ldc, N, 0, st)) return 1;
   dim3 grid((M + BM - 1) / BM, (N + BN - 1) / BN);
   gemm_nn_kernel<2><<<grid, GEMM_THREADS, 0, st>>>(A, lda, M, Kdim, B, nullptr, ldb, N, nullptr, C, nullptr,
                                                   ldc, nullptr, nullptr, 0, 0, 0, nullptr);
@@ -552,6 +554,7 @@ int gemm_acc_launch(const double* A, int lda, int M, int Kdim, const double* B, 
                    st);
     return 1;
   }
+  if (dgemm_dmma_launch(A, lda, M, Kdim, B, ldb, C, ldc, N, 1, st)) return 1;
   dim3 grid((M + BM - 1) / BM, (N + BN - 1) / BN);
   gemm_nn_kernel<1><<<grid, GEMM_THREADS, 0, st>>>(A, lda, M, Kdim, B, nullptr, ldb, N, nullptr, C, nullptr,
                                                   ldc, nullptr, nullptr, 0, 0, 0, nullptr);

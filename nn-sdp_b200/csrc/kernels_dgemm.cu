@@ -1,0 +1,146 @@
+// FP64 tensor-core GEMM for the plain products of the path:  C (+)= A B,  all column-major.
+// Used by the CROWN chain steps on wide layers (A = W_k', B = the stack of relaxed rows: N = 2 x queries x rows),
+// by the affine-column product of the QC preparation and by the factored matvec of the lambda_max check when
+// many queries share a launch.  tcgen05 has no f64 kind, so this is the DMMA path (mma.sync.m8n8k4.f64), the same
+// building block as the Gram kernel (kernels_gram.cu): 128 x 128 tiles, 8 warps of 32 x 64, 3 cp.async stages.
+//   A tile: As[k][m]   (columns of A are contiguous in m: 16 B chunks along m)
+//   B tile: Bs[n][k]   (columns of B are contiguous in k: 16 B chunks along k; leading dimension 20 doubles puts
+//                       the 4 x 4 (k, n) addresses of a half warp's fragment load in 16 distinct 8-byte banks)
+// Edges are zero-filled by the copies (src-size 0 / 8 / 16).  Operands must allow 16 B copies: A, B 16 B aligned and
+// lda, ldb even; otherwise the caller keeps the SIMT kernel (kernels_bounds.cu).
+#include "internal.h"
+#include <stdint.h>
+#include <stdlib.h>
+
+namespace nnsdp {
+
+namespace {
+
+constexpr int DT = 128;         // tile side
+constexpr int DK = 16;          // contraction indices per stage
+constexpr int DSTAGES = 3;
+constexpr int DLDA = DT + 8;    // As leading dimension (as in the Gram kernel)
+constexpr int DLDB = DK + 4;    // Bs leading dimension
+constexpr int DTHREADS = 256;
+
+struct DgemmSmem {
+  double A[DSTAGES][DK][DLDA];
+  double B[DSTAGES][DT][DLDB];
+};
+
+__device__ __forceinline__ void cp16(void* smem, const void* gmem, int src_bytes) {
+  const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(s), "l"(gmem), "r"(src_bytes));
+}
+__device__ __forceinline__ void cp_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N>
+__device__ __forceinline__ void cp_wait() {
+  asm volatile("cp.async.wait_group %0;\n" ::"n"(N));
+}
+__device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+               : "+d"(c0), "+d"(c1)
+               : "d"(a), "d"(b));
+}
+
+template <int ACC>  // 0: C = A B, 1: C += A B
+__global__ void __launch_bounds__(DTHREADS, 1)
+dgemm_dmma_kernel(const double* __restrict__ A, int lda, int M, int K, const double* __restrict__ B, long long ldb,
+                  double* __restrict__ C, long long ldc, int N) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  DgemmSmem& sm = *reinterpret_cast<DgemmSmem*>(smem_raw);
+  const int m0 = blockIdx.x * DT, n0 = blockIdx.y * DT;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int wm = (warp & 3) * 32, wn = (warp >> 2) * 64;
+  const int nsteps = (K + DK - 1) / DK;
+
+  auto load_stage = [&](int stage, int step) {
+    const int k0 = step * DK;
+    // A: 16 columns x 64 chunks of two rows
+    for (int c = tid; c < DK * (DT / 2); c += DTHREADS) {
+      const int kk = c / (DT / 2), ch = c % (DT / 2);
+      const int m = m0 + ch * 2, k = k0 + kk;
+      const int rows = (k < K) ? max(0, min(2, M - m)) : 0;      // 0 bytes read: the chunk is zero-filled
+      cp16(&sm.A[stage][kk][ch * 2], rows ? A + (long long)k * lda + m : A, rows * 8);
+    }
+    // B: 128 columns x 8 chunks of two contraction indices
+    for (int c = tid; c < DT * (DK / 2); c += DTHREADS) {
+      const int nn = c / (DK / 2), ch = c % (DK / 2);
+      const int n = n0 + nn, k = k0 + ch * 2;
+      const int cnt = (n < N) ? max(0, min(2, K - k)) : 0;
+      cp16(&sm.B[stage][nn][ch * 2], cnt ? B + (long long)n * ldb + k : B, cnt * 8);
+    }
+  };
+
+  double acc[4][8][2];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+  for (int s = 0; s < DSTAGES - 1; ++s) {
+    if (s < nsteps) load_stage(s, s);
+    cp_commit();
+  }
+  for (int step = 0; step < nsteps; ++step) {
+    cp_wait<DSTAGES - 2>();
+    __syncthreads();
+    {
+      const int nxt = step + DSTAGES - 1;
+      if (nxt < nsteps) load_stage(nxt % DSTAGES, nxt);
+      cp_commit();
+    }
+    const int st = step % DSTAGES;
+    const double(*As)[DLDA] = sm.A[st];
+    const double(*Bs)[DLDB] = sm.B[st];
+#pragma unroll
+    for (int k4 = 0; k4 < DK; k4 += 4) {
+      const int k = k4 + (lane & 3);
+      double af[4], bf[8];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) af[i] = As[k][wm + i * 8 + (lane >> 2)];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) bf[j] = Bs[wn + j * 8 + (lane >> 2)][k];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) dmma(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+    }
+  }
+  cp_wait<0>();
+
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int r = m0 + wm + i * 8 + (lane >> 2);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int c = n0 + wn + j * 8 + (lane & 3) * 2 + e;
+        if (r < M && c < N) {
+          double* p = C + r + (long long)c * ldc;
+          *p = ACC ? *p + acc[i][j][e] : acc[i][j][e];
+        }
+      }
+    }
+  }
+}
+
+}  // namespace
+
+// Returns 1 when the product was launched, 0 when the operands do not fit this kernel (the caller falls back).
+int dgemm_dmma_launch(const double* A, int lda, int M, int K, const double* B, long long ldb, double* C, long long ldc,
+                      int N, int accumulate, cudaStream_t st) {
+  static const bool off = [] { const char* e = getenv("NNSDP_NO_DMMA_GEMM"); return e && atoi(e) != 0; }();
+  if (off || M < 192 || N < 128 || K < 128) return 0;   // smaller products: the 64 x 64 SIMT tiles waste less
+  if (((uintptr_t)A | (uintptr_t)B) & 15) return 0;
+  if ((lda & 1) || (ldb & 1)) return 0;
+  cudaFuncSetAttribute(dgemm_dmma_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DgemmSmem));
+  cudaFuncSetAttribute(dgemm_dmma_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DgemmSmem));
+  const dim3 grid((M + DT - 1) / DT, (N + DT - 1) / DT);
+  if (accumulate) dgemm_dmma_kernel<1><<<grid, DTHREADS, sizeof(DgemmSmem), st>>>(A, lda, M, K, B, ldb, C, ldc, N);
+  else dgemm_dmma_kernel<0><<<grid, DTHREADS, sizeof(DgemmSmem), st>>>(A, lda, M, K, B, ldb, C, ldc, N);
+  return 1;
+}
+
+}  // namespace nnsdp

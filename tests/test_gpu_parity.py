@@ -768,7 +768,8 @@ def test_multi_device_context_shards_queries(ctx):
 # CROWN bounds: the reference's default IntervalsAutoLirpa, sliced variant
 # ---------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("xdims", [[2, 3, 2], [2, 6, 5, 7, 2], [2] + [10] * 10 + [2], [5, 50, 50, 50, 50, 50, 50, 5],
-                                   [2] + [20] * 10 + [2], [3, 150, 260, 140, 2], [2, 4, 7, 3, 5, 2]])
+                                   [2] + [20] * 10 + [2], [3, 150, 260, 140, 2], [2, 4, 7, 3, 5, 2],
+                                   [3, 131, 257, 193, 129, 2]])   # odd widths >= 192 x 128: every edge of the tensor-core GEMM tiles
 def test_crown_bounds_against_oracle(ctx, xdims):
     import nnsdp_b200 as nb
 
