@@ -9,18 +9,22 @@
 // the active set looks like).  Only upper-triangular 128x128 tile pairs are computed; every tile
 // is written to G[r,c] and mirrored to G[c,r] from the same accumulators, so G is bit-symmetric.
 #include "internal.h"
+#include <stdlib.h>
 
 namespace nnsdp {
 
 namespace {
 
-constexpr int GT = 128;        // tile side
+// Tile side GT is 128, or 64 when the work list is too short to fill the GPU with 128 x 128 tiles (a single query
+// on a wide net: 36 tiles of one active layer on 148 SMs).  Every entry accumulates its neurons in the same order
+// (four per DMMA, stage after stage) whatever the tile side, so the result does not depend on the choice.
 constexpr int GK = 16;         // neurons per pipeline stage
 constexpr int GSTAGES = 3;
-constexpr int GLD = GT + 8;    // smem leading dimension: (k*GLD + row) hits 32 distinct banks pairs
-constexpr int GTHREADS = 256;  // 8 warps: 4 (rows) x 2 (cols), warp tile 32 x 64
+constexpr int GTHREADS = 256;  // 8 warps: 4 (rows) x 2 (cols), warp tile GT/4 x GT/2
 
+template <int GT>
 struct GramSmem {
+  static constexpr int GLD = GT + 8;   // smem leading dimension: (k*GLD + row) hits 32 distinct banks pairs
   double A[GSTAGES][GK][GLD];
   double B[GSTAGES][GK][GLD];
   double d[GSTAGES][GK];
@@ -43,10 +47,12 @@ __device__ __forceinline__ void dmma_m8n8k4(double& c0, double& c1, double a, do
                : "d"(a), "d"(b));
 }
 
+template <int GT>
 __global__ void __launch_bounds__(GTHREADS, 1)
 gram_kernel(NetDev net, BatchDev b, GramDev g, int q0, const int* __restrict__ pairs) {
+  constexpr int GLD = GramSmem<GT>::GLD, WM = GT / 4, WN = GT / 2, NI = WM / 8, NJ = WN / 8;
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  GramSmem& sm = *reinterpret_cast<GramSmem*>(smem_raw);
+  GramSmem<GT>& sm = *reinterpret_cast<GramSmem<GT>*>(smem_raw);
 
   // work list: only (query, block) pairs with active neurons; Gram of block blk uses layer matrix M[blk]
   const int q = pairs[2 * blockIdx.y], blk = pairs[2 * blockIdx.y + 1], slot = q - q0;
@@ -72,12 +78,12 @@ gram_kernel(NetDev net, BatchDev b, GramDev g, int q0, const int* __restrict__ p
   const double* d11 = b.d11 + (long long)q * net.acdim + L0;
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int wm = (warp & 3) * 32, wn = (warp >> 2) * 64;
+  const int wm = (warp & 3) * WM, wn = (warp >> 2) * WN;
   const int nsteps = (cnt + GK - 1) / GK;
 
   auto load_stage = [&](int stage, int step) {
     const int k0 = step * GK;
-    // 16 neurons x 128 rows = 16 x 64 chunks of 16 B per operand
+    // 16 neurons x GT rows = 16 x GT/2 chunks of 16 B per operand
     for (int c = tid; c < GK * (GT / 2); c += GTHREADS) {
       const int kk = c / (GT / 2), ch = c % (GT / 2);
       const bool valid = (k0 + kk) < cnt;
@@ -89,11 +95,11 @@ gram_kernel(NetDev net, BatchDev b, GramDev g, int q0, const int* __restrict__ p
     if (tid < GK) sm.d[stage][tid] = (k0 + tid < cnt) ? d11[act[k0 + tid]] : 0.0;
   };
 
-  double acc[4][8][2];
+  double acc[NI][NJ][2];
 #pragma unroll
-  for (int i = 0; i < 4; ++i)
+  for (int i = 0; i < NI; ++i)
 #pragma unroll
-    for (int j = 0; j < 8; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+    for (int j = 0; j < NJ; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
 
   for (int s = 0; s < GSTAGES - 1; ++s) {
     if (s < nsteps) load_stage(s, s);
@@ -114,15 +120,15 @@ gram_kernel(NetDev net, BatchDev b, GramDev g, int q0, const int* __restrict__ p
     for (int k4 = 0; k4 < GK; k4 += 4) {
       const int k = k4 + (lane & 3);
       const double dk = sm.d[st][k];
-      double af[4], bf[8];
+      double af[NI], bf[NJ];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) af[i] = As[k][wm + i * 8 + (lane >> 2)] * dk;
+      for (int i = 0; i < NI; ++i) af[i] = As[k][wm + i * 8 + (lane >> 2)] * dk;
 #pragma unroll
-      for (int j = 0; j < 8; ++j) bf[j] = Bs[k][wn + j * 8 + (lane >> 2)];
+      for (int j = 0; j < NJ; ++j) bf[j] = Bs[k][wn + j * 8 + (lane >> 2)];
 #pragma unroll
-      for (int i = 0; i < 4; ++i)
+      for (int i = 0; i < NI; ++i)
 #pragma unroll
-        for (int j = 0; j < 8; ++j) dmma_m8n8k4(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+        for (int j = 0; j < NJ; ++j) dmma_m8n8k4(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
     }
   }
   cp_async_wait<0>();
@@ -131,10 +137,10 @@ gram_kernel(NetDev net, BatchDev b, GramDev g, int q0, const int* __restrict__ p
   double* G = g.scratch + (long long)slot * g.per_query + g.goff[blk];
   const int ldG = g.ldG[blk];
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
+  for (int i = 0; i < NI; ++i) {
     const int r = m0 + wm + i * 8 + (lane >> 2);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
+    for (int j = 0; j < NJ; ++j) {
       const int c = n0 + wn + j * 8 + (lane & 3) * 2;
 #pragma unroll
       for (int e = 0; e < 2; ++e) {
@@ -151,16 +157,24 @@ gram_kernel(NetDev net, BatchDev b, GramDev g, int q0, const int* __restrict__ p
 
 }  // namespace
 
+template <int GT>
+static void launch_gram_t(const NetDev& net, const BatchDev& b, const GramDev& g, int max_n, int q0, const int* pairs,
+                          int npairs, cudaStream_t st) {
+  cudaFuncSetAttribute(gram_kernel<GT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(GramSmem<GT>));
+  const int ntile = (max_n + GT - 1) / GT;
+  dim3 grid(ntile * (ntile + 1) / 2, npairs);
+  gram_kernel<GT><<<grid, GTHREADS, sizeof(GramSmem<GT>), st>>>(net, b, g, q0, pairs);
+}
+
 int launch_gram(const NetDev& net, const BatchDev& b, const GramDev& g, int max_n, int q0, const int* pairs,
                 int npairs, cudaStream_t st) {
   if (net.K < 2 || npairs <= 0) return 0;
-  static bool attr_set = false;  // per process; harmless if repeated per device
-  (void)attr_set;
-  cudaFuncSetAttribute(gram_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                       (int)sizeof(GramSmem));
-  const int ntile = (max_n + GT - 1) / GT;
-  dim3 grid(ntile * (ntile + 1) / 2, npairs);
-  gram_kernel<<<grid, GTHREADS, sizeof(GramSmem), st>>>(net, b, g, q0, pairs);
+  static const int force = [] { const char* e = getenv("NNSDP_GRAM_TILE"); return e ? atoi(e) : 0; }();
+  const int nt128 = (max_n + 127) / 128;
+  const long long items128 = (long long)nt128 * (nt128 + 1) / 2 * npairs;
+  const bool small = force ? force == 64 : items128 < 148;   // fewer 128 x 128 tiles than SMs
+  if (small) launch_gram_t<64>(net, b, g, max_n, q0, pairs, npairs, st);
+  else launch_gram_t<128>(net, b, g, max_n, q0, pairs, npairs, st);
   return 1;
 }
 
