@@ -953,9 +953,14 @@ int32_t nnsdp_batch_bounds(nnsdp_batch* b) {
   int launches = 0;
   int max_out = 0;
   for (int k = 1; k <= sh.K; ++k) max_out = std::max(max_out, (int)sh.n[k]);
-  const int whole = ibp_all_launch(nd.nd, max_out, b->bd.x1min, b->bd.s_x1min, b->bd.x1max, b->bd.s_x1max, xmin, xmax,
-                                   sh.xtot, b->acxmin.as<double>(), b->acxmax.as<double>(), b->smin_c.as<double>(),
-                                   b->smax_c.as<double>(), sh.acdim, Q, nullptr, b->st);
+  const int max_w = std::max(max_out, (int)sh.n[0]);
+  int whole = ibp_chain_launch(nd.nd, max_w, b->bd.x1min, b->bd.s_x1min, b->bd.x1max, b->bd.s_x1max, xmin, xmax, sh.xtot,
+                               b->acxmin.as<double>(), b->acxmax.as<double>(), b->smin_c.as<double>(),
+                               b->smax_c.as<double>(), sh.acdim, Q, nullptr, b->st);
+  if (whole == 0)
+    whole = ibp_all_launch(nd.nd, max_out, b->bd.x1min, b->bd.s_x1min, b->bd.x1max, b->bd.s_x1max, xmin, xmax,
+                           sh.xtot, b->acxmin.as<double>(), b->acxmax.as<double>(), b->smin_c.as<double>(),
+                           b->smax_c.as<double>(), sh.acdim, Q, nullptr, b->st);
   NN_CHECK(whole >= 0, NNSDP_ERR_CUDA, "cooperative launch of the interval propagation failed: %s",
            cudaGetErrorString(cudaGetLastError()));
   launches += whole;

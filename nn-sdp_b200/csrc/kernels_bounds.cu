@@ -445,6 +445,92 @@ ibp_all_kernel(NetDev net, const double* __restrict__ x1min, long long s_min, co
   }
 }
 
+// (c) narrow nets (every width <= 256), any number of queries: queries are independent, so a CTA takes ICH_NQ of
+// them through ALL layers by itself -- no barrier between CTAs, one launch for the whole propagation.  Thread m owns
+// output row m of the current layer (W is read column by column, coalesced, from L2 after the first CTA), the
+// (centre, radius) of the layer input sits in shared memory, double buffered.
+constexpr int ICH_NQ = 8, ICH_MAXW = 256, ICH_UNROLL = 16;
+
+__global__ void __launch_bounds__(ICH_MAXW)
+ibp_chain_kernel(NetDev net, int maxw, const double* __restrict__ x1min, long long s_min, const double* __restrict__ x1max,
+                 long long s_max, double* __restrict__ xmin, double* __restrict__ xmax, long long x_stride,
+                 double* __restrict__ acxmin, double* __restrict__ acxmax, double* __restrict__ smin,
+                 double* __restrict__ smax, long long acx_stride, int N, int* flag_bad) {
+  extern __shared__ double ich[];                       // [2 buffers][maxw][2][ICH_NQ]
+  const int tid = threadIdx.x, K = net.K, n_in = net.n_in;
+  const int q0 = blockIdx.x * ICH_NQ, nq = min(ICH_NQ, N - q0);
+  double* cur = ich;
+  double* nxt = ich + (size_t)maxw * 2 * ICH_NQ;
+  for (int i = tid; i < n_in * ICH_NQ; i += blockDim.x) {
+    const int r = i / ICH_NQ, q = i % ICH_NQ;
+    double lo = 0.0, hi = 0.0;
+    if (q < nq) {
+      lo = x1min[(long long)(q0 + q) * s_min + r];
+      hi = x1max[(long long)(q0 + q) * s_max + r];
+      xmin[(long long)(q0 + q) * x_stride + r] = lo;
+      xmax[(long long)(q0 + q) * x_stride + r] = hi;
+    }
+    cur[(r * 2 + 0) * ICH_NQ + q] = 0.5 * (lo + hi);
+    cur[(r * 2 + 1) * ICH_NQ + q] = 0.5 * (hi - lo);
+  }
+  __syncthreads();
+  for (int k = 0; k < K; ++k) {
+    const int M = net.n[k + 1], Kdim = net.n[k];
+    const double* A = net.M[k];
+    const bool last = (k == K - 1);
+    {
+      double ac[ICH_NQ], ar[ICH_NQ];
+#pragma unroll
+      for (int q = 0; q < ICH_NQ; ++q) ac[q] = ar[q] = 0.0;
+      const double* Ar = A + min(tid, M - 1);            // idle threads load a valid row: the barrier below is uniform
+      for (int k0 = 0; k0 < Kdim; k0 += ICH_UNROLL) {     // ICH_UNROLL loads of W in flight per thread
+        double a[ICH_UNROLL];
+#pragma unroll
+        for (int j = 0; j < ICH_UNROLL; ++j) a[j] = __ldcg(Ar + (long long)min(k0 + j, Kdim - 1) * M);   // not .nc: stays above the barrier
+        __syncthreads();                                  // all ICH_UNROLL loads are issued before the first is consumed
+#pragma unroll
+        for (int j = 0; j < ICH_UNROLL; ++j) {
+          const double av = (k0 + j < Kdim) ? a[j] : 0.0;
+          const double aa = fabs(av);
+          const double* x = cur + min(k0 + j, Kdim - 1) * 2 * ICH_NQ;
+#pragma unroll
+          for (int q = 0; q < ICH_NQ; ++q) {
+            ac[q] = fma(av, x[q], ac[q]);
+            ar[q] = fma(aa, x[ICH_NQ + q], ar[q]);
+          }
+        }
+      }
+      const double bias = A[(long long)Kdim * M + min(tid, M - 1)];
+#pragma unroll
+      for (int q = 0; q < ICH_NQ && tid < M; ++q) {
+        const double mid = ac[q] + bias;
+        const double ymin = mid - ar[q], ymax = mid + ar[q];
+        const double lo = last ? ymin : fmax(ymin, 0.0), hi = last ? ymax : fmax(ymax, 0.0);
+        nxt[(tid * 2 + 0) * ICH_NQ + q] = 0.5 * (lo + hi);
+        nxt[(tid * 2 + 1) * ICH_NQ + q] = 0.5 * (hi - lo);
+        if (q < nq) {
+          const long long qg = q0 + q;
+          if (!(ymin <= ymax) && flag_bad) atomicOr(flag_bad, 1);
+          if (!last) {
+            const long long o = qg * acx_stride + (net.off[k + 1] - n_in) + tid;
+            acxmin[o] = ymin;
+            acxmax[o] = ymax;
+            const double eps = 1e-4;  // activ_sector.jl:65
+            smin[o] = (ymin > eps) ? 1.0 : 0.0;
+            smax[o] = (ymax < -eps) ? 0.0 : 1.0;
+          }
+          xmin[qg * x_stride + net.xoff[k + 1] + tid] = lo;
+          xmax[qg * x_stride + net.xoff[k + 1] + tid] = hi;
+        }
+      }
+    }
+    __syncthreads();
+    double* t = cur;
+    cur = nxt;
+    nxt = t;
+  }
+}
+
 __global__ void sector_minmax_kernel(long long n, const double* __restrict__ lo,
                                      const double* __restrict__ hi, double* __restrict__ smin,
                                      double* __restrict__ smax) {
@@ -573,7 +659,8 @@ int launch_sector_minmax(long long n, const double* acxmin, const double* acxmax
 // All affine-column GEMVs of a batch of few queries in one launch; 0 = not applicable (caller loops over layers).
 int affine_all_launch(const NetDev& nd, int K, int max_rows, const double* u, long long u_stride, double* aff,
                       long long aff_stride, int Q, cudaStream_t st) {
-  if (Q > GV_MAX_N || !gemv_enabled() || K < 2) return 0;
+  // few queries, or narrow nets (the per-layer launches cost more than their products)
+  if ((Q > GV_MAX_N && max_rows > ICH_MAXW) || !gemv_enabled() || K < 2) return 0;
   const int nqt = Q == 1 ? 1 : Q == 2 ? 2 : Q <= 4 ? 4 : 8;
   const dim3 grid((max_rows + AFA_ROWS - 1) / AFA_ROWS, K - 1, (Q + nqt - 1) / nqt);
   if (nqt == 1) affine_all_kernel<1><<<grid, GVT_THREADS, 0, st>>>(nd, u, u_stride, aff, aff_stride, Q);
@@ -622,6 +709,23 @@ int ibp_all_launch(const NetDev& nd, int max_out, const double* x1min, long long
   if (Q <= 4) return NNSDP_IBA(4);
   return NNSDP_IBA(8);
 #undef NNSDP_IBA
+}
+
+// Interval propagation of narrow nets (max width <= 256) for any number of queries: one launch, a CTA per 8 queries
+// walks every layer.  0 = not applicable.
+int ibp_chain_launch(const NetDev& nd, int max_w, const double* x1min, long long s_min, const double* x1max,
+                     long long s_max, double* xmin, double* xmax, long long x_stride, double* acxmin, double* acxmax,
+                     double* smin, double* smax, long long acx_stride, int Q, int* flag_bad, cudaStream_t st) {
+  static const bool off = [] { const char* e = getenv("NNSDP_NO_IBP_CHAIN"); return e && atoi(e) != 0; }();
+  if (off || max_w > ICH_MAXW || !gemv_enabled()) return 0;
+  const int threads = max_w <= 64 ? 64 : max_w <= 128 ? 128 : 256;
+  const size_t smem = (size_t)2 * max_w * 2 * ICH_NQ * sizeof(double);
+  if (smem > 48 * 1024)
+    cudaFuncSetAttribute(ibp_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  ibp_chain_kernel<<<(Q + ICH_NQ - 1) / ICH_NQ, threads, smem, st>>>(nd, max_w, x1min, s_min, x1max, s_max, xmin, xmax,
+                                                                   x_stride, acxmin, acxmax, smin, smax, acx_stride, Q,
+                                                                   flag_bad);
+  return 1;
 }
 
 }  // namespace nnsdp

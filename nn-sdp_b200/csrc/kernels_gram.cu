@@ -172,7 +172,11 @@ int launch_gram(const NetDev& net, const BatchDev& b, const GramDev& g, int max_
   static const int force = [] { const char* e = getenv("NNSDP_GRAM_TILE"); return e ? atoi(e) : 0; }();
   const int nt128 = (max_n + 127) / 128;
   const long long items128 = (long long)nt128 * (nt128 + 1) / 2 * npairs;
-  const bool small = force ? force == 64 : items128 < 148;   // fewer 128 x 128 tiles than SMs
+  const int nt64 = (max_n + 63) / 64;
+  const long long pad128 = (long long)nt128 * (nt128 + 1) / 2 * 4, pad64 = (long long)nt64 * (nt64 + 1) / 2;
+  // 64 x 64 tiles when there are fewer 128 x 128 tiles than SMs, or when they would be mostly padding (width 100:
+  // one 128 tile against three 64 tiles)
+  const bool small = force ? force == 64 : (items128 < 148 || pad64 * 100 <= pad128 * 85);
   if (small) launch_gram_t<64>(net, b, g, max_n, q0, pairs, npairs, st);
   else launch_gram_t<128>(net, b, g, max_n, q0, pairs, npairs, st);
   return 1;
