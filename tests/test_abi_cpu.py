@@ -324,3 +324,73 @@ def test_vnnlib_reader_errors(tmp_path):
         nb.read_vnnlib(str(tmp_path / "missing.vnnlib"), 1, 1)
     ok = run("(assert (<= X_0 1.0))\n(assert (>= X_0 0.0)) ; both\n(assert (<= Y_0 0.5))\n")
     assert ok["nclauses"] == 1 and ok["S"].shape == (1, 3, 3) and ok["S"][0, 2, 2] == -2 * (-0.5 - 1e-4)
+
+
+# ---------------------------------------------------------------------------------------------
+# the (never executed) Julia wrapper against the header: every ccall names a declared symbol with the right
+# number and kinds of arguments
+# ---------------------------------------------------------------------------------------------
+def _c_kind(p):
+    p = re.sub(r"\b(const|struct)\b", " ", p)
+    p = re.sub(r"\s+", " ", p).strip()
+    m = re.match(r"^([A-Za-z_0-9]+)\s*(\*+)?\s*(?:\*\s*)?[A-Za-z_0-9]*$", p.replace("* *", "**").replace("* ", "*"))
+    stars = p.count("*")
+    base = p.replace("*", " ").split()[0]
+    scalar = {"int32_t": "i32", "int64_t": "i64", "double": "f64", "float": "f32", "char": "char", "uint64_t": "u64"}
+    if stars == 0:
+        return scalar.get(base, "struct")
+    if base == "char" and stars == 1:
+        return "str"
+    if base in scalar:
+        return "p" * stars + "_" + scalar[base]
+    return "p" * stars + "_struct"
+
+
+def _jl_kind(t):
+    t = t.strip()
+    scalar = {"Int32": "i32", "Int64": "i64", "Float64": "f64", "Float32": "f32", "UInt64": "u64", "Cstring": "str"}
+    if t in scalar:
+        return scalar[t]
+    depth = 0
+    while t.startswith("Ptr{") or t.startswith("Ref{"):
+        t = t[4:-1]
+        depth += 1
+    if t in scalar:
+        return "p" * depth + "_" + scalar[t]
+    return "p" * depth + "_struct"      # Cvoid (opaque handles) and mirrored structs
+
+
+def test_julia_wrapper_ccalls_match_the_header():
+    jl = open(os.path.join(ROOT, "nn-sdp_b200", "julia", "NnSdpB200.jl")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", open(HEADER).read(), flags=re.S)
+    protos = {}
+    for m in re.finditer(r"\b([a-z_0-9 ]+?\*?)\s*\b(nnsdp_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;", hdr, flags=re.S):
+        ret, name, params = m.groups()
+        params = params.replace("\n", " ").strip()
+        protos[name] = (ret.strip(), [] if params in ("", "void") else [p.strip() for p in params.split(",")])
+    calls = []
+    for m in re.finditer(r"ccall\(\(:(nnsdp_[a-z0-9_]+), LIB\),\s*([A-Za-z0-9{}]+),\s*\(", jl):
+        j = k = m.end()
+        depth = 1
+        while depth:
+            depth += (jl[k] == "(") - (jl[k] == ")")
+            k += 1
+        parts, cur, d = [], "", 0
+        for c in jl[j:k - 1]:
+            d += (c in "{(") - (c in "})")
+            if c == "," and d == 0:
+                parts.append(cur.strip())
+                cur = ""
+            else:
+                cur += c
+        if cur.strip():
+            parts.append(cur.strip())
+        calls.append((m.group(1), m.group(2), parts))
+    assert len(calls) >= 20
+    for name, ret, parts in calls:
+        assert name in protos, f"{name} is not declared in include/nnsdp_b200.h"
+        cret, cparams = protos[name]
+        assert _jl_kind(ret) == _c_kind(cret), (name, ret, cret)
+        assert len(parts) == len(cparams), (name, parts, cparams)
+        for jt, cp in zip(parts, cparams):
+            assert _jl_kind(jt) == _c_kind(cp), (name, jt, cp)
