@@ -228,6 +228,7 @@ struct nnsdp_batch {
   // prepared
   DevBuf d11, Md, T0, Bt, u, aff, part, act, cnt, Z11, Z1K, U;
   DevBuf gram, ringbuf, flags;
+  DevBuf cr_rowsA, cr_rowsB, cr_bias, cr_prel, cr_preu, cr_du, cr_bu, cr_dl;  // CROWN work buffers (kept when small)
   BatchDev bd{};
   GramDev gd{};
   PlanDev pd{};
@@ -282,7 +283,7 @@ struct nnsdp_batch {
     return {&d_tiles, &d_strips, &d_mats, &d_goff, &d_ldG, &x1min, &x1max, &ymin, &ymax, &smin, &smax,
             &gin, &gbnd, &gsec, &outS, &outvec, &outinvP, &gout, &xmin, &xmax, &acxmin, &acxmax,
             &smin_c, &smax_c, &d11, &Md, &T0, &Bt, &u, &aff, &part, &act, &cnt, &Z11, &Z1K, &U,
-            &gram, &ringbuf, &flags};
+            &gram, &ringbuf, &flags, &cr_rowsA, &cr_rowsB, &cr_bias, &cr_prel, &cr_preu, &cr_du, &cr_bu, &cr_dl};
   }
 };
 
@@ -1622,11 +1623,16 @@ int32_t crown_bounds_device(nnsdp_batch* b) {
   // queries per chunk: two row buffers of 2 * Qc * rows_cap * ld doubles, kept under ~1.5 GiB together
   int Qc = (int)std::max<int64_t>(1, std::min<int64_t>(b->Q, (int64_t(3) << 26) / std::max<int64_t>(1, 4 * rows_cap * ld)));
   Qc = std::min(Qc, 256);
-  DevBuf rowsA, rowsB, bias, prel, preu, du, bu, dl;
+  // work buffers live in the batch; large ones (wide nets) are given back on return, small ones are kept so that
+  // repeated calls on narrow nets do not pay cudaMalloc / cudaFree (milliseconds, more than the kernels)
+  DevBuf &rowsA = b->cr_rowsA, &rowsB = b->cr_rowsB, &bias = b->cr_bias, &prel = b->cr_prel, &preu = b->cr_preu,
+         &du = b->cr_du, &bu = b->cr_bu, &dl = b->cr_dl;
+  const size_t work_bytes = ((size_t)4 * Qc * rows_cap * ld + (size_t)2 * Qc * rows_cap + (size_t)5 * Qc * P) * 8;
   struct Rel {
     std::vector<DevBuf*> v;
-    ~Rel() { for (DevBuf* x : v) x->release(); }
-  } rel{{&rowsA, &rowsB, &bias, &prel, &preu, &du, &bu, &dl}};
+    bool keep;
+    ~Rel() { if (!keep) for (DevBuf* x : v) x->release(); }
+  } rel{{&rowsA, &rowsB, &bias, &prel, &preu, &du, &bu, &dl}, work_bytes <= ((size_t)64 << 20)};
   NN_TRY(rowsA.ensure((size_t)2 * Qc * rows_cap * ld * 8));
   NN_TRY(rowsB.ensure((size_t)2 * Qc * rows_cap * ld * 8));
   NN_TRY(bias.ensure((size_t)2 * Qc * rows_cap * 8));
@@ -1691,10 +1697,17 @@ int32_t crown_bounds_device(nnsdp_batch* b) {
     // y_t, t = 1 .. K-1: backward from A = W_t
     for (int t = 1; t <= K - 1; ++t) {
       const int nrows = (int)sh.n[t + 1];
-      launches += launch_crown_init_bias(bias_of(t), nrows, nq, bias.as<double>(), st);
-      const double* wrows = npd.Wt[t].as<double>();  // row r of W_t = column r of Wt_t
-      chain(wrows, wrows, b->net->ldT[t], 0, t - 1, nrows, prel.as<double>() + poff(t), preu.as<double>() + poff(t),
-            P, 0);
+      // narrow nets: the whole chain of this target in one launch
+      const int fusedc = launch_crown_chain(npd.nd, t, (int)maxn, nq, du.as<double>(), bu.as<double>(), dl.as<double>(), P,
+                                            b->bd.x1min, b->bd.s_x1min, b->bd.x1max, b->bd.s_x1max, (int)q0,
+                                            prel.as<double>() + poff(t), preu.as<double>() + poff(t), P, st);
+      launches += fusedc;
+      if (!fusedc) {
+        launches += launch_crown_init_bias(bias_of(t), nrows, nq, bias.as<double>(), st);
+        const double* wrows = npd.Wt[t].as<double>();  // row r of W_t = column r of Wt_t
+        chain(wrows, wrows, b->net->ldT[t], 0, t - 1, nrows, prel.as<double>() + poff(t), preu.as<double>() + poff(t),
+              P, 0);
+      }
       if (t <= K - 2)
         launches += launch_crown_params(prel.as<double>() + poff(t), preu.as<double>() + poff(t), P, nrows, nq,
                                         du.as<double>() + poff(t), bu.as<double>() + poff(t),
