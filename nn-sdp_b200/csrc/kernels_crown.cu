@@ -274,18 +274,53 @@ crown_concretize_kernel(const double* __restrict__ rowsL, const double* __restri
 // pre-activation targets alone were 4,950 launches.
 constexpr int CC_THREADS = 256, CC_MAXW = 64;
 
+__device__ __forceinline__ void cc_cp16(void* smem, const void* gmem) {
+  const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sa), "l"(gmem));
+}
+
 __global__ void __launch_bounds__(CC_THREADS)
 crown_chain_kernel(NetDev net, int t, int maxw, const double* __restrict__ d_u, const double* __restrict__ b_u,
                    const double* __restrict__ d_l, long long par_stride, const double* __restrict__ x1min,
                    long long s_min, const double* __restrict__ x1max, long long s_max, int q_first,
                    double* __restrict__ out_lo, double* __restrict__ out_hi, long long out_stride) {
-  extern __shared__ double csh[];
-  const int ldw = maxw + 1;
-  double* cur = csh;                                   // [2][maxw][ldw]: half 0 = lower, 1 = upper
-  double* nxt = csh + (size_t)2 * maxw * ldw;
+  extern __shared__ __align__(16) double csh[];
+  const int ldw = maxw + 1, wp = (maxw + 1) & ~1;
+  double* wbuf = csh;                                  // [2][maxw][wp]: W_k of this step and of the next one
+  double* cur = wbuf + (size_t)2 * maxw * wp;          // [2][maxw][ldw]: half 0 = lower, 1 = upper
+  double* nxt = cur + (size_t)2 * maxw * ldw;
   double* bias = nxt + (size_t)2 * maxw * ldw;         // [2][maxw]
   const int q = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int nrows = net.n[t + 1], n_in = net.n_in;
+  // operands of a step, requested one step ahead: W_k by cp.async into shared memory, the relaxation of y_k and
+  // b_k into registers (lane c and c + 32: widths are <= 64), so that no step waits on L2
+  auto stage_w = [&](int k, int buf) {
+    const double* Wt = net.Wt[k];
+    const int ldT = net.ldT[k], cols = net.n[k + 1], chunks = (net.n[k] + 1) / 2;
+    double* dst = wbuf + (size_t)buf * maxw * wp;
+    for (int i = tid; i < cols * chunks; i += CC_THREADS) {
+      const int c = i / chunks, j = i % chunks;
+      cc_cp16(dst + c * wp + 2 * j, Wt + (long long)c * ldT + 2 * j);   // Wt is zero padded to ldT rows
+    }
+  };
+  double pu[2], pb[2], pl[2], bk[2];
+  auto load_par = [&](int k, double (&u)[2], double (&bb)[2], double (&l)[2], double (&bs)[2]) {
+    const int n = net.n[k + 1];
+    const long long po = (long long)q * par_stride + (net.xoff[k + 1] - n_in);
+    const double* bsrc = net.M[k] + (long long)net.n[k] * n;
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      const int c = lane + 32 * e;
+      const bool ok = c < n;
+      u[e] = ok ? d_u[po + c] : 0.0;
+      bb[e] = ok ? b_u[po + c] : 0.0;
+      l[e] = ok ? d_l[po + c] : 0.0;
+      bs[e] = ok ? bsrc[c] : 0.0;
+    }
+  };
+  stage_w(t - 1, 0);
+  asm volatile("cp.async.commit_group;\n" ::);
+  load_par(t - 1, pu, pb, pl, bk);
   {  // rows of W_t (row r of W_t = column r of Wt_t), bias b_t
     const int n = net.n[t];
     const double* Wt = net.Wt[t];
@@ -300,50 +335,60 @@ crown_chain_kernel(NetDev net, int t, int maxw, const double* __restrict__ d_u, 
     for (int i = tid; i < 2 * nrows; i += CC_THREADS) bias[(i / nrows) * maxw + i % nrows] = bt[i % nrows];
   }
   __syncthreads();
+  int wb = 0;
   for (int k = t - 1; k >= 0; --k) {
     const int nk1 = net.n[k + 1], nk = net.n[k];
-    const long long po = (long long)q * par_stride + (net.xoff[k + 1] - n_in);
-    const double* pu = d_u + po;
-    const double* pb = b_u + po;
-    const double* pl = d_l + po;
-    const double* bk = net.M[k] + (long long)nk * nk1;
+    double pu2[2], pb2[2], pl2[2], bk2[2];
+    if (k > 0) {
+      stage_w(k - 1, wb ^ 1);
+      load_par(k - 1, pu2, pb2, pl2, bk2);
+    }
+    asm volatile("cp.async.commit_group;\n" ::);
     // relaxation through relu_k and the bias sums (same rules as crown_row_kernel)
     for (int hr = warp; hr < 2 * nrows; hr += CC_THREADS / 32) {
       const int h = hr / nrows, r = hr % nrows;
       double* a = cur + (h * maxw + r) * ldw;
       double acc = 0.0;
-      for (int c = lane; c < nk1; c += 32) {
-        double v = a[c];
-        const bool steep = h ? (v > 0.0) : (v < 0.0);   // the side that takes the chord (upper relaxation)
-        if (steep) {
-          acc = fma(v, pb[c], acc);
-          v *= pu[c];
-        } else {
-          v *= pl[c];
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int c = lane + 32 * e;
+        if (c < nk1) {
+          double v = a[c];
+          const bool steep = h ? (v > 0.0) : (v < 0.0);   // the side that takes the chord (upper relaxation)
+          if (steep) {
+            acc = fma(v, pb[e], acc);
+            v *= pu[e];
+          } else {
+            v *= pl[e];
+          }
+          acc = fma(v, bk[e], acc);
+          a[c] = v;
         }
-        acc = fma(v, bk[c], acc);
-        a[c] = v;
       }
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
       if (lane == 0) bias[h * maxw + r] += acc;
     }
+    asm volatile("cp.async.wait_group 1;\n" ::);       // W_k has landed (the group just committed may be in flight)
     __syncthreads();
-    // product with W_k: nxt[h][r][i] = sum_c cur[h][r][c] W_k[c, i],  W_k[c, i] = Wt_k[i + c ldT]
-    const double* Wt = net.Wt[k];
-    const int ldT = net.ldT[k];
+    // product with W_k: nxt[h][r][i] = sum_c cur[h][r][c] W_k[c, i]
+    const double* W = wbuf + (size_t)wb * maxw * wp;
     for (int idx = tid; idx < 2 * nrows * nk; idx += CC_THREADS) {
       const int i = idx % nk, hr = idx / nk;
       const double* a = cur + ((hr / nrows) * maxw + hr % nrows) * ldw;
       double sum = 0.0;
-      for (int c = 0; c < nk1; ++c) sum = fma(a[c], Wt[i + (long long)c * ldT], sum);
+      for (int c = 0; c < nk1; ++c) sum = fma(a[c], W[c * wp + i], sum);
       nxt[((hr / nrows) * maxw + hr % nrows) * ldw + i] = sum;
     }
     __syncthreads();
     double* tmp = cur;
     cur = nxt;
     nxt = tmp;
+    wb ^= 1;
+#pragma unroll
+    for (int e = 0; e < 2; ++e) pu[e] = pu2[e], pb[e] = pb2[e], pl[e] = pl2[e], bk[e] = bk2[e];
   }
+  asm volatile("cp.async.wait_group 0;\n" ::);
   // concretise on the input box (crown_concretize_kernel without post-processing)
   const double* lo = x1min + (long long)(q_first + q) * s_min;
   const double* hi = x1max + (long long)(q_first + q) * s_max;
@@ -428,7 +473,7 @@ int launch_crown_chain(const NetDev& net, int t, int maxw, int Qc, const double*
                        int q_first, double* out_lo, double* out_hi, long long out_stride, cudaStream_t st) {
   static const bool off = [] { const char* e = getenv("NNSDP_NO_CROWN_CHAIN"); return e && atoi(e) != 0; }();
   if (off || maxw > CC_MAXW || t < 1) return 0;
-  const size_t smem = ((size_t)4 * maxw * (maxw + 1) + 2 * maxw) * sizeof(double);
+  const size_t smem = ((size_t)2 * maxw * ((maxw + 1) & ~1) + (size_t)4 * maxw * (maxw + 1) + 2 * maxw) * sizeof(double);
   if (smem > 48 * 1024) cudaFuncSetAttribute(crown_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   crown_chain_kernel<<<Qc, CC_THREADS, smem, st>>>(net, t, maxw, d_u, b_u, d_l, par_stride, x1min, s_min, x1max, s_max,
                                                   q_first, out_lo, out_hi, out_stride);
