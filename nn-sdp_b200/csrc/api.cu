@@ -1698,7 +1698,7 @@ int32_t crown_bounds_device(nnsdp_batch* b) {
     for (int t = 1; t <= K - 1; ++t) {
       const int nrows = (int)sh.n[t + 1];
       // narrow nets: the whole chain of this target in one launch
-      const int fusedc = launch_crown_chain(npd.nd, t, (int)maxn, nq, du.as<double>(), bu.as<double>(), dl.as<double>(), P,
+      const int fusedc = launch_crown_chain(npd.nd, t, 0, 1, (int)maxn, nq, du.as<double>(), bu.as<double>(), dl.as<double>(), P,
                                             b->bd.x1min, b->bd.s_x1min, b->bd.x1max, b->bd.s_x1max, (int)q0,
                                             prel.as<double>() + poff(t), preu.as<double>() + poff(t), P, st);
       launches += fusedc;
@@ -1714,7 +1714,13 @@ int32_t crown_bounds_device(nnsdp_batch* b) {
                                         dl.as<double>() + poff(t), st);
     }
     // x_{k+1} = relu(y_k), k = 0 .. K-2: the output of the (k+1)-layer prefix followed by an identity layer
-    if (wavefront) {
+    const int post_fused = launch_crown_chain(npd.nd, 0, 1, K - 1, (int)maxn, nq, du.as<double>(), bu.as<double>(),
+                                              dl.as<double>(), P, b->bd.x1min, b->bd.s_x1min, b->bd.x1max, b->bd.s_x1max,
+                                              (int)q0, xmin + q0 * sh.xtot, xmax + q0 * sh.xtot, sh.xtot, st);
+    launches += post_fused;
+    if (post_fused) {
+      // narrow nets: every target is a CTA of one launch
+    } else if (wavefront) {
       // Narrow nets: all K-1 targets walk back together.  Their rows are stacked (target K-2 first); the step
       // through (relu_j, W_j) handles the rows of every target k > j in one fused launch, after which target j
       // joins the stack: 2 (K-1) launches instead of (K-1)(K-2)/2 chain steps.

@@ -343,9 +343,10 @@ int launch_crown_init_post(const double* Wt, int ldT, int n_in_k, const double* 
                            const double* b_u, const double* d_l, long long par_stride, double* dst,
                            long long dst_row_stride, int nrows, int Rs, int row0, int Qc, double* bias,
                            cudaStream_t st);
-int launch_crown_chain(const NetDev& net, int t, int maxw, int Qc, const double* d_u, const double* b_u, const double* d_l,
-                       long long par_stride, const double* x1min, long long s_min, const double* x1max, long long s_max,
-                       int q_first, double* out_lo, double* out_hi, long long out_stride, cudaStream_t st);
+int launch_crown_chain(const NetDev& net, int t, int post, int ntargets, int maxw, int Qc, const double* d_u,
+                       const double* b_u, const double* d_l, long long par_stride, const double* x1min, long long s_min,
+                       const double* x1max, long long s_max, int q_first, double* out_lo, double* out_hi,
+                       long long out_stride, cudaStream_t st);
 int launch_crown_concretize(const double* rowsL, const double* rowsU, long long row_stride, long long q_stride,
                             int nrows, int Rs, int row0, int Qc, int n0, const double* x1min, long long s_min,
                             const double* x1max, long long s_max, int q_first, const double* bias, double* out_lo,

@@ -280,10 +280,15 @@ __device__ __forceinline__ void cc_cp16(void* smem, const void* gmem) {
 }
 
 __global__ void __launch_bounds__(CC_THREADS)
-crown_chain_kernel(NetDev net, int t, int maxw, const double* __restrict__ d_u, const double* __restrict__ b_u,
-                   const double* __restrict__ d_l, long long par_stride, const double* __restrict__ x1min,
-                   long long s_min, const double* __restrict__ x1max, long long s_max, int q_first,
-                   double* __restrict__ out_lo, double* __restrict__ out_hi, long long out_stride) {
+crown_chain_kernel(NetDev net, int t_pre, int post, int maxw, const double* __restrict__ d_u,
+                   const double* __restrict__ b_u, const double* __restrict__ d_l, long long par_stride,
+                   const double* __restrict__ x1min, long long s_min, const double* __restrict__ x1max, long long s_max,
+                   int q_first, double* __restrict__ out_lo, double* __restrict__ out_hi, long long out_stride) {
+  // pre (post == 0): target y_t, t = t_pre, rows = W_t, results at out[q * out_stride + r]
+  // post (post == 1): target x_{t+1} = relu(y_t) seen through the relaxation of relu_t, t = blockIdx.y (all K-1 of
+  //   them in one launch: they only need the relaxations, which are complete), rows = d_l / d_u scaled W_t, results
+  //   min/max post-processed (intervals_auto_lirpa.jl:37-39) at out[q * out_stride + xoff[t + 1] + r]
+  const int t = post ? (int)blockIdx.y : t_pre;
   extern __shared__ __align__(16) double csh[];
   const int ldw = maxw + 1, wp = (maxw + 1) & ~1;
   double* wbuf = csh;                                  // [2][maxw][wp]: W_k of this step and of the next one
@@ -318,21 +323,28 @@ crown_chain_kernel(NetDev net, int t, int maxw, const double* __restrict__ d_u, 
       bs[e] = ok ? bsrc[c] : 0.0;
     }
   };
-  stage_w(t - 1, 0);
+  if (t >= 1) stage_w(t - 1, 0);
   asm volatile("cp.async.commit_group;\n" ::);
-  load_par(t - 1, pu, pb, pl, bk);
-  {  // rows of W_t (row r of W_t = column r of Wt_t), bias b_t
+  pu[0] = pu[1] = pb[0] = pb[1] = pl[0] = pl[1] = bk[0] = bk[1] = 0.0;
+  if (t >= 1) load_par(t - 1, pu, pb, pl, bk);
+  {  // rows of W_t (row r of W_t = column r of Wt_t), bias b_t; post: scaled by the relaxation of relu_t
     const int n = net.n[t];
     const double* Wt = net.Wt[t];
     const int ldT = net.ldT[t];
+    const long long pt = (long long)q * par_stride + (net.xoff[t + 1] - n_in);
     for (int i = tid; i < nrows * n; i += CC_THREADS) {
       const int c = i % n, r = i / n;
       const double w = Wt[c + (long long)r * ldT];
-      cur[(0 * maxw + r) * ldw + c] = w;
-      cur[(1 * maxw + r) * ldw + c] = w;
+      cur[(0 * maxw + r) * ldw + c] = post ? d_l[pt + r] * w : w;
+      cur[(1 * maxw + r) * ldw + c] = post ? d_u[pt + r] * w : w;
     }
     const double* bt = net.M[t] + (long long)net.n[t] * nrows;
-    for (int i = tid; i < 2 * nrows; i += CC_THREADS) bias[(i / nrows) * maxw + i % nrows] = bt[i % nrows];
+    for (int i = tid; i < 2 * nrows; i += CC_THREADS) {
+      const int h = i / nrows, r = i % nrows;
+      double v = bt[r];
+      if (post) v = h ? b_u[pt + r] + d_u[pt + r] * v : d_l[pt + r] * v;
+      bias[h * maxw + r] = v;
+    }
   }
   __syncthreads();
   int wb = 0;
@@ -407,8 +419,15 @@ crown_chain_kernel(NetDev net, int t, int maxw, const double* __restrict__ d_u, 
       su += __shfl_xor_sync(0xffffffffu, su, o);
     }
     if (lane == 0) {
-      out_lo[(long long)q * out_stride + r] = sl + bias[0 * maxw + r];
-      out_hi[(long long)q * out_stride + r] = su + bias[1 * maxw + r];
+      double L = sl + bias[0 * maxw + r], U = su + bias[1 * maxw + r];
+      long long o = (long long)q * out_stride + r;
+      if (post) {
+        L = fmin(L, U);
+        U = fmax(L, U);
+        o += net.xoff[t + 1];
+      }
+      out_lo[o] = L;
+      out_hi[o] = U;
     }
   }
 }
@@ -467,16 +486,20 @@ int launch_crown_concretize(const double* rowsL, const double* rowsU, long long 
   return 1;
 }
 
-// Pre-activation bounds of y_t for Qc queries of a narrow net in one launch; 0 = not applicable (max width > 64).
-int launch_crown_chain(const NetDev& net, int t, int maxw, int Qc, const double* d_u, const double* b_u, const double* d_l,
-                       long long par_stride, const double* x1min, long long s_min, const double* x1max, long long s_max,
-                       int q_first, double* out_lo, double* out_hi, long long out_stride, cudaStream_t st) {
+// Narrow nets (max width <= 64).  post == 0: pre-activation bounds of y_t for Qc queries in one launch.
+// post == 1: the K-1 post-activation targets x_{t+1}, t = 0 .. K-2, of Qc queries in one launch (out = base of
+// xmin / xmax of the chunk, stride xtot).  0 = not applicable.
+int launch_crown_chain(const NetDev& net, int t, int post, int ntargets, int maxw, int Qc, const double* d_u,
+                       const double* b_u, const double* d_l, long long par_stride, const double* x1min, long long s_min,
+                       const double* x1max, long long s_max, int q_first, double* out_lo, double* out_hi,
+                       long long out_stride, cudaStream_t st) {
   static const bool off = [] { const char* e = getenv("NNSDP_NO_CROWN_CHAIN"); return e && atoi(e) != 0; }();
-  if (off || maxw > CC_MAXW || t < 1) return 0;
+  if (off || maxw > CC_MAXW || (!post && t < 1) || ntargets < 1) return 0;
   const size_t smem = ((size_t)2 * maxw * ((maxw + 1) & ~1) + (size_t)4 * maxw * (maxw + 1) + 2 * maxw) * sizeof(double);
   if (smem > 48 * 1024) cudaFuncSetAttribute(crown_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  crown_chain_kernel<<<Qc, CC_THREADS, smem, st>>>(net, t, maxw, d_u, b_u, d_l, par_stride, x1min, s_min, x1max, s_max,
-                                                  q_first, out_lo, out_hi, out_stride);
+  crown_chain_kernel<<<dim3(Qc, post ? ntargets : 1), CC_THREADS, smem, st>>>(net, t, post, maxw, d_u, b_u, d_l, par_stride,
+                                                                             x1min, s_min, x1max, s_max, q_first, out_lo,
+                                                                             out_hi, out_stride);
   return 1;
 }
 
