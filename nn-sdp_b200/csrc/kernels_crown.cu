@@ -284,6 +284,8 @@ crown_chain_kernel(NetDev net, int t_pre, int post, int maxw, const double* __re
                    const double* __restrict__ b_u, const double* __restrict__ d_l, long long par_stride,
                    const double* __restrict__ x1min, long long s_min, const double* __restrict__ x1max, long long s_max,
                    int q_first, double* __restrict__ out_lo, double* __restrict__ out_hi, long long out_stride) {
+  // The rows of a target never mix, so they are also split over gridDim.z CTAs (a few targets x queries would not
+  // fill the GPU, and the steps are latency bound: fewer rows per CTA = shorter steps).
   // pre (post == 0): target y_t, t = t_pre, rows = W_t, results at out[q * out_stride + r]
   // post (post == 1): target x_{t+1} = relu(y_t) seen through the relaxation of relu_t, t = blockIdx.y (all K-1 of
   //   them in one launch: they only need the relaxations, which are complete), rows = d_l / d_u scaled W_t, results
@@ -296,7 +298,10 @@ crown_chain_kernel(NetDev net, int t_pre, int post, int maxw, const double* __re
   double* nxt = cur + (size_t)2 * maxw * ldw;
   double* bias = nxt + (size_t)2 * maxw * ldw;         // [2][maxw]
   const int q = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int nrows = net.n[t + 1], n_in = net.n_in;
+  const int n_in = net.n_in;
+  const int rows_per = (net.n[t + 1] + (int)gridDim.z - 1) / (int)gridDim.z, r0 = blockIdx.z * rows_per;
+  const int nrows = min(rows_per, net.n[t + 1] - r0);
+  if (nrows <= 0) return;
   // operands of a step, requested one step ahead: W_k by cp.async into shared memory, the relaxation of y_k and
   // b_k into registers (lane c and c + 32: widths are <= 64), so that no step waits on L2
   auto stage_w = [&](int k, int buf) {
@@ -334,15 +339,15 @@ crown_chain_kernel(NetDev net, int t_pre, int post, int maxw, const double* __re
     const long long pt = (long long)q * par_stride + (net.xoff[t + 1] - n_in);
     for (int i = tid; i < nrows * n; i += CC_THREADS) {
       const int c = i % n, r = i / n;
-      const double w = Wt[c + (long long)r * ldT];
-      cur[(0 * maxw + r) * ldw + c] = post ? d_l[pt + r] * w : w;
-      cur[(1 * maxw + r) * ldw + c] = post ? d_u[pt + r] * w : w;
+      const double w = Wt[c + (long long)(r0 + r) * ldT];
+      cur[(0 * maxw + r) * ldw + c] = post ? d_l[pt + r0 + r] * w : w;
+      cur[(1 * maxw + r) * ldw + c] = post ? d_u[pt + r0 + r] * w : w;
     }
-    const double* bt = net.M[t] + (long long)net.n[t] * nrows;
+    const double* bt = net.M[t] + (long long)net.n[t] * net.n[t + 1] + r0;
     for (int i = tid; i < 2 * nrows; i += CC_THREADS) {
       const int h = i / nrows, r = i % nrows;
       double v = bt[r];
-      if (post) v = h ? b_u[pt + r] + d_u[pt + r] * v : d_l[pt + r] * v;
+      if (post) v = h ? b_u[pt + r0 + r] + d_u[pt + r0 + r] * v : d_l[pt + r0 + r] * v;
       bias[h * maxw + r] = v;
     }
   }
@@ -420,7 +425,7 @@ crown_chain_kernel(NetDev net, int t_pre, int post, int maxw, const double* __re
     }
     if (lane == 0) {
       double L = sl + bias[0 * maxw + r], U = su + bias[1 * maxw + r];
-      long long o = (long long)q * out_stride + r;
+      long long o = (long long)q * out_stride + r0 + r;
       if (post) {
         L = fmin(L, U);
         U = fmax(L, U);
@@ -497,7 +502,11 @@ int launch_crown_chain(const NetDev& net, int t, int post, int ntargets, int max
   if (off || maxw > CC_MAXW || (!post && t < 1) || ntargets < 1) return 0;
   const size_t smem = ((size_t)2 * maxw * ((maxw + 1) & ~1) + (size_t)4 * maxw * (maxw + 1) + 2 * maxw) * sizeof(double);
   if (smem > 48 * 1024) cudaFuncSetAttribute(crown_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  crown_chain_kernel<<<dim3(Qc, post ? ntargets : 1), CC_THREADS, smem, st>>>(net, t, post, maxw, d_u, b_u, d_l, par_stride,
+  // enough CTAs to occupy the SMs: split the rows of a target when targets x queries are few
+  int rgroups = 1;
+  const int ctas = Qc * (post ? ntargets : 1);
+  if (ctas < 128) rgroups = std::min(8, (128 + ctas - 1) / ctas);
+  crown_chain_kernel<<<dim3(Qc, post ? ntargets : 1, rgroups), CC_THREADS, smem, st>>>(net, t, post, maxw, d_u, b_u, d_l, par_stride,
                                                                              x1min, s_min, x1max, s_max, q_first, out_lo,
                                                                              out_hi, out_stride);
   return 1;
