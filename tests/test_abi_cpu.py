@@ -394,3 +394,67 @@ def test_julia_wrapper_ccalls_match_the_header():
         assert len(parts) == len(cparams), (name, parts, cparams)
         for jt, cp in zip(parts, cparams):
             assert _jl_kind(jt) == _c_kind(cp), (name, jt, cp)
+
+
+@settings(max_examples=60, deadline=None)
+@given(st.integers(1, 4), st.integers(1, 4), st.integers(0, 2**31 - 1))
+def test_vnnlib_reader_random_properties(n_in, n_out, seed):
+    """Random files in the supported subset (boxes, simple output asserts, up to two disjunctions mixing input and
+    output constraints, comments, statements broken over lines): library == restated reference parser, bit for bit."""
+    import tempfile
+
+    import nnsdp_b200 as nb
+
+    rng = np.random.default_rng(seed)
+    num = lambda v: rng.choice([f"{v:.6g}", f"{v:.3e}", repr(float(v))])      # noqa: E731
+    yterm = lambda: f"Y_{rng.integers(n_out)}"                                  # noqa: E731
+    lines = [f"(declare-const X_{i} Real)" for i in range(n_in)] + [f"(declare-const Y_{i} Real)" for i in range(n_out)]
+    for i in range(n_in):
+        lines.append(f"(assert (<= X_{i} {num(rng.uniform(0.5, 1.0))}))" + ("  ; upper" if rng.random() < 0.3 else ""))
+        lines.append(f"(assert (>= X_{i} {num(rng.uniform(-1.0, -0.5))}))")
+
+    def ycmp():
+        op = rng.choice(["<=", ">="])
+        kind = rng.integers(3)
+        if kind == 0:
+            return f"({op} {yterm()} {yterm()})"
+        if kind == 1:
+            return f"({op} {yterm()} {num(rng.normal())})"
+        return f"({op} {num(rng.normal())} {yterm()})"
+
+    for _ in range(rng.integers(0, 3)):
+        lines.append(f"(assert {ycmp()})")
+    have_y = False
+    for _ in range(rng.integers(0, 3)):
+        alts = []
+        for _ in range(rng.integers(1, 4)):
+            cs = [ycmp() for _ in range(rng.integers(1, 3))]
+            if rng.random() < 0.5:
+                i = rng.integers(n_in)
+                a, b = sorted(rng.uniform(-0.4, 0.4, 2))
+                cs += [f"(<= X_{i} {num(b)})", f"(>= X_{i} {num(a)})"]
+            sep = rng.choice(["", " ", "\n    "])
+            alts.append("(and " + sep.join(cs) + ")")
+        have_y = True
+        lines.append("(assert (or " + rng.choice(["", " ", "\n  "]).join(alts) + "))")
+    if not have_y:
+        lines.append(f"(assert {ycmp()})")
+    with tempfile.TemporaryDirectory() as d:
+        path = os.path.join(d, "p.vnnlib")
+        open(path, "w").write("\n".join(lines) + "\n")
+        net = o.FeedFwdNet(xdims=[n_in, 3, n_out], Ms=[np.zeros((3, n_in + 1)), np.zeros((n_out, 4))])
+        try:
+            cnf = o.load_vnnlib_cnf(path, net)
+        except AssertionError:      # two disjunctions emptied an input interval: the reader's assert (:60)
+            with pytest.raises(nb.NnsdpError) as e:
+                nb.read_vnnlib(path, n_in, n_out)
+            assert e.value.code == -5
+            return
+        got = nb.read_vnnlib(path, n_in, n_out)
+    flat = [(c, qi, qs) for c, clause in enumerate(cnf) for qi, qs in clause]
+    assert got["nclauses"] == len(cnf) and len(flat) == len(got["clause"])
+    for i, (c, qi, qs) in enumerate(flat):
+        assert got["clause"][i] == c
+        assert np.array_equal(got["x1min"][i], qi.x1min) and np.array_equal(got["x1max"][i], qi.x1max)
+        S = np.asarray(qs.S)
+        assert np.array_equal(got["S"][i], S) and np.array_equal(np.signbit(got["S"][i]), np.signbit(S))
