@@ -267,12 +267,12 @@ crown_concretize_kernel(const double* __restrict__ rowsL, const double* __restri
   }
 }
 
-// Narrow nets (every width <= CC_MAXW): the whole backward chain of one pre-activation target y_t in ONE launch.
+// Narrow nets (every width <= ~110): the whole backward chain of one pre-activation target y_t in ONE launch.
 // A CTA owns a query: the rows of (lA, uA) live in shared memory (two buffers), each step relaxes them through
 // relu_k in place (a warp per row, shuffle-reduced bias sums), multiplies by W_k out of L1/L2 and swaps buffers;
 // the last step concretises on the input box.  Replaces t fused step launches per target: on W20-D100 the
 // pre-activation targets alone were 4,950 launches.
-constexpr int CC_THREADS = 256, CC_MAXW = 64;
+constexpr int CC_THREADS = 256, CC_MAXW = 128, CC_NE = 4;   // widths up to 128 if the buffers fit (see the launcher)
 
 __device__ __forceinline__ void cc_cp16(void* smem, const void* gmem) {
   const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
@@ -280,7 +280,7 @@ __device__ __forceinline__ void cc_cp16(void* smem, const void* gmem) {
 }
 
 __global__ void __launch_bounds__(CC_THREADS)
-crown_chain_kernel(NetDev net, int t_pre, int post, int maxw, const double* __restrict__ d_u,
+crown_chain_kernel(NetDev net, int t_pre, int post, int maxw, int rcap, const double* __restrict__ d_u,
                    const double* __restrict__ b_u, const double* __restrict__ d_l, long long par_stride,
                    const double* __restrict__ x1min, long long s_min, const double* __restrict__ x1max, long long s_max,
                    int q_first, double* __restrict__ out_lo, double* __restrict__ out_hi, long long out_stride) {
@@ -294,16 +294,16 @@ crown_chain_kernel(NetDev net, int t_pre, int post, int maxw, const double* __re
   extern __shared__ __align__(16) double csh[];
   const int ldw = maxw + 1, wp = (maxw + 1) & ~1;
   double* wbuf = csh;                                  // [2][maxw][wp]: W_k of this step and of the next one
-  double* cur = wbuf + (size_t)2 * maxw * wp;          // [2][maxw][ldw]: half 0 = lower, 1 = upper
-  double* nxt = cur + (size_t)2 * maxw * ldw;
-  double* bias = nxt + (size_t)2 * maxw * ldw;         // [2][maxw]
+  double* cur = wbuf + (size_t)2 * maxw * wp;          // [2][rcap][ldw]: half 0 = lower, 1 = upper; rcap >= rows of this CTA
+  double* nxt = cur + (size_t)2 * rcap * ldw;
+  double* bias = nxt + (size_t)2 * rcap * ldw;         // [2][rcap]
   const int q = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int n_in = net.n_in;
   const int rows_per = (net.n[t + 1] + (int)gridDim.z - 1) / (int)gridDim.z, r0 = blockIdx.z * rows_per;
   const int nrows = min(rows_per, net.n[t + 1] - r0);
   if (nrows <= 0) return;
   // operands of a step, requested one step ahead: W_k by cp.async into shared memory, the relaxation of y_k and
-  // b_k into registers (lane c and c + 32: widths are <= 64), so that no step waits on L2
+  // b_k into registers (lanes c, c + 32, ...: widths are <= 32 CC_NE), so that no step waits on L2
   auto stage_w = [&](int k, int buf) {
     const double* Wt = net.Wt[k];
     const int ldT = net.ldT[k], cols = net.n[k + 1], chunks = (net.n[k] + 1) / 2;
@@ -313,13 +313,13 @@ crown_chain_kernel(NetDev net, int t_pre, int post, int maxw, const double* __re
       cc_cp16(dst + c * wp + 2 * j, Wt + (long long)c * ldT + 2 * j);   // Wt is zero padded to ldT rows
     }
   };
-  double pu[2], pb[2], pl[2], bk[2];
-  auto load_par = [&](int k, double (&u)[2], double (&bb)[2], double (&l)[2], double (&bs)[2]) {
+  double pu[CC_NE], pb[CC_NE], pl[CC_NE], bk[CC_NE];
+  auto load_par = [&](int k, double (&u)[CC_NE], double (&bb)[CC_NE], double (&l)[CC_NE], double (&bs)[CC_NE]) {
     const int n = net.n[k + 1];
     const long long po = (long long)q * par_stride + (net.xoff[k + 1] - n_in);
     const double* bsrc = net.M[k] + (long long)net.n[k] * n;
 #pragma unroll
-    for (int e = 0; e < 2; ++e) {
+    for (int e = 0; e < CC_NE; ++e) {
       const int c = lane + 32 * e;
       const bool ok = c < n;
       u[e] = ok ? d_u[po + c] : 0.0;
@@ -330,7 +330,8 @@ crown_chain_kernel(NetDev net, int t_pre, int post, int maxw, const double* __re
   };
   if (t >= 1) stage_w(t - 1, 0);
   asm volatile("cp.async.commit_group;\n" ::);
-  pu[0] = pu[1] = pb[0] = pb[1] = pl[0] = pl[1] = bk[0] = bk[1] = 0.0;
+#pragma unroll
+  for (int e = 0; e < CC_NE; ++e) pu[e] = pb[e] = pl[e] = bk[e] = 0.0;
   if (t >= 1) load_par(t - 1, pu, pb, pl, bk);
   {  // rows of W_t (row r of W_t = column r of Wt_t), bias b_t; post: scaled by the relaxation of relu_t
     const int n = net.n[t];
@@ -340,22 +341,24 @@ crown_chain_kernel(NetDev net, int t_pre, int post, int maxw, const double* __re
     for (int i = tid; i < nrows * n; i += CC_THREADS) {
       const int c = i % n, r = i / n;
       const double w = Wt[c + (long long)(r0 + r) * ldT];
-      cur[(0 * maxw + r) * ldw + c] = post ? d_l[pt + r0 + r] * w : w;
-      cur[(1 * maxw + r) * ldw + c] = post ? d_u[pt + r0 + r] * w : w;
+      cur[(0 * rcap + r) * ldw + c] = post ? d_l[pt + r0 + r] * w : w;
+      cur[(1 * rcap + r) * ldw + c] = post ? d_u[pt + r0 + r] * w : w;
     }
     const double* bt = net.M[t] + (long long)net.n[t] * net.n[t + 1] + r0;
     for (int i = tid; i < 2 * nrows; i += CC_THREADS) {
       const int h = i / nrows, r = i % nrows;
       double v = bt[r];
       if (post) v = h ? b_u[pt + r0 + r] + d_u[pt + r0 + r] * v : d_l[pt + r0 + r] * v;
-      bias[h * maxw + r] = v;
+      bias[h * rcap + r] = v;
     }
   }
   __syncthreads();
   int wb = 0;
   for (int k = t - 1; k >= 0; --k) {
     const int nk1 = net.n[k + 1], nk = net.n[k];
-    double pu2[2], pb2[2], pl2[2], bk2[2];
+    double pu2[CC_NE], pb2[CC_NE], pl2[CC_NE], bk2[CC_NE];
+#pragma unroll
+    for (int e = 0; e < CC_NE; ++e) pu2[e] = pb2[e] = pl2[e] = bk2[e] = 0.0;
     if (k > 0) {
       stage_w(k - 1, wb ^ 1);
       load_par(k - 1, pu2, pb2, pl2, bk2);
@@ -364,10 +367,10 @@ crown_chain_kernel(NetDev net, int t_pre, int post, int maxw, const double* __re
     // relaxation through relu_k and the bias sums (same rules as crown_row_kernel)
     for (int hr = warp; hr < 2 * nrows; hr += CC_THREADS / 32) {
       const int h = hr / nrows, r = hr % nrows;
-      double* a = cur + (h * maxw + r) * ldw;
+      double* a = cur + (h * rcap + r) * ldw;
       double acc = 0.0;
 #pragma unroll
-      for (int e = 0; e < 2; ++e) {
+      for (int e = 0; e < CC_NE; ++e) {
         const int c = lane + 32 * e;
         if (c < nk1) {
           double v = a[c];
@@ -384,7 +387,7 @@ crown_chain_kernel(NetDev net, int t_pre, int post, int maxw, const double* __re
       }
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-      if (lane == 0) bias[h * maxw + r] += acc;
+      if (lane == 0) bias[h * rcap + r] += acc;
     }
     asm volatile("cp.async.wait_group 1;\n" ::);       // W_k has landed (the group just committed may be in flight)
     __syncthreads();
@@ -392,10 +395,10 @@ crown_chain_kernel(NetDev net, int t_pre, int post, int maxw, const double* __re
     const double* W = wbuf + (size_t)wb * maxw * wp;
     for (int idx = tid; idx < 2 * nrows * nk; idx += CC_THREADS) {
       const int i = idx % nk, hr = idx / nk;
-      const double* a = cur + ((hr / nrows) * maxw + hr % nrows) * ldw;
+      const double* a = cur + ((hr / nrows) * rcap + hr % nrows) * ldw;
       double sum = 0.0;
       for (int c = 0; c < nk1; ++c) sum = fma(a[c], W[c * wp + i], sum);
-      nxt[((hr / nrows) * maxw + hr % nrows) * ldw + i] = sum;
+      nxt[((hr / nrows) * rcap + hr % nrows) * ldw + i] = sum;
     }
     __syncthreads();
     double* tmp = cur;
@@ -403,15 +406,15 @@ crown_chain_kernel(NetDev net, int t_pre, int post, int maxw, const double* __re
     nxt = tmp;
     wb ^= 1;
 #pragma unroll
-    for (int e = 0; e < 2; ++e) pu[e] = pu2[e], pb[e] = pb2[e], pl[e] = pl2[e], bk[e] = bk2[e];
+    for (int e = 0; e < CC_NE; ++e) pu[e] = pu2[e], pb[e] = pb2[e], pl[e] = pl2[e], bk[e] = bk2[e];
   }
   asm volatile("cp.async.wait_group 0;\n" ::);
   // concretise on the input box (crown_concretize_kernel without post-processing)
   const double* lo = x1min + (long long)(q_first + q) * s_min;
   const double* hi = x1max + (long long)(q_first + q) * s_max;
   for (int r = warp; r < nrows; r += CC_THREADS / 32) {
-    const double* al = cur + (0 * maxw + r) * ldw;
-    const double* au = cur + (1 * maxw + r) * ldw;
+    const double* al = cur + (0 * rcap + r) * ldw;
+    const double* au = cur + (1 * rcap + r) * ldw;
     double sl = 0.0, su = 0.0;
     for (int c = lane; c < n_in; c += 32) {
       const double cc = 0.5 * (lo[c] + hi[c]), rr = 0.5 * (hi[c] - lo[c]);
@@ -424,7 +427,7 @@ crown_chain_kernel(NetDev net, int t_pre, int post, int maxw, const double* __re
       su += __shfl_xor_sync(0xffffffffu, su, o);
     }
     if (lane == 0) {
-      double L = sl + bias[0 * maxw + r], U = su + bias[1 * maxw + r];
+      double L = sl + bias[0 * rcap + r], U = su + bias[1 * rcap + r];
       long long o = (long long)q * out_stride + r0 + r;
       if (post) {
         L = fmin(L, U);
@@ -491,7 +494,8 @@ int launch_crown_concretize(const double* rowsL, const double* rowsU, long long 
   return 1;
 }
 
-// Narrow nets (max width <= 64).  post == 0: pre-activation bounds of y_t for Qc queries in one launch.
+// Narrow nets (widths up to ~110: whatever fits the shared memory).  post == 0: pre-activation bounds of y_t for Qc
+// queries in one launch.
 // post == 1: the K-1 post-activation targets x_{t+1}, t = 0 .. K-2, of Qc queries in one launch (out = base of
 // xmin / xmax of the chunk, stride xtot).  0 = not applicable.
 int launch_crown_chain(const NetDev& net, int t, int post, int ntargets, int maxw, int Qc, const double* d_u,
@@ -500,15 +504,23 @@ int launch_crown_chain(const NetDev& net, int t, int post, int ntargets, int max
                        long long out_stride, cudaStream_t st) {
   static const bool off = [] { const char* e = getenv("NNSDP_NO_CROWN_CHAIN"); return e && atoi(e) != 0; }();
   if (off || maxw > CC_MAXW || (!post && t < 1) || ntargets < 1) return 0;
-  const size_t smem = ((size_t)2 * maxw * ((maxw + 1) & ~1) + (size_t)4 * maxw * (maxw + 1) + 2 * maxw) * sizeof(double);
-  if (smem > 48 * 1024) cudaFuncSetAttribute(crown_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  // enough CTAs to occupy the SMs: split the rows of a target when targets x queries are few
+  // Row groups: enough CTAs to occupy the SMs when targets x queries are few, and few enough rows per CTA for the
+  // two row buffers to fit next to the two W buffers (widths near 100 need >= 8 groups)
   int rgroups = 1;
   const int ctas = Qc * (post ? ntargets : 1);
   if (ctas < 128) rgroups = std::min(8, (128 + ctas - 1) / ctas);
-  crown_chain_kernel<<<dim3(Qc, post ? ntargets : 1, rgroups), CC_THREADS, smem, st>>>(net, t, post, maxw, d_u, b_u, d_l, par_stride,
-                                                                             x1min, s_min, x1max, s_max, q_first, out_lo,
-                                                                             out_hi, out_stride);
+  auto bytes = [&](int rg) {
+    const size_t rcap = (size_t)(maxw + rg - 1) / rg;
+    return ((size_t)2 * maxw * ((maxw + 1) & ~1) + (size_t)4 * rcap * (maxw + 1) + 2 * rcap) * sizeof(double);
+  };
+  while (bytes(rgroups) > (size_t)220 * 1024 && rgroups < 32) rgroups *= 2;
+  if (bytes(rgroups) > (size_t)220 * 1024) return 0;
+  const size_t smem = bytes(rgroups);
+  const int rcap = (maxw + rgroups - 1) / rgroups;
+  if (smem > 48 * 1024) cudaFuncSetAttribute(crown_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  crown_chain_kernel<<<dim3(Qc, post ? ntargets : 1, rgroups), CC_THREADS, smem, st>>>(net, t, post, maxw, rcap, d_u, b_u, d_l,
+                                                                                      par_stride, x1min, s_min, x1max, s_max,
+                                                                                      q_first, out_lo, out_hi, out_stride);
   return 1;
 }
 
