@@ -140,14 +140,32 @@ def measured_peaks():
 _W = {}
 
 
+_BLAS_ENV = ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS")
+
+
+def _blas_threads():
+    """Largest BLAS/OpenMP thread-pool size of this process, as the libraries report it (threadpoolctl)."""
+    from threadpoolctl import threadpool_info
+
+    return max([int(i.get("num_threads", 1)) for i in threadpool_info()] or [1])
+
+
 def _cpu_worker_init(name, root):
-    for v in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):
-        os.environ[v] = "1"
+    # The thread-pool size is fixed when numpy's BLAS is loaded, and a spawned child re-imports this module
+    # (numpy included) BEFORE the initializer runs: the variables must already be in the environment the
+    # child inherits (CpuPool sets them in the parent).  Here the result is only checked.
+    nt = _blas_threads()
+    if nt != 1:
+        raise RuntimeError(f"CPU arm worker runs {nt} BLAS threads, expected 1 (environment not inherited)")
     sys.path.insert(0, os.path.join(root, "oracle"))
     import nnsdp_oracle as o
 
     xdims, Ms, beta, inp = make_workload(name, 0, Q=64)
     _W.update(o=o, net=o.FeedFwdNet(xdims, Ms), beta=beta, inp=inp)
+
+
+def _cpu_worker_threads(_):
+    return _blas_threads()
 
 
 def _cpu_worker_query(i):
@@ -175,7 +193,19 @@ class CpuPool:
         except (ValueError, OSError):
             avail_gb = 32.0
         self.procs = int(max(1, min(cores, 0.6 * avail_gb / per_proc_gb)))
-        self.pool = mp.get_context("spawn").Pool(self.procs, initializer=_cpu_worker_init, initargs=(name, ROOT))
+        saved = {v: os.environ.get(v) for v in _BLAS_ENV}
+        for v in _BLAS_ENV:                                      # inherited by the spawned workers
+            os.environ[v] = "1"
+        try:
+            self.pool = mp.get_context("spawn").Pool(self.procs, initializer=_cpu_worker_init, initargs=(name, ROOT))
+            self.blas_threads = max(self.pool.map(_cpu_worker_threads, range(self.procs)))   # verified, not assumed
+        finally:
+            for v, old in saved.items():
+                if old is None:
+                    os.environ.pop(v, None)
+                else:
+                    os.environ[v] = old
+        assert self.blas_threads == 1, self.blas_threads
         self.pool.map(_cpu_worker_query, range(self.procs))      # warm-up: imports, page faults
 
     def run(self, n_queries):
@@ -212,7 +242,8 @@ def run_reference(args):
                            "the reference itself is single-threaded, the port runs one query per worker process"},
         "cpu_baseline": {"value": value, "unit": "queries/s", "cores": pool.procs, "kind": "port",
                          "sample": f"{per_step} queries per step x {args.steps} steps of the same workload, numpy closed form, "
-                                   f"{pool.procs} worker processes x 1 BLAS thread on {os.cpu_count()} host cores"},
+                                   f"{pool.procs} worker processes x {pool.blas_threads} BLAS thread (verified with threadpoolctl in the workers) "
+                                   f"on {os.cpu_count()} host cores"},
         "e2e": {"value": value, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -383,7 +414,8 @@ def run_ours(args):
             pool.close()
             cpu = {"value": nq_cpu / dt, "unit": "queries/s", "cores": pool.procs, "kind": "port",
                    "sample": f"{nq_cpu} queries of the same workload in {dt:.1f} s, numpy closed-form oracle, "
-                             f"{pool.procs} worker processes x 1 BLAS thread on {os.cpu_count()} host cores"}
+                             f"{pool.procs} worker processes x {pool.blas_threads} BLAS thread (verified with threadpoolctl in the "
+                             f"workers) on {os.cpu_count()} host cores"}
         launches_per_step = sum(stage[k][1] for k in stage) / max(args.steps, 1)
         line = {
             "metric": "queries/sec (clique LMI blocks assembled: value * cliques_per_query)",
