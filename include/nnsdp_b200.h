@@ -44,6 +44,11 @@ extern "C" {
 #define NNSDP_OUT_CIRCLE 2    /* QcReachCircle(yc)                                      */
 #define NNSDP_OUT_ELLIPSOID 3 /* QcReachEllipsoid(invP, yc)                             */
 
+/* Output formats of a batch (the `dense_Z` argument of nnsdp_batch_create and of the plan introspection calls) */
+#define NNSDP_FORMAT_BLOCKS 0   /* every clique block Z[C_k, C_k] dense, back to back                       */
+#define NNSDP_FORMAT_DENSE_Z 1  /* the whole Z, dense                                                        */
+#define NNSDP_FORMAT_PACKED 2   /* packed records: the block-sparse upper triangle of Z (see below)          */
+
 typedef struct nnsdp_ctx nnsdp_ctx;     /* devices + streams                             */
 typedef struct nnsdp_net nnsdp_net;     /* FeedFwdNet uploaded (replicated per device)   */
 typedef struct nnsdp_batch nnsdp_batch; /* device-resident state of a batch of queries   */
@@ -214,11 +219,54 @@ int32_t nnsdp_assemble_blocks(nnsdp_ctx* ctx, const nnsdp_net* net, int64_t beta
 int32_t nnsdp_assemble_dense(nnsdp_ctx* ctx, const nnsdp_net* net, int64_t beta, int64_t Q,
                              const nnsdp_query_inputs* in, double* Z_out);
 
+/* ---- packed records (NNSDP_FORMAT_PACKED) ---------------------------------------------------
+ * 78 % of the entries of the dense clique blocks of a wide net are structural zeros, every diagonal block is held
+ * by two cliques and the x_K block by all of them.  Every clique block is a principal submatrix Z[C_k, C_k] and the
+ * cliques cover the non-zeros of Z (the scatter structure of setupZksum!, src/Methods/chordal_sdp.jl:60-93,
+ * chordal_cliques.jl:31-57), so a packed record stores each region of Z that can be non-zero ONCE, as column-major
+ * cells (ld = nrows) at fixed offsets, upper triangle only (cells that straddle the diagonal are stored as
+ * rectangles; only their entries with row <= column are defined, like Julia's Symmetric(A, :U)):
+ *   NNSDP_CELL_WINDOW  rows x_b against x_{b+1}: the W' M window sums (and the band corner)            always
+ *   NNSDP_CELL_DIAG    interior of the diagonal block of x_b (Gram W_b' diag(.) W_b | W_K' S22 W_K, band included);
+ *                      written only for a query whose layer has a stably-active neuron / whose output QC has an S22
+ *                      part -- present[] says which; an absent cell is all zero apart from its BAND cell and its
+ *                      bytes in the record are not touched
+ *   NNSDP_CELL_BAND    (beta+1) x m: band[t + (beta+1) i] = Z[row0+i, row0+i+t], the band inside the DIAG range  always
+ *   NNSDP_CELL_RECT    everything else (affine column, slivers of width beta, x_1 block, x_1 / x_K coupling)     always
+ * Where cells overlap they hold bit-identical values.  Small nets (a hidden layer under 48 neurons) have one RECT
+ * cell, the whole Z.  Z[C_k, C_k] of any clique is a set of sub-rectangles of the cells (nnsdp_packed_unpack does
+ * exactly that; Julia: views into the record, or sparse(...) from the cell table). */
+#define NNSDP_CELL_WINDOW 1
+#define NNSDP_CELL_DIAG 2
+#define NNSDP_CELL_BAND 3
+#define NNSDP_CELL_RECT 4
+typedef struct {
+  int32_t kind;          /* NNSDP_CELL_*                                                                  */
+  int32_t blk;           /* b of WINDOW (x_b, x_{b+1}) / DIAG / BAND (1-based block); 0 for RECT           */
+  int64_t row0, col0;    /* 1-based index in Z of the cell's first row / column                            */
+  int64_t nrows, ncols;
+  int64_t offset;        /* doubles from the start of a query's record                                     */
+  int32_t always;        /* 1: written for every query; 0: only when present                               */
+  int32_t reserved;
+} nnsdp_packed_cell;
+/* Cell table of (xdims, beta), host only.  cells == NULL queries the count.  A record is record_doubles long; the
+ * always-written cells occupy its first always_doubles. */
+int32_t nnsdp_packed_layout(int64_t K, const int64_t* xdims, int64_t beta, int64_t max_cells, nnsdp_packed_cell* cells,
+                            int64_t* ncells, int64_t* record_doubles, int64_t* always_doubles);
+/* One record -> the dense output of NNSDP_FORMAT_BLOCKS (every Z[C_k, C_k], sum_ck_sq doubles) or
+ * NNSDP_FORMAT_DENSE_Z (Zdim^2), both triangles filled; present = the record's ncells bytes.  Host only. */
+int32_t nnsdp_packed_unpack(int64_t K, const int64_t* xdims, int64_t beta, const double* record, const uint8_t* present,
+                            int32_t format, double* out);
+/* One-shot: packed records of Q queries into records_out[q * record_doubles], present_out[q * ncells] (may be NULL). */
+int32_t nnsdp_assemble_packed(nnsdp_ctx* ctx, const nnsdp_net* net, int64_t beta, int64_t Q,
+                              const nnsdp_query_inputs* in, double* records_out, uint8_t* present_out);
+
 /* ---- device-resident batch (what bench.py times with inputs already in HBM) -----------
  * A batch lives on ONE device of the ctx (dev_index into the ctx's device list).
  * ring_queries = number of per-query output slots kept on the device; 0 = bounds only
- * (no gamma inputs are read and nothing can be emitted).  dense_Z != 0 makes the output
- * of every query the whole Zdim x Zdim matrix instead of the clique blocks. */
+ * (no gamma inputs are read and nothing can be emitted).  dense_Z is the output format of a query:
+ * NNSDP_FORMAT_BLOCKS (0) the clique blocks, NNSDP_FORMAT_DENSE_Z (1) the whole Zdim x Zdim matrix,
+ * NNSDP_FORMAT_PACKED (2) a packed record. */
 int32_t nnsdp_batch_create(nnsdp_ctx* ctx, int32_t dev_index, const nnsdp_net* net, int64_t beta,
                            int64_t Qcap, int64_t ring_queries, int32_t dense_Z, nnsdp_batch** batch);
 int32_t nnsdp_batch_destroy(nnsdp_batch* batch);
@@ -254,6 +302,15 @@ int32_t nnsdp_batch_run(nnsdp_batch* batch, double* host_out);
 #define NNSDP_RUN_HOST_PREZEROED 1
 #define NNSDP_RUN_DENSE_COPY 2
 int32_t nnsdp_batch_run_ex(nnsdp_batch* batch, double* host_out, int32_t flags);
+/* A batch created with NNSDP_FORMAT_PACKED: the same pass with packed records in the ring.  host_records
+ * (Q * record_doubles, may be NULL) receives the always-written part of every record and the DIAG cells that are
+ * present; present (Q * ncells bytes, may be NULL) says which cells of each record were written.  Nothing is
+ * zero-filled or scattered on the host.  flags: NNSDP_RUN_DENSE_COPY copies whole records. */
+int32_t nnsdp_batch_run_packed(nnsdp_batch* batch, double* host_records, uint8_t* present, int32_t flags);
+/* Sizes of a packed batch and, for its last run: bytes the emitter wrote, bytes moved to the host, number of
+ * optional (DIAG) cells present over all queries. */
+int32_t nnsdp_batch_packed_stats(nnsdp_batch* batch, int64_t* record_doubles, int64_t* ncells, int64_t* emitted_bytes,
+                                 int64_t* d2h_bytes, int64_t* present_optional_cells);
 /* Bytes the host gather of the last run moved: DMA (strided cells or dense), packed thin entries, and
  * bytes zero-filled by host threads; *sparse_usable = 1 if the sparse gather applies to this batch. */
 int32_t nnsdp_batch_gather_stats(nnsdp_batch* batch, int64_t* dma_bytes, int64_t* thin_bytes,

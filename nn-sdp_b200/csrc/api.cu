@@ -215,6 +215,11 @@ struct nnsdp_batch {
   const NetPerDev* nd = nullptr;
   int64_t beta = 0, Qcap = 0, ring = 0, Q = 0;
   bool dense = false;
+  bool packed = false;   // output = packed records (the block-sparse upper triangle of Z), see PackedLayout
+  PackedLayout lay;
+  DevBuf d_bands;
+  int nbands = 0, band_max_m = 0;
+  int64_t packed_emitted_bytes = 0, packed_present_cells = 0;  // of the last run
   nnsdp_sizes sz{};
   PlanHost plan;
   DevBuf d_tiles, d_strips, d_mats, d_goff, d_ldG;
@@ -280,7 +285,7 @@ struct nnsdp_batch {
     spans.clear();
   }
   std::vector<DevBuf*> all_bufs() {
-    return {&d_tiles, &d_strips, &d_mats, &d_goff, &d_ldG, &x1min, &x1max, &ymin, &ymax, &smin, &smax,
+    return {&d_bands, &d_tiles, &d_strips, &d_mats, &d_goff, &d_ldG, &x1min, &x1max, &ymin, &ymax, &smin, &smax,
             &gin, &gbnd, &gsec, &outS, &outvec, &outinvP, &gout, &xmin, &xmax, &acxmin, &acxmax,
             &smin_c, &smax_c, &d11, &Md, &T0, &Bt, &u, &aff, &part, &act, &cnt, &Z11, &Z1K, &U,
             &gram, &ringbuf, &flags, &cr_rowsA, &cr_rowsB, &cr_bias, &cr_prel, &cr_preu, &cr_du, &cr_bu, &cr_dl};
@@ -587,6 +592,24 @@ int32_t nnsdp_cliques_from_xdims(int64_t K, const int64_t* xdims, int64_t beta, 
   return cliques_out(sh, beta, ck_off, ck_idx, ck1_len, d_off, d_idx);
 }
 
+/* The output matrices of a format: 0 = clique blocks, 1 / 2 = the whole Z (dense / packed). */
+static int32_t format_mats(const Shape& sh, int64_t beta, int32_t format, std::vector<CliqueRanges>* mats) {
+  NN_CHECK(format >= 0 && format <= 2, NNSDP_ERR_ARG, "format must be NNSDP_FORMAT_BLOCKS, _DENSE_Z or _PACKED");
+  mats->clear();
+  if (format != NNSDP_FORMAT_BLOCKS) {
+    CliqueRanges c;
+    c.nseg = 1;
+    c.lo[0] = 0;
+    c.hi[0] = sh.Zdim - 1;
+    mats->push_back(c);
+  } else {
+    CliqueInfoHost ci;
+    NN_TRY(make_cliques_host(sh, beta, &ci));
+    *mats = ci.ck;
+  }
+  return NNSDP_OK;
+}
+
 /* Host-only introspection of the emission plan: number of tiles and of output entries per tile
  * program (index = TileProg, 8 entries each) and per flag combination is not exposed. */
 int32_t nnsdp_plan_stats(int64_t K, const int64_t* xdims, int64_t beta, int32_t dense_Z,
@@ -598,19 +621,10 @@ int32_t nnsdp_plan_stats(int64_t K, const int64_t* xdims, int64_t beta, int32_t 
   nnsdp_sizes sz;
   NN_TRY(fill_sizes(sh, beta, &sz));
   std::vector<CliqueRanges> mats;
-  if (dense_Z) {
-    CliqueRanges c;
-    c.nseg = 1;
-    c.lo[0] = 0;
-    c.hi[0] = sh.Zdim - 1;
-    mats.push_back(c);
-  } else {
-    CliqueInfoHost ci;
-    NN_TRY(make_cliques_host(sh, beta, &ci));
-    mats = ci.ck;
-  }
+  NN_TRY(format_mats(sh, beta, dense_Z, &mats));
   PlanHost plan;
-  NN_TRY(build_plan(sh, beta, mats, true, &plan));
+  PackedLayout lay;
+  NN_TRY(build_plan(sh, beta, mats, true, &plan, dense_Z == NNSDP_FORMAT_PACKED ? &lay : nullptr));
   for (int i = 0; i < 8; ++i) tiles_per_prog[i] = entries_per_prog[i] = 0;
   for (const TileDev& t : plan.tiles) {
     tiles_per_prog[t.prog] += 1;
@@ -632,19 +646,10 @@ int32_t nnsdp_plan_tiles(int64_t K, const int64_t* xdims, int64_t beta, int32_t 
   nnsdp_sizes sz;
   NN_TRY(fill_sizes(sh, beta, &sz));
   std::vector<CliqueRanges> mats;
-  if (dense_Z) {
-    CliqueRanges c;
-    c.nseg = 1;
-    c.lo[0] = 0;
-    c.hi[0] = sh.Zdim - 1;
-    mats.push_back(c);
-  } else {
-    CliqueInfoHost ci;
-    NN_TRY(make_cliques_host(sh, beta, &ci));
-    mats = ci.ck;
-  }
+  NN_TRY(format_mats(sh, beta, dense_Z, &mats));
   PlanHost plan;
-  NN_TRY(build_plan(sh, beta, mats, true, &plan));
+  PackedLayout lay;
+  NN_TRY(build_plan(sh, beta, mats, true, &plan, dense_Z == NNSDP_FORMAT_PACKED ? &lay : nullptr));
   *ntiles = (int64_t)plan.tiles.size();
   if (tiles_out) {
     NN_CHECK(max_tiles >= *ntiles, NNSDP_ERR_ARG, "tiles_out too small");
@@ -666,17 +671,8 @@ int32_t nnsdp_gather_plan(int64_t K, const int64_t* xdims, int64_t beta, int32_t
   nnsdp_sizes sz;
   NN_TRY(fill_sizes(sh, beta, &sz));
   std::vector<CliqueRanges> mats;
-  if (dense_Z) {
-    CliqueRanges c;
-    c.nseg = 1;
-    c.lo[0] = 0;
-    c.hi[0] = sh.Zdim - 1;
-    mats.push_back(c);
-  } else {
-    CliqueInfoHost ci;
-    NN_TRY(make_cliques_host(sh, beta, &ci));
-    mats = ci.ck;
-  }
+  NN_CHECK(dense_Z == 0 || dense_Z == 1, NNSDP_ERR_ARG, "the host-gather plan exists for the dense formats only");
+  NN_TRY(format_mats(sh, beta, dense_Z, &mats));
   PlanHost plan;
   NN_TRY(build_plan(sh, beta, mats, true, &plan));
   GatherPlan gp;
@@ -750,7 +746,9 @@ int32_t nnsdp_batch_create(nnsdp_ctx* ctx, int32_t dev_index, const nnsdp_net* n
   b->beta = beta;
   b->Qcap = Qcap;
   b->ring = std::min<int64_t>(ring_queries, Qcap);
-  b->dense = dense_Z != 0;
+  NN_CHECK(dense_Z >= 0 && dense_Z <= 2, NNSDP_ERR_ARG, "format must be NNSDP_FORMAT_BLOCKS, _DENSE_Z or _PACKED");
+  b->dense = dense_Z == NNSDP_FORMAT_DENSE_Z;
+  b->packed = dense_Z == NNSDP_FORMAT_PACKED;
   NN_TRY(fill_sizes(sh, beta, &b->sz));
   NN_CHECK(b->sz.sdim * b->sz.sdim * 8 + b->sz.n_out * 8 <= 40000, NNSDP_ERR_ARG,
            "n_in + n_out + 1 = %lld too large for the output-QC kernel", (long long)b->sz.sdim);
@@ -797,21 +795,24 @@ int32_t nnsdp_batch_create(nnsdp_ctx* ctx, int32_t dev_index, const nnsdp_net* n
     NN_TRY(b->gram.ensure((size_t)go * b->ring * 8));
     // plan
     std::vector<CliqueRanges> mats;
-    if (b->dense) {
-      CliqueRanges c;
-      c.nseg = 1;
-      c.lo[0] = 0;
-      c.hi[0] = sh.Zdim - 1;
-      mats.push_back(c);
-    } else {
-      CliqueInfoHost ci;
-      NN_TRY(make_cliques_host(sh, beta, &ci));
-      mats = ci.ck;
-    }
+    NN_TRY(format_mats(sh, beta, dense_Z, &mats));
     const char* noclass = getenv("NNSDP_NO_TILE_CLASSES");  // validation aid: evaluate every term everywhere
-    NN_TRY(build_plan(sh, beta, mats, !(noclass && noclass[0] == '1'), &b->plan));
+    NN_TRY(build_plan(sh, beta, mats, b->packed || !(noclass && noclass[0] == '1'), &b->plan,
+                      b->packed ? &b->lay : nullptr));
     b->mats_host = mats;
-    NN_TRY(build_gather_plan(sh, beta, mats, b->plan, &b->gp));
+    if (b->packed) {
+      std::vector<BandDev> bands;
+      for (const PackedCell& c : b->lay.cells)
+        if (c.kind == PK_BAND) {
+          bands.push_back({(long long)c.offset, (int)c.grow0, (int)c.ncols, c.blk, 0});
+          b->band_max_m = std::max(b->band_max_m, (int)c.ncols);
+        }
+      b->nbands = (int)bands.size();
+      NN_TRY(upload(b->d_bands, bands.data(), bands.size() * sizeof(BandDev), b->st));
+      NN_CUDA(cudaStreamSynchronize(b->st));  // `bands` goes out of scope
+    } else {
+      NN_TRY(build_gather_plan(sh, beta, mats, b->plan, &b->gp));
+    }
     if (const char* e = getenv("NNSDP_DENSE_GATHER"))  // developer aid: always copy the dense output
       if (e[0] == '1') b->gp.usable = false;
     if (b->gp.usable) {
@@ -832,6 +833,7 @@ int32_t nnsdp_batch_create(nnsdp_ctx* ctx, int32_t dev_index, const nnsdp_net* n
     b->pd.n_edge = b->plan.n_edge;
     b->pd.tile_rows = b->plan.tile_rows;
     b->pd.per_query = b->plan.per_query_doubles;
+    b->pd.packed = b->plan.skip_absent ? 1 : 0;
     b->gd.scratch = b->gram.as<double>();
     b->gd.per_query = go;
     b->gd.goff = b->d_goff.as<long long>();
@@ -1045,6 +1047,13 @@ static void emit_pass(nnsdp_batch* b, const GramDev& gd, int q0, int nq, double*
     b->span_end(b->st, l);
     total += l;
   }
+  if (b->packed && b->nbands > 0) {
+    b->span_begin(ST_EMIT_EDGE, b->st);
+    const int l = launch_emit_band(nd.nd, b->bd, gd, b->d_bands.as<BandDev>(), b->nbands, b->band_max_m, b->pd.per_query,
+                                   q0, nq, dst, b->st);
+    b->span_end(b->st, l);
+    total += l;
+  }
   b->stage_launches[ST_EMIT] += total;
 }
 
@@ -1195,7 +1204,7 @@ static int32_t gather_chunk(nnsdp_batch* b, int ci, int64_t q0, int64_t nq, int 
 
 extern "C" int32_t nnsdp_batch_bounds_crown(nnsdp_batch* b);
 
-int32_t nnsdp_batch_run_ex(nnsdp_batch* b, double* host_out, int32_t flags) {
+static int32_t run_impl(nnsdp_batch* b, double* host_out, uint8_t* present, int32_t flags) {
   NN_CHECK(b != nullptr, NNSDP_ERR_ARG, "batch is NULL");
   NN_CHECK(b->have_inputs, NNSDP_ERR_STATE, "nnsdp_batch_run before nnsdp_batch_set_inputs");
   NN_CHECK(b->ring > 0, NNSDP_ERR_STATE, "batch was created without an output ring");
@@ -1208,8 +1217,27 @@ int32_t nnsdp_batch_run_ex(nnsdp_batch* b, double* host_out, int32_t flags) {
   // emission of the other
   const int nhalf = (host_out && b->ring >= 2) ? 2 : 1;
   const int64_t chunk = (nhalf == 2) ? b->ring / 2 : b->ring;
-  const bool sparse = host_out && b->gp.usable && !(flags & NNSDP_RUN_DENSE_COPY);
+  const bool sparse = host_out && !b->packed && b->gp.usable && !(flags & NNSDP_RUN_DENSE_COPY);
   b->gather_bytes_dma = b->gather_bytes_zeroed = b->gather_bytes_thin = 0;
+  b->packed_emitted_bytes = b->packed_present_cells = 0;
+  const int K = b->net->sh.K;
+  const size_t ncells = b->lay.cells.size();
+  // packed records: which DIAG cells a query carries is known from the Gram-active counts of prepare
+  auto cell_present = [&](int64_t q, const PackedCell& c) {
+    if (c.always) return true;
+    return c.blk <= K - 2 ? b->h_cnt[(size_t)q * K + c.blk] > 0 : b->bd.has_s22 != 0;
+  };
+  if (b->packed)
+    for (int64_t q = 0; q < b->Q; ++q) {
+      int64_t ent = b->lay.always_entries;
+      for (size_t i = 0; i < ncells; ++i) {
+        const PackedCell& c = b->lay.cells[i];
+        const bool p = cell_present(q, c);
+        if (present) present[(size_t)q * ncells + i] = p ? 1 : 0;
+        if (!c.always && p) ent += b->plan.skip_absent ? b->lay.diag_entries[c.blk] : 0, ++b->packed_present_cells;
+      }
+      b->packed_emitted_bytes += ent * 8;
+    }
   if (sparse) {
     const size_t need = (size_t)GATHER_STAGES * chunk * b->gp.thin_idx.size();
     if (need > b->h_packed_doubles) {
@@ -1249,6 +1277,31 @@ int32_t nnsdp_batch_run_ex(nnsdp_batch* b, double* host_out, int32_t flags) {
     if (sparse) {
       status = gather_chunk(b, ci, q0, nq, h, dst, host_out, flags);
       used[h] = true;
+    } else if (host_out && b->packed && !(flags & NNSDP_RUN_DENSE_COPY)) {
+      // packed records: the always-written part of all records of the chunk is one strided copy, every DIAG
+      // cell a query carries one contiguous copy; absent cells are not moved (and the host bytes not touched)
+      NN_CUDA(cudaEventRecord(b->ev_done[h], b->st));
+      NN_CUDA(cudaStreamWaitEvent(b->st_copy, b->ev_done[h], 0));
+      b->span_begin(ST_D2H, b->st_copy);
+      const int64_t alw = b->lay.always_doubles;
+      if (alw == per)
+        NN_CUDA(cudaMemcpyAsync(host_out + q0 * per, dst, (size_t)nq * per * 8, cudaMemcpyDeviceToHost, b->st_copy));
+      else
+        NN_CUDA(cudaMemcpy2DAsync(host_out + q0 * per, (size_t)per * 8, dst, (size_t)per * 8, (size_t)alw * 8, (size_t)nq,
+                                  cudaMemcpyDeviceToHost, b->st_copy));
+      b->gather_bytes_dma += nq * alw * 8;
+      for (int64_t q = q0; q < q0 + nq; ++q)
+        for (size_t i = 0; i < ncells; ++i) {
+          const PackedCell& c = b->lay.cells[i];
+          if (c.always || !cell_present(q, c)) continue;
+          const int64_t cells_doubles = c.nrows * c.ncols;
+          NN_CUDA(cudaMemcpyAsync(host_out + q * per + c.offset, dst + (q - q0) * per + c.offset, (size_t)cells_doubles * 8,
+                                  cudaMemcpyDeviceToHost, b->st_copy));
+          b->gather_bytes_dma += cells_doubles * 8;
+        }
+      b->span_end(b->st_copy, 0);
+      NN_CUDA(cudaEventRecord(b->ev_free[h], b->st_copy));
+      used[h] = true;
     } else if (host_out) {
       NN_CUDA(cudaEventRecord(b->ev_done[h], b->st));
       NN_CUDA(cudaStreamWaitEvent(b->st_copy, b->ev_done[h], 0));
@@ -1274,7 +1327,27 @@ int32_t nnsdp_batch_run_ex(nnsdp_batch* b, double* host_out, int32_t flags) {
   return NNSDP_OK;
 }
 
-int32_t nnsdp_batch_run(nnsdp_batch* b, double* host_out) { return nnsdp_batch_run_ex(b, host_out, 0); }
+int32_t nnsdp_batch_run_ex(nnsdp_batch* b, double* host_out, int32_t flags) { return run_impl(b, host_out, nullptr, flags); }
+
+int32_t nnsdp_batch_run(nnsdp_batch* b, double* host_out) { return run_impl(b, host_out, nullptr, 0); }
+
+int32_t nnsdp_batch_run_packed(nnsdp_batch* b, double* host_records, uint8_t* present, int32_t flags) {
+  NN_CHECK(b != nullptr, NNSDP_ERR_ARG, "batch is NULL");
+  NN_CHECK(b->packed, NNSDP_ERR_STATE, "the batch was not created with NNSDP_FORMAT_PACKED");
+  return run_impl(b, host_records, present, flags);
+}
+
+int32_t nnsdp_batch_packed_stats(nnsdp_batch* b, int64_t* record_doubles, int64_t* ncells, int64_t* emitted_bytes,
+                                 int64_t* d2h_bytes, int64_t* present_optional_cells) {
+  NN_CHECK(b != nullptr, NNSDP_ERR_ARG, "batch is NULL");
+  NN_CHECK(b->packed, NNSDP_ERR_STATE, "the batch was not created with NNSDP_FORMAT_PACKED");
+  if (record_doubles) *record_doubles = b->lay.record_doubles;
+  if (ncells) *ncells = (int64_t)b->lay.cells.size();
+  if (emitted_bytes) *emitted_bytes = b->packed_emitted_bytes;
+  if (d2h_bytes) *d2h_bytes = b->gather_bytes_dma;
+  if (present_optional_cells) *present_optional_cells = b->packed_present_cells;
+  return NNSDP_OK;
+}
 
 /* Bytes moved by the host gather of the last nnsdp_batch_run*: strided / dense DMA, packed thin
  * entries, and bytes zero-filled by host threads. */
@@ -1594,6 +1667,84 @@ int32_t nnsdp_assemble_blocks(nnsdp_ctx* ctx, const nnsdp_net* net, int64_t beta
 int32_t nnsdp_assemble_dense(nnsdp_ctx* ctx, const nnsdp_net* net, int64_t beta, int64_t Q,
                              const nnsdp_query_inputs* in, double* Z_out) {
   return assemble_impl(ctx, net, beta, Q, in, Z_out, 1);
+}
+
+int32_t nnsdp_assemble_packed(nnsdp_ctx* ctx, const nnsdp_net* net, int64_t beta, int64_t Q,
+                              const nnsdp_query_inputs* in, double* records_out, uint8_t* present_out) {
+  NN_CHECK(ctx && net && in && records_out, NNSDP_ERR_ARG, "NULL argument");
+  NN_CHECK(Q >= 1, NNSDP_ERR_ARG, "Q must be >= 1");
+  return shard_queries(ctx, Q, [&](int d, int64_t q0, int64_t nq) -> int32_t {
+    // the record size is known once a batch (and with it the plan) exists: probe with the smallest ring first
+    BatchHolder h;
+    NN_TRY(h.acquire(ctx, d, net, beta, nq, std::min<int64_t>(nq, 2), NNSDP_FORMAT_PACKED));
+    const int64_t per = h.b->lay.record_doubles;
+    const int64_t want = std::min<int64_t>(std::min<int64_t>(std::max<int64_t>(2, (int64_t)((4ll << 30) / (per * 8))), nq), 4096);
+    if (h.b->ring < want) {  // worth a larger ring: re-acquire (the small batch goes back to the cache)
+      BatchHolder big;
+      NN_TRY(big.acquire(ctx, d, net, beta, nq, want, NNSDP_FORMAT_PACKED));
+      nnsdp_query_inputs sub = shift_inputs(*in, q0);
+      NN_TRY(nnsdp_batch_set_inputs(big.b, nq, &sub));
+      return run_impl(big.b, records_out + q0 * per, present_out ? present_out + q0 * big.b->lay.cells.size() : nullptr, 0);
+    }
+    nnsdp_query_inputs sub = shift_inputs(*in, q0);
+    NN_TRY(nnsdp_batch_set_inputs(h.b, nq, &sub));
+    return run_impl(h.b, records_out + q0 * per, present_out ? present_out + q0 * h.b->lay.cells.size() : nullptr, 0);
+  });
+}
+
+/* Layout of a packed record (host only). */
+int32_t nnsdp_packed_layout(int64_t K, const int64_t* xdims, int64_t beta, int64_t max_cells, nnsdp_packed_cell* cells,
+                            int64_t* ncells, int64_t* record_doubles, int64_t* always_doubles) {
+  NN_CHECK(ncells != nullptr, NNSDP_ERR_ARG, "NULL argument");
+  Shape sh;
+  NN_TRY(shape_from_xdims(K, xdims, &sh));
+  nnsdp_sizes sz;
+  NN_TRY(fill_sizes(sh, beta, &sz));
+  std::vector<CliqueRanges> mats;
+  NN_TRY(format_mats(sh, beta, NNSDP_FORMAT_PACKED, &mats));
+  PlanHost plan;
+  PackedLayout lay;
+  NN_TRY(build_plan(sh, beta, mats, true, &plan, &lay));
+  *ncells = (int64_t)lay.cells.size();
+  if (record_doubles) *record_doubles = lay.record_doubles;
+  if (always_doubles) *always_doubles = lay.always_doubles;
+  if (cells) {
+    NN_CHECK(max_cells >= *ncells, NNSDP_ERR_ARG, "cells too small");
+    for (size_t i = 0; i < lay.cells.size(); ++i) {
+      const PackedCell& c = lay.cells[i];
+      nnsdp_packed_cell& o = cells[i];
+      o.kind = c.kind;
+      o.blk = c.blk < 0 ? 0 : c.blk + 1;  // 1-based block (x_blk), 0 = none
+      o.row0 = c.grow0 + 1;               // 1-based on the wire
+      o.col0 = c.gcol0 + 1;
+      o.nrows = c.nrows;
+      o.ncols = c.ncols;
+      o.offset = c.offset;
+      o.always = c.always;
+      o.reserved = 0;
+    }
+  }
+  return NNSDP_OK;
+}
+
+/* One packed record -> the dense matrices of NNSDP_FORMAT_BLOCKS (all clique blocks back to back) or
+ * NNSDP_FORMAT_DENSE_Z, both triangles filled (host only). */
+int32_t nnsdp_packed_unpack(int64_t K, const int64_t* xdims, int64_t beta, const double* record, const uint8_t* present,
+                            int32_t format, double* out) {
+  NN_CHECK(record && present && out, NNSDP_ERR_ARG, "NULL argument");
+  NN_CHECK(format == NNSDP_FORMAT_BLOCKS || format == NNSDP_FORMAT_DENSE_Z, NNSDP_ERR_ARG, "format must be _BLOCKS or _DENSE_Z");
+  Shape sh;
+  NN_TRY(shape_from_xdims(K, xdims, &sh));
+  nnsdp_sizes sz;
+  NN_TRY(fill_sizes(sh, beta, &sz));
+  std::vector<CliqueRanges> whole, mats;
+  NN_TRY(format_mats(sh, beta, NNSDP_FORMAT_PACKED, &whole));
+  NN_TRY(format_mats(sh, beta, format, &mats));
+  PlanHost plan;
+  PackedLayout lay;
+  NN_TRY(build_plan(sh, beta, whole, true, &plan, &lay));
+  unpack_record(sh, beta, lay, mats, record, present, out);
+  return NNSDP_OK;
 }
 
 }  // extern "C"

@@ -133,6 +133,38 @@ struct MatDev {
   int32_t ld;       // leading dimension (= n)
 };
 
+// ---------------------------------------------------------------------------------
+// packed output (NNSDP_FORMAT_PACKED): the block-sparse upper triangle of Z.  Every clique block is a principal
+// submatrix of Z and the cliques cover its non-zeros, so one query's record holds each structurally non-zero
+// region of Z ONCE, as a list of column-major cells (ld = nrows) at fixed offsets:
+//   WINDOW  rows of block b against block b+1 (the W' M window and the band corner)        always written
+//   DIAG    the interior of the diagonal block of a hidden layer (Gram | W_K' S22 W_K, with its band); written
+//           only for a query whose layer has a stably-active neuron (b <= K-2) / whose output QC has an S22 part
+//   BAND    (beta+1) x m: band[t + (beta+1) i] = Z[g0+i, g0+i+t] inside the DIAG cell's range              always
+//   RECT    everything else that can be non-zero (affine column, slivers, x_1 block, x_1/x_K coupling)    always
+// Cells that are always written come first in the record; the DIAG cells follow.
+// ---------------------------------------------------------------------------------
+enum PackedKind : int32_t { PK_WINDOW = 1, PK_DIAG = 2, PK_BAND = 3, PK_RECT = 4 };
+struct PackedCell {
+  int32_t kind, blk;       // blk: b of WINDOW(b, b+1) / DIAG(b) / BAND(b); -1 for RECT
+  int64_t grow0, gcol0;    // global 0-based z index of the first row / column (BAND: of Z[g0, g0])
+  int64_t nrows, ncols;
+  int64_t offset;          // doubles from the start of the record
+  int32_t always;
+};
+struct PackedLayout {
+  std::vector<PackedCell> cells;
+  int64_t record_doubles = 0;   // size of one query's record
+  int64_t always_doubles = 0;   // the always-written cells occupy [0, always_doubles)
+  int64_t always_entries = 0;   // output entries the emitter writes for every query
+  std::vector<int32_t> diag_cell;     // per block (K entries): index of its DIAG cell or -1
+  std::vector<int64_t> diag_entries;  // per block: entries the fill strips of its DIAG cell write when present
+};
+struct BandDev {  // one BAND cell for the band kernel
+  long long off;        // offset of the cell inside the record
+  int g0, m, blk, pad;  // first z index, side of the DIAG range, block
+};
+
 struct PlanHost {
   std::vector<StripDev> strips;  // fill class, built from tiles[0 .. n_fill)
   std::vector<TileDev> tiles;
@@ -140,6 +172,7 @@ struct PlanHost {
   int64_t per_query_doubles = 0;
   int tile_rows = 0, tile_cols = 0;
   int n_fill = 0, n_window = 0, n_edge = 0;  // tiles are sorted by kernel class
+  bool skip_absent = false;  // packed plans of wide nets: the fill strips of an absent DIAG cell are not written
 };
 
 // ---------------------------------------------------------------------------------
@@ -175,8 +208,14 @@ struct GatherPlan {
 };
 
 // tile_rows in {32, 64, 128}; classify = false marks every tile TF_ALL (validation mode).
+// packed != nullptr: mats must be the single matrix 1:Zdim; the plan then keeps only the tiles of the upper
+// triangle that can be non-zero and addresses them inside the cells of *packed (PlanHost::mats = the cells).
 int32_t build_plan(const Shape& sh, int64_t beta, const std::vector<CliqueRanges>& mats,
-                   bool classify, PlanHost* plan);
+                   bool classify, PlanHost* plan, PackedLayout* packed = nullptr);
+// Expands one packed record into dense matrices Z[C, C] (both triangles) for the index sets in mats, back to
+// back (the dense formats of the ABI).  present: one byte per cell of the layout.
+void unpack_record(const Shape& sh, int64_t beta, const PackedLayout& lay, const std::vector<CliqueRanges>& mats,
+                   const double* record, const uint8_t* present, double* out);
 int32_t build_gather_plan(const Shape& sh, int64_t beta, const std::vector<CliqueRanges>& mats,
                           const PlanHost& plan, GatherPlan* gp);
 
@@ -246,6 +285,7 @@ struct PlanDev {
   int n_fill, n_window, n_edge;
   int tile_rows;
   long long per_query;       // doubles per query in the output
+  int packed;                // packed records: fill strips of an absent DIAG cell are skipped
 };
 
 // ---------------------------------------------------------------------------------
@@ -352,6 +392,9 @@ int launch_crown_concretize(const double* rowsL, const double* rowsU, long long 
                             const double* x1max, long long s_max, int q_first, const double* bias, double* out_lo,
                             double* out_hi, long long out_stride, int postprocess, cudaStream_t st);
 
+// BAND cells of packed records for queries [q0, q0+nq)
+int launch_emit_band(const NetDev& net, const BatchDev& b, const GramDev& g, const BandDev* bands, int nbands,
+                     int max_m, long long per_query, int q0, int nq, double* out, cudaStream_t st);
 // thin-entry pack: packed[s * nthin + i] = ring[s * per_query + idx[i]] for the nq slots of a chunk
 int launch_pack_thin(const double* ring, long long per_query, const long long* idx, long long nthin,
                      double* packed, int nq, cudaStream_t st);

@@ -420,6 +420,7 @@ emit_fill_kernel(NetDev net, BatchDev b, GramDev g, PlanDev plan, int q0, int nq
   const long long goff = ((long long)(unsigned)d0.z) | ((long long)d0.w << 32);
   const bool copy = Br <= K - 2 && b.cnt[(long long)q * K + Br] > 0;  // Gram of an active layer
   const bool s22 = Br == K - 1 && b.has_s22;                           // W_K' S22 W_K of the output QC
+  if (plan.packed && !copy && !s22) return;  // packed record: the DIAG cell of this block is absent for this query
   const double* WK = net.M[K - 1];
   const double* U = b.U + (long long)q * net.n_out * net.n[K - 1];
   const double* G = g.scratch + (long long)slot * g.per_query + goff + rl0;  // G[r + cl*ldG]
@@ -526,6 +527,43 @@ emit_edge_kernel(NetDev net, BatchDev b, GramDev g, PlanDev plan, int tile0, int
 }
 
 }  // namespace
+
+// ---- BAND cells of packed records: band[t + (beta+1) i] = Z[g0+i, g0+i+t] inside the DIAG range of a block.
+// Same operation sequence as the band patch of the DIAG strips (bit-identical values).
+namespace {
+__global__ void __launch_bounds__(ETHREADS)
+emit_band_kernel(NetDev net, BatchDev b, GramDev g, const BandDev* __restrict__ bands, long long per_query, int q0,
+                 double* __restrict__ out) {
+  const BandDev bd = bands[blockIdx.y];
+  const int slot = blockIdx.z, q = q0 + slot, K = net.K, beta = b.beta, nt = beta + 1;
+  const int idx = blockIdx.x * ETHREADS + threadIdx.x;
+  if (idx >= bd.m * nt) return;
+  const int i = idx / nt, t = idx - i * nt;
+  double val = 0.0;
+  if (i + t < bd.m) {
+    const int Br = bd.blk, n0 = net.n_in;
+    const long long acdim = net.acdim;
+    const int rl = bd.g0 - net.off[Br] + i, cl = rl + t;
+    const int jr = bd.g0 + i - n0, jc = jr + t;
+    if (Br <= K - 2 && b.cnt[(long long)q * K + Br] > 0)
+      val += g.scratch[(long long)slot * g.per_query + g.goff[Br] + rl + (long long)cl * g.ldG[Br]];
+    if (Br == K - 1 && b.has_s22)
+      val += s22_entry(net.M[K - 1], b.U + (long long)q * net.n_out * net.n[K - 1], net.n_out, rl, cl);
+    val += 0.0;
+    val = __dadd_rn(val, band_term(b.T0 + (long long)q * acdim, b.gbnd + q * b.s_gbnd, b.Bt + (long long)q * beta * acdim,
+                                   acdim, jr, jc));
+  }
+  out[(long long)slot * per_query + bd.off + idx] = val;
+}
+}  // namespace
+
+int launch_emit_band(const NetDev& net, const BatchDev& b, const GramDev& g, const BandDev* bands, int nbands,
+                     int max_m, long long per_query, int q0, int nq, double* out, cudaStream_t st) {
+  if (nbands <= 0 || nq <= 0 || max_m <= 0) return 0;
+  const int nx = (max_m * (b.beta + 1) + ETHREADS - 1) / ETHREADS;
+  emit_band_kernel<<<dim3(nx, nbands, nq), ETHREADS, 0, st>>>(net, b, g, bands, per_query, q0, out);
+  return 1;
+}
 
 namespace {
 __global__ void pack_thin_kernel(const double* __restrict__ ring, long long per_query,

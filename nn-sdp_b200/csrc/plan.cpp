@@ -174,10 +174,16 @@ void cut(const Shape& sh, const CliqueRanges& c, bool split_blocks, int64_t step
 }  // namespace
 
 int32_t build_plan(const Shape& sh, int64_t beta, const std::vector<CliqueRanges>& mats,
-                   bool classify, PlanHost* plan) {
+                   bool classify, PlanHost* plan, PackedLayout* packed) {
   const int K = sh.K;
+  if (packed)
+    NN_CHECK(mats.size() == 1 && mats[0].nseg == 1 && mats[0].lo[0] == 0 && mats[0].hi[0] == sh.Zdim - 1, NNSDP_ERR_ARG,
+             "packed plans are built over the whole Z");
+  // packed records hold the upper triangle: a tile strictly below the diagonal is never written
+  auto strictly_lower = [](const TileDev& t) { return t.grow0 > t.gcol0 + t.ncols - 1; };
   plan->tiles.clear();
   plan->mats.clear();
+  plan->skip_absent = false;
   int64_t max_n = 0;
   for (auto& c : mats) max_n = std::max(max_n, c.size());
   int64_t min_hidden = sh.n[1];
@@ -290,6 +296,14 @@ int32_t build_plan(const Shape& sh, int64_t beta, const std::vector<CliqueRanges
     out_off += n * n;
   }
   plan->per_query_doubles = out_off;
+  if (packed) {
+    std::vector<TileDev> keep;
+    for (const TileDev& t : plan->tiles)
+      if (!(split_blocks && t.prog == PROG_ZERO) && !strictly_lower(t)) keep.push_back(t);
+    plan->tiles.swap(keep);
+    // small nets keep one cell, the whole Z, with every tile of its upper triangle (zeros included)
+    plan->skip_absent = split_blocks;
+  }
   auto cls = [](const TileDev& t) {
     return (t.prog == PROG_ZERO || t.prog == PROG_SAME || t.prog == PROG_DIAG || t.prog == PROG_AFF) ? 0 : (t.prog == PROG_RC || t.prog == PROG_CR) ? 1 : 2;
   };
@@ -374,6 +388,135 @@ int32_t build_plan(const Shape& sh, int64_t beta, const std::vector<CliqueRanges
     plan->tiles = strips;
     plan->tiles.insert(plan->tiles.end(), rest.begin(), rest.end());
   }
+  if (packed) {
+    // ---- cells of the packed record, and every tile re-addressed inside its cell -------------------------
+    std::vector<TileDev> keep;
+    for (const TileDev& t : plan->tiles)
+      if (!strictly_lower(t)) keep.push_back(t);  // strips cut out of a tile that straddled the diagonal
+    plan->tiles.swap(keep);
+    PackedLayout& L = *packed;
+    L = PackedLayout();
+    L.diag_cell.assign(K, -1);
+    L.diag_entries.assign(K, 0);
+    std::vector<PackedCell> rect, band, window, diag;
+    auto is_diag_strip = [&](const TileDev& t) {
+      return (t.prog == PROG_SAME || t.prog == PROG_DIAG) && cls(t) == 0 && t.rblk >= 1 && t.rblk == t.cblk;
+    };
+    auto inside = [](const TileDev& t, const PackedCell& c) {
+      return t.grow0 >= c.grow0 && t.grow0 + t.nrows <= c.grow0 + c.nrows && t.gcol0 >= c.gcol0 &&
+             t.gcol0 + t.ncols <= c.gcol0 + c.ncols;
+    };
+    if (split_blocks) {
+      for (int b = 0; b <= K - 2; ++b)
+        window.push_back({PK_WINDOW, b, sh.off[b], sh.off[b + 1], sh.n[b], sh.n[b + 1], 0, 1});
+      std::vector<int64_t> lo(K, sh.Zdim), hi(K, -1);
+      for (const TileDev& t : plan->tiles)
+        if (is_diag_strip(t)) {
+          lo[t.rblk] = std::min<int64_t>(lo[t.rblk], std::min(t.grow0, t.gcol0));
+          hi[t.rblk] = std::max<int64_t>(hi[t.rblk], std::max(t.grow0 + t.nrows, t.gcol0 + t.ncols) - 1);
+        }
+      for (int b = 1; b <= K - 1; ++b)
+        if (hi[b] >= lo[b]) {
+          const int64_t m = hi[b] - lo[b] + 1;
+          diag.push_back({PK_DIAG, b, lo[b], lo[b], m, m, 0, 0});
+          band.push_back({PK_BAND, b, lo[b], lo[b], beta + 1, m, 0, 1});
+        }
+    }
+    // which cell a tile is written into: -1 = none of the explicit ones
+    auto find_cell = [&](const TileDev& t, int* which) -> int {
+      if (is_diag_strip(t)) {
+        for (size_t i = 0; i < diag.size(); ++i)
+          if (diag[i].blk == t.rblk && inside(t, diag[i])) { *which = PK_DIAG; return (int)i; }
+      } else {
+        for (size_t i = 0; i < window.size(); ++i)
+          if (inside(t, window[i])) { *which = PK_WINDOW; return (int)i; }
+      }
+      return -1;
+    };
+    // leftover tiles: vertically adjacent ones of equal column range merge into one RECT cell
+    std::vector<int> left;
+    for (size_t i = 0; i < plan->tiles.size(); ++i) {
+      int which = 0;
+      if (find_cell(plan->tiles[i], &which) < 0) left.push_back((int)i);
+    }
+    if (!split_blocks) {  // small nets: one cell, the whole Z
+      rect.push_back({PK_RECT, -1, 0, 0, sh.Zdim, sh.Zdim, 0, 1});
+    } else {
+      std::sort(left.begin(), left.end(), [&](int x, int y) {
+        const TileDev &a = plan->tiles[x], &b2 = plan->tiles[y];
+        if (a.gcol0 != b2.gcol0) return a.gcol0 < b2.gcol0;
+        if (a.ncols != b2.ncols) return a.ncols < b2.ncols;
+        return a.grow0 < b2.grow0;
+      });
+      for (int i : left) {
+        const TileDev& t = plan->tiles[i];
+        if (!rect.empty()) {
+          PackedCell& c = rect.back();
+          if (c.gcol0 == t.gcol0 && c.ncols == t.ncols && c.grow0 + c.nrows == t.grow0) {
+            c.nrows += t.nrows;
+            continue;
+          }
+        }
+        rect.push_back({PK_RECT, -1, t.grow0, t.gcol0, t.nrows, t.ncols, 0, 1});
+      }
+      // ... and horizontally adjacent ones of equal row range (the x_1 / x_K coupling, cut into 32-column tiles)
+      std::sort(rect.begin(), rect.end(), [](const PackedCell& a, const PackedCell& b2) {
+        if (a.grow0 != b2.grow0) return a.grow0 < b2.grow0;
+        if (a.nrows != b2.nrows) return a.nrows < b2.nrows;
+        return a.gcol0 < b2.gcol0;
+      });
+      std::vector<PackedCell> merged;
+      for (const PackedCell& c : rect) {
+        if (!merged.empty()) {
+          PackedCell& m = merged.back();
+          if (m.grow0 == c.grow0 && m.nrows == c.nrows && m.gcol0 + m.ncols == c.gcol0) {
+            m.ncols += c.ncols;
+            continue;
+          }
+        }
+        merged.push_back(c);
+      }
+      rect.swap(merged);
+    }
+    // record: [RECT | BAND | WINDOW | DIAG], every cell on a 128 B boundary
+    int64_t off = 0;
+    auto place = [&](std::vector<PackedCell>& v) {
+      for (PackedCell& c : v) {
+        c.offset = off;
+        off += ((c.nrows * c.ncols + 15) / 16) * 16;
+        L.cells.push_back(c);
+      }
+    };
+    place(rect);
+    place(band);
+    place(window);
+    L.always_doubles = off;
+    const size_t first_diag = L.cells.size();
+    place(diag);
+    L.record_doubles = off;
+    for (size_t i = first_diag; i < L.cells.size(); ++i) L.diag_cell[L.cells[i].blk] = (int32_t)i;
+    const size_t first_window = rect.size() + band.size();
+    plan->mats.clear();
+    for (const PackedCell& c : L.cells) plan->mats.push_back({c.offset, (int32_t)c.nrows, (int32_t)c.nrows});
+    for (TileDev& t : plan->tiles) {
+      int which = 0, ci = find_cell(t, &which), cell = -1;
+      if (ci >= 0) {
+        cell = (int)((which == PK_DIAG ? first_diag : first_window) + ci);
+      } else {
+        for (size_t i = 0; i < rect.size() && cell < 0; ++i)
+          if (inside(t, L.cells[i])) cell = (int)i;
+      }
+      NN_CHECK(cell >= 0, NNSDP_ERR_STATE, "packed plan: a tile lies in no cell");
+      const PackedCell& c = L.cells[cell];
+      t.mat = cell;
+      t.row0 = (int32_t)(t.grow0 - c.grow0);
+      t.col0 = (int32_t)(t.gcol0 - c.gcol0);
+      if (c.kind == PK_DIAG) L.diag_entries[c.blk] += (int64_t)t.nrows * t.ncols;
+      else L.always_entries += (int64_t)t.nrows * t.ncols;
+    }
+    for (const PackedCell& c : band) L.always_entries += c.nrows * c.ncols;
+    plan->per_query_doubles = L.record_doubles;
+  }
   // sort by kernel class: fill (ZERO, SAME, DIAG, AFF strips) | window (RC, CR) | edge (MIXED, GENERAL)
   std::stable_sort(plan->tiles.begin(), plan->tiles.end(),
                    [&](const TileDev& x, const TileDev& y) { return cls(x) < cls(y); });
@@ -408,6 +551,64 @@ int32_t build_plan(const Shape& sh, int64_t beta, const std::vector<CliqueRanges
   return NNSDP_OK;
 }
 
+
+void unpack_record(const Shape& sh, int64_t beta, const PackedLayout& lay, const std::vector<CliqueRanges>& mats,
+                   const double* record, const uint8_t* present, double* out) {
+  (void)sh;
+  int64_t out_off = 0;
+  for (const CliqueRanges& ck : mats) {
+    const int64_t n = ck.size();
+    double* o = out + out_off;
+    std::fill(o, o + n * n, 0.0);
+    auto put = [&](int64_t lr, int64_t lc, double v) {
+      o[lr + lc * n] = v;
+      o[lc + lr * n] = v;
+    };
+    // rows [r0, r1] x columns [c0, c1] of a cell (global, inclusive) restricted to the index set
+    auto copy_rect = [&](const PackedCell& c) {
+      const double* src = record + c.offset;
+      int64_t rbase = 0;
+      for (int sr = 0; sr < ck.nseg; rbase += ck.hi[sr] - ck.lo[sr] + 1, ++sr) {
+        const int64_t r0 = std::max(c.grow0, ck.lo[sr]), r1 = std::min(c.grow0 + c.nrows - 1, ck.hi[sr]);
+        if (r0 > r1) continue;
+        int64_t cbase = 0;
+        for (int sc = 0; sc < ck.nseg; cbase += ck.hi[sc] - ck.lo[sc] + 1, ++sc) {
+          const int64_t c0 = std::max(c.gcol0, ck.lo[sc]), c1 = std::min(c.gcol0 + c.ncols - 1, ck.hi[sc]);
+          for (int64_t gc = c0; gc <= c1; ++gc) {
+            const double* col = src + (gc - c.gcol0) * c.nrows - c.grow0;
+            const int64_t lc = cbase + gc - ck.lo[sc];
+            for (int64_t gr = r0; gr <= std::min(r1, gc); ++gr) put(rbase + gr - ck.lo[sr], lc, col[gr]);
+          }
+        }
+      }
+    };
+    auto local = [&](int64_t g) -> int64_t {
+      int64_t base = 0;
+      for (int s = 0; s < ck.nseg; base += ck.hi[s] - ck.lo[s] + 1, ++s)
+        if (g >= ck.lo[s] && g <= ck.hi[s]) return base + g - ck.lo[s];
+      return -1;
+    };
+    for (int pass : {PK_DIAG, PK_WINDOW, PK_BAND, PK_RECT})  // later passes are authoritative where cells overlap
+      for (size_t i = 0; i < lay.cells.size(); ++i) {
+        const PackedCell& c = lay.cells[i];
+        if (c.kind != pass || !present[i]) continue;
+        if (c.kind != PK_BAND) {
+          copy_rect(c);
+          continue;
+        }
+        const double* src = record + c.offset;
+        for (int64_t j = 0; j < c.ncols; ++j) {
+          const int64_t lr = local(c.grow0 + j);
+          if (lr < 0) continue;
+          for (int64_t t = 0; t <= beta && j + t < c.ncols; ++t) {
+            const int64_t lc = local(c.grow0 + j + t);
+            if (lc >= 0) put(lr, lc, src[t + (beta + 1) * j]);
+          }
+        }
+      }
+    out_off += n * n;
+  }
+}
 
 int32_t build_gather_plan(const Shape& sh, int64_t beta, const std::vector<CliqueRanges>& mats,
                           const PlanHost& plan, GatherPlan* gp) {

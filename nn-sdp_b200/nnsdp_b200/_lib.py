@@ -14,6 +14,8 @@ LIB_PATH = os.environ.get("NNSDP_B200_LIB", os.path.join(_HERE, "..", "lib", "li
 OK, ERR_ARG, ERR_CUDA, ERR_NOMEM, ERR_STATE, ERR_ASSERT = 0, -1, -2, -3, -4, -5
 OUT_SAFETY, OUT_HPLANE, OUT_CIRCLE, OUT_ELLIPSOID = 0, 1, 2, 3
 RUN_HOST_PREZEROED, RUN_DENSE_COPY = 1, 2
+FORMAT_BLOCKS, FORMAT_DENSE_Z, FORMAT_PACKED = 0, 1, 2
+CELL_WINDOW, CELL_DIAG, CELL_BAND, CELL_RECT = 1, 2, 3, 4
 
 c_i32, c_i64, c_u64 = C.c_int32, C.c_int64, C.c_uint64
 c_dp = C.POINTER(C.c_double)
@@ -35,6 +37,11 @@ class AffineSizes(C.Structure):
 
     def as_dict(self):
         return {n: int(getattr(self, n)) for n, _ in self._fields_}
+
+
+class PackedCell(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("blk", C.c_int32), ("row0", C.c_int64), ("col0", C.c_int64), ("nrows", C.c_int64),
+                ("ncols", C.c_int64), ("offset", C.c_int64), ("always", C.c_int32), ("reserved", C.c_int32)]
 
 
 class QueryInputs(C.Structure):
@@ -97,6 +104,11 @@ PROTOTYPES = {
     "nnsdp_batch_emit": (c_i32, [c_vp, c_i64, c_i64]),
     "nnsdp_batch_run": (c_i32, [c_vp, c_dp]),
     "nnsdp_batch_run_ex": (c_i32, [c_vp, c_dp, c_i32]),
+    "nnsdp_batch_run_packed": (c_i32, [c_vp, c_dp, C.POINTER(C.c_uint8), c_i32]),
+    "nnsdp_batch_packed_stats": (c_i32, [c_vp, c_i64p, c_i64p, c_i64p, c_i64p, c_i64p]),
+    "nnsdp_packed_layout": (c_i32, [c_i64, c_i64p, c_i64, c_i64, C.POINTER(PackedCell), c_i64p, c_i64p, c_i64p]),
+    "nnsdp_packed_unpack": (c_i32, [c_i64, c_i64p, c_i64, c_dp, C.POINTER(C.c_uint8), c_i32, c_dp]),
+    "nnsdp_assemble_packed": (c_i32, [c_vp, c_vp, c_i64, c_i64, C.POINTER(QueryInputs), c_dp, C.POINTER(C.c_uint8)]),
     "nnsdp_batch_gather_stats": (c_i32, [c_vp, c_i64p, c_i64p, c_i64p, C.POINTER(c_i32)]),
     "nnsdp_batch_sync": (c_i32, [c_vp]),
     "nnsdp_batch_get_bounds": (c_i32, [c_vp, c_dp, c_dp, c_dp, c_dp, c_dp, c_dp]),

@@ -185,6 +185,49 @@ def gather_plan(xdims: Sequence[int], beta: int, dense: bool = False) -> dict:
     return {"cells": cells, "thin": thin, "usable": bool(us.value)}
 
 
+CELL_DTYPE = np.dtype([("kind", "<i4"), ("blk", "<i4"), ("row0", "<i8"), ("col0", "<i8"), ("nrows", "<i8"),
+                       ("ncols", "<i8"), ("offset", "<i8"), ("always", "<i4"), ("reserved", "<i4")])
+
+
+def packed_layout(xdims: Sequence[int], beta: int) -> dict:
+    """Cell table of the packed records of (xdims, beta) (nnsdp_packed_layout, host only): a structured array
+    `cells` (fields of nnsdp_packed_cell, row0 / col0 / blk 1-based) and the record sizes in doubles."""
+    K = len(xdims) - 1
+    xd = (L.c_i64 * (K + 1))(*[int(x) for x in xdims])
+    n, rec, alw = L.c_i64(0), L.c_i64(0), L.c_i64(0)
+    L.check(L.lib.nnsdp_packed_layout(K, xd, beta, 0, None, C.byref(n), C.byref(rec), C.byref(alw)))
+    cells = np.zeros(int(n.value), dtype=CELL_DTYPE)
+    assert CELL_DTYPE.itemsize == C.sizeof(L.PackedCell)
+    L.check(L.lib.nnsdp_packed_layout(K, xd, beta, int(n.value), cells.ctypes.data_as(C.POINTER(L.PackedCell)),
+                                      C.byref(n), C.byref(rec), C.byref(alw)))
+    return {"cells": cells, "record_doubles": int(rec.value), "always_doubles": int(alw.value)}
+
+
+def packed_unpack(xdims: Sequence[int], beta: int, record: np.ndarray, present: np.ndarray, dense_Z: bool = False) -> np.ndarray:
+    """One packed record -> the flat dense clique blocks (or the dense Z, column-major) through nnsdp_packed_unpack."""
+    K = len(xdims) - 1
+    xd = (L.c_i64 * (K + 1))(*[int(x) for x in xdims])
+    sz = sizes_from_xdims(xdims, beta)
+    out = np.empty(sz["Zdim"] ** 2 if dense_Z else sz["sum_ck_sq"])
+    record = np.ascontiguousarray(record, dtype=np.float64)
+    present = np.ascontiguousarray(present, dtype=np.uint8)
+    L.check(L.lib.nnsdp_packed_unpack(K, xd, beta, _dp(record), present.ctypes.data_as(C.POINTER(C.c_uint8)),
+                                      L.FORMAT_DENSE_Z if dense_Z else L.FORMAT_BLOCKS, _dp(out)))
+    return out
+
+
+def assemble_packed(net: "Net", beta: int, batch: "NumericBatch", Q: Optional[int] = None):
+    """Packed records of every query: (records (Q, record_doubles), present (Q, ncells) uint8, layout)."""
+    Q = Q or _infer_Q(batch)
+    lay = packed_layout(net.xdims, beta)
+    rec = np.zeros((Q, lay["record_doubles"]))
+    present = np.zeros((Q, len(lay["cells"])), dtype=np.uint8)
+    qi, keep = batch.pack(Q)
+    L.check(L.lib.nnsdp_assemble_packed(net.ctx._h, net._h, beta, Q, C.byref(qi), _dp(rec),
+                                        present.ctypes.data_as(C.POINTER(C.c_uint8))))
+    return rec, present, lay
+
+
 def _cliques_call(fn, sz):
     p = sz["ncliques"]
     ck_off = np.zeros(p + 1, dtype=np.int64)
@@ -383,12 +426,17 @@ def _infer_Q(batch: NumericBatch) -> int:
 class Batch:
     """Device-resident batch (nnsdp_batch): what bench.py times with inputs already in HBM."""
 
-    def __init__(self, net: Net, beta: int, Qcap: int, ring: int, dense: bool = False, dev_index: int = 0):
-        self.net, self.beta, self.Qcap, self.ring, self.dense = net, beta, Qcap, ring, dense
+    def __init__(self, net: Net, beta: int, Qcap: int, ring: int, dense: bool = False, dev_index: int = 0,
+                 packed: bool = False):
+        self.net, self.beta, self.Qcap, self.ring, self.dense, self.packed = net, beta, Qcap, ring, dense, packed
+        fmt = L.FORMAT_PACKED if packed else (L.FORMAT_DENSE_Z if dense else L.FORMAT_BLOCKS)
         self._h = L.c_vp()
-        L.check(L.lib.nnsdp_batch_create(net.ctx._h, dev_index, net._h, beta, Qcap, ring, int(dense), C.byref(self._h)))
+        L.check(L.lib.nnsdp_batch_create(net.ctx._h, dev_index, net._h, beta, Qcap, ring, fmt, C.byref(self._h)))
         self.sz = net.sizes(beta)
         self.per_query = self.sz["Zdim"] ** 2 if dense else self.sz["sum_ck_sq"]
+        if packed:
+            st = self.packed_stats()
+            self.per_query, self.ncells = st["record_doubles"], st["ncells"]
         self.Q = 0
 
     def close(self):
@@ -433,6 +481,19 @@ class Batch:
         else:
             p = _dp(host_out)
         L.check(L.lib.nnsdp_batch_run_ex(self._h, p, flags))
+
+    def run_packed(self, host_records: Optional[np.ndarray] = None, present: Optional[np.ndarray] = None,
+                   host_ptr: Optional[int] = None, flags: int = 0):
+        """nnsdp_batch_run_packed: records into host memory (Q x record_doubles), present flags (Q x ncells uint8)."""
+        p = C.cast(C.c_void_p(host_ptr), L.c_dp) if host_ptr is not None else _dp(host_records)
+        pp = None if present is None else present.ctypes.data_as(C.POINTER(C.c_uint8))
+        L.check(L.lib.nnsdp_batch_run_packed(self._h, p, pp, flags))
+
+    def packed_stats(self) -> dict:
+        v = [L.c_i64(0) for _ in range(5)]
+        L.check(L.lib.nnsdp_batch_packed_stats(self._h, *[C.byref(x) for x in v]))
+        return dict(zip(("record_doubles", "ncells", "emitted_bytes", "d2h_bytes", "present_optional_cells"),
+                        [int(x.value) for x in v]))
 
     def lambda_max(self, max_iters: int = 200, tol: float = 1e-10):
         """lambda_max(Z(gamma)) of every query (matrix-free Lanczos on the device); needs bounds + prepare."""
