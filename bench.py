@@ -268,6 +268,9 @@ def run_ours(args):
     name = args.workload
     w = WORKLOADS[name]
     Q = args.queries or w["Q"]
+    if args.scaling == "strong":                         # BASELINE config 5 read literally: 1024 queries in total
+        from nnsdp_b200.dist import shard_range
+        _, Q = shard_range(Q, world, rank)
     xdims, Ms, beta, inp = make_workload(name, rank, Q=Q, radius_scale=args.radius_scale)
     ctx = nb.Context([local])
     net = nb.Net(ctx, xdims, Ms)
@@ -307,7 +310,14 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
     ms_per_step = ms / args.steps
-    value = world * Q / (ms_per_step * 1e-3)
+    Qtot = Q
+    if world > 1:
+        t = torch.tensor([Q], device="cuda", dtype=torch.int64)
+        dist.all_reduce(t)
+        Qtot = int(t.item())
+    else:
+        Qtot = Q
+    value = Qtot / (ms_per_step * 1e-3)
 
     # ---- roofline of the emitter (HBM-write bound).  One pass = emit_fill_kernel, emit_window_kernel,
     # emit_edge_kernel back to back over `ring` queries; each kernel is timed with its own CUDA-event
@@ -350,6 +360,40 @@ def run_ours(args):
                 "emitter_pass": {"kernels": kernels, "algorithmic_bytes": pass_bytes, "ms": emit_ms / passes,
                                  "achieved": pass_gbs, "frac": pass_gbs / peak, "share_of_step": emit_ms / ms if ms > 0 else None,
                                  "note": "8*sum|Ck|^2 bytes per query over the three kernels of a pass"}}
+
+    # ---- the same pass with packed records (NNSDP_FORMAT_PACKED): the block-sparse upper triangle of Z, every
+    # region once, no structural zero written.  Same bounds / prepare / Gram work, same values (bit-identical to the
+    # dense blocks, tests/test_gpu_packed.py); the emitter writes `emitted_bytes` instead of 8 * sum|Ck|^2 per query.
+    batch.close()
+    pring = min(4 * ring, Q)
+    pb = nb.Batch(net, beta, Qcap=Q, ring=pring, packed=True)
+    pb.set_inputs(nbatch, Q=Q)
+    for _ in range(args.warmup):
+        pb.run_packed(None)
+    pb.stage_reset()
+    barrier_p = lambda: (dist.barrier() if world > 1 else None, pb.sync(), torch.cuda.synchronize())
+    barrier_p()
+    pb.event_record(0)
+    for _ in range(args.steps):
+        pb.run_packed(None)
+    pb.event_record(1)
+    barrier_p()
+    pms = pb.elapsed_ms()
+    if world > 1:
+        t = torch.tensor([pms], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        pms = float(t.item())
+    pst = pb.packed_stats()
+    pstage = {k: pb.stage_ms(k) for k in ("bounds", "prepare", "gram", "emit", "emit_fill", "emit_window", "emit_edge")}
+    p_emit_ms = pstage["emit"][0] / args.steps
+    packed = {"value": Qtot / (pms / args.steps * 1e-3), "unit": "queries/s", "ms_per_step": pms / args.steps,
+              "record_bytes": 8 * pst["record_doubles"], "cells": pst["ncells"],
+              "emitted_bytes_per_step": pst["emitted_bytes"], "ring_slots": pring,
+              "stage_ms_per_step": {k: pstage[k][0] / args.steps for k in pstage},
+              "emitter": {"ms": p_emit_ms, "achieved": pst["emitted_bytes"] / max(p_emit_ms, 1e-9) / 1e6, "unit": "GB/s",
+                          "frac": pst["emitted_bytes"] / max(p_emit_ms, 1e-9) / 1e6 / peak},
+              "note": "device-timed like `value`, records left in HBM; dense blocks are recovered by views / nnsdp_packed_unpack"}
+    pb.close()
 
     # ---- end-to-end through the public API with host buffers (bounded sample of the same workload), on
     # EVERY rank at the same time: the ranks share the host's memory bandwidth and PCIe root complexes,
@@ -403,6 +447,36 @@ def run_ours(args):
     eb.close()
     pin.close()
 
+    # packed records end to end: nnsdp_batch_set_inputs + nnsdp_batch_run_packed with pinned host buffers; the D2H moves
+    # the always-written part of every record plus the DIAG cells a query carries, nothing is filled on the host
+    Qp = min(Q, args.e2e_packed_queries)
+    epb = nb.Batch(net, beta, Qcap=Qp, ring=min(pring, Qp), packed=True)
+    ppin = nb.PinnedBuffer(Qp * epb.per_query)
+    ppresent = np.zeros((Qp, epb.ncells), dtype=np.uint8)
+    psub = {k: (v[:Qp] if v.shape[0] == Q else v) for k, v in inp.items()}
+    pebatch = nb.NumericBatch(out_kind=nb.OUT_SAFETY, **psub)
+    ph2d = sum(int(np.asarray(v).nbytes) for v in psub.values())
+
+    def e2e_packed_step(flags=0):
+        epb.set_inputs(pebatch, Q=Qp)
+        epb.run_packed(ppin.array, ppresent, flags=flags)
+
+    e2e_step = e2e_packed_step
+    tp = time_e2e(0)
+    pst2 = epb.packed_stats()
+    e2e_dense = e2e
+    e2e = {"value": world * Qp / tp, "unit": "queries/s", "format": "packed", "h2d_bytes_per_step": world * ph2d,
+           "d2h_bytes_per_step": world * pst2["d2h_bytes"], "queries_per_step": world * Qp, "ms_per_step": 1e3 * tp,
+           "host_result_bytes_per_step": world * pst2["d2h_bytes"],
+           "d2h_gbs": world * pst2["d2h_bytes"] / tp / 1e9,
+           "note": "nnsdp_batch_set_inputs + nnsdp_batch_run_packed with pinned host buffers on every rank concurrently "
+                   "(bounded sample of the workload): packed records = the block-sparse upper triangle of Z, from which "
+                   "every Z[C_k, C_k] is a set of views (bit-identical to the dense blocks); `dense` = the same through "
+                   "nnsdp_batch_run with complete dense blocks in host memory",
+           "dense": e2e_dense}
+    epb.close()
+    ppin.close()
+
     line = None
     if rank == 0:
         # ---- CPU baseline on this box's host cores (bounded sample)
@@ -420,9 +494,9 @@ def run_ours(args):
         line = {
             "metric": "queries/sec (clique LMI blocks assembled: value * cliques_per_query)",
             "value": value, "unit": "queries/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": {"workload": name, "xdims": f"[2, {w['W']} x {w['D']}, 2]", "beta": beta,
+            "config": {"workload": name, "output_format": "dense clique blocks (value); packed records in `packed` and `e2e`", "xdims": f"[2, {w['W']} x {w['D']}, 2]", "beta": beta,
                        "queries_per_gpu_per_step": Q, "cliques_per_query": sz["ncliques"],
                        "blocks_per_sec": value * sz["ncliques"],
                        "dense_block_bytes_per_query": 8 * sz["sum_ck_sq"], "ring_slots": ring,
@@ -430,16 +504,47 @@ def run_ours(args):
                        "gram_contractions_per_step": ncon, "gram_active_rows_per_step": nact,
                        "radius_scale": args.radius_scale,
                        "parallelism": f"queries sharded over {world} GPU(s), no collective"},
-            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks,
+            "roofline": roofline, "packed": packed, "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks,
             "gpu_launches": int(round(launches_per_step * args.steps)),
             "stage_ms_per_step": {k: stage[k][0] / args.steps for k in stage},
         }
-    batch.close()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+    if line is not None and world > 1:
+        line["ctx_multi_device"] = multi_device_context_check(nb, world)
     if line is not None:
         print(json.dumps(line), flush=True)
+
+
+def multi_device_context_check(nb, ndev):
+    """The second multi-GPU form of SURVEY.md 8e on the box's GPUs: ONE nnsdp_ctx over `ndev` devices (what a Julia
+    process would hold) shards the queries of a one-shot call over them; the gathered result must equal the
+    single-device result bit for bit, for the dense blocks and for the packed records."""
+    try:
+        rng = np.random.default_rng(42)
+        xdims, beta = [2, 300, 270, 2], 2
+        nq = 2 * ndev + 1
+        Ms = [0.1 * rng.standard_normal((xdims[k + 1], xdims[k] + 1)) for k in range(len(xdims) - 1)]
+        acdim = sum(xdims[1:-1])
+        lamdim = sum(range(acdim - beta, acdim + 1))
+        c = rng.uniform(0.5, 1.5, (nq, 2))
+        r = rng.uniform(0.0, 0.05, (nq, 1))
+        A = rng.standard_normal((nq, 5, 5))
+        b = nb.NumericBatch(x1min=c - r, x1max=c + r, gamma_in=rng.random((nq, 2)), gamma_bnd=rng.random((nq, acdim)),
+                            gamma_sec=rng.random((nq, lamdim + 2 * acdim)), out_kind=nb.OUT_SAFETY,
+                            out_S=A + np.transpose(A, (0, 2, 1)))
+        c1 = nb.Context([0])
+        one = nb.assemble_blocks(nb.Net(c1, xdims, Ms), beta, b)
+        cn = nb.Context(list(range(ndev)))
+        netn = nb.Net(cn, xdims, Ms)
+        many = nb.assemble_blocks(netn, beta, b)
+        rec, present, _ = nb.assemble_packed(netn, beta, b)
+        same_packed = all(np.array_equal(nb.packed_unpack(xdims, beta, rec[i], present[i]), one[i]) for i in range(nq))
+        return {"devices": ndev, "queries": nq, "bit_identical": bool(np.array_equal(one, many)),
+                "packed_bit_identical": bool(same_packed)}
+    except Exception as e:  # reported, never fatal for the bench line
+        return {"devices": ndev, "bit_identical": False, "error": repr(e)[:300]}
 
 
 def main():
@@ -453,6 +558,9 @@ def main():
     ap.add_argument("--e2e-queries", type=int, default=8)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--ring", type=int, default=None, help="override the number of device-resident output slots")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak: --queries per GPU (default); strong: --queries in total, sharded over the ranks")
+    ap.add_argument("--e2e-packed-queries", type=int, default=24)
     ap.add_argument("--radius-scale", type=float, default=1.0,
                     help="scale of the input-box radii (default 1 = BASELINE config 5); small values make every ReLU stable (Gram-heavy)")
     args = ap.parse_args()
