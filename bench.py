@@ -398,6 +398,14 @@ def run_ours(args):
     # ---- end-to-end through the public API with host buffers (bounded sample of the same workload), on
     # EVERY rank at the same time: the ranks share the host's memory bandwidth and PCIe root complexes,
     # so the whole-job figure is world * Qe / (slowest rank's time), not N times a single-GPU number.
+    if args.no_e2e:
+        if rank == 0:
+            print(json.dumps({"value": value, "ms_per_step": ms_per_step, "roofline": roofline, "packed": packed,
+                              "stage_ms_per_step": {k: stage[k][0] / args.steps for k in stage}}), flush=True)
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
     Qe = min(Q, args.e2e_queries)
     # host worker threads of the gather: share the box's cores between the ranks of this node
     os.environ.setdefault("NNSDP_HOST_THREADS", str(max(2, min(16, (os.cpu_count() or 16) // max(world, 1)))))
@@ -557,6 +565,7 @@ def main():
     ap.add_argument("--queries", type=int, default=None, help="override queries per GPU per step")
     ap.add_argument("--e2e-queries", type=int, default=8)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true", help="developer runs: device-timed figures only")
     ap.add_argument("--ring", type=int, default=None, help="override the number of device-resident output slots")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="weak: --queries per GPU (default); strong: --queries in total, sharded over the ranks")

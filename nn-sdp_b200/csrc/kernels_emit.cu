@@ -31,11 +31,10 @@ namespace nnsdp {
 namespace {
 
 constexpr int ETHREADS = 256;
-constexpr int SLOT_GROUP = 8;   // queries handled by one CTA
+constexpr int SLOT_GROUP = 8;   // queries handled by one CTA (edge kernel; default of the RC kernel)
 constexpr int FAST_TR = 128, FAST_TC = 32, FAST_NCOL = 16;
 constexpr int MAX_TAPS = 2 * MAX_FAST_BETA + 1;
 constexpr int MAX_TC = 32;
-constexpr int SMEM_DOUBLES = 4608;  // 36 KB: max(CR tile 32 x 136, RC coefs 8 x 32 x 9, MIXED coefs 160 x 17)
 
 struct QView {  // per-query pointers
   const double* Md;
@@ -248,13 +247,21 @@ __device__ __forceinline__ void emit_general(const NetDev& net, const BatchDev& 
 // ---------------------------------------------------------------------------------------------
 // RC: out[r, c] = sum_t Wt[r, jc - beta + t] * M[jc - beta + t, jc].  Thread = (row, 16 contiguous
 // columns); the 16 + 2 beta values of W' it needs are loaded once (coalesced over rows) and reused
-// for every query of the group; the per-column taps of all queries are staged in shared memory.
+// for every query of the group.  M is a symmetric band, so the taps of a column are shifted reads of beta + 1
+// vectors (value_0(i) = M[i, i], value_d(i) = M[i, i + d] = T[i, i + d]): they are staged per query as beta + 1
+// rows in shared memory, read two columns at a time with 16-byte broadcast loads, and the values a later column
+// needs again stay in registers -- (beta + 1) / 2 shared-memory loads per output instead of 2 beta + 1.
+// The output pointer advances by one column per store (no per-entry address arithmetic); FULL = all 32 columns
+// of the tile exist (no column predicate).
 // ---------------------------------------------------------------------------------------------
-template <int BETA>
+template <int BETA, bool FULL>
 __device__ __forceinline__ void emit_rc(const NetDev& net, const BatchDev& b, const PlanDev& plan,
                                         const TileDev& t, const MatDev& mat, int q0, int slot0,
                                         int nslots, double* __restrict__ out, double* smem) {
   constexpr int NTAP = 2 * BETA + 1;
+  constexpr int PB = BETA + (BETA & 1);     // even, so that 16-byte loads stay aligned
+  constexpr int RS = FAST_TC + PB;          // staged entries per vector: neurons jc0 - PB .. jc0 + 31
+  constexpr int QS = (BETA + 1) * RS;       // doubles per query
   const int n0 = net.n_in;
   const long long acdim = net.acdim;
   const int Br = t.rblk;
@@ -263,22 +270,21 @@ __device__ __forceinline__ void emit_rc(const NetDev& net, const BatchDev& b, co
   const int jc0 = t.gcol0 - n0;
   const int Lr0 = net.off[Br + 1] - n0, nLr = net.n[Br + 1];
 
-  // taps of every query of the group: coef[s][c][tt]
-  const int per_slot = t.ncols * NTAP;
-  for (int i = threadIdx.x; i < nslots * per_slot; i += ETHREADS) {
-    const int s = i / per_slot, rem = i - s * per_slot;
-    const int c = rem / NTAP, tt = rem - c * NTAP, jc = jc0 + c, j = jc - BETA + tt;
-    double cf = 0.0;
-    if (j >= Lr0 && j < Lr0 + nLr) {
+  for (int i = threadIdx.x; i < nslots * QS; i += ETHREADS) {
+    const int s = i / QS, rem = i - s * QS, d = rem / RS, e = rem - d * RS;
+    const long long idx = (long long)jc0 - PB + e;
+    double v = 0.0;
+    if (idx >= 0 && idx < acdim) {
       const long long q = q0 + slot0 + s;
-      cf = m_coef(b.Md + q * acdim, b.Bt + q * BETA * acdim, acdim, j, jc);
+      v = d == 0 ? b.Md[q * acdim + idx] : b.Bt[q * BETA * acdim + (long long)(d - 1) * acdim + idx];
     }
-    smem[(s * FAST_TC + c) * NTAP + tt] = cf;
+    smem[i] = v;
   }
   __syncthreads();
   if (tr >= t.nrows) return;
 
   const int cbase = cg * FAST_NCOL;
+  // w[i] = W'[r, jc0 + cbase - beta + i]; zero outside the layer, which is what restricts the sum to the layer
   double w[FAST_NCOL + NTAP - 1];
   {
     const double* WtR = net.Wt[Br] + rl;
@@ -290,18 +296,46 @@ __device__ __forceinline__ void emit_rc(const NetDev& net, const BatchDev& b, co
       w[i] = (j >= Lr0 && j < Lr0 + nLr) ? WtR[(long long)(j - Lr0) * ldTR] : 0.0;
     }
   }
-  for (int s = 0; s < nslots; ++s) {
-    double* o = out + (long long)(slot0 + s) * plan.per_query + mat.out_off + (t.row0 + tr) +
-                (long long)(t.col0 + cbase) * mat.ld;
-    const double* cf = smem + (s * FAST_TC + cbase) * NTAP;
+  const long long ld = mat.ld;
+  double* o0 = out + (long long)slot0 * plan.per_query + mat.out_off + (t.row0 + tr) + (long long)(t.col0 + cbase) * ld;
+  const int ncl = t.ncols - cbase;  // columns of this thread's strip that exist
+  for (int s = 0; s < nslots; ++s, o0 += plan.per_query) {
+    const double* cf = smem + s * QS + cbase;  // cf[d * RS + PB + c] = value_d(jc0 + cbase + c)
+    double h[BETA + 1][BETA > 0 ? BETA : 1];   // h[d][k] = value_d(jc - d + k) of the current column, k < d
 #pragma unroll
-    for (int c = 0; c < FAST_NCOL; ++c) {
-      if (cbase + c < t.ncols) {
-        double f = 0.0;
+    for (int d = 1; d <= BETA; ++d)
 #pragma unroll
-        for (int tt = 0; tt < NTAP; ++tt) f = fma(w[c + tt], cf[c * NTAP + tt], f);
-        o[(long long)c * mat.ld] = f;
+      for (int k = 0; k < d; ++k) h[d][k] = cf[d * RS + PB - d + k];
+    double* o = o0;
+#pragma unroll
+    for (int c = 0; c < FAST_NCOL; c += 2) {
+      double x[BETA + 1], y[BETA + 1];
+#pragma unroll
+      for (int d = 0; d <= BETA; ++d) {
+        const double2 v = *reinterpret_cast<const double2*>(cf + d * RS + PB + c);
+        x[d] = v.x;
+        y[d] = v.y;
       }
+      double f = 0.0, g = 0.0;  // columns c and c + 1, taps in ascending neuron order
+#pragma unroll
+      for (int tt = 0; tt < BETA; ++tt) {
+        f = fma(w[c + tt], h[BETA - tt][0], f);
+        g = fma(w[c + 1 + tt], (BETA - tt >= 2) ? h[BETA - tt][1] : x[BETA - tt], g);
+      }
+      f = fma(w[c + BETA], x[0], f);
+      g = fma(w[c + 1 + BETA], y[0], g);
+#pragma unroll
+      for (int d = 1; d <= BETA; ++d) {
+        f = fma(w[c + BETA + d], x[d], f);
+        g = fma(w[c + 1 + BETA + d], y[d], g);
+      }
+      if (FULL || c < ncl) o[0] = f;
+      if (FULL || c + 1 < ncl) o[ld] = g;
+      o += 2 * ld;
+#pragma unroll
+      for (int d = 1; d <= BETA; ++d)
+#pragma unroll
+        for (int k = 0; k < d; ++k) h[d][k] = (k + 2 < d) ? h[d][k + 2] : (k + 2 == d ? x[d] : y[d]);
     }
   }
 }
@@ -469,21 +503,27 @@ emit_fill_kernel(NetDev net, BatchDev b, GramDev g, PlanDev plan, int q0, int nq
 }
 
 // ---- kernel 2: RC / CR window sums (128 x 32 tiles, beta <= 4) ------------------------------------
+// One kernel for both programs: their CTAs interleave in plan order, so the rows a CR tile writes and the rows the
+// RC tile of the same columns writes reach DRAM close in time (dense formats: a column of a clique block is
+// written by several programs, and the write bandwidth depends on how soon its pieces follow each other).
 template <int BETA>
 __global__ void __launch_bounds__(ETHREADS, 4)
 emit_window_kernel(NetDev net, BatchDev b, PlanDev plan, int tile0, int q0, int nq, int group,
                    double* __restrict__ out) {
-  __shared__ double smem[SMEM_DOUBLES];
+  constexpr int RC_DOUBLES = SLOT_GROUP * (BETA + 1) * (FAST_TC + BETA + 1), CR_DOUBLES = FAST_TC * (FAST_TR + 2 * BETA);
+  __shared__ __align__(16) double smem[RC_DOUBLES > CR_DOUBLES ? RC_DOUBLES : CR_DOUBLES];
   // slot group is the fastest grid index: CTAs that share a W tile run back to back (L2 reuse)
   const int ngroups = (nq + group - 1) / group;
   const TileDev t = plan.tiles[tile0 + blockIdx.x / ngroups];
   const MatDev mat = plan.mats[t.mat];
   const int slot0 = (blockIdx.x % ngroups) * group;
   const int nslots = min(group, nq - slot0);
-  if (t.prog == PROG_RC)
-    emit_rc<BETA>(net, b, plan, t, mat, q0, slot0, nslots, out, smem);
-  else
+  if (t.prog == PROG_RC) {
+    if (t.ncols == FAST_TC) emit_rc<BETA, true>(net, b, plan, t, mat, q0, slot0, nslots, out, smem);
+    else emit_rc<BETA, false>(net, b, plan, t, mat, q0, slot0, nslots, out, smem);
+  } else {
     emit_cr<BETA>(net, b, plan, t, mat, q0, slot0, nslots, out, smem);
+  }
 }
 
 // ---- kernel 3: everything else (band / sliver / corner tiles, affine row and column, small nets) -
@@ -590,7 +630,7 @@ int launch_pack_thin(const double* ring, long long per_query, const long long* i
 int launch_emit(const NetDev& net, const BatchDev& b, const GramDev& g, const PlanDev& plan,
                 int q0, int nq, double* out, cudaStream_t st, int which) {
   if (nq <= 0) return 0;
-  static const int wgroup = [] { const char* e = getenv("NNSDP_WINDOW_GROUP"); int v = e ? atoi(e) : SLOT_GROUP; return v < 1 ? 1 : (v > SLOT_GROUP ? SLOT_GROUP : v); }();
+  static const int wgroup = [] { const char* e = getenv("NNSDP_WINDOW_GROUP"); int v = e ? atoi(e) : 4; return v < 1 ? 1 : (v > SLOT_GROUP ? SLOT_GROUP : v); }();
   // queries per edge CTA: one when a pass holds few queries (wide nets, 8 ring slots), eight when it holds many
   static const int egroup_env = [] { const char* e = getenv("NNSDP_EDGE_GROUP"); int v = e ? atoi(e) : 0; return v < 0 ? 0 : (v > SLOT_GROUP ? SLOT_GROUP : v); }();
   const int egroup = egroup_env > 0 ? egroup_env : (nq >= 64 ? SLOT_GROUP : (nq >= 16 ? 2 : 1));

@@ -1,0 +1,405 @@
+#!/usr/bin/env python
+"""The clique-DECOMPOSED SDP of Chordal-DeepSDP, built from the hand-off a query path delivers and solved here.
+
+TEST INFRASTRUCTURE (like everything under oracle/): not imported by the product.
+
+What the reference builds (src/Methods/chordal_sdp.jl:96-153, findEllipsoid / setupReach!):
+    variables   [gamma_in; gamma_out; gamma_ac1 (bounded); gamma_ac2 (sector)]  >= 0        (:124-139, creation order)
+    blocks      one symmetric Z_k, -Z_k PSD, per clique (C_k, parts, D_k) of makeCliques     (setupZs!, :19-57)
+                DoubleDecomp: for 1 < k < p two blocks Y_k1, Y_k2 embedded at Z_k[D_k1, D_k1], Z_k[D_k2, D_k2]  (:25-46)
+    equalities  Z(gamma) .== Zksum = sum_k E_k' Z_k E_k                                     (setupZksum!, :60-93; :150)
+    objective   gamma_out                                                                    (NnSdp.jl:46)
+The GPU library hands over exactly the data of the equalities (nnsdp_affine_get: entries of the cover's upper
+triangle, z0, COO triplets with duplicates to be summed, variables in the order above) and the cliques
+(nnsdp_cliques: C_k, |C_k1|, D_k1, D_k2).  `problem_from_handoff` turns that into the block LMI -- every cover entry
+equals the sum of the block entries that sit on it, entries of Z outside every block must carry no coefficient --
+and `solve` finds its optimum with a block log-barrier method (no SDP solver is installed).  By Agler's theorem the
+optimum equals that of the dense LMI Z(gamma) <= 0 (oracle/sdp_crosscheck.py) when, and only when, the cliques and
+the entry numbering / duplicate summation / D_k embedding of the hand-off are right: a misplaced entry makes the
+problem infeasible or moves the optimum.
+
+    python oracle/sdp_decomposed.py <handoff.npz> [single|double] [out.json]
+
+The .npz files are written on the GPU box by tools/dump_handoff.py (library outputs only); the solutions are
+committed under tests/golden/ and re-checked WITHOUT the solver by tests/test_oracle_cpu.py.
+"""
+import json
+import os
+import sys
+import time
+
+import numpy as np
+import scipy.sparse as sp
+from scipy.linalg import lu_factor
+from scipy.linalg import lu_solve as _lu_solve
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+
+
+# ------------------------------------------------------------------------------------------------
+# hand-off -> block LMI
+# ------------------------------------------------------------------------------------------------
+def blocks_of(cliques, mode):
+    """Global 0-based index sets of the PSD blocks, in the order setupZs! creates them."""
+    out = []
+    for Ck, _, Dks in cliques:
+        Ck = np.asarray(Ck, dtype=np.int64)
+        if mode == "single" or len(Dks) == 1:
+            out.append(Ck - 1)
+        else:
+            assert len(Dks) == 2
+            for D in Dks:
+                out.append(Ck[np.asarray(D, dtype=np.int64) - 1] - 1)
+    return out
+
+
+def problem_from_handoff(h, cliques, mode="single"):
+    """h: dict with nvar, nent, var_out, ent_row, ent_col (1-based), z0, coo_ent, coo_var (1-based), coo_val.
+    Returns the block LMI in the variables x = [gamma (those with a coefficient or a cost); splits]:
+    for block j, Z_j(x) = Z0_j + sum_i x[V_j[i]] * A_j[i]   (dense, symmetric), to be kept negative definite."""
+    nvar, nent = int(h["nvar"]), int(h["nent"])
+    er, ec = np.asarray(h["ent_row"]) - 1, np.asarray(h["ent_col"]) - 1
+    assert np.all(er <= ec)
+    A = sp.coo_matrix((h["coo_val"], (np.asarray(h["coo_ent"]) - 1, np.asarray(h["coo_var"]) - 1)), shape=(nent, nvar)).tocsr()
+    A.sum_duplicates()                       # "duplicate (entry, variable) pairs are to be summed"
+    z0 = np.asarray(h["z0"], dtype=float)
+    c = np.zeros(nvar)
+    c[int(h["var_out"])] = 1.0               # obj_func = gamma_out[1]
+    colmax = np.asarray(abs(A).max(axis=0).todense()).ravel()
+    keep = (colmax > 1e-13 * colmax.max()) | (c != 0)
+    kidx = np.nonzero(keep)[0]
+    A = A[:, kidx].tocsr()
+    ng = len(kidx)
+    blocks = blocks_of(cliques, mode)
+    Zdim = int(max(ec.max(), max(b.max() for b in blocks))) + 1
+    # owners of every cover entry
+    member = np.zeros((len(blocks), Zdim), dtype=bool)
+    for j, B in enumerate(blocks):
+        member[j, B] = True
+    own = member[:, er] & member[:, ec]                       # (nblocks, nent)
+    nown = own.sum(0)
+    # entries of Z that no block holds must be structurally zero (chordal_sdp.jl:150 would read 0 == 0 there)
+    orphan = nown == 0
+    assert np.all(z0[orphan] == 0.0) and abs(A[orphan]).sum() == 0.0, "Z has a coefficient outside every block"
+    primary = np.where(nown > 0, len(blocks) - 1 - np.argmax(own[::-1], axis=0), -1)   # the last owner
+    # split variables: one per (entry, non-primary owner)
+    split_id = -np.ones(own.shape, dtype=np.int64)
+    ns = 0
+    for j in range(len(blocks)):
+        sel = own[j] & (primary != j)
+        split_id[j, sel] = ng + ns + np.arange(sel.sum())
+        ns += int(sel.sum())
+    n = ng + ns
+    loc = [-np.ones(Zdim, dtype=np.int64) for _ in blocks]
+    for j, B in enumerate(blocks):
+        loc[j][B] = np.arange(len(B))
+    out_blocks = []
+    for j, B in enumerate(blocks):
+        m = len(B)
+        ents = np.nonzero(own[j])[0]
+        lr, lc = loc[j][er[ents]], loc[j][ec[ents]]
+        assert len(ents) == m * (m + 1) // 2, "a block must lie inside the cover"
+        rows, cols, vals = [], [], []
+        Z0 = np.zeros((m, m))
+        pe = ents[primary[ents] == j]                          # entries this block is the primary owner of
+        if len(pe):
+            sub = A[pe].tocoo()
+            f = loc[j][er[pe]] * m + loc[j][ec[pe]]
+            rows.append(f[sub.row]); cols.append(sub.col); vals.append(sub.data)
+            Z0[loc[j][er[pe]], loc[j][ec[pe]]] = z0[pe]
+            for j2 in range(len(blocks)):                      # minus what the other owners hold
+                if j2 == j:
+                    continue
+                s = split_id[j2, pe]
+                ok = s >= 0
+                rows.append(f[ok]); cols.append(s[ok]); vals.append(-np.ones(ok.sum()))
+        se = ents[primary[ents] != j]
+        if len(se):
+            f = loc[j][er[se]] * m + loc[j][ec[se]]
+            rows.append(f); cols.append(split_id[j, se]); vals.append(np.ones(len(se)))
+        G = sp.coo_matrix((np.concatenate(vals), (np.concatenate(rows), np.concatenate(cols))), shape=(m * m, n)).tocsc()
+        V = np.nonzero(np.diff(G.indptr))[0]                      # variables with a coefficient in this block
+        Aj = np.asarray(G[:, V].todense()).T.reshape(len(V), m, m)
+        Aj = Aj + np.transpose(Aj, (0, 2, 1)) - Aj * np.eye(m)[None]      # upper triangle -> symmetric
+        Z0 = Z0 + Z0.T - np.diag(np.diag(Z0))
+        out_blocks.append({"idx": B, "V": V, "A": Aj, "Z0": Z0})
+    cx = np.concatenate([c[kidx], np.zeros(ns)])
+    return {"blocks": out_blocks, "c": cx, "ng": ng, "ns": ns, "keep": keep, "nvar": nvar}
+
+
+def block_matrices(prob, x):
+    return [b["Z0"] + np.tensordot(x[b["V"]], b["A"], 1) for b in prob["blocks"]]
+
+
+def lambda_max(prob, x):
+    return max(float(np.linalg.eigvalsh(Z).max()) for Z in block_matrices(prob, x))
+
+
+# ------------------------------------------------------------------------------------------------
+# block log-barrier
+# ------------------------------------------------------------------------------------------------
+def barrier(prob, x, U, gap, shift_var=None, stop=None, mu=5.0, max_newton=300, verbose=False):
+    """min c'x s.t. 0 < x[:ng] < U, Z_j(x) - s I < 0 for every block (s = x[shift_var] or 0).
+    Damped Newton on the barrier; the multipliers are scaled by the iterate, the split variables are free."""
+    blocks, c, ng = prob["blocks"], prob["c"], prob["ng"]
+    n = len(c)
+    msum = sum(len(b["idx"]) for b in blocks)
+
+    def mats(x):
+        s = x[shift_var] if shift_var is not None else 0.0
+        return [s * np.eye(len(b["idx"])) - (b["Z0"] + np.tensordot(x[b["V"]], b["A"], 1)) for b in blocks]
+
+    def feasible(x):
+        g = x[:ng]
+        if np.any(g <= 0) or np.any(g >= U):
+            return False
+        for M in mats(x):
+            try:
+                np.linalg.cholesky(M)
+            except np.linalg.LinAlgError:
+                return False
+        return True
+
+    t, it = 1.0, 0
+    while True:
+        for _ in range(max_newton):
+            g = t * c.copy()
+            H = np.zeros((n, n))
+            for b, M in zip(blocks, mats(x)):
+                Mi = np.linalg.inv(M)
+                Mi = 0.5 * (Mi + Mi.T)
+                V, A = b["V"], b["A"]
+                nv, m = len(V), M.shape[0]
+                g[V] += A.reshape(nv, -1) @ Mi.ravel()
+                T = (Mi @ A @ Mi).reshape(nv, -1)
+                Hj = T @ A.reshape(nv, -1).T
+                H[np.ix_(V, V)] += 0.5 * (Hj + Hj.T)
+                if shift_var is not None:          # the shift enters every block as -s I  (A_s = -I)
+                    g[shift_var] -= np.trace(Mi)
+                    hv = -(T @ np.eye(m).ravel())
+                    H[V, shift_var] += hv
+                    H[shift_var, V] += hv
+                    H[shift_var, shift_var] += float(np.sum(Mi * Mi))
+            gam = x[:ng]
+            g[:ng] += -1.0 / gam + 1.0 / (U - gam)
+            H[np.arange(ng), np.arange(ng)] += 1.0 / gam ** 2 + 1.0 / (U - gam) ** 2
+            sc = np.ones(n)
+            sc[:ng] = gam
+            Hs = sc[:, None] * H * sc[None, :]
+            gs = sc * g
+            Hs[np.arange(n), np.arange(n)] += 1e-14 * np.abs(np.diag(Hs)).max()
+            du = -np.linalg.solve(Hs, gs)
+            lam = np.sqrt(max(-gs @ du, 0.0))
+            it += 1
+            if verbose:
+                print(f"    t {t:.1e} it {it} lam {lam:.3e} obj {c @ x:.8f}", flush=True)
+            if lam < 1e-4:
+                break
+            step = 1.0 if lam < 0.25 else 1.0 / (1.0 + lam)
+            dx = sc * du
+            while not feasible(x + step * dx) and step > 1e-14:
+                step *= 0.5
+            if step <= 1e-14:
+                break
+            x = x + step * dx
+            if stop is not None and stop(x):
+                return x, it
+        if (2 * ng + msum) / t < gap:
+            return x, it
+        t *= mu
+
+
+def primal_dual(prob, y, U, tol=1e-9, max_iter=200, verbose=False):
+    """Primal-dual path following (HKM direction) from a strictly feasible y for
+         min c'y   s.t.  S_j(y) = -Z_j(y) >= 0 (blocks),  y[:ng] >= 0,  U - y[:ng] >= 0.
+    Multipliers X_j >= 0 (blocks), xl, xu >= 0 (bounds); the dual objective -sum <C_j, X_j> - U sum xu bounds the
+    optimum from below once the dual residual c + sum_j A_j^*(X_j) - xl + xu vanishes, so the returned gap is a
+    certificate and not an estimate.  Returns (y, info)."""
+    blocks, c, ng = prob["blocks"], prob["c"], prob["ng"]
+    n = len(c)
+
+    def S_of(y):
+        return [-(b["Z0"] + np.tensordot(y[b["V"]], b["A"], 1)) for b in blocks]
+
+    S = S_of(y)
+    sl, su = y[:ng].copy(), U - y[:ng]
+    msum = sum(M.shape[0] for M in S) + 2 * ng
+    mu = (abs(c @ y) + 1.0) / msum
+    X = [mu * np.linalg.inv(M) for M in S]
+    xl, xu = mu / sl, mu / su
+
+    def max_step(M, dM):
+        """largest a with M + a dM >= 0 (M > 0)"""
+        L = np.linalg.cholesky(M)
+        Li = np.linalg.inv(L)
+        w = np.linalg.eigvalsh(Li @ dM @ Li.T).min()
+        return np.inf if w >= 0 else -1.0 / w
+
+    info, best = {}, None
+    for it in range(max_iter):
+        gap = sum(float(np.sum(Xj * Sj)) for Xj, Sj in zip(X, S)) + xl @ sl + xu @ su
+        rd = c.copy()                                   # dual residual
+        for b, Xj in zip(blocks, X):
+            rd[b["V"]] += b["A"].reshape(len(b["V"]), -1) @ Xj.ravel()
+        rd[:ng] += -xl + xu
+        pobj = float(c @ y)
+        dobj = -sum(float(np.sum(Xj * (-b["Z0"]))) for b, Xj in zip(blocks, X)) - U * xu.sum()
+        rdn = float(np.abs(rd).max())
+        info = {"iter": it, "pobj": pobj, "dobj": dobj, "gap": gap, "rd": rdn}
+        if verbose:
+            print(f"    it {it:3d} pobj {pobj:.10f} dobj {dobj:.10f} gap {gap:.2e} rd {rdn:.2e}", flush=True)
+        if rdn < 1e-6 and (best is None or pobj - dobj < best["pobj"] - best["dobj"]):
+            best = dict(info, y=y.copy())
+        if gap < tol * (1 + abs(pobj)) and rdn < tol * (1 + np.abs(c).max()):
+            break
+        if best is not None and rdn > 1e-4:             # numerical breakdown near the (degenerate) optimum: stop
+            break
+        mu = gap / msum
+        Si = [np.linalg.inv(M) for M in S]
+        Mat = np.zeros((n, n))
+        for b, Xj, Sij in zip(blocks, X, Si):
+            V, A = b["V"], b["A"]
+            nv = len(V)
+            T = (Sij @ A @ Xj)                         # S^-1 A_k X
+            Mj = A.reshape(nv, -1) @ np.transpose(T, (0, 2, 1)).reshape(nv, -1).T
+            Mat[np.ix_(V, V)] += 0.5 * (Mj + Mj.T)
+        Mat[np.arange(ng), np.arange(ng)] += xl / sl + xu / su
+        dscale = 1.0 / np.sqrt(np.maximum(np.diag(Mat), 1e-300))   # Jacobi scaling: multipliers and splits differ by orders
+        lu = lu_factor(dscale[:, None] * Mat * dscale[None, :])
+        lu_solve = lambda f, r: dscale * _lu_solve(f, dscale * r)
+
+        def direction(sigma_mu, corr=None):
+            rhs = -rd.copy()
+            # targets: X + dX = sigma_mu S^-1 + sum_k dy_k S^-1 A_k X  (+ correction)
+            for b, Xj, Sij in zip(blocks, X, Si):
+                rhs[b["V"]] -= b["A"].reshape(len(b["V"]), -1) @ (sigma_mu * Sij - Xj).ravel()
+            rhs[:ng] -= -(sigma_mu / sl - xl) + (sigma_mu / su - xu)
+            if corr is not None:
+                rhs -= corr
+            dy = lu_solve(lu, rhs)
+            for _ in range(2):                          # iterative refinement of the Schur system
+                dy += lu_solve(lu, rhs - Mat @ dy)
+            dS = [-np.tensordot(dy[b["V"]], b["A"], 1) for b in blocks]
+            dX = []
+            for Xj, Sij, dSj in zip(X, Si, dS):
+                G = sigma_mu * Sij - Xj - Sij @ dSj @ Xj
+                dX.append(0.5 * (G + G.T))
+            dsl, dsu = dy[:ng], -dy[:ng]
+            dxl = sigma_mu / sl - xl - xl / sl * dsl
+            dxu = sigma_mu / su - xu - xu / su * dsu
+            return dy, dS, dX, dsl, dsu, dxl, dxu
+
+        def steps(dS, dX, dsl, dsu, dxl, dxu):
+            ap = min([max_step(M, d) for M, d in zip(S, dS)] + [np.inf])
+            for v, d in ((sl, dsl), (su, dsu)):
+                neg = d < 0
+                if np.any(neg):
+                    ap = min(ap, float(np.min(-v[neg] / d[neg])))
+            ad = min([max_step(M, d) for M, d in zip(X, dX)] + [np.inf])
+            for v, d in ((xl, dxl), (xu, dxu)):
+                neg = d < 0
+                if np.any(neg):
+                    ad = min(ad, float(np.min(-v[neg] / d[neg])))
+            return ap, ad
+
+        # predictor (sigma = 0) gives the centring parameter (Mehrotra's rule); the step itself is the centred one
+        dy, dS, dX, dsl, dsu, dxl, dxu = direction(0.0)
+        ap, ad = steps(dS, dX, dsl, dsu, dxl, dxu)
+        ap, ad = min(1.0, ap), min(1.0, ad)
+        gap_aff = sum(float(np.sum((Xj + ad * dXj) * (Sj + ap * dSj))) for Xj, dXj, Sj, dSj in zip(X, dX, S, dS)) \
+            + (xl + ad * dxl) @ (sl + ap * dsl) + (xu + ad * dxu) @ (su + ap * dsu)
+        sigma = min(0.9, max(0.05, (gap_aff / gap) ** 2)) if gap > 0 else 0.3
+        dy, dS, dX, dsl, dsu, dxl, dxu = direction(sigma * mu)
+        ap, ad = steps(dS, dX, dsl, dsu, dxl, dxu)
+        ap, ad = min(1.0, 0.9 * ap), min(1.0, 0.9 * ad)
+        y = y + ap * dy
+        S = S_of(y)
+        sl, su = y[:ng].copy(), U - y[:ng]
+        X = [Xj + ad * d for Xj, d in zip(X, dX)]
+        xl, xu = xl + ad * dxl, xu + ad * dxu
+    if best is not None:
+        return best["y"], best
+    return y, info
+
+
+def solve(prob, gamma_start=None, U=1e4, tol=1e-9, verbose=False):
+    """Phase I by the barrier (a common shift s of every block driven below zero) from gamma_start (or ones), then
+    the optimum by the primal-dual method."""
+    ng, ns = prob["ng"], prob["ns"]
+    n = ng + ns
+    x = np.ones(n)
+    x[ng:] = 0.0
+    if gamma_start is not None:
+        x[:ng] = np.clip(np.asarray(gamma_start)[prob["keep"]], 1e-6, None)
+    U = max(U, 4 * x[:ng].max())
+    p1 = dict(prob)
+    p1["c"] = np.concatenate([np.zeros(n), [1.0]])
+    xs = np.concatenate([x, [lambda_max(prob, x) + 1.0]])
+    xs, it1 = barrier(p1, xs, U, gap=1e-3, shift_var=n, stop=lambda z: z[n] < -1e-3, verbose=False)
+    assert xs[n] < 0, "phase I did not find a strictly feasible point"
+    x = xs[:n]
+    assert lambda_max(prob, x) < 0
+    x, info = primal_dual(prob, x, U, tol=tol, verbose=verbose)
+    gamma = np.ones(prob["nvar"])
+    gamma[prob["keep"]] = x[:ng]
+    return {"obj": float(prob["c"] @ x), "dual_obj": info["dobj"], "gap": info["gap"], "dual_residual": info["rd"], "x": x,
+            "gamma": gamma, "newton": it1 + info["iter"], "lambda_max": lambda_max(prob, x), "U": U}
+
+
+# ------------------------------------------------------------------------------------------------
+# the hand-off in the library's format, from the ORACLE (for CPU development and as a second source)
+# ------------------------------------------------------------------------------------------------
+def handoff_from_oracle(net, beta, x1min, x1max, qc_out, intv_info=None):
+    import nnsdp_oracle as o
+
+    Z0, Zv = o.affine_structure(net, beta, x1min, x1max, qc_out, intv_info=intv_info)
+    cliques = o.make_cliques(net, beta)
+    er, ec = o.cover_upper_entries(net, cliques)
+    nent, nvar = len(er), len(Zv)
+    ce, cv, cval = [], [], []
+    for v, M in enumerate(Zv):
+        vals = M[er - 1, ec - 1]
+        nz = np.nonzero(vals)[0]
+        ce.append(nz + 1); cv.append(np.full(len(nz), v + 1)); cval.append(vals[nz])
+    n1 = net.xdims[0]
+    has_out = not isinstance(qc_out, o.QcSafety)
+    return {"nvar": nvar, "nent": nent, "var_in": 0, "var_out": n1, "var_bnd": n1 + (1 if has_out else 0),
+            "ent_row": er, "ent_col": ec, "z0": Z0[er - 1, ec - 1], "coo_ent": np.concatenate(ce),
+            "coo_var": np.concatenate(cv), "coo_val": np.concatenate(cval)}, cliques
+
+
+def cliques_from_npz(d):
+    """[(Ck, parts, Dks)] from the flat arrays of nnsdp_cliques stored by tools/dump_handoff.py."""
+    ck_off, ck_idx, ck1, d_off, d_idx = (d[k] for k in ("ck_off", "ck_idx", "ck1_len", "d_off", "d_idx"))
+    out = []
+    for k in range(len(ck1)):
+        Ck = ck_idx[ck_off[k]:ck_off[k + 1]]
+        parts = [Ck[:ck1[k]]] + ([Ck[ck1[k]:]] if ck1[k] < len(Ck) else [])
+        Ds = [d_idx[d_off[2 * k]:d_off[2 * k + 1]]]
+        if d_off[2 * k + 2] > d_off[2 * k + 1]:
+            Ds.append(d_idx[d_off[2 * k + 1]:d_off[2 * k + 2]])
+        out.append((Ck, parts, Ds))
+    return out
+
+
+def main():
+    path = sys.argv[1]
+    mode = sys.argv[2] if len(sys.argv) > 2 else "single"
+    d = np.load(path)
+    cliques = cliques_from_npz(d)
+    t0 = time.time()
+    prob = problem_from_handoff(d, cliques, mode)
+    print(f"{os.path.basename(path)} [{mode}]: {len(prob['blocks'])} blocks, {prob['ng']} multipliers + {prob['ns']} splits, "
+          f"build {time.time() - t0:.1f} s", flush=True)
+    start = d["gamma_start"] if "gamma_start" in d else None
+    r = solve(prob, gamma_start=start, verbose="-v" in sys.argv)
+    print(f"  optimum {r['obj']:.8f}  lambda_max over blocks {r['lambda_max']:.2e}  {r['newton']} Newton steps, "
+          f"{time.time() - t0:.0f} s", flush=True)
+    if len(sys.argv) > 3 and not sys.argv[3].startswith("-"):
+        json.dump({"obj": r["obj"], "lambda_max": r["lambda_max"], "newton": r["newton"], "mode": mode,
+                   "gamma": r["gamma"].tolist(), "splits": r["x"][prob["ng"]:].tolist()}, open(sys.argv[3], "w"))
+
+
+if __name__ == "__main__":
+    main()

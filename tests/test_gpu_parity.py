@@ -402,14 +402,92 @@ def test_stress_config_properties(ctx):
     assert np.abs((f1 - f0) + (f2 - f0) - (f12 - f0)).max() <= 1e-12 * scale
     del f2, f0, f12
 
-    # (5) clique 3 against the oracle, assembled from the closed form on that clique's rows only
-    k = 3
-    Ck = cliques[k][0] - 1
+    # (5) cliques against the oracle, assembled from the closed form on each clique's rows only: the first clique
+    # (x_1 coupling, Z_in), one of the regular ones, a middle one and the last (W_K' S22 W_K, x_K against itself),
+    # for BOTH queries -- the wide box (no Gram-active layer) and the tight one
     net = o.FeedFwdNet(xdims, Ms)
-    q = o.NumericQuery(x1min=inp["x1min"][1], x1max=inp["x1max"][1], gin=inp["gamma_in"][1], gbnd=inp["gamma_bnd"][1],
-                       gsec=inp["gamma_sec"][1], qc_out=o.QcSafety(S=inp["out_S"][0]))
-    ref = clique_block_oracle(net, beta, q, Ck)
-    assert relerr(blocks[k], ref) <= TOL
+    b = nb.Batch(dnet, beta, Qcap=2, ring=1)
+    b.set_inputs(nb.NumericBatch(x1min=inp["x1min"], x1max=inp["x1max"], out_kind=nb.OUT_SAFETY, out_S=inp["out_S"],
+                                 **{k: inp[k] for k in ("gamma_in", "gamma_bnd", "gamma_sec")}), Q=2)
+    b.bounds()
+    b.prepare()
+    for qi in (0, 1):
+        b.emit(qi, 1)
+        b.sync()
+        blocks = nb.split_blocks(b.get_slot(0), cliques)
+        q = o.NumericQuery(x1min=inp["x1min"][qi], x1max=inp["x1max"][qi], gin=inp["gamma_in"][qi], gbnd=inp["gamma_bnd"][qi],
+                           gsec=inp["gamma_sec"][qi], qc_out=o.QcSafety(S=inp["out_S"][0]))
+        for k in ((0, 3, 9, 18) if qi == 1 else (0, 18)):
+            ref = clique_block_oracle(net, beta, q, cliques[k][0] - 1)
+            assert relerr(blocks[k], ref) <= TOL, (qi, k)
+        del blocks
+    b.close()
+
+
+@pytest.mark.parametrize("beta", [1, 2, 3])
+def test_config2_top_W100_D50(ctx, beta):
+    """Top of BASELINE.json configs[1] (experiments/scale.jl sweep: width 100, depth 50, beta in {1,2,3}) with the
+    box of scale.jl:26-27 and a tight box -- the shapes the narrow-net kernels serve (ibp_chain_kernel, 100-row
+    register-window tiles): bounds, dense Z, every clique block and the packed records against the oracle."""
+    import nnsdp_b200 as nb
+
+    xdims = [2] + [100] * 50 + [2]
+    net = rand_net(xdims, seed=50100)               # sigma by the rule of scripts/make_networks.jl:44
+    rng = np.random.default_rng(7)
+    qs = [rand_query(net, beta, rng, kind="ellipsoid", radius=0.5, centre=[1.0, 1.0]),
+          rand_query(net, beta, rng, kind="safety", radius=1e-4, centre=[1.0, 1.0])]
+    dnet = nb.Net(ctx, net.xdims, net.Ms)
+    cliques = dnet.cliques(beta)
+    ref_cliques = o.make_cliques(net, beta)
+    assert all(np.array_equal(a[0], b[0]) for a, b in zip(cliques, ref_cliques)) and len(cliques) == len(ref_cliques)
+    for q in qs:
+        batch = to_numeric_batch(nb, net, [q])
+        r = nb.bounds_ibp(dnet, q.x1min[None], q.x1max[None])
+        _, xmin, xmax, amin, amax = _oracle_bounds(net, q)
+        scale = max(np.abs(xmax).max(), np.abs(xmin).max(), 1.0)
+        assert np.abs(r["xmin"][0] - xmin).max() <= TOL * scale and np.abs(r["acxmax"][0] - amax).max() <= TOL * scale
+        ref = o.run_query(net, beta, q)
+        Z = nb.assemble_dense(dnet, beta, batch)[0]
+        assert relerr(Z, ref["Z"]) <= TOL and np.array_equal(Z, Z.T)
+        flat = nb.assemble_blocks(dnet, beta, batch)[0]
+        for blk, (Ck, _, _), rb in zip(nb.split_blocks(flat, cliques), cliques, ref["blocks"]):
+            assert np.array_equal(blk, Z[np.ix_(Ck - 1, Ck - 1)])
+            assert relerr(blk, rb) <= TOL
+        rec, present, _ = nb.assemble_packed(dnet, beta, batch)
+        assert np.array_equal(nb.packed_unpack(xdims, beta, rec[0], present[0]), flat)
+
+
+def test_config2_reference_net_W20_D100(ctx):
+    """The reference's largest recorded run (dump/scale/chordalsdp-scale-I2-O2-W20-D100.nnet.csv): its shipped
+    bench/rand/scale-I2-O2-W20-D100.nnet read through nnsdp_nnet_read, beta = 2, box of scale.jl:26-27, 99 cliques."""
+    import nnsdp_b200 as nb
+
+    path = os.path.join(GOLD, "scale-I2-O2-W20-D100.nnet")
+    xdims, Ms = nb.read_nnet(path)
+    net = o.load_nnet(path)
+    assert xdims == list(net.xdims) and all(np.array_equal(a, b) for a, b in zip(Ms, net.Ms))
+    beta = 2
+    rng = np.random.default_rng(3)
+    qs = [rand_query(net, beta, rng, kind="ellipsoid", radius=0.5, centre=[1.0, 1.0]),
+          rand_query(net, beta, rng, kind="hplane", radius=0.0, centre=[1.0, 1.0])]
+    dnet = nb.Net(ctx, xdims, Ms)
+    cliques = dnet.cliques(beta)
+    assert len(cliques) == 99
+    for q in qs:
+        batch = to_numeric_batch(nb, net, [q])
+        ref = o.run_query(net, beta, q)
+        Z = nb.assemble_dense(dnet, beta, batch)[0]
+        assert relerr(Z, ref["Z"]) <= TOL
+        flat = nb.assemble_blocks(dnet, beta, batch)[0]
+        for blk, (Ck, _, _), rb in zip(nb.split_blocks(flat, cliques), ref["cliques"], ref["blocks"]):
+            assert relerr(blk, rb) <= TOL
+        rec, present, _ = nb.assemble_packed(dnet, beta, batch)
+        assert np.array_equal(nb.packed_unpack(xdims, beta, rec[0], present[0]), flat)
+        # CROWN bounds (the reference's default) on the same net against the restatement
+        rc = nb.bounds_crown(dnet, q.x1min[None], q.x1max[None])
+        info = o.intervals_crown(q.x1min, q.x1max, net)
+        xr = np.concatenate([p[1] for p in info.x_intvs])
+        assert np.abs(rc["xmax"][0] - xr).max() <= 1e-9 * max(np.abs(xr).max(), 1.0)
 
 
 def clique_block_oracle(net, beta, q, Ck):
