@@ -37,6 +37,7 @@ extern "C" {
 #define NNSDP_ERR_NOMEM (-3)  /* host or device allocation failed                       */
 #define NNSDP_ERR_STATE (-4)  /* call sequence error (e.g. emit before prepare)         */
 #define NNSDP_ERR_ASSERT (-5) /* an @assert of the reference would have failed          */
+#define NNSDP_ERR_NOCONV (-6) /* an iteration stopped at its cap (results are still written) */
 
 /* Output QC kinds, src/Qc/output.jl:3-31 */
 #define NNSDP_OUT_SAFETY 0    /* QcSafety(S)                                            */
@@ -263,6 +264,9 @@ int32_t nnsdp_assemble_packed(nnsdp_ctx* ctx, const nnsdp_net* net, int64_t beta
 
 /* ---- device-resident batch (what bench.py times with inputs already in HBM) -----------
  * A batch lives on ONE device of the ctx (dev_index into the ctx's device list).
+ * Limits: n_in + n_out + 1 <= 160 for batches that assemble (ring_queries > 0; the output-QC matrix S is held in
+ * shared memory) -- bounds-only batches (ring_queries = 0: IBP / CROWN on image-sized inputs) have no such limit;
+ * hidden widths up to ~46,000 (tile pairs of the Gram kernel); any Qcap < 2^30.
  * ring_queries = number of per-query output slots kept on the device; 0 = bounds only
  * (no gamma inputs are read and nothing can be emitted).  dense_Z is the output format of a query:
  * NNSDP_FORMAT_BLOCKS (0) the clique blocks, NNSDP_FORMAT_DENSE_Z (1) the whole Zdim x Zdim matrix,
@@ -339,10 +343,17 @@ int32_t nnsdp_batch_gram_stats(nnsdp_batch* batch, int64_t* n_contractions, int6
 /* ---- certificate check -----------------------------------------------------
  * lambda_max of Z(gamma) for every query of a prepared batch, without forming Z: Z x is evaluated from the
  * factored form R' Q R + Zin + Zout (one GEMM per layer over the batch) inside a Lanczos iteration with full
- * re-orthogonalisation, at most max_iters steps; a query stops when its largest Ritz value has moved by less
- * than tol (relative) over the last three steps.  Replaces eigmax(Symmetric(Matrix(value.(Z))))
- * (src/Methods/Methods.jl:116-117; acceptance test experiments/acas.jl:71-79, scale.jl:76).
- * lam_max[Q]; iters[Q] may be NULL.  The Ritz value converges to lambda_max from below. */
+ * re-orthogonalisation, at most max_iters steps.  A query stops when the residual ||Z v - theta v|| of its largest
+ * Ritz pair is below tol * (largest |Ritz value|) -- a tolerance relative to the spectral scale, so it also
+ * triggers when lambda_max is near zero, the regime of the acceptance gate eigmax(Z) <= 1e-4 -- or when the Krylov
+ * space is invariant.  Replaces eigmax(Symmetric(Matrix(value.(Z)))) (src/Methods/Methods.jl:116-117; acceptance
+ * test experiments/acas.jl:71-79, scale.jl:76).
+ * The Ritz value is a LOWER bound of lambda_max and converges from below: a query that stopped at max_iters is NOT
+ * a certificate.  Outputs: lam_max[Q]; iters[Q], resid[Q] (the residual norm: an eigenvalue of Z lies within resid of
+ * lam_max) and converged[Q] (1 / 0) may be NULL.  Returns NNSDP_ERR_NOCONV -- with every output written -- when
+ * some query did not converge.  nnsdp_batch_lambda_max is the same call without the last two outputs. */
+int32_t nnsdp_batch_lambda_max_ex(nnsdp_batch* batch, int32_t max_iters, double tol, double* lam_max, int32_t* iters,
+                                  double* resid, int32_t* converged);
 int32_t nnsdp_batch_lambda_max(nnsdp_batch* batch, int32_t max_iters, double tol, double* lam_max,
                                int32_t* iters);
 

@@ -750,8 +750,11 @@ int32_t nnsdp_batch_create(nnsdp_ctx* ctx, int32_t dev_index, const nnsdp_net* n
   b->dense = dense_Z == NNSDP_FORMAT_DENSE_Z;
   b->packed = dense_Z == NNSDP_FORMAT_PACKED;
   NN_TRY(fill_sizes(sh, beta, &b->sz));
-  NN_CHECK(b->sz.sdim * b->sz.sdim * 8 + b->sz.n_out * 8 <= 40000, NNSDP_ERR_ARG,
-           "n_in + n_out + 1 = %lld too large for the output-QC kernel", (long long)b->sz.sdim);
+  // the output-QC kernel keeps S (sdim^2 doubles) in shared memory: sdim = n_in + n_out + 1 <= 160.  Bounds-only
+  // batches (ring_queries == 0) never run it.
+  NN_CHECK(ring_queries == 0 || b->sz.sdim * b->sz.sdim * 8 + b->sz.n_out * 8 <= 200 * 1024, NNSDP_ERR_ARG,
+           "n_in + n_out + 1 = %lld too large for the output-QC kernel (limit 160); bounds-only batches "
+           "(ring_queries = 0) have no such limit", (long long)b->sz.sdim);
   NN_CUDA(cudaSetDevice(b->dev));
   NN_CUDA(cudaStreamCreateWithFlags(&b->st, cudaStreamNonBlocking));
   NN_CUDA(cudaStreamCreateWithFlags(&b->st_copy, cudaStreamNonBlocking));
@@ -1075,7 +1078,9 @@ int32_t nnsdp_batch_emit(nnsdp_batch* b, int64_t q0, int64_t nq) {
     l = launch_gram(nd.nd, b->bd, gd, (int)b->net->max_block, (int)q0, b->d_pairs.as<int>() + 2 * b->pair_begin[q0],
                     (int)(b->pair_begin[q0 + nq] - b->pair_begin[q0]), b->st);
   }
-  b->span_end(b->st, l);
+  b->span_end(b->st, l > 0 ? l : 0);
+  NN_CHECK(l >= 0, NNSDP_ERR_ARG, "a hidden layer of %lld neurons is too wide for the Gram kernel's grid", (long long)b->net->max_block);
+  NN_CUDA(cudaGetLastError());
   emit_pass(b, gd, (int)q0, (int)nq, b->ringbuf.as<double>());
   NN_CUDA(cudaGetLastError());
   return NNSDP_OK;
@@ -1271,7 +1276,10 @@ static int32_t run_impl(nnsdp_batch* b, double* host_out, uint8_t* present, int3
                   ? launch_gram(nd.nd, b->bd, b->gd, (int)b->net->max_block, 0, b->d_pairs.as<int>(), (int)b->pair_begin[1], b->st)
                   : launch_gram(nd.nd, b->bd, gd, (int)b->net->max_block, (int)q0, b->d_pairs.as<int>() + 2 * b->pair_begin[q0],
                                 (int)(b->pair_begin[q0 + nq] - b->pair_begin[q0]), b->st);
-      b->span_end(b->st, l);
+      b->span_end(b->st, l > 0 ? l : 0);
+      NN_CHECK(l >= 0, NNSDP_ERR_ARG, "a hidden layer of %lld neurons is too wide for the Gram kernel's grid",
+               (long long)b->net->max_block);
+      NN_CUDA(cudaGetLastError());  // a failed Gram launch must not go unnoticed until the emitter has read its scratch
     }
     emit_pass(b, gd, (int)q0, (int)nq, dst);
     if (sparse) {
@@ -1959,8 +1967,9 @@ extern "C" int32_t nnsdp_batch_bounds_crown(nnsdp_batch* b) {
 // -----------------------------------------------------------------------------------------
 namespace {
 
-// largest eigenvalue of the symmetric tridiagonal (alpha[0..m), beta[0..m-1)) by Sturm bisection
-double tridiag_lambda_max(const double* alpha, const double* beta, int m) {
+// extreme eigenvalue of the symmetric tridiagonal (alpha[0..m), beta[0..m-1)) by Sturm bisection:
+// the largest (which = +1) or the smallest (which = -1)
+double tridiag_extreme(const double* alpha, const double* beta, int m, int which) {
   if (m <= 0) return 0.0;
   double lo = alpha[0], hi = alpha[0];
   for (int i = 0; i < m; ++i) {
@@ -1979,17 +1988,68 @@ double tridiag_lambda_max(const double* alpha, const double* beta, int m) {
     }
     return cnt;
   };
+  const int target = which > 0 ? m : 1;  // smallest x with count_below(x) >= target brackets the wanted eigenvalue
   for (int it = 0; it < 200 && hi - lo > 4e-16 * std::max(fabs(lo), fabs(hi)); ++it) {
     const double mid = 0.5 * (lo + hi);
-    if (count_below(mid) >= m) hi = mid; else lo = mid;
+    if (count_below(mid) >= target) hi = mid; else lo = mid;
   }
   return 0.5 * (lo + hi);
 }
 
+double tridiag_lambda_max(const double* alpha, const double* beta, int m) { return tridiag_extreme(alpha, beta, m, +1); }
+
+// |last component| of the unit eigenvector of the tridiagonal for its eigenvalue theta: two steps of inverse
+// iteration with (T - theta' I), theta' nudged off the eigenvalue, solved by Gaussian elimination with partial
+// pivoting.  beta_m * |s_last| is the residual norm ||Z v - theta v|| of the Ritz pair.
+double tridiag_last_component(const double* alpha, const double* beta, int m, double theta, double scale) {
+  if (m <= 1) return 1.0;
+  const double shift = theta + 1e-13 * std::max(scale, 1e-300);
+  std::vector<double> x(m, 1.0), dl(m), d(m), du(m), du2(m);
+  for (int rep = 0; rep < 2; ++rep) {
+    for (int i = 0; i < m; ++i) {
+      d[i] = alpha[i] - shift;
+      dl[i] = i > 0 ? beta[i - 1] : 0.0;   // sub-diagonal entry in row i
+      du[i] = i + 1 < m ? beta[i] : 0.0;   // super-diagonal entry in row i
+      du2[i] = 0.0;
+    }
+    for (int i = 0; i + 1 < m; ++i) {      // eliminate row i+1's sub-diagonal
+      if (fabs(d[i]) >= fabs(dl[i + 1])) {
+        const double piv = d[i] != 0.0 ? d[i] : 1e-300;
+        const double f = dl[i + 1] / piv;
+        d[i + 1] -= f * du[i];
+        x[i + 1] -= f * x[i];
+        d[i] = piv;
+      } else {                              // swap rows i and i+1
+        const double f = d[i] / dl[i + 1];
+        const double nd = dl[i + 1], ndu = d[i + 1], ndu2 = du[i + 1];
+        d[i + 1] = du[i] - f * ndu;
+        du[i + 1] = -f * ndu2;
+        d[i] = nd;
+        du[i] = ndu;
+        du2[i] = ndu2;
+        const double t = x[i];
+        x[i] = x[i + 1];
+        x[i + 1] = t - f * x[i + 1];
+      }
+    }
+    if (d[m - 1] == 0.0) d[m - 1] = 1e-300;
+    x[m - 1] /= d[m - 1];
+    if (m >= 2) x[m - 2] = (x[m - 2] - du[m - 2] * x[m - 1]) / d[m - 2];
+    for (int i = m - 3; i >= 0; --i) x[i] = (x[i] - du[i] * x[i + 1] - du2[i] * x[i + 2]) / d[i];
+    double nrm = 0.0, mx = 0.0;
+    for (double v : x) mx = std::max(mx, fabs(v));
+    if (!(mx > 0.0) || !std::isfinite(mx)) return 1.0;
+    for (double& v : x) { v /= mx; nrm += v * v; }
+    nrm = sqrt(nrm);
+    for (double& v : x) v /= nrm;
+  }
+  return fabs(x[m - 1]);
+}
+
 }  // namespace
 
-extern "C" int32_t nnsdp_batch_lambda_max(nnsdp_batch* b, int32_t max_iters, double tol, double* lam_max,
-                                          int32_t* iters_out) {
+extern "C" int32_t nnsdp_batch_lambda_max_ex(nnsdp_batch* b, int32_t max_iters, double tol, double* lam_max,
+                                             int32_t* iters_out, double* resid_out, int32_t* converged_out) {
   NN_CHECK(b && lam_max, NNSDP_ERR_ARG, "NULL argument");
   NN_CHECK(b->prepared, NNSDP_ERR_STATE, "nnsdp_batch_lambda_max before nnsdp_batch_prepare");
   NN_CHECK(max_iters >= 1, NNSDP_ERR_ARG, "max_iters must be >= 1");
@@ -2015,6 +2075,7 @@ extern "C" int32_t nnsdp_batch_lambda_max(nnsdp_batch* b, int32_t max_iters, dou
   NN_TRY(dnrm.ensure((size_t)Qc * 8));
   cudaStream_t st = b->st;
   std::vector<double> hc((size_t)Qc * (m + 1)), hn((size_t)Qc);
+  bool all_converged = true;
   for (int64_t q0 = 0; q0 < b->Q; q0 += Qc) {
     const int nq = (int)std::min<int64_t>(Qc, b->Q - q0);
     double* V = dV.as<double>();
@@ -2023,9 +2084,8 @@ extern "C" int32_t nnsdp_batch_lambda_max(nnsdp_batch* b, int32_t max_iters, dou
     launch_eig_init(w, n, nq, (int)q0, st);
     launch_eig_normalize(w, Vj(0), n, nq, dnrm.as<double>(), st);
     std::vector<std::vector<double>> alpha(nq), beta(nq);
-    std::vector<double> theta(nq, 0.0);
-    std::vector<std::vector<double>> hist(nq);
-    std::vector<int> done(nq, 0), its(nq, 0);
+    std::vector<double> theta(nq, 0.0), resid(nq, 0.0);
+    std::vector<int> done(nq, 0), its(nq, 0), conv(nq, 0);
     int j = 0;
     for (; j < m; ++j) {
       // ---- w = Z v_j ----
@@ -2056,15 +2116,15 @@ extern "C" int32_t nnsdp_batch_lambda_max(nnsdp_batch* b, int32_t max_iters, dou
         alpha[q][j] += hc[(size_t)q * (m + 1) + j];  // second-pass correction of alpha_j
         if (done[q]) continue;
         its[q] = j + 1;
-        theta[q] = tridiag_lambda_max(alpha[q].data(), beta[q].data(), j + 1);
-        hist[q].push_back(theta[q]);
-        const double scale = std::max(fabs(theta[q]), 1e-300);
-        // stop on an invariant subspace (beta_j ~ 0) or when the largest Ritz value has not moved by more
-        // than tol (relative) over the last three steps
-        bool stable = (int)hist[q].size() >= 10;
-        for (int back = 2; stable && back <= 4; ++back)
-          stable = fabs(hist[q][hist[q].size() - back] - theta[q]) <= tol * scale;
-        if (hn[q] <= 1e-13 * std::max(scale, fabs(alpha[q][j])) || stable) done[q] = 1;
+        theta[q] = tridiag_extreme(alpha[q].data(), beta[q].data(), j + 1, +1);
+        // The tolerance is relative to the SPECTRAL SCALE (the largest |Ritz value|), not to |theta|: the acceptance
+        // gate eigmax(Z) <= 1e-4 (experiments/acas.jl:76-79) asks about a lambda_max near zero, where a test relative
+        // to theta itself can never trigger.  ||Z v - theta v|| = beta_j |s_last| for the Ritz pair (theta, v).
+        const double tmin = tridiag_extreme(alpha[q].data(), beta[q].data(), j + 1, -1);
+        const double scale = std::max(std::max(fabs(theta[q]), fabs(tmin)), 1e-300);
+        resid[q] = hn[q] * tridiag_last_component(alpha[q].data(), beta[q].data(), j + 1, theta[q], scale);
+        // stop on an invariant subspace (beta_j ~ 0: the Ritz values are eigenvalues) or on a small residual
+        if (hn[q] <= 1e-13 * scale || resid[q] <= tol * scale || j + 1 == n) done[q] = conv[q] = 1;
         beta[q].push_back(hn[q]);
         if (!done[q]) all_done = false;
       }
@@ -2076,10 +2136,23 @@ extern "C" int32_t nnsdp_batch_lambda_max(nnsdp_batch* b, int32_t max_iters, dou
     for (int q = 0; q < nq; ++q) {
       lam_max[q0 + q] = theta[q];
       if (iters_out) iters_out[q0 + q] = its[q];
+      if (resid_out) resid_out[q0 + q] = resid[q];
+      if (converged_out) converged_out[q0 + q] = conv[q];
+      all_converged &= conv[q] != 0;
     }
   }
   NN_CUDA(cudaGetLastError());
+  if (!all_converged) {
+    set_error("nnsdp_batch_lambda_max: some query did not reach the residual tolerance within max_iters = %d "
+              "(its value is a LOWER bound of lambda_max; see the residual)", (int)max_iters);
+    return NNSDP_ERR_NOCONV;
+  }
   return NNSDP_OK;
+}
+
+extern "C" int32_t nnsdp_batch_lambda_max(nnsdp_batch* b, int32_t max_iters, double tol, double* lam_max,
+                                          int32_t* iters_out) {
+  return nnsdp_batch_lambda_max_ex(b, max_iters, tol, lam_max, iters_out, nullptr, nullptr);
 }
 
 // -----------------------------------------------------------------------------------------

@@ -55,13 +55,14 @@ gram_kernel(NetDev net, BatchDev b, GramDev g, int q0, const int* __restrict__ p
   GramSmem<GT>& sm = *reinterpret_cast<GramSmem<GT>*>(smem_raw);
 
   // work list: only (query, block) pairs with active neurons; Gram of block blk uses layer matrix M[blk]
-  const int q = pairs[2 * blockIdx.y], blk = pairs[2 * blockIdx.y + 1], slot = q - q0;
+  // (pairs on grid.x: up to 2^31 - 1; tile pairs on grid.y)
+  const int q = pairs[2 * blockIdx.x], blk = pairs[2 * blockIdx.x + 1], slot = q - q0;
   const int cnt = b.cnt[(long long)q * net.K + blk];
   if (cnt == 0) return;
   const int nb = net.n[blk];
   const int ntile = (nb + GT - 1) / GT;
-  // decode the upper-triangular tile pair (ti <= tj) from blockIdx.x
-  int ti = 0, rem = blockIdx.x;
+  // decode the upper-triangular tile pair (ti <= tj) from blockIdx.y
+  int ti = 0, rem = blockIdx.y;
   while (ti < ntile && rem >= ntile - ti) {
     rem -= ntile - ti;
     ++ti;
@@ -162,13 +163,17 @@ static void launch_gram_t(const NetDev& net, const BatchDev& b, const GramDev& g
                           int npairs, cudaStream_t st) {
   cudaFuncSetAttribute(gram_kernel<GT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(GramSmem<GT>));
   const int ntile = (max_n + GT - 1) / GT;
-  dim3 grid(ntile * (ntile + 1) / 2, npairs);
+  dim3 grid(npairs, ntile * (ntile + 1) / 2);  // grid.y <= 65535 is checked by launch_gram
   gram_kernel<GT><<<grid, GTHREADS, sizeof(GramSmem<GT>), st>>>(net, b, g, q0, pairs);
 }
 
 int launch_gram(const NetDev& net, const BatchDev& b, const GramDev& g, int max_n, int q0, const int* pairs,
                 int npairs, cudaStream_t st) {
   if (net.K < 2 || npairs <= 0) return 0;
+  {  // tile pairs of the widest block must fit grid.y (widths up to ~23,000 with 64 x 64 tiles, ~46,000 with 128 x 128)
+    const long long nt = (max_n + 127) / 128;
+    if (nt * (nt + 1) / 2 > 65535) return -1;
+  }
   static const int force = [] { const char* e = getenv("NNSDP_GRAM_TILE"); return e ? atoi(e) : 0; }();
   const int nt128 = (max_n + 127) / 128;
   const long long items128 = (long long)nt128 * (nt128 + 1) / 2 * npairs;

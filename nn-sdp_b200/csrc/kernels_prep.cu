@@ -25,8 +25,8 @@ __device__ __forceinline__ long long pair_base(long long i, long long acdim, lon
 }
 
 __global__ void __launch_bounds__(PREP_THREADS)
-prep_neuron_kernel(NetDev net, BatchDev b, int* __restrict__ err_flag) {
-  const int q = blockIdx.y;
+prep_neuron_kernel(NetDev net, BatchDev b, int* __restrict__ err_flag, int q_base) {
+  const int q = q_base + blockIdx.y;
   const long long acdim = net.acdim, beta = b.beta;
   const long long j = (long long)blockIdx.x * PREP_THREADS + threadIdx.x;
   double part = 0.0;
@@ -214,10 +214,10 @@ prep_final_kernel(NetDev net, BatchDev b) {
 
 // Ordered compaction of the Gram-active neurons (d11 != 0) of one layer of one query: grid (K - 1, Q).
 __global__ void __launch_bounds__(PREP_THREADS)
-prep_compact_kernel(NetDev net, BatchDev b) {
+prep_compact_kernel(NetDev net, BatchDev b, int q_base) {
   __shared__ int wsum[PREP_THREADS / 32];
   __shared__ int base_sh;
-  const int blk = blockIdx.x, q = blockIdx.y, tid = threadIdx.x;
+  const int blk = blockIdx.x, q = q_base + blockIdx.y, tid = threadIdx.x;
   const int K = net.K, n_in = net.n_in;
   const double* d11 = b.d11 + (long long)q * net.acdim;
   int* act = b.act + (long long)q * net.acdim;
@@ -249,12 +249,24 @@ prep_compact_kernel(NetDev net, BatchDev b) {
 }  // namespace
 
 int launch_prep(const NetDev& net, const BatchDev& b, int* err_flag, cudaStream_t st) {
-  dim3 grid(b.npart, b.Q);
-  prep_neuron_kernel<<<grid, PREP_THREADS, 0, st>>>(net, b, err_flag);
+  // queries ride on grid.y (<= 65535): larger batches are launched in slices
+  int launches = 0;
+  for (int q_base = 0; q_base < b.Q; q_base += 65535) {
+    const int nq = min(65535, b.Q - q_base);
+    prep_neuron_kernel<<<dim3(b.npart, nq), PREP_THREADS, 0, st>>>(net, b, err_flag, q_base);
+    ++launches;
+  }
   const size_t shbytes = (size_t)(b.sdim * b.sdim + net.n_out) * sizeof(double);
+  if (shbytes > 40000)  // beyond the default 48 KB of dynamic shared memory (the host checks sdim <= 160)
+    cudaFuncSetAttribute(prep_final_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shbytes);
   prep_final_kernel<<<b.Q, PREP_THREADS, shbytes, st>>>(net, b);
-  if (net.K >= 2) prep_compact_kernel<<<dim3(net.K - 1, b.Q), PREP_THREADS, 0, st>>>(net, b);
-  return net.K >= 2 ? 3 : 2;
+  ++launches;
+  if (net.K >= 2)
+    for (int q_base = 0; q_base < b.Q; q_base += 65535) {
+      prep_compact_kernel<<<dim3(net.K - 1, min(65535, b.Q - q_base)), PREP_THREADS, 0, st>>>(net, b, q_base);
+      ++launches;
+    }
+  return launches;
 }
 
 }  // namespace nnsdp

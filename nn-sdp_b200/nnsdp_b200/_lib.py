@@ -11,7 +11,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("NNSDP_B200_LIB", os.path.join(_HERE, "..", "lib", "libnnsdp_b200.so"))
 
-OK, ERR_ARG, ERR_CUDA, ERR_NOMEM, ERR_STATE, ERR_ASSERT = 0, -1, -2, -3, -4, -5
+OK, ERR_ARG, ERR_CUDA, ERR_NOMEM, ERR_STATE, ERR_ASSERT, ERR_NOCONV = 0, -1, -2, -3, -4, -5, -6
 OUT_SAFETY, OUT_HPLANE, OUT_CIRCLE, OUT_ELLIPSOID = 0, 1, 2, 3
 RUN_HOST_PREZEROED, RUN_DENSE_COPY = 1, 2
 FORMAT_BLOCKS, FORMAT_DENSE_Z, FORMAT_PACKED = 0, 1, 2
@@ -93,6 +93,7 @@ PROTOTYPES = {
     "nnsdp_assemble_blocks": (c_i32, [c_vp, c_vp, c_i64, c_i64, C.POINTER(QueryInputs), c_dp]),
     "nnsdp_assemble_dense": (c_i32, [c_vp, c_vp, c_i64, c_i64, C.POINTER(QueryInputs), c_dp]),
     "nnsdp_batch_lambda_max": (c_i32, [c_vp, c_i32, C.c_double, c_dp, C.POINTER(c_i32)]),
+    "nnsdp_batch_lambda_max_ex": (c_i32, [c_vp, c_i32, C.c_double, c_dp, C.POINTER(c_i32), c_dp, C.POINTER(c_i32)]),
     "nnsdp_affine_create": (c_i32, [c_vp, c_vp, c_i64, C.POINTER(QueryInputs), c_i64, C.POINTER(c_vp), C.POINTER(AffineSizes)]),
     "nnsdp_affine_get": (c_i32, [c_vp, c_i64p, c_i64p, c_dp, c_i64p, c_i64p, c_dp]),
     "nnsdp_affine_destroy": (c_i32, [c_vp]),

@@ -495,11 +495,21 @@ class Batch:
         return dict(zip(("record_doubles", "ncells", "emitted_bytes", "d2h_bytes", "present_optional_cells"),
                         [int(x.value) for x in v]))
 
-    def lambda_max(self, max_iters: int = 200, tol: float = 1e-10):
-        """lambda_max(Z(gamma)) of every query (matrix-free Lanczos on the device); needs bounds + prepare."""
+    def lambda_max(self, max_iters: int = 200, tol: float = 1e-10, full: bool = False):
+        """lambda_max(Z(gamma)) of every query (matrix-free Lanczos on the device); needs bounds + prepare.
+        full=True returns (lam, iters, resid, converged) and does not raise when a query stops at max_iters (its
+        value is then only a lower bound); otherwise non-convergence raises NnsdpError(ERR_NOCONV)."""
         lam = np.zeros(self.Q)
         its = np.zeros(self.Q, dtype=np.int32)
-        L.check(L.lib.nnsdp_batch_lambda_max(self._h, max_iters, tol, _dp(lam), its.ctypes.data_as(C.POINTER(L.c_i32))))
+        resid = np.zeros(self.Q)
+        conv = np.zeros(self.Q, dtype=np.int32)
+        st = L.lib.nnsdp_batch_lambda_max_ex(self._h, max_iters, tol, _dp(lam), its.ctypes.data_as(C.POINTER(L.c_i32)),
+                                             _dp(resid), conv.ctypes.data_as(C.POINTER(L.c_i32)))
+        if full:
+            if st not in (L.OK, L.ERR_NOCONV):
+                L.check(st)
+            return lam, its, resid, conv
+        L.check(st)
         return lam, its
 
     def gather_stats(self) -> dict:

@@ -210,7 +210,7 @@ def barrier(prob, x, U, gap, shift_var=None, stop=None, mu=5.0, max_newton=300, 
         t *= mu
 
 
-def primal_dual(prob, y, U, tol=1e-9, max_iter=200, verbose=False):
+def primal_dual(prob, y, U, tol=1e-9, max_iter=200, verbose=False, stop=None):
     """Primal-dual path following (HKM direction) from a strictly feasible y for
          min c'y   s.t.  S_j(y) = -Z_j(y) >= 0 (blocks),  y[:ng] >= 0,  U - y[:ng] >= 0.
     Multipliers X_j >= 0 (blocks), xl, xu >= 0 (bounds); the dual objective -sum <C_j, X_j> - U sum xu bounds the
@@ -236,7 +236,7 @@ def primal_dual(prob, y, U, tol=1e-9, max_iter=200, verbose=False):
         w = np.linalg.eigvalsh(Li @ dM @ Li.T).min()
         return np.inf if w >= 0 else -1.0 / w
 
-    info, best = {}, None
+    info, best, stall = {}, None, 0
     for it in range(max_iter):
         gap = sum(float(np.sum(Xj * Sj)) for Xj, Sj in zip(X, S)) + xl @ sl + xu @ su
         rd = c.copy()                                   # dual residual
@@ -249,13 +249,25 @@ def primal_dual(prob, y, U, tol=1e-9, max_iter=200, verbose=False):
         info = {"iter": it, "pobj": pobj, "dobj": dobj, "gap": gap, "rd": rdn}
         if verbose:
             print(f"    it {it:3d} pobj {pobj:.10f} dobj {dobj:.10f} gap {gap:.2e} rd {rdn:.2e}", flush=True)
+        if stop is not None and stop(y):
+            return y, info
         if rdn < 1e-6 and (best is None or pobj - dobj < best["pobj"] - best["dobj"]):
-            best = dict(info, y=y.copy())
+            best = dict(info, y=y.copy(), X=[Xj.copy() for Xj in X], xl=xl.copy(), xu=xu.copy())
+            stall = 0
+        else:
+            stall += 1
+        if best is not None and stall >= 6:             # no better bracket for six iterations: the iterates sit on
+            break                                       # the boundary of the (degenerate) optimal face
         if gap < tol * (1 + abs(pobj)) and rdn < tol * (1 + np.abs(c).max()):
             break
         if best is not None and rdn > 1e-4:             # numerical breakdown near the (degenerate) optimum: stop
             break
         mu = gap / msum
+        try:
+            for M in S + X:
+                np.linalg.cholesky(M)
+        except np.linalg.LinAlgError:                   # rounding pushed an iterate out of the cone: stop here
+            break
         Si = [np.linalg.inv(M) for M in S]
         Mat = np.zeros((n, n))
         for b, Xj, Sij in zip(blocks, X, Si):
@@ -333,10 +345,15 @@ def solve(prob, gamma_start=None, U=1e4, tol=1e-9, verbose=False):
     if gamma_start is not None:
         x[:ng] = np.clip(np.asarray(gamma_start)[prob["keep"]], 1e-6, None)
     U = max(U, 4 * x[:ng].max())
-    p1 = dict(prob)
-    p1["c"] = np.concatenate([np.zeros(n), [1.0]])
+    # phase I: min s  s.t.  Z_j(y) - s I <= 0 -- the same primal-dual method on the problem with one more free
+    # variable (coefficient -I in every block), started at s = lambda_max + 1 and stopped as soon as s < 0 by a margin
+    p1 = {"c": np.concatenate([np.zeros(n), [1.0]]), "ng": ng, "ns": ns + 1, "blocks": [
+        {"idx": b["idx"], "Z0": b["Z0"], "V": np.concatenate([b["V"], [n]]),
+         "A": np.concatenate([b["A"], -np.eye(len(b["idx"]))[None]], 0)} for b in prob["blocks"]]}
     xs = np.concatenate([x, [lambda_max(prob, x) + 1.0]])
-    xs, it1 = barrier(p1, xs, U, gap=1e-3, shift_var=n, stop=lambda z: z[n] < -1e-3, verbose=False)
+    scale = max(1.0, max(float(np.abs(b["Z0"]).max()) for b in prob["blocks"]))
+    xs, info1 = primal_dual(p1, xs, U, tol=1e-9, verbose=verbose, stop=lambda z: z[n] < -1e-6 * scale)
+    it1 = info1.get("iter", 0)
     assert xs[n] < 0, "phase I did not find a strictly feasible point"
     x = xs[:n]
     assert lambda_max(prob, x) < 0
@@ -344,7 +361,22 @@ def solve(prob, gamma_start=None, U=1e4, tol=1e-9, verbose=False):
     gamma = np.ones(prob["nvar"])
     gamma[prob["keep"]] = x[:ng]
     return {"obj": float(prob["c"] @ x), "dual_obj": info["dobj"], "gap": info["gap"], "dual_residual": info["rd"], "x": x,
-            "gamma": gamma, "newton": it1 + info["iter"], "lambda_max": lambda_max(prob, x), "U": U}
+            "gamma": gamma, "newton": it1 + info["iter"], "lambda_max": lambda_max(prob, x), "U": U,
+            "X": info.get("X"), "xl": info.get("xl"), "xu": info.get("xu")}
+
+
+def certificate(prob, x, X, xl, xu, U):
+    """Solver-free check of a stored solution.  Returns (primal objective, lambda_max over the blocks, dual objective,
+    max |dual residual|, rd' x): x is feasible iff lambda_max <= 0 and 0 <= x[:ng] <= U, so the optimum is AT MOST the
+    primal objective; with X_j, xl, xu >= 0 weak duality gives  c'y >= dual objective + rd'y  for every feasible y."""
+    c, ng = prob["c"], prob["ng"]
+    rd = c.copy()
+    dobj = -U * float(np.sum(xu))
+    for b, Xj in zip(prob["blocks"], X):
+        rd[b["V"]] += b["A"].reshape(len(b["V"]), -1) @ Xj.ravel()
+        dobj += float(np.sum(Xj * b["Z0"]))
+    rd[:ng] += -xl + xu
+    return float(c @ x), lambda_max(prob, x), dobj, float(np.abs(rd).max()), float(rd @ x)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -392,13 +424,18 @@ def main():
     prob = problem_from_handoff(d, cliques, mode)
     print(f"{os.path.basename(path)} [{mode}]: {len(prob['blocks'])} blocks, {prob['ng']} multipliers + {prob['ns']} splits, "
           f"build {time.time() - t0:.1f} s", flush=True)
-    start = d["gamma_start"] if "gamma_start" in d else None
+    start = None
+    if "--start" in sys.argv:   # multipliers of the dense optimum (tests/golden/scale_W10_D10_optimum.json) as a start
+        res = json.load(open(sys.argv[sys.argv.index("--start") + 1]))
+        start = np.array(res["oracle_optimum"][str(int(d["beta"]))]["gamma"])
     r = solve(prob, gamma_start=start, verbose="-v" in sys.argv)
     print(f"  optimum {r['obj']:.8f}  lambda_max over blocks {r['lambda_max']:.2e}  {r['newton']} Newton steps, "
           f"{time.time() - t0:.0f} s", flush=True)
+    print(f"  dual objective {r['dual_obj']:.8f}  gap {r['gap']:.1e}  dual residual {r['dual_residual']:.1e}", flush=True)
     if len(sys.argv) > 3 and not sys.argv[3].startswith("-"):
-        json.dump({"obj": r["obj"], "lambda_max": r["lambda_max"], "newton": r["newton"], "mode": mode,
-                   "gamma": r["gamma"].tolist(), "splits": r["x"][prob["ng"]:].tolist()}, open(sys.argv[3], "w"))
+        np.savez_compressed(sys.argv[3], obj=r["obj"], dual_obj=r["dual_obj"], lambda_max=r["lambda_max"], U=r["U"],
+                            iterations=r["newton"], mode=mode, x=r["x"], gamma=r["gamma"],
+                            X=np.concatenate([Xj.ravel() for Xj in r["X"]]), xl=r["xl"], xu=r["xu"])
 
 
 if __name__ == "__main__":

@@ -786,14 +786,49 @@ def test_lambda_max_matrix_free(ctx, xdims, beta, kind):
     b.set_inputs(to_numeric_batch(nb, net, qs))
     b.bounds()
     b.prepare()
-    lam, its = b.lambda_max(max_iters=400, tol=1e-12)
+    lam, its, resid, conv = b.lambda_max(max_iters=400, tol=1e-10, full=True)
+    assert conv.all()
     for i, q in enumerate(qs):
         Z = o.run_query(net, beta, q, form="closed")["Z"]
         ev = np.linalg.eigvalsh(Z)
         scale = max(abs(ev[0]), abs(ev[-1]))
         assert abs(lam[i] - ev[-1]) <= 1e-9 * scale, (lam[i], ev[-1], its[i])
         assert lam[i] <= ev[-1] + 1e-12 * scale           # a Ritz value never exceeds lambda_max
+        assert np.abs(ev - lam[i]).min() <= resid[i] + 1e-12 * scale   # an eigenvalue lies within the residual
         assert 1 <= its[i] <= min(400, Z.shape[0])
+    b.close()
+
+
+def test_lambda_max_reports_non_convergence(ctx):
+    """Zdim >> max_iters with lambda_max near zero -- the regime of the acceptance gate eigmax(Z) <= 1e-4
+    (experiments/acas.jl:76-79): a run that stops at max_iters must say so (converged = 0, NNSDP_ERR_NOCONV from the
+    plain call) and its value must be a LOWER bound; with enough iterations the same batch converges."""
+    import nnsdp_b200 as nb
+
+    xdims, beta = [2, 300, 300, 2], 1
+    net = rand_net(xdims, seed=1, sigma=0.0)       # zero weights: Z is (almost) diagonal, eigenvalues ~ -2 gamma
+    rng = np.random.default_rng(0)
+    q = rand_query(net, beta, rng, kind="hplane", radius=0.1)
+    q.gsec[:] = 0.0
+    q.gbnd[:] = rng.uniform(0.5, 2.0, q.gbnd.size)
+    q.gbnd[17] = 1e-9                               # lambda_max = -2e-9 against a spectral scale of ~4
+    q.qc_out = o.QcReachHplane(np.zeros(2))
+    dnet = nb.Net(ctx, net.xdims, net.Ms)
+    b = nb.Batch(dnet, beta, Qcap=1, ring=1)
+    b.set_inputs(to_numeric_batch(nb, net, [q]))
+    b.bounds()
+    b.prepare()
+    ev = np.linalg.eigvalsh(o.run_query(net, beta, q, form="closed")["Z"])
+    scale = max(abs(ev[0]), abs(ev[-1]))
+    assert abs(ev[-1]) < 1e-6 * scale
+    lam, its, resid, conv = b.lambda_max(max_iters=12, tol=1e-10, full=True)
+    assert conv[0] == 0 and its[0] == 12 and resid[0] > 1e-10 * scale
+    assert lam[0] <= ev[-1] + 1e-12 * scale and lam[0] < ev[-1] - 1e-6 * scale      # a lower bound, visibly short
+    with pytest.raises(nb.NnsdpError) as e:
+        b.lambda_max(max_iters=12, tol=1e-10)
+    assert e.value.code == -6
+    lam, its, resid, conv = b.lambda_max(max_iters=700, tol=1e-10, full=True)
+    assert conv[0] == 1 and abs(lam[0] - ev[-1]) <= 1e-9 * scale
     b.close()
 
 
@@ -813,7 +848,7 @@ def test_lambda_max_negative_definite_certificate(ctx):
     b.set_inputs(to_numeric_batch(nb, net, [q]))
     b.bounds()
     b.prepare()
-    lam, _ = b.lambda_max(max_iters=100, tol=1e-12)
+    lam, _ = b.lambda_max(max_iters=100, tol=1e-10)
     Z = o.run_query(net, beta, q, form="closed")["Z"]
     ev = np.linalg.eigvalsh(Z)
     assert ev[-1] < 0 and abs(lam[0] - ev[-1]) <= 1e-9 * abs(ev[0])
@@ -985,7 +1020,7 @@ def test_crown_and_lambda_max_over_several_chunks(ctx):
     b.set_inputs(to_numeric_batch(nb, net, qs))
     b.bounds()
     b.prepare()
-    lam, its = b.lambda_max(max_iters=100, tol=1e-12)
+    lam, its = b.lambda_max(max_iters=100, tol=1e-10)
     for i in (0, 63, 64, 69):
         ev = np.linalg.eigvalsh(o.run_query(net, beta, qs[i])["Z"])
         assert abs(lam[i] - ev[-1]) <= 1e-9 * max(abs(ev[0]), abs(ev[-1]))
@@ -1036,7 +1071,7 @@ def test_random_shapes_around_planner_thresholds(ctx, xdims, beta, kind):
         assert np.array_equal(Zd[i], Zd[i].T)
         for blk, (Ck, _, _) in zip(nb.split_blocks(out[i], cliques), cliques):
             assert np.array_equal(blk, Zd[i][np.ix_(Ck - 1, Ck - 1)])
-    lam, _ = b.lambda_max(max_iters=300, tol=1e-12)
+    lam, _, _, _ = b.lambda_max(max_iters=300, tol=1e-10, full=True)
     ev = np.linalg.eigvalsh(o.run_query(net, beta, qs[1], form="closed")["Z"])
     assert abs(lam[1] - ev[-1]) <= 1e-8 * max(abs(ev[0]), abs(ev[-1]))
     b.close()
@@ -1170,7 +1205,7 @@ def test_recorded_optimum_minimiser_through_the_device_pipeline(ctx):
         b.run(out)
         for blk, rb in zip(nb.split_blocks(out[0], ref["cliques"]), ref["blocks"]):
             assert relerr(blk, rb) <= 1e-10        # multipliers span 1e-9 .. 1e4: normwise per block
-        lam, its = b.lambda_max(max_iters=400, tol=1e-12)
+        lam, its = b.lambda_max(max_iters=400, tol=1e-10)
         want = np.linalg.eigvalsh(0.5 * (ref["Z"] + ref["Z"].T)).max()
         scale = np.abs(ref["Z"]).max()
         assert abs(lam[0] - want) <= 1e-8 * scale and lam[0] <= 1e-7 * scale
