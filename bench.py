@@ -34,43 +34,169 @@ WORKLOADS = {
     "stress-W1000-D20-beta2-Q1024": dict(W=1000, D=20, beta=2, Q=1024, ring=32),   # 32 slots = 42.6 GB of blocks in HBM
     "mid-W100-D50-beta2-Q1024": dict(W=100, D=50, beta=2, Q=1024, ring=256),
     "tiny-W10-D10-beta1-Q64": dict(W=10, D=10, beta=1, Q=64, ring=64),
+    # BASELINE configs[2]: experiments/reach.jl / findReach2Dpoly (src/NnSdp.jl:73-95): one net and box, 64 hyperplane
+    # directions -- a reach batch (shared bounds and multipliers, per-query normal and gamma_out)
+    "reach-W20-D10-beta2-Q64": dict(W=20, D=10, beta=2, Q=64, ring=64, kind="reach"),
+    # BASELINE configs[3]: ACAS Xu shape 5 x (6 x 50) x 5 (exts/nnet_parser.jl), 45 safety queries (one vnnlib property
+    # flattened over its boxes and half-spaces, experiments/vnnlib_utils.jl:18-56)
+    "acas-5x50x6-beta2-Q45": dict(xdims=[5] + [50] * 6 + [5], beta=2, Q=45, ring=45, kind="acas"),
 }
+EXTRA_WORKLOADS = ("mid-W100-D50-beta2-Q1024", "tiny-W10-D10-beta1-Q64", "reach-W20-D10-beta2-Q64", "acas-5x50x6-beta2-Q45")
 DEFAULT_WORKLOAD = "stress-W1000-D20-beta2-Q1024"
-# dram__bytes_read.sum + dram__bytes_write.sum per launch from the `ncu --set full` capture of the same
-# command (profiles/): filled in when a capture exists for the current kernels, else null.
-NCU_TRAFFIC = {  # DRAM bytes (write + read) of one 32-query launch / 4, profiles/r1_emit_full.summary.csv
-    "emit_fill_kernel": (33.256634e9 + 480.637184e6) / 4,    # algorithmic 8.17 GB per 8 queries
-    "emit_window_kernel": (9.852402e9 + 476.953344e6) / 4,   # algorithmic 2.46 GB (+ the W tiles it reads)
-    "emit_edge_kernel": (0.055518e9 + 49.865472e6) / 4,
-}
 
 
 def make_workload(name: str, rank: int, Q: int | None = None, radius_scale: float = 1.0):
     """Seeded synthetic inputs.  Returns (xdims, Ms, inputs)."""
     w = WORKLOADS[name]
-    W, D, beta = w["W"], w["D"], w["beta"]
+    beta = w["beta"]
     Q = Q or w["Q"]
-    xdims = [2] + [W] * D + [2]
+    xdims = w.get("xdims") or [2] + [w["W"]] * w["D"] + [2]
+    W, D = max(xdims[1:-1]), len(xdims) - 2
+    n_in, n_out = xdims[0], xdims[-1]
     rng = np.random.default_rng(1000 * D + W)          # net: the same on every rank
     sigma = 2.0 / np.sqrt(W * np.log(W))               # scripts/make_networks.jl:44
     Ms = []
     for k in range(len(xdims) - 1):
         Ms.append(sigma * rng.standard_normal((xdims[k + 1], xdims[k] + 1)))
     rq = np.random.default_rng(777 + rank)             # queries: distinct per rank
-    acdim = W * D
+    acdim = sum(xdims[1:-1])
     lamdim = sum(range(acdim - beta, acdim + 1))
-    centre = rq.uniform(0.5, 1.5, (Q, 2))
+    kind = w.get("kind", "safety")
+    if kind == "reach":                                # shared box and multipliers, one hyperplane normal per query
+        th = 2 * np.pi * np.arange(Q) / Q
+        inputs = dict(x1min=np.full((1, n_in), 0.5), x1max=np.full((1, n_in), 1.5), gamma_in=rq.random((1, n_in)),
+                      gamma_bnd=rq.random((1, acdim)), gamma_sec=rq.random((1, lamdim + 2 * acdim)),
+                      out_vec=np.stack([np.cos(th), np.sin(th)], 1), gamma_out=rq.random((Q, 1)))
+        return xdims, Ms, beta, inputs
+    centre = rq.uniform(0.5, 1.5, (Q, n_in))
     radius = rq.uniform(0.01, 0.5, (Q, 1)) * radius_scale   # radius_scale << 1: stable ReLUs, Gram-heavy
-    normal = np.array([1.0, 0.0])
-    S = np.zeros((5, 5))
-    S[2:4, 4] = normal
-    S[4, 2:4] = normal
-    S[4, 4] = -2.0 * 1.0                               # hplaneS([1,0], 1.0) (src/Utils/qc.jl:27-38)
+    sd = n_in + n_out + 1
+    if kind == "acas":                                 # one half-space per query: hplaneS(-A_i, -b_i - 1e-4)
+        normals = rq.standard_normal((Q, n_out))
+        S = np.zeros((Q, sd, sd))
+        S[:, n_in:n_in + n_out, sd - 1] = normals
+        S[:, sd - 1, n_in:n_in + n_out] = normals
+        S[:, sd - 1, sd - 1] = -2.0 * rq.random(Q)
+        radius = radius * 0.1
+    else:
+        normal = np.zeros(n_out)
+        normal[0] = 1.0
+        S = np.zeros((1, sd, sd))
+        S[0, n_in:n_in + n_out, sd - 1] = normal
+        S[0, sd - 1, n_in:n_in + n_out] = normal
+        S[0, sd - 1, sd - 1] = -2.0 * 1.0              # hplaneS([1,0], 1.0) (src/Utils/qc.jl:27-38)
     inputs = dict(
         x1min=centre - radius, x1max=centre + radius,
-        gamma_in=rq.random((Q, 2)), gamma_bnd=rq.random((Q, acdim)),
-        gamma_sec=rq.random((Q, lamdim + 2 * acdim)), out_S=S[None])
+        gamma_in=rq.random((Q, n_in)), gamma_bnd=rq.random((Q, acdim)),
+        gamma_sec=rq.random((Q, lamdim + 2 * acdim)), out_S=S)
     return xdims, Ms, beta, inputs
+
+
+def numeric_batch(nb, name, inp):
+    kind = nb.OUT_HPLANE if WORKLOADS[name].get("kind") == "reach" else nb.OUT_SAFETY
+    return nb.NumericBatch(out_kind=kind, **inp)
+
+
+def ncu_traffic(kernel):
+    """dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of `kernel` from the committed `ncu --set full`
+    summary of this round (profiles/r2_emit_full.summary.csv: a 32-query pass of the stress workload), or None.
+    Fails loudly when the capture does not hold the kernel: a stale table must not go unnoticed."""
+    import csv
+
+    path = os.path.join(ROOT, "profiles", "r2_emit_full.summary.csv")
+    if not os.path.exists(path):
+        return None
+    rows = list(csv.reader(open(path)))
+    hdr = rows[0]
+    unit = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+
+    def col(prefix):
+        i = [j for j, h in enumerate(hdr) if h.startswith(prefix)][0]
+        return i, unit[hdr[i].split("[")[1].rstrip("]")]
+
+    (ir, ur), (iw, uw) = col("dram__bytes_read.sum"), col("dram__bytes_write.sum")
+    for r in rows[1:]:
+        if r[0].split("<")[0] == kernel:
+            return float(r[ir]) * ur + float(r[iw]) * uw
+    raise RuntimeError(f"{path} holds no launch of {kernel}: re-capture the profile (tools/ncu_summary.py)")
+
+
+def quick_measure(nb, torch, name, peak, steps=5, warmup=3):
+    """Device-timed dense and packed passes of one of the other BASELINE configs (single GPU, short)."""
+    w = WORKLOADS[name]
+    xdims, Ms, beta, inp = make_workload(name, 0)
+    Q = w["Q"]
+    ctx = nb.Context([torch.cuda.current_device()])
+    net = nb.Net(ctx, xdims, Ms)
+    sz = net.sizes(beta)
+    out = {"workload": name, "xdims": f"{xdims[0]}, {max(xdims[1:-1])} x {len(xdims) - 2}, {xdims[-1]}", "beta": beta, "queries": Q,
+           "cliques_per_query": sz["ncliques"], "dense_block_bytes_per_query": 8 * sz["sum_ck_sq"]}
+    nbatch = numeric_batch(nb, name, inp)
+    for fmt in ("dense", "packed"):
+        b = nb.Batch(net, beta, Qcap=Q, ring=min(w["ring"], Q), packed=(fmt == "packed"))
+        b.set_inputs(nbatch, Q=Q)
+        run = (lambda: b.run_packed(None)) if fmt == "packed" else (lambda: b.run(None))
+        for _ in range(warmup):
+            run()
+        b.stage_reset()
+        b.sync()
+        torch.cuda.synchronize()
+        b.event_record(0)
+        for _ in range(steps):
+            run()
+        b.event_record(1)
+        b.sync()
+        torch.cuda.synchronize()
+        ms = b.elapsed_ms() / steps
+        emit_ms = b.stage_ms("emit")[0] / steps
+        nbytes = b.packed_stats()["emitted_bytes"] if fmt == "packed" else 8.0 * sz["sum_ck_sq"] * Q
+        launches = sum(b.stage_ms(k)[1] for k in ("bounds", "prepare", "gram", "emit")) / steps
+        out[fmt] = {"queries_per_s": Q / (ms * 1e-3), "ms_per_step": ms, "us_per_query": 1e3 * ms / Q,
+                    "emitter_ms": emit_ms, "emitted_bytes_per_step": nbytes,
+                    "emitter_gbs": nbytes / max(emit_ms, 1e-9) / 1e6, "emitter_frac_of_peak": nbytes / max(emit_ms, 1e-9) / 1e6 / peak,
+                    "launches_per_step": launches,
+                    "stage_ms": {k: b.stage_ms(k)[0] / steps for k in ("bounds", "prepare", "gram", "emit")}}
+        b.close()
+    net.close()
+    return out
+
+
+def crown_line(nb, torch, net, name, beta, inp, Q, steps=2):
+    """The stress workload with the reference's DEFAULT bounds (IntervalsAutoLirpa -> CROWN on the device) instead of
+    interval arithmetic: realistic bounds leave stably-active neurons in every layer, so the FP64 tensor-core Gram
+    contractions (K3) run on wide layers.  Bounded sample of Q queries; packed records left in HBM."""
+    sub = {k: (v[:Q] if v.shape[0] >= Q and v.shape[0] != 1 else v) for k, v in inp.items()}
+    b = nb.Batch(net, beta, Qcap=Q, ring=min(Q, 16), packed=True)
+    b.set_inputs(numeric_batch(nb, name, sub), Q=Q)
+    b.set_bounds_method("crown")
+    b.run_packed(None)
+    b.stage_reset()
+    b.sync()
+    torch.cuda.synchronize()
+    b.event_record(0)
+    for _ in range(steps):
+        b.run_packed(None)
+    b.event_record(1)
+    b.sync()
+    torch.cuda.synchronize()
+    ms = b.elapsed_ms() / steps
+    st = {k: b.stage_ms(k)[0] / steps for k in ("bounds", "prepare", "gram", "emit")}
+    ncon, nact = b.gram_stats()
+    W = WORKLOADS[name]["W"]
+    flops = float(W) * (W + 128) * nact          # executed: upper 128 x 128 tile pairs, 2 flops per (entry, active neuron)
+    full = 2.0 * W * W * nact                    # algorithmic: the full W' diag W product over the active neurons
+    dgemm_peak = 36.06                           # TFLOP/s, cuBLAS DGEMM 8192^3 on this pool (profiles/r1_probe_dgemm.txt)
+    out = {"bounds": "crown (nnsdp_batch_set_bounds_method: the reference's default IntervalsAutoLirpa)", "queries": Q,
+           "queries_per_s": Q / (ms * 1e-3), "ms_per_step": ms, "stage_ms": st,
+           "gram_contractions_per_step": ncon, "gram_active_rows_per_step": nact,
+           "present_diag_cells_per_query": b.packed_stats()["present_optional_cells"] / Q,
+           "roofline": {"bound": "tensor", "kernel": "gram_kernel (FP64 DMMA)", "achieved": flops / max(st["gram"], 1e-9) / 1e9,
+                        "achieved_algorithmic": full / max(st["gram"], 1e-9) / 1e9, "peak": dgemm_peak, "unit": "TFLOP/s",
+                        "frac": flops / max(st["gram"], 1e-9) / 1e9 / dgemm_peak,
+                        "peak_source": "measured cuBLAS DGEMM on this pool (tools/probe_dgemm.cu, profiles/r1_probe_dgemm.txt); "
+                                       "MEASURED_PEAKS.json has no FP64 figure"}}
+    b.close()
+    return out
 
 
 # ------------------------------------------------------------------------------------------
@@ -277,7 +403,7 @@ def run_ours(args):
     sz = net.sizes(beta)
     ring = min(args.ring or w["ring"], Q)
     batch = nb.Batch(net, beta, Qcap=Q, ring=ring)
-    nbatch = nb.NumericBatch(out_kind=nb.OUT_SAFETY, **inp)
+    nbatch = numeric_batch(nb, name, inp)
     batch.set_inputs(nbatch, Q=Q)
 
     def barrier():
@@ -353,7 +479,8 @@ def run_ours(args):
     pass_gbs = pass_bytes / (emit_ms / passes * 1e-3) / 1e9
     roofline = {"bound": "hbm", "kernel": dom["kernel"], "achieved": dom["achieved"], "peak": peak, "unit": "GB/s",
                 "frac": dom["achieved"] / peak,
-                "traffic": (NCU_TRAFFIC[dom["kernel"]] * q_per_pass / 8.0) if dom["kernel"] in NCU_TRAFFIC and name == DEFAULT_WORKLOAD else None,
+                "traffic": (ncu_traffic(dom["kernel"]) * q_per_pass / 32.0) if name == DEFAULT_WORKLOAD and ncu_traffic(dom["kernel"]) else None,
+                "traffic_source": "profiles/r2_emit_full.summary.csv (ncu --set full, one 32-query pass), scaled to the queries of a pass",
                 "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": dom["algorithmic_bytes_per_launch"], "avg_launch_ms": dom["avg_launch_ms"],
                 "share_of_step": dom["share_of_step"],
@@ -411,8 +538,8 @@ def run_ours(args):
     os.environ.setdefault("NNSDP_HOST_THREADS", str(max(2, min(16, (os.cpu_count() or 16) // max(world, 1)))))
     pin = nb.PinnedBuffer(Qe * sz["sum_ck_sq"])
     eb = nb.Batch(net, beta, Qcap=Qe, ring=min(ring, Qe))
-    sub = {k: (v[:Qe] if v.shape[0] == Q else v) for k, v in inp.items()}
-    ebatch = nb.NumericBatch(out_kind=nb.OUT_SAFETY, **sub)
+    sub = {k: (v[:Qe] if v.shape[0] == Q and Q > 1 else v) for k, v in inp.items()}
+    ebatch = numeric_batch(nb, name, sub)
     h2d = sum(int(np.asarray(v).nbytes) for v in sub.values())
     d2h = Qe * sz["sum_ck_sq"] * 8
 
@@ -461,8 +588,8 @@ def run_ours(args):
     epb = nb.Batch(net, beta, Qcap=Qp, ring=min(pring, Qp), packed=True)
     ppin = nb.PinnedBuffer(Qp * epb.per_query)
     ppresent = np.zeros((Qp, epb.ncells), dtype=np.uint8)
-    psub = {k: (v[:Qp] if v.shape[0] == Q else v) for k, v in inp.items()}
-    pebatch = nb.NumericBatch(out_kind=nb.OUT_SAFETY, **psub)
+    psub = {k: (v[:Qp] if v.shape[0] == Q and Q > 1 else v) for k, v in inp.items()}
+    pebatch = numeric_batch(nb, name, psub)
     ph2d = sum(int(np.asarray(v).nbytes) for v in psub.values())
 
     def e2e_packed_step(flags=0):
@@ -485,6 +612,10 @@ def run_ours(args):
     epb.close()
     ppin.close()
 
+    extras, crown = None, None
+    if rank == 0 and world == 1 and name == DEFAULT_WORKLOAD and not args.no_extras:
+        crown = crown_line(nb, torch, net, name, beta, inp, Q=min(Q, args.crown_queries))
+        extras = [quick_measure(nb, torch, n, peak) for n in EXTRA_WORKLOADS]
     line = None
     if rank == 0:
         # ---- CPU baseline on this box's host cores (bounded sample)
@@ -512,7 +643,8 @@ def run_ours(args):
                        "gram_contractions_per_step": ncon, "gram_active_rows_per_step": nact,
                        "radius_scale": args.radius_scale,
                        "parallelism": f"queries sharded over {world} GPU(s), no collective"},
-            "roofline": roofline, "packed": packed, "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks,
+            "roofline": roofline, "packed": packed, "crown_bounds": crown, "other_workloads": extras,
+            "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks,
             "gpu_launches": int(round(launches_per_step * args.steps)),
             "stage_ms_per_step": {k: stage[k][0] / args.steps for k in stage},
         }
@@ -566,6 +698,8 @@ def main():
     ap.add_argument("--e2e-queries", type=int, default=8)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="developer runs: device-timed figures only")
+    ap.add_argument("--no-extras", action="store_true", help="skip the CROWN-bounds line and the other BASELINE configs")
+    ap.add_argument("--crown-queries", type=int, default=16)
     ap.add_argument("--ring", type=int, default=None, help="override the number of device-resident output slots")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="weak: --queries per GPU (default); strong: --queries in total, sharded over the ranks")

@@ -1872,13 +1872,20 @@ int32_t crown_bounds_device(nnsdp_batch* b) {
                                         du.as<double>() + poff(t), bu.as<double>() + poff(t),
                                         dl.as<double>() + poff(t), st);
     }
-    // x_{k+1} = relu(y_k), k = 0 .. K-2: the output of the (k+1)-layer prefix followed by an identity layer
-    const int post_fused = launch_crown_chain(npd.nd, 0, 1, K - 1, (int)maxn, nq, du.as<double>(), bu.as<double>(),
+    // x_{k+1} = relu(y_k), k = 0 .. K-2: the output of the (k+1)-layer prefix followed by an identity layer.  Its
+    // chains are row scalings of the chains of y_k that are already finished (see crown_post_kernel): one launch.
+    // NNSDP_CROWN_POST_CHAINS=1 walks the K-1 chains instead (the first implementation, kept for A/B runs).
+    static const bool post_chains = [] { const char* e = getenv("NNSDP_CROWN_POST_CHAINS"); return e && e[0] == '1'; }();
+    if (!post_chains) {
+      launches += launch_crown_post(prel.as<double>(), preu.as<double>(), du.as<double>(), bu.as<double>(), dl.as<double>(),
+                                    P, (int)sh.acdim, nq, xmin + q0 * sh.xtot + n0, xmax + q0 * sh.xtot + n0, sh.xtot, st);
+    }
+    const int post_fused = !post_chains ? 1 : launch_crown_chain(npd.nd, 0, 1, K - 1, (int)maxn, nq, du.as<double>(), bu.as<double>(),
                                               dl.as<double>(), P, b->bd.x1min, b->bd.s_x1min, b->bd.x1max, b->bd.s_x1max,
                                               (int)q0, xmin + q0 * sh.xtot, xmax + q0 * sh.xtot, sh.xtot, st);
-    launches += post_fused;
+    if (post_chains) launches += post_fused;
     if (post_fused) {
-      // narrow nets: every target is a CTA of one launch
+      // done above, or (narrow nets, A/B path) every target was a CTA of one launch
     } else if (wavefront) {
       // Narrow nets: all K-1 targets walk back together.  Their rows are stacked (target K-2 first); the step
       // through (relu_j, W_j) handles the rows of every target k > j in one fused launch, after which target j

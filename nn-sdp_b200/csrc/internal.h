@@ -369,6 +369,10 @@ int gemm_set_launch(const double* A, int lda, int M, int Kdim, const double* B, 
 // works on nrows rows starting at row slot row0 of every (half, query) group (Rs = nrows, row0 = 0 for one target)
 int launch_crown_params(const double* l, const double* u, long long stride, int n, int Qc, double* d_u,
                         double* b_u, double* d_l, cudaStream_t st);
+// x_intvs of the hidden layers from the finished pre-activation bounds and relaxations (n stacked neurons per query)
+int launch_crown_post(const double* prel, const double* preu, const double* d_u, const double* b_u, const double* d_l,
+                      long long par_stride, int n, int Qc, double* out_lo, double* out_hi, long long out_stride,
+                      cudaStream_t st);
 int launch_crown_row(const double* srcL, const double* srcU, long long src_row_stride, long long src_q_stride,
                      double* dst, long long dst_row_stride, int nrows, int Qc, int n, const double* d_u,
                      const double* b_u, const double* d_l, long long par_stride, const double* bias_k,

@@ -51,6 +51,28 @@ __global__ void crown_params_kernel(const double* __restrict__ l, const double* 
   d_l[o] = ud > 0.5 ? 1.0 : 0.0;
 }
 
+// Post-activation bounds from the finished pre-activation bounds.  x_{k+1} = relu(y_k) is bounded by the reference as
+// the output of "identity o relu_k o prefix": the backward pass starts from A = I, whose rows leave relu_k as
+// d_u[i] e_i (+ bias b_u[i]) for the upper and d_l[i] e_i for the lower bound.  Every later step is positively
+// homogeneous per row and d >= 0, so the chain of row i is d[i] times the chain of y_k[i] that already produced
+// (prel, preu):  hi(x_{k+1}) = d_u o hi(y_k) + b_u,  lo(x_{k+1}) = d_l o lo(y_k)  -- no second set of chains.
+// Then lb = min(lb, ub), ub = max(lb, ub) (intervals_auto_lirpa.jl:37-39).
+__global__ void crown_post_kernel(const double* __restrict__ prel, const double* __restrict__ preu,
+                                  const double* __restrict__ d_u, const double* __restrict__ b_u,
+                                  const double* __restrict__ d_l, long long par_stride, int n, double* __restrict__ out_lo,
+                                  double* __restrict__ out_hi, long long out_stride) {
+  const int q = blockIdx.y;
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= n) return;
+  const long long o = (long long)q * par_stride + c;
+  double L = __dmul_rn(d_l[o], prel[o]);
+  double U = __dadd_rn(__dmul_rn(d_u[o], preu[o]), b_u[o]);
+  L = fmin(L, U);
+  U = fmax(L, U);
+  out_lo[(long long)q * out_stride + c] = L;
+  out_hi[(long long)q * out_stride + c] = U;
+}
+
 // One chain step for one row of one query: relaxation through relu_k (params of y_k) and the bias part of
 // the linear layer k.  src rows may be shared by all queries (q_stride_src = 0: the target's own W rows).
 //   rows: [2][Qc][nrows][ld]  (0 = lower, 1 = upper);  bias: [2][Qc][nrows]
@@ -445,6 +467,15 @@ crown_chain_kernel(NetDev net, int t_pre, int post, int maxw, int rcap, const do
 int launch_crown_params(const double* l, const double* u, long long stride, int n, int Qc, double* d_u,
                         double* b_u, double* d_l, cudaStream_t st) {
   crown_params_kernel<<<dim3((n + 127) / 128, Qc), 128, 0, st>>>(l, u, stride, n, d_u, b_u, d_l);
+  return 1;
+}
+
+int launch_crown_post(const double* prel, const double* preu, const double* d_u, const double* b_u, const double* d_l,
+                      long long par_stride, int n, int Qc, double* out_lo, double* out_hi, long long out_stride,
+                      cudaStream_t st) {
+  if (n <= 0 || Qc <= 0) return 0;
+  crown_post_kernel<<<dim3((n + 127) / 128, Qc), 128, 0, st>>>(prel, preu, d_u, b_u, d_l, par_stride, n, out_lo, out_hi,
+                                                              out_stride);
   return 1;
 }
 

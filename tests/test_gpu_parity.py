@@ -1252,3 +1252,35 @@ def test_vnnlib_property_as_one_batch(ctx, tmp_path):
         ref = o.run_query(net, beta, q)
         for blk, rb in zip(nb.split_blocks(out[i], cliques), ref["blocks"]):
             assert relerr(blk, rb) <= TOL
+
+
+# ---------------------------------------------------------------------------------------------
+# the hand-off the decomposed SDP was solved from (tests/test_decomposed_cpu.py) is what the library computes
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", ["W10-D10_beta0", "W10-D10_beta2", "W10-D10_beta5", "W10-D20_beta2"])
+def test_affine_handoff_equals_the_committed_fixture(ctx, name):
+    """tests/golden/handoff_*.npz were dumped from nnsdp_affine_get / nnsdp_cliques on a B200
+    (tests/golden/make_handoff.py); recomputing them must give the same index arrays exactly and the same values
+    to 1e-12, and the cliques must be the oracle's makeCliques -- so the certificates of
+    tests/test_decomposed_cpu.py are statements about THIS library's hand-off
+    (/root/reference/src/Methods/chordal_sdp.jl:19-57,96-153)."""
+    import importlib.util
+    import nnsdp_b200 as nb
+
+    spec = importlib.util.spec_from_file_location("make_handoff", os.path.join(GOLD, "make_handoff.py"))
+    mh = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mh)
+    net_name, beta = name.split("_beta")
+    data, rec = mh.handoff(nb, ctx, net_name, int(beta), reps=1)
+    fix = np.load(os.path.join(GOLD, f"handoff_{name}.npz"))
+    for k in ("ent_row", "ent_col", "coo_ent", "coo_var", "ck_off", "ck_idx", "ck1_len", "d_off", "d_idx", "nvar", "nent", "nnz",
+              "var_in", "var_out", "var_bnd", "var_sec"):
+        assert np.array_equal(data[k], fix[k]), k
+    for k in ("z0", "coo_val", "ymin", "ymax", "smin", "smax"):
+        scale = max(np.abs(fix[k]).max(), 1e-300)
+        assert np.abs(data[k] - fix[k]).max() <= 1e-12 * scale, k
+    net = o.load_nnet(os.path.join(GOLD, f"scale-I2-O2-{net_name}.nnet"))
+    import sdp_decomposed as sd
+
+    for (Ck, parts, Ds), (Rk, rparts, rDs) in zip(sd.cliques_from_npz(fix), o.make_cliques(net, int(beta))):
+        assert np.array_equal(Ck, Rk) and len(Ds) == len(rDs) and all(np.array_equal(a, b) for a, b in zip(Ds, rDs))
