@@ -262,7 +262,10 @@ int32_t build_plan(const Shape& sh, int64_t beta, const std::vector<CliqueRanges
     for (const Piece& cp : cols) {
       for (const Piece& rp : rows) {
         TileDev t = make_tile(rp.g0, rp.g1, rp.l0, cp.g0, cp.g1, cp.l0);
-        if (classify && t.prog == PROG_MIXED && plan->tile_rows == 128) {
+        // (the same for a window tile over the block pair (b, b+2) / (b+2, b): only its beta columns / rows next to
+        // layer b+1 carry a window sum, the rest of the 32-column tile is structurally zero)
+        const bool thin_window = (t.prog == PROG_RC && t.cblk == t.rblk + 2) || (t.prog == PROG_CR && t.rblk == t.cblk + 2);
+        if (classify && (t.prog == PROG_MIXED || thin_window) && plan->tile_rows == 128) {
           // A tile is MIXED when several terms meet in it.  Often that is one thin sliver inside a tile
           // whose bulk is a plain copy / fill / window: split at the sliver boundaries and classify the
           // pieces separately, so that only the slivers are evaluated entry by entry.
@@ -276,7 +279,7 @@ int32_t build_plan(const Shape& sh, int64_t beta, const std::vector<CliqueRanges
               for (size_t i = 0; i + 1 < rc.size(); ++i) {
                 TileDev u = make_tile(rc[i], rc[i + 1] - 1, rp.l0 + (rc[i] - rp.g0), cc[j], cc[j + 1] - 1,
                                       cp.l0 + (cc[j] - cp.g0));
-                gain |= (u.prog != PROG_MIXED);
+                gain |= thin_window ? (u.prog == PROG_ZERO) : (u.prog != PROG_MIXED);
                 sub.push_back(u);
               }
             if (gain) {
