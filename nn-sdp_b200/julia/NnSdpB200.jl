@@ -48,6 +48,24 @@ struct QueryInputs
   gamma_out::Ptr{Float64}; gamma_out_stride::Int64
 end
 
+# mirrors `nnsdp_packed_cell`
+struct PackedCell
+  kind::Int32; blk::Int32
+  row0::Int64; col0::Int64; nrows::Int64; ncols::Int64; offset::Int64
+  always::Int32; reserved::Int32
+end
+const CELL_WINDOW, CELL_DIAG, CELL_BAND, CELL_RECT = Int32(1), Int32(2), Int32(3), Int32(4)
+const FORMAT_BLOCKS, FORMAT_DENSE_Z, FORMAT_PACKED = Int32(0), Int32(1), Int32(2)
+
+# the hand-mirrored structs must have the layout of the C header (include/nnsdp_b200.h); checked when the module loads
+function __init__()
+  @assert sizeof(Sizes) == 14 * 8 "nnsdp_sizes layout drifted"
+  @assert sizeof(QueryInputs) == 13 * 16 + 8 "nnsdp_query_inputs layout drifted"
+  @assert fieldoffset(QueryInputs, 19) == 9 * 16 "nnsdp_query_inputs.out_kind offset drifted"   # out_kind is field 19
+  @assert sizeof(PackedCell) == 56 "nnsdp_packed_cell layout drifted"
+  @assert ccall((:nnsdp_version, LIB), Int32, ()) >= 100
+end
+
 lasterror() = unsafe_string(ccall((:nnsdp_last_error, LIB), Cstring, ()))
 check(status::Int32) = status == 0 ? nothing : error("nnsdp_b200 error $(status): $(lasterror())")
 
@@ -212,8 +230,56 @@ function assembleZ(net::DeviceNet, β::Int, qc_input, qc_out, qc_bounded, qc_sec
   return Z
 end
 
+# ---- packed records: the block-sparse upper triangle of Z (NNSDP_FORMAT_PACKED) --------------------------------
+# One record holds every region of Z that can be non-zero once; Z[C_k, C_k] of any clique is a set of sub-rectangles of
+# its cells.  cellView gives a cell as a zero-copy matrix; cliqueBlocks expands a record into the dense blocks the
+# reference's setupZksum! scatters (src/Methods/chordal_sdp.jl:60-93) through the library's own nnsdp_packed_unpack.
+function packedLayout(ffnet::FeedFwdNet, β::Int)
+  n, rec, alw = Ref{Int64}(0), Ref{Int64}(0), Ref{Int64}(0)
+  xd = Int64.(ffnet.xdims)
+  check(ccall((:nnsdp_packed_layout, LIB), Int32,
+              (Int64, Ptr{Int64}, Int64, Int64, Ptr{PackedCell}, Ptr{Int64}, Ptr{Int64}, Ptr{Int64}),
+              ffnet.K, xd, β, 0, C_NULL, n, rec, alw))
+  cells = Vector{PackedCell}(undef, n[])
+  check(ccall((:nnsdp_packed_layout, LIB), Int32,
+              (Int64, Ptr{Int64}, Int64, Int64, Ptr{PackedCell}, Ptr{Int64}, Ptr{Int64}, Ptr{Int64}),
+              ffnet.K, xd, β, n[], cells, n, rec, alw))
+  return cells, rec[], alw[]
+end
+
+cellView(record::AbstractVector{Float64}, c::PackedCell) =
+  reshape(view(record, (c.offset + 1):(c.offset + c.nrows * c.ncols)), Int(c.nrows), Int(c.ncols))
+
+function assemblePacked(net::DeviceNet, β::Int, qc_input, qc_out, qc_bounded, qc_sector, γin, γacs, γout = Float64[])
+  cells, rec, _ = packedLayout(net.ffnet, β)
+  keep = Any[]
+  qi = Ref(query_inputs(qc_input, qc_out, qc_bounded, qc_sector, Vector{Float64}(γin),
+                        [Vector{Float64}(g) for g in γacs], Vector{Float64}(γout), keep))
+  record, present = zeros(rec), zeros(UInt8, length(cells))
+  GC.@preserve keep check(ccall((:nnsdp_assemble_packed, LIB), Int32,
+              (Ptr{Cvoid}, Ptr{Cvoid}, Int64, Int64, Ptr{QueryInputs}, Ptr{Float64}, Ptr{UInt8}),
+              net.ctx.h, net.h, β, 1, qi, record, present))
+  return cells, record, present
+end
+
+function cliqueBlocks(ffnet::FeedFwdNet, β::Int, cliques, record::Vector{Float64}, present::Vector{UInt8})
+  out = Vector{Float64}(undef, sum(length(Ck)^2 for (Ck, _, _) in cliques))
+  check(ccall((:nnsdp_packed_unpack, LIB), Int32,
+              (Int64, Ptr{Int64}, Int64, Ptr{Float64}, Ptr{UInt8}, Int32, Ptr{Float64}),
+              ffnet.K, Int64.(ffnet.xdims), β, record, present, FORMAT_BLOCKS, out))
+  blocks, o = Vector{Matrix{Float64}}(), 0
+  for (Ck, _, _) in cliques
+    n = length(Ck)
+    push!(blocks, reshape(out[o+1:o+n*n], n, n))
+    o += n * n
+  end
+  return blocks
+end
+
 # ---- certificate check: eigmax(Z) without forming Z (src/Methods/Methods.jl:116-117, experiments/acas.jl:71-79) ----
-# λmax of Z(γ) for numeric multipliers, matrix-free Lanczos on the device (nnsdp_batch_lambda_max).
+# λmax of Z(γ) for numeric multipliers, matrix-free Lanczos on the device (nnsdp_batch_lambda_max_ex).  Returns
+# (λ, residual, converged): the Ritz value λ is a LOWER bound of λmax; it certifies eigmax(Z) <= 1e-4 only when
+# `converged` is true (an eigenvalue of Z then lies within `residual` of λ).
 function eigmaxZ(net::DeviceNet, β::Int, qc_input, qc_out, qc_bounded, qc_sector, γin, γacs, γout = Float64[];
                  max_iters::Int = 300, tol::Float64 = 1e-10)
   keep = Any[]
@@ -223,16 +289,18 @@ function eigmaxZ(net::DeviceNet, β::Int, qc_input, qc_out, qc_bounded, qc_secto
   check(ccall((:nnsdp_batch_create, LIB), Int32,
               (Ptr{Cvoid}, Int32, Ptr{Cvoid}, Int64, Int64, Int64, Int32, Ptr{Ptr{Cvoid}}),
               net.ctx.h, 0, net.h, β, 1, 1, 0, h))
-  lam, its = zeros(1), zeros(Int32, 1)
+  lam, its, resid, conv = zeros(1), zeros(Int32, 1), zeros(1), zeros(Int32, 1)
   try
     GC.@preserve keep check(ccall((:nnsdp_batch_set_inputs, LIB), Int32, (Ptr{Cvoid}, Int64, Ptr{QueryInputs}), h[], 1, qi))
     check(ccall((:nnsdp_batch_prepare, LIB), Int32, (Ptr{Cvoid},), h[]))
-    check(ccall((:nnsdp_batch_lambda_max, LIB), Int32, (Ptr{Cvoid}, Int32, Float64, Ptr{Float64}, Ptr{Int32}),
-                h[], max_iters, tol, lam, its))
+    st = ccall((:nnsdp_batch_lambda_max_ex, LIB), Int32,
+               (Ptr{Cvoid}, Int32, Float64, Ptr{Float64}, Ptr{Int32}, Ptr{Float64}, Ptr{Int32}),
+               h[], max_iters, tol, lam, its, resid, conv)
+    st == Int32(-6) || check(st)          # NNSDP_ERR_NOCONV: the outputs are written, converged = 0
   finally
     ccall((:nnsdp_batch_destroy, LIB), Int32, (Ptr{Cvoid},), h[])
   end
-  return lam[1]
+  return lam[1], resid[1], conv[1] == 1
 end
 
 # ---- vnnlib property -> batched safety queries (experiments/vnnlib_utils.jl:18-56) -------------------
@@ -335,9 +403,10 @@ function setupB200!(model, query, qc_out, opts::ChordalB200Options)
   cliques = Methods.makeCliques(query.qcs, ffnet)
   ref_opts = Methods.ChordalSdpOptions(decomp_mode = opts.decomp_mode)
   Zs, _ = Methods.setupZs!(model, cliques, query, ref_opts)
-  col_first = Dict{Int64, Int64}()                      # column -> index of its first entry
-  for e in length(ent_col):-1:1; col_first[ent_col[e]] = e end
-  entry(r, c) = col_first[c] + (r - ent_row[col_first[c]])
+  entry_of = Dict{Tuple{Int64, Int64}, Int64}()         # (row, column) of the cover's upper triangle -> entry number
+  for e in 1:s.nent; entry_of[(ent_row[e], ent_col[e])] = e end
+  @assert length(entry_of) == s.nent
+  entry(r, c) = entry_of[(r, c)]                        # KeyError if a clique reaches outside the cover
   Zksum = [zero(Methods.JuMP.AffExpr) for _ in 1:s.nent]   # distinct objects: add_to_expression! mutates in place
   for (k, (Ck, _, _)) in enumerate(cliques)
     for j in 1:length(Ck), i in 1:j
@@ -345,7 +414,8 @@ function setupB200!(model, query, qc_out, opts::ChordalB200Options)
     end
   end
   Methods.JuMP.@constraint(model, Zvec .== Zksum)
-  vars[:Z] = sparse(ent_row, ent_col, Zvec, sum(ffnet.zdims), sum(ffnet.zdims))   # upper triangle of Z(γ)
+  # Z(γ) as the reference's consumers index it (soln.values[:Z], Methods.jl:116): symmetric, backed by its upper triangle
+  vars[:Z] = Symmetric(sparse(ent_row, ent_col, Zvec, sum(ffnet.zdims), sum(ffnet.zdims)), :U)
   return vars
 end
 
@@ -363,6 +433,6 @@ function Methods.setupReach!(model, query::Methods.ReachQuery, opts::ChordalB200
 end
 
 export Context, DeviceNet, IntervalsB200, IntervalsCrownB200, makeCliquesB200, assembleCliqueBlocks, assembleZ
-export affineForm, ChordalB200Options, eigmaxZ
+export affineForm, ChordalB200Options, eigmaxZ, packedLayout, cellView, assemblePacked, cliqueBlocks
 
 end # module
