@@ -659,32 +659,40 @@ def run_ours(args):
 
 def multi_device_context_check(nb, ndev):
     """The second multi-GPU form of SURVEY.md 8e on the box's GPUs: ONE nnsdp_ctx over `ndev` devices (what a Julia
-    process would hold) shards the queries of a one-shot call over them; the gathered result must equal the
-    single-device result bit for bit, for the dense blocks and for the packed records."""
+    process would hold) shards the queries of a one-shot call over them; the gathered result is compared with the
+    single-device result, for the dense blocks and for the packed records.  Which bounds / affine kernels run depends
+    on how many queries a device gets (<= 8, 9..32, more: different summation orders), so bit-identity is asserted on
+    a net whose kernels do not depend on the query count (widths <= 256) and the wide net is compared to rounding."""
+    out = {"devices": ndev}
     try:
         rng = np.random.default_rng(42)
-        xdims, beta = [2, 300, 270, 2], 2
-        nq = 2 * ndev + 1
-        Ms = [0.1 * rng.standard_normal((xdims[k + 1], xdims[k] + 1)) for k in range(len(xdims) - 1)]
-        acdim = sum(xdims[1:-1])
-        lamdim = sum(range(acdim - beta, acdim + 1))
-        c = rng.uniform(0.5, 1.5, (nq, 2))
-        r = rng.uniform(0.0, 0.05, (nq, 1))
-        A = rng.standard_normal((nq, 5, 5))
-        b = nb.NumericBatch(x1min=c - r, x1max=c + r, gamma_in=rng.random((nq, 2)), gamma_bnd=rng.random((nq, acdim)),
-                            gamma_sec=rng.random((nq, lamdim + 2 * acdim)), out_kind=nb.OUT_SAFETY,
-                            out_S=A + np.transpose(A, (0, 2, 1)))
-        c1 = nb.Context([0])
-        one = nb.assemble_blocks(nb.Net(c1, xdims, Ms), beta, b)
-        cn = nb.Context(list(range(ndev)))
-        netn = nb.Net(cn, xdims, Ms)
-        many = nb.assemble_blocks(netn, beta, b)
-        rec, present, _ = nb.assemble_packed(netn, beta, b)
-        same_packed = all(np.array_equal(nb.packed_unpack(xdims, beta, rec[i], present[i]), one[i]) for i in range(nq))
-        return {"devices": ndev, "queries": nq, "bit_identical": bool(np.array_equal(one, many)),
-                "packed_bit_identical": bool(same_packed)}
+        for tag, xdims in (("narrow", [2, 200, 180, 2]), ("wide", [2, 300, 270, 2])):
+            beta, nq = 2, 2 * ndev + 1
+            Ms = [0.1 * rng.standard_normal((xdims[k + 1], xdims[k] + 1)) for k in range(len(xdims) - 1)]
+            acdim = sum(xdims[1:-1])
+            lamdim = sum(range(acdim - beta, acdim + 1))
+            c = rng.uniform(0.5, 1.5, (nq, 2))
+            r = rng.uniform(0.0, 0.05, (nq, 1))
+            A = rng.standard_normal((nq, 5, 5))
+            b = nb.NumericBatch(x1min=c - r, x1max=c + r, gamma_in=rng.random((nq, 2)), gamma_bnd=rng.random((nq, acdim)),
+                                gamma_sec=rng.random((nq, lamdim + 2 * acdim)), out_kind=nb.OUT_SAFETY,
+                                out_S=A + np.transpose(A, (0, 2, 1)))
+            c1 = nb.Context([0])
+            one = nb.assemble_blocks(nb.Net(c1, xdims, Ms), beta, b)
+            cn = nb.Context(list(range(ndev)))
+            netn = nb.Net(cn, xdims, Ms)
+            many = nb.assemble_blocks(netn, beta, b)
+            rec, present, _ = nb.assemble_packed(netn, beta, b)
+            unp = np.stack([nb.packed_unpack(xdims, beta, rec[i], present[i]) for i in range(nq)])
+            scale = np.abs(one).max()
+            out[tag] = {"queries": nq, "bit_identical": bool(np.array_equal(one, many)),
+                        "packed_equals_dense_of_the_same_context": bool(np.array_equal(unp, many)),
+                        "max_abs_diff_over_scale": float(np.abs(one - many).max() / scale)}
+        out["bit_identical"] = out["narrow"]["bit_identical"] and out["narrow"]["packed_equals_dense_of_the_same_context"]
+        out["wide_equal_to_rounding"] = out["wide"]["max_abs_diff_over_scale"] <= 1e-12
     except Exception as e:  # reported, never fatal for the bench line
-        return {"devices": ndev, "bit_identical": False, "error": repr(e)[:300]}
+        out.update({"bit_identical": False, "error": repr(e)[:300]})
+    return out
 
 
 def main():
