@@ -803,19 +803,10 @@ int32_t nnsdp_batch_create(nnsdp_ctx* ctx, int32_t dev_index, const nnsdp_net* n
     NN_TRY(build_plan(sh, beta, mats, b->packed || !(noclass && noclass[0] == '1'), &b->plan,
                       b->packed ? &b->lay : nullptr));
     b->mats_host = mats;
-    if (b->packed) {
-      std::vector<BandDev> bands;
-      for (const PackedCell& c : b->lay.cells)
-        if (c.kind == PK_BAND) {
-          bands.push_back({(long long)c.offset, (int)c.grow0, (int)c.ncols, c.blk, 0});
-          b->band_max_m = std::max(b->band_max_m, (int)c.ncols);
-        }
-      b->nbands = (int)bands.size();
-      NN_TRY(upload(b->d_bands, bands.data(), bands.size() * sizeof(BandDev), b->st));
-      NN_CUDA(cudaStreamSynchronize(b->st));  // `bands` goes out of scope
-    } else {
-      NN_TRY(build_gather_plan(sh, beta, mats, b->plan, &b->gp));
-    }
+    for (const BandDev& j : b->plan.bands) b->band_max_m = std::max(b->band_max_m, j.m);
+    b->nbands = (int)b->plan.bands.size();
+    NN_TRY(upload(b->d_bands, b->plan.bands.data(), b->plan.bands.size() * sizeof(BandDev), b->st));
+    if (!b->packed) NN_TRY(build_gather_plan(sh, beta, mats, b->plan, &b->gp));
     if (const char* e = getenv("NNSDP_DENSE_GATHER"))  // developer aid: always copy the dense output
       if (e[0] == '1') b->gp.usable = false;
     if (b->gp.usable) {
@@ -837,6 +828,7 @@ int32_t nnsdp_batch_create(nnsdp_ctx* ctx, int32_t dev_index, const nnsdp_net* n
     b->pd.tile_rows = b->plan.tile_rows;
     b->pd.per_query = b->plan.per_query_doubles;
     b->pd.packed = b->plan.skip_absent ? 1 : 0;
+    b->pd.band_inline = b->plan.band_inline ? 1 : 0;
     b->gd.scratch = b->gram.as<double>();
     b->gd.per_query = go;
     b->gd.goff = b->d_goff.as<long long>();
@@ -1050,7 +1042,7 @@ static void emit_pass(nnsdp_batch* b, const GramDev& gd, int q0, int nq, double*
     b->span_end(b->st, l);
     total += l;
   }
-  if (b->packed && b->nbands > 0) {
+  if (b->nbands > 0) {  // after the fill kernel: in-place band of the DIAG ranges (wide layers), BAND cells (packed)
     b->span_begin(ST_EMIT_EDGE, b->st);
     const int l = launch_emit_band(nd.nd, b->bd, gd, b->d_bands.as<BandDev>(), b->nbands, b->band_max_m, b->pd.per_query,
                                    q0, nq, dst, b->st);

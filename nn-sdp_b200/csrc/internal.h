@@ -160,9 +160,19 @@ struct PackedLayout {
   std::vector<int32_t> diag_cell;     // per block (K entries): index of its DIAG cell or -1
   std::vector<int64_t> diag_entries;  // per block: entries the fill strips of its DIAG cell write when present
 };
-struct BandDev {  // one BAND cell for the band kernel
-  long long off;        // offset of the cell inside the record
-  int g0, m, blk, pad;  // first z index, side of the DIAG range, block
+// One job of the band kernel: the band |jr - jc| <= beta inside the square range of a diagonal block that the fill
+// strips of one output matrix cover.  Two ways to get the band right, chosen per plan (PlanHost::band_inline):
+//   inline    (narrow layers) the DIAG strips add the band term to the entries they store; jobs exist only for
+//             the BAND cells of packed records;
+//   separate  (wide layers) the strips store the bulk only and the band kernel, which runs after the fill kernel,
+//             re-writes the band entries in place (ld > 0) -- the strips then need no per-entry test.
+struct BandDev {
+  long long out_off;    // offset of the output matrix (dense formats) / of the DIAG cell (packed) inside one query
+  long long band_off;   // packed records: offset of the BAND cell; -1 in the dense formats
+  int ld, row0, col0;   // in-place patch: leading dimension (0 = none) and local position of the range's first entry
+  int g0, m, blk;       // first z index of the range, its side, the block
+  int optional;         // packed records: the matrix is a DIAG cell, patched only when present for the query
+  int upper_only;       // packed records: entries with row <= column only
 };
 
 struct PlanHost {
@@ -171,6 +181,8 @@ struct PlanHost {
   std::vector<MatDev> mats;
   int64_t per_query_doubles = 0;
   int tile_rows = 0, tile_cols = 0;
+  std::vector<BandDev> bands;    // jobs of the band kernel
+  bool band_inline = true;       // see BandDev
   int n_fill = 0, n_window = 0, n_edge = 0;  // tiles are sorted by kernel class
   bool skip_absent = false;  // packed plans of wide nets: the fill strips of an absent DIAG cell are not written
 };
@@ -286,6 +298,7 @@ struct PlanDev {
   int tile_rows;
   long long per_query;       // doubles per query in the output
   int packed;                // packed records: fill strips of an absent DIAG cell are skipped
+  int band_inline;           // DIAG strips add the band term themselves (else the band kernel patches it in)
 };
 
 // ---------------------------------------------------------------------------------
@@ -396,7 +409,7 @@ int launch_crown_concretize(const double* rowsL, const double* rowsU, long long 
                             const double* x1max, long long s_max, int q_first, const double* bias, double* out_lo,
                             double* out_hi, long long out_stride, int postprocess, cudaStream_t st);
 
-// BAND cells of packed records for queries [q0, q0+nq)
+// band jobs (in-place band of the DIAG ranges, BAND cells of packed records) for queries [q0, q0+nq); after the fill kernel
 int launch_emit_band(const NetDev& net, const BatchDev& b, const GramDev& g, const BandDev* bands, int nbands,
                      int max_m, long long per_query, int q0, int nq, double* out, cudaStream_t st);
 // thin-entry pack: packed[s * nthin + i] = ring[s * per_query + idx[i]] for the nq slots of a chunk

@@ -394,7 +394,7 @@ __device__ __forceinline__ void emit_cr(const NetDev& net, const BatchDev& b, co
 
 // ---- kernel 1: tiles whose bulk is a plain store stream; one (tile, query) per CTA -----------------
 //   ZERO  fill                 SAME  Gram copy | S22 Gram | fill
-//   DIAG  SAME + the (2 beta + 1)-wide band patched in afterwards by the thread that owns the entry
+//   DIAG  SAME + the band term added to the entries with |jr - jc| <= beta as they are stored
 //   AFF   the affine row / column Z[a, :], Z[:, a]
 __device__ __forceinline__ double s22_entry(const double* WK, const double* U, int n_out, int rl, int cl) {
   const int lo = rl < cl ? rl : cl, hi = rl < cl ? cl : rl;  // (min, max): bit-symmetric
@@ -409,7 +409,11 @@ __device__ __forceinline__ double s22_entry(const double* WK, const double* U, i
 // first store of a ZERO strip.  Thread = row inside a TR-row chunk (x column group when the strip is
 // short); for every column the chunks start on a 32 B sector boundary of the output (rows before the strip
 // are masked), so each warp store covers whole sectors although ld is odd.  TR is a power of two.
-__global__ void __launch_bounds__(ETHREADS, 8)
+#ifndef NNSDP_FILL_MINB
+#define NNSDP_FILL_MINB 6
+#endif
+template <bool BAND_INLINE>  // DIAG strips add the band term themselves (narrow layers) or leave it to the band kernel
+__global__ void __launch_bounds__(ETHREADS, NNSDP_FILL_MINB)
 emit_fill_kernel(NetDev net, BatchDev b, GramDev g, PlanDev plan, int q0, int nq,
                  double* __restrict__ out) {
   const int4* dp = reinterpret_cast<const int4*>(plan.strips + blockIdx.x);
@@ -458,7 +462,33 @@ emit_fill_kernel(NetDev net, BatchDev b, GramDev g, PlanDev plan, int q0, int nq
   const double* WK = net.M[K - 1];
   const double* U = b.U + (long long)q * net.n_out * net.n[K - 1];
   const double* G = g.scratch + (long long)slot * g.per_query + goff + rl0;  // G[r + cl*ldG]
-  if (copy) {
+  if (BAND_INLINE && prog == PROG_DIAG) {
+    // The strip crosses the band |jr - jc| <= beta: the entry is  (bulk) + (absent window terms) + band term, in the
+    // operation order of the general programs; everywhere else the bulk value is stored as it is.
+    const int beta = b.beta;
+    const long long acdim = net.acdim;
+    const int jr_base = grow0 - net.n_in - row0, jc0 = gcol0 - net.n_in;  // neuron of local row r: jr_base + r
+    const double* T0 = b.T0 + (long long)q * acdim;
+    const double* Bt = b.Bt + (long long)q * beta * acdim;
+    const double* gbnd = b.gbnd + q * b.s_gbnd;
+    const double* Gc = G + (long long)(cl0 + cg) * ldG;
+    const long long gstep = (long long)ncg * ldG;
+    for (int c = cg; c < ncols; c += ncg, col += cstep, Gc += gstep) {
+      const int jc = jc0 + c;
+      int r = row0 - (int)(((size_t)(col + row0) >> 3) & 3) + tr;
+      for (; r < row_end; r += TR) {
+        if (r < row0) continue;
+        double v = copy ? Gc[r] : (s22 ? s22_entry(WK, U, net.n_out, rl0 + r, cl0 + c) : 0.0);
+        const int d = jr_base + r - jc;
+        if (d >= -beta && d <= beta) {
+          v = 0.0 + v;
+          v += 0.0;
+          v = __dadd_rn(v, band_term(T0, gbnd, Bt, acdim, jc + d, jc));
+        }
+        col[r] = v;
+      }
+    }
+  } else if (copy) {
     const double* Gc = G + (long long)(cl0 + cg) * ldG;
     const long long gstep = (long long)ncg * ldG;
     for (int c = cg; c < ncols; c += ncg, col += cstep, Gc += gstep) {
@@ -472,34 +502,6 @@ emit_fill_kernel(NetDev net, BatchDev b, GramDev g, PlanDev plan, int q0, int nq
     NNSDP_STRIP_LOOP(0.0)
   }
 #undef NNSDP_STRIP_LOOP
-  if (prog == PROG_DIAG) {
-    // band entries |jr - jc| <= beta inside the strip: each is re-written by the thread that stored the
-    // bulk value of that entry (same thread, program order), with the formula of the general programs.
-    // A thread owns at most one row of a column's (2 beta + 1 <= TR) band rows.
-    const int beta = b.beta, n0 = net.n_in;
-    const long long acdim = net.acdim;
-    const int jr0 = grow0 - n0, jc0 = gcol0 - n0;
-    if (jc0 + ncols - 1 + beta < jr0 || jc0 - beta > jr0 + nrows - 1) return;  // no band entry in this strip
-    const double* T0 = b.T0 + (long long)q * acdim;
-    const double* Bt = b.Bt + (long long)q * beta * acdim;
-    const double* gbnd = b.gbnd + q * b.s_gbnd;
-    for (int c = cg; c < ncols; c += ncg) {
-      const int jc = jc0 + c;
-      const int lo = max(jc - beta, jr0), hi = min(jc + beta, jr0 + nrows - 1);
-      if (lo > hi) continue;
-      double* cp = o + (col0 + c) * ld;
-      const int base = row0 - (int)(((size_t)(cp + row0) >> 3) & 3);
-      const int rlo = row0 + (lo - jr0);
-      const int d = (tr - (rlo - base)) & (TR - 1);  // offset of this thread's row inside the band rows
-      if (d > hi - lo) continue;
-      const int r = rlo + d, jr = lo + d;
-      double val = 0.0;
-      if (copy) val += G[r + (long long)(cl0 + c) * ldG];
-      if (s22) val += s22_entry(WK, U, net.n_out, rl0 + r, cl0 + c);
-      val += 0.0;  // the (absent) window terms f1 + f2 of the general formula
-      cp[r] = __dadd_rn(val, band_term(T0, gbnd, Bt, acdim, jr, jc));
-    }
-  }
 }
 
 // ---- kernel 2: RC / CR window sums (128 x 32 tiles, beta <= 4) ------------------------------------
@@ -568,39 +570,46 @@ emit_edge_kernel(NetDev net, BatchDev b, GramDev g, PlanDev plan, int tile0, int
 
 }  // namespace
 
-// ---- BAND cells of packed records: band[t + (beta+1) i] = Z[g0+i, g0+i+t] inside the DIAG range of a block.
-// Same operation sequence as the band patch of the DIAG strips (bit-identical values).
+// ---- the band |jr - jc| <= beta of the DIAG ranges: Z[r, c] = (Gram | S22 Gram | 0) + (absent window terms) +
+// (-2 T[jr, jc] - 2 gamma_bnd [jr = jc]), the operation sequence of the general programs.  In place over what the
+// fill strips stored (plans with separate band handling; stream order makes this kernel the last writer; packed
+// records: only when the DIAG cell is present, upper triangle) and / or into the BAND cell of a packed record.
 namespace {
 __global__ void __launch_bounds__(ETHREADS)
 emit_band_kernel(NetDev net, BatchDev b, GramDev g, const BandDev* __restrict__ bands, long long per_query, int q0,
                  double* __restrict__ out) {
   const BandDev bd = bands[blockIdx.y];
-  const int slot = blockIdx.z, q = q0 + slot, K = net.K, beta = b.beta, nt = beta + 1;
+  const int slot = blockIdx.z, q = q0 + slot, K = net.K, beta = b.beta, nt = 2 * beta + 1;
   const int idx = blockIdx.x * ETHREADS + threadIdx.x;
   if (idx >= bd.m * nt) return;
-  const int i = idx / nt, t = idx - i * nt;
-  double val = 0.0;
-  if (i + t < bd.m) {
-    const int Br = bd.blk, n0 = net.n_in;
-    const long long acdim = net.acdim;
-    const int rl = bd.g0 - net.off[Br] + i, cl = rl + t;
-    const int jr = bd.g0 + i - n0, jc = jr + t;
-    if (Br <= K - 2 && b.cnt[(long long)q * K + Br] > 0)
-      val += g.scratch[(long long)slot * g.per_query + g.goff[Br] + rl + (long long)cl * g.ldG[Br]];
-    if (Br == K - 1 && b.has_s22)
-      val += s22_entry(net.M[K - 1], b.U + (long long)q * net.n_out * net.n[K - 1], net.n_out, rl, cl);
-    val += 0.0;
-    val = __dadd_rn(val, band_term(b.T0 + (long long)q * acdim, b.gbnd + q * b.s_gbnd, b.Bt + (long long)q * beta * acdim,
-                                   acdim, jr, jc));
+  const int i = idx / nt, t = idx - i * nt - beta, c = i + t;  // entry (i, c) of the range, |t| <= beta
+  if (bd.upper_only && t < 0) return;
+  double* o = out + (long long)slot * per_query;
+  if (c < 0 || c >= bd.m) {  // outside the range: the BAND cell holds a zero there
+    if (bd.band_off >= 0 && t >= 0) o[bd.band_off + t + (long long)(beta + 1) * i] = 0.0;
+    return;
   }
-  out[(long long)slot * per_query + bd.off + idx] = val;
+  const int Br = bd.blk, n0 = net.n_in;
+  const long long acdim = net.acdim;
+  const int rl = bd.g0 - net.off[Br] + i, cl = rl + t;
+  const int jr = bd.g0 + i - n0, jc = jr + t;
+  const bool copy = Br <= K - 2 && b.cnt[(long long)q * K + Br] > 0;
+  const bool s22 = Br == K - 1 && b.has_s22;
+  double val = 0.0;
+  if (copy) val += g.scratch[(long long)slot * g.per_query + g.goff[Br] + rl + (long long)cl * g.ldG[Br]];
+  if (s22) val += s22_entry(net.M[K - 1], b.U + (long long)q * net.n_out * net.n[K - 1], net.n_out, rl, cl);
+  val += 0.0;
+  val = __dadd_rn(val, band_term(b.T0 + (long long)q * acdim, b.gbnd + q * b.s_gbnd, b.Bt + (long long)q * beta * acdim,
+                                 acdim, jr, jc));
+  if (bd.ld > 0 && (!bd.optional || copy || s22)) o[bd.out_off + (bd.row0 + i) + (long long)(bd.col0 + c) * bd.ld] = val;
+  if (bd.band_off >= 0 && t >= 0) o[bd.band_off + t + (long long)(beta + 1) * i] = val;
 }
 }  // namespace
 
 int launch_emit_band(const NetDev& net, const BatchDev& b, const GramDev& g, const BandDev* bands, int nbands,
                      int max_m, long long per_query, int q0, int nq, double* out, cudaStream_t st) {
   if (nbands <= 0 || nq <= 0 || max_m <= 0) return 0;
-  const int nx = (max_m * (b.beta + 1) + ETHREADS - 1) / ETHREADS;
+  const int nx = (max_m * (2 * b.beta + 1) + ETHREADS - 1) / ETHREADS;
   emit_band_kernel<<<dim3(nx, nbands, nq), ETHREADS, 0, st>>>(net, b, g, bands, per_query, q0, out);
   return 1;
 }
@@ -636,7 +645,8 @@ int launch_emit(const NetDev& net, const BatchDev& b, const GramDev& g, const Pl
   const int egroup = egroup_env > 0 ? egroup_env : (nq >= 64 ? SLOT_GROUP : (nq >= 16 ? 2 : 1));
   int launches = 0;
   if (plan.n_fill > 0 && (which < 0 || which == 0)) {
-    emit_fill_kernel<<<dim3(plan.n_fill, nq), ETHREADS, 0, st>>>(net, b, g, plan, q0, nq, out);
+    if (plan.band_inline) emit_fill_kernel<true><<<dim3(plan.n_fill, nq), ETHREADS, 0, st>>>(net, b, g, plan, q0, nq, out);
+    else emit_fill_kernel<false><<<dim3(plan.n_fill, nq), ETHREADS, 0, st>>>(net, b, g, plan, q0, nq, out);
     ++launches;
   }
   if (plan.n_window > 0 && (which < 0 || which == 1)) {

@@ -3,6 +3,7 @@
 // make_cliques_host restates makeCliques (reference: src/Methods/chordal_cliques.jl:13-59)
 // with index arithmetic only; nothing is materialised as a selector matrix (the reference
 // builds Ec(Ck, Zdim) at src/Methods/chordal_sdp.jl:54 and then discards it).
+#include <stdint.h>
 #include <stdlib.h>
 
 #include <algorithm>
@@ -342,8 +343,14 @@ int32_t build_plan(const Shape& sh, int64_t beta, const std::vector<CliqueRanges
     auto flush = [&](const TileDev& m) {
       const int nchunk = (m.nrows + strip_rows - 1) / strip_rows;
       const int h = (m.nrows + nchunk - 1) / nchunk;
-      // short strips are made wider so that a CTA still has ~32 KB to write (at most a tile's 32 columns)
-      const int strip_cols = std::max(strip_cols_min, std::min(32, 4096 / std::max(h, 1)));
+      // short strips are made wider so that a CTA still has ~32 KB to write (tall ones: at most a tile's 32 columns;
+      // strips of at most 128 rows -- narrow layers -- up to 128 columns, in equal parts)
+      int strip_cols = std::max(strip_cols_min, std::min(32, 4096 / std::max(h, 1)));
+      if (h <= 128) {
+        const int limit = std::max(strip_cols_min, std::min(128, 8192 / std::max(h, 1)));
+        const int nparts = (m.ncols + limit - 1) / limit;
+        strip_cols = (m.ncols + nparts - 1) / nparts;
+      }
       for (int c0 = 0; c0 < m.ncols; c0 += strip_cols)
         for (int r0 = 0; r0 < m.nrows; r0 += h) {
           TileDev u = m;
@@ -356,6 +363,8 @@ int32_t build_plan(const Shape& sh, int64_t beta, const std::vector<CliqueRanges
           strips.push_back(u);
         }
     };
+    // vertical merge of equal column ranges, then horizontal merge of equal row ranges
+    std::vector<TileDev> vm;
     for (size_t i = 0; i < colv.size();) {
       TileDev m = colv[i];
       size_t j = i + 1;
@@ -368,9 +377,39 @@ int32_t build_plan(const Shape& sh, int64_t beta, const std::vector<CliqueRanges
         if (n.prog == PROG_DIAG) m.prog = PROG_DIAG;
         m.flags |= n.flags;
       }
+      vm.push_back(m);
+      i = j;
+    }
+    std::stable_sort(vm.begin(), vm.end(), [&](const TileDev& x, const TileDev& y) {
+      if (x.mat != y.mat) return x.mat < y.mat;
+      if (x.row0 != y.row0) return x.row0 < y.row0;
+      if (x.nrows != y.nrows) return x.nrows < y.nrows;
+      if (kind(x) != kind(y)) return kind(x) < kind(y);
+      return x.col0 < y.col0;
+    });
+    for (size_t i = 0; i < vm.size();) {
+      TileDev m = vm[i];
+      size_t j = i + 1;
+      for (; j < vm.size(); ++j) {
+        const TileDev& n = vm[j];
+        if (n.mat != m.mat || n.row0 != m.row0 || n.nrows != m.nrows || kind(n) != kind(m) || n.grow0 != m.grow0) break;
+        if (n.col0 != m.col0 + m.ncols) break;
+        if (m.prog != PROG_ZERO && n.gcol0 != m.gcol0 + m.ncols) break;  // value depends on the global column
+        if (m.prog == PROG_AFF) break;                                    // the affine column stays one column wide
+        m.ncols += n.ncols;
+        if (n.prog == PROG_DIAG) m.prog = PROG_DIAG;
+        m.flags |= n.flags;
+      }
       flush(m);
       i = j;
     }
+    // CTA order = memory order: strips of one column range back to back, top to bottom (consecutive CTAs then write
+    // vertically adjacent, i.e. contiguous, pieces of the same columns)
+    std::stable_sort(strips.begin(), strips.end(), [](const TileDev& x, const TileDev& y) {
+      if (x.mat != y.mat) return x.mat < y.mat;
+      if (x.col0 != y.col0) return x.col0 < y.col0;
+      return x.row0 < y.row0;
+    });
     std::stable_sort(rowjobs.begin(), rowjobs.end(), [](const TileDev& x, const TileDev& y) {
       if (x.mat != y.mat) return x.mat < y.mat;
       return x.col0 < y.col0;
@@ -545,6 +584,47 @@ int32_t build_plan(const Shape& sh, int64_t beta, const std::vector<CliqueRanges
       }
       plan->strips.push_back(d);
     }
+  }
+  {  // band jobs: per (matrix, diagonal block), the square range its SAME / DIAG strips cover
+    plan->bands.clear();
+    struct Box { int64_t lo = INT64_MAX, hi = -1, l0 = 0; bool band = false; };
+    std::vector<std::vector<Box>> box(plan->mats.size(), std::vector<Box>(K));
+    int64_t widest = 0;
+    for (const TileDev& t : plan->tiles) {
+      if (cls(t) != 0 || !(t.prog == PROG_SAME || t.prog == PROG_DIAG) || t.rblk < 1 || t.rblk != t.cblk) continue;
+      Box& bx = box[t.mat][t.rblk];
+      const int64_t lo = std::min<int64_t>(t.grow0, t.gcol0);
+      if (lo < bx.lo) {
+        bx.lo = lo;
+        bx.l0 = (t.grow0 <= t.gcol0) ? t.row0 : t.col0;  // local index of z index lo (rows and columns index alike)
+      }
+      bx.hi = std::max<int64_t>(bx.hi, std::max<int64_t>(t.grow0 + t.nrows, t.gcol0 + t.ncols) - 1);
+      bx.band |= (t.prog == PROG_DIAG);
+      widest = std::max<int64_t>(widest, bx.hi - bx.lo + 1);
+    }
+    // wide layers: tall strips of which a few rows per column lie in the band -> bulk-only strips + the band kernel
+    plan->band_inline = widest < 256;
+    for (size_t m = 0; m < plan->mats.size(); ++m)
+      for (int blk = 1; blk < K; ++blk) {
+        const Box& bx = box[m][blk];
+        if (bx.hi < bx.lo || !bx.band) continue;
+        BandDev j{};
+        j.out_off = plan->mats[m].out_off;
+        j.band_off = -1;
+        j.ld = plan->band_inline ? 0 : plan->mats[m].ld;
+        j.row0 = j.col0 = (int)bx.l0;
+        j.g0 = (int)bx.lo;
+        j.m = (int)(bx.hi - bx.lo + 1);
+        j.blk = blk;
+        if (packed) {  // the matrix is the DIAG cell of the block; its BAND cell holds the band for every query
+          const PackedCell& c = packed->cells[m];
+          j.optional = (c.kind == PK_DIAG);
+          j.upper_only = 1;
+          for (const PackedCell& bc : packed->cells)
+            if (bc.kind == PK_BAND && bc.blk == blk) j.band_off = bc.offset;
+        }
+        if (j.ld > 0 || j.band_off >= 0) plan->bands.push_back(j);
+      }
   }
   plan->n_fill = plan->n_window = plan->n_edge = 0;
   for (const TileDev& t : plan->tiles) {
