@@ -367,27 +367,29 @@ __device__ __forceinline__ void emit_cr(const NetDev& net, const BatchDev& b, co
   __syncthreads();
   if (tr >= t.nrows) return;
   const int cbase = cg * FAST_NCOL;
-  for (int s = 0; s < nslots; ++s) {
-    const long long q = q0 + slot0 + s;
-    const double* Md = b.Md + q * acdim;
-    const double* Bt = b.Bt + q * BETA * acdim;
+  const long long ld = mat.ld;
+  double* o0 = out + (long long)slot0 * plan.per_query + mat.out_off + (t.row0 + tr) + (long long)(t.col0 + cbase) * ld;
+  const int ncl = min(FAST_NCOL, t.ncols - cbase);
+  const double* ws0 = smem + cbase * LDW + tr;
+  const double* Md = b.Md + (long long)(q0 + slot0) * acdim;
+  const double* Bt = b.Bt + (long long)(q0 + slot0) * BETA * acdim;
+  for (int s = 0; s < nslots; ++s, o0 += plan.per_query, Md += acdim, Bt += BETA * acdim) {
     double cf[NTAP];
 #pragma unroll
     for (int tt = 0; tt < NTAP; ++tt) {
       const int j = jr - BETA + tt;
       cf[tt] = (j >= Lc0 && j < Lc0 + nLc) ? m_coef(Md, Bt, acdim, j, jr) : 0.0;
     }
-    double* o = out + (long long)(slot0 + s) * plan.per_query + mat.out_off + (t.row0 + tr) +
-                (long long)(t.col0 + cbase) * mat.ld;
+    double* o = o0;
+    const double* ws = ws0;
+    // (not fully unrolled on purpose: the W values do not depend on the query, and a fully unrolled column loop lets
+    // the compiler hoist all of them out of the query loop -- spills)
 #pragma unroll 4
-    for (int c = 0; c < FAST_NCOL; ++c) {
-      if (cbase + c < t.ncols) {
-        const double* ws = smem + (cbase + c) * LDW + tr;
-        double f = 0.0;
+    for (int c = 0; c < ncl; ++c, o += ld, ws += LDW) {
+      double f = 0.0;
 #pragma unroll
-        for (int tt = 0; tt < NTAP; ++tt) f = fma(ws[tt], cf[tt], f);
-        o[(long long)c * mat.ld] = f;
-      }
+      for (int tt = 0; tt < NTAP; ++tt) f = fma(ws[tt], cf[tt], f);
+      *o = f;
     }
   }
 }
