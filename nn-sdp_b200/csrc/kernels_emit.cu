@@ -373,7 +373,36 @@ __device__ __forceinline__ void emit_cr(const NetDev& net, const BatchDev& b, co
   const double* ws0 = smem + cbase * LDW + tr;
   const double* Md = b.Md + (long long)(q0 + slot0) * acdim;
   const double* Bt = b.Bt + (long long)(q0 + slot0) * BETA * acdim;
-  for (int s = 0; s < nslots; ++s, o0 += plan.per_query, Md += acdim, Bt += BETA * acdim) {
+  // two queries per trip: the 2 beta + 1 values of W a column needs are read from shared memory once for both
+  const long long pq = plan.per_query;
+  int s = 0;
+  for (; s + 2 <= nslots; s += 2, o0 += 2 * pq, Md += 2 * acdim, Bt += 2 * BETA * acdim) {
+    double cf0[NTAP], cf1[NTAP];
+#pragma unroll
+    for (int tt = 0; tt < NTAP; ++tt) {
+      const int j = jr - BETA + tt;
+      const bool in = j >= Lc0 && j < Lc0 + nLc;
+      cf0[tt] = in ? m_coef(Md, Bt, acdim, j, jr) : 0.0;
+      cf1[tt] = in ? m_coef(Md + acdim, Bt + BETA * acdim, acdim, j, jr) : 0.0;
+    }
+    double* o = o0;
+    const double* ws = ws0;
+    // (not fully unrolled on purpose: the W values do not depend on the query, and a fully unrolled column loop lets
+    // the compiler hoist all of them out of the query loop -- spills)
+#pragma unroll 4
+    for (int c = 0; c < ncl; ++c, o += ld, ws += LDW) {
+      double f0 = 0.0, f1 = 0.0;
+#pragma unroll
+      for (int tt = 0; tt < NTAP; ++tt) {
+        const double w = ws[tt];
+        f0 = fma(w, cf0[tt], f0);
+        f1 = fma(w, cf1[tt], f1);
+      }
+      o[0] = f0;
+      o[pq] = f1;
+    }
+  }
+  if (s < nslots) {
     double cf[NTAP];
 #pragma unroll
     for (int tt = 0; tt < NTAP; ++tt) {
@@ -382,8 +411,6 @@ __device__ __forceinline__ void emit_cr(const NetDev& net, const BatchDev& b, co
     }
     double* o = o0;
     const double* ws = ws0;
-    // (not fully unrolled on purpose: the W values do not depend on the query, and a fully unrolled column loop lets
-    // the compiler hoist all of them out of the query loop -- spills)
 #pragma unroll 4
     for (int c = 0; c < ncl; ++c, o += ld, ws += LDW) {
       double f = 0.0;
