@@ -833,6 +833,7 @@ int32_t nnsdp_batch_create(nnsdp_ctx* ctx, int32_t dev_index, const nnsdp_net* n
     b->gd.per_query = go;
     b->gd.goff = b->d_goff.as<long long>();
     b->gd.ldG = b->d_ldG.as<int>();
+    b->gd.mirror = b->packed && b->plan.skip_absent ? 0 : 1;  // packed records of wide nets hold the upper triangle only
   }
   NN_CUDA(cudaStreamSynchronize(b->st));
   guard.b = nullptr;

@@ -287,6 +287,7 @@ struct GramDev {
   long long per_query;       // doubles
   const long long* goff;     // K : offset of block b's Gram inside one query's scratch (b <= K-2)
   const int* ldG;            // K : leading dimension of block b's Gram
+  int mirror;                // write G[c, r] as well as G[r, c] (dense formats; packed records read the upper triangle only)
 };
 
 struct PlanDev {

@@ -149,7 +149,7 @@ gram_kernel(NetDev net, BatchDev b, GramDev g, int q0, const int* __restrict__ p
         if (r < nb && cc < nb && (!diag || r <= cc)) {
           const double v = acc[i][j][e];
           G[r + (long long)cc * ldG] = v;
-          if (r != cc) G[cc + (long long)r * ldG] = v;
+          if (r != cc && g.mirror) G[cc + (long long)r * ldG] = v;
         }
       }
     }
