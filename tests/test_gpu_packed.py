@@ -192,3 +192,26 @@ def test_packed_multi_device_context(ctx):
     assert np.array_equal(p1, p2)
     for i in range(nq):
         assert np.array_equal(nb.packed_unpack(xdims, beta, one[i], p1[i]), nb.packed_unpack(xdims, beta, two[i], p2[i]))
+
+
+def test_packed_call_sequence_errors(ctx):
+    import nnsdp_b200 as nb
+
+    net = rand_net([2, 60, 60, 2], seed=1)
+    dnet = nb.Net(ctx, net.xdims, net.Ms)
+    rng = np.random.default_rng(0)
+    batch = to_numeric_batch(nb, net, [rand_query(net, 1, rng)])
+    b = nb.Batch(dnet, 1, Qcap=1, ring=1)                  # dense blocks: the packed calls must refuse
+    b.set_inputs(batch)
+    with pytest.raises(nb.NnsdpError) as e:
+        b.run_packed(np.zeros(4), None)
+    assert e.value.code == -4
+    with pytest.raises(nb.NnsdpError) as e:
+        b.packed_stats()
+    assert e.value.code == -4
+    b.close()
+    pb = nb.Batch(dnet, 1, Qcap=1, ring=1, packed=True)
+    with pytest.raises(nb.NnsdpError) as e:                 # no inputs yet
+        pb.run_packed(None, None)
+    assert e.value.code == -4
+    pb.close()

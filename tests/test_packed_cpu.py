@@ -147,3 +147,63 @@ def test_unpack_reproduces_every_clique_block(xdims, beta, kind):
     sz = nb.sizes_from_xdims(xdims, beta)
     if min(xdims[1:-1]) >= 100 and sz["ncliques"] >= 3:
         assert lay["record_doubles"] < 0.6 * sz["sum_ck_sq"]
+
+
+def _random_shapes(n=40, seed=5):
+    rng = np.random.default_rng(seed)
+    out = []
+    for _ in range(n):
+        depth = int(rng.integers(2, 6))
+        wide = rng.random() < 0.7
+        widths = [int(rng.integers(48, 300)) if wide else int(rng.integers(2, 60)) for _ in range(depth)]
+        if wide and rng.random() < 0.3:
+            widths[int(rng.integers(0, depth))] = int(rng.integers(48, 64))      # a layer just above the split threshold
+        xdims = [int(rng.integers(1, 6))] + widths + [int(rng.integers(1, 5))]
+        beta = int(rng.integers(0, min(7, sum(widths)) + 1))
+        out.append((xdims, beta))
+    return out
+
+
+@pytest.mark.parametrize("xdims,beta", _random_shapes())
+def test_random_shapes_layout_coverage_and_unpack(xdims, beta):
+    """Seeded random shapes around the planner's thresholds (48-neuron split, 128-row tiles, 256-wide band mode,
+    beta up to 7 and beyond MAX_WINDOW_BETA): the cell table is well formed, the tiles cover their cells, and a
+    record packed from the oracle's Z unpacks to every clique block."""
+    import nnsdp_b200 as nb
+
+    test_layout_is_well_formed(xdims, beta)
+    test_plan_tiles_cover_their_cells(xdims, beta)
+    net = rand_net(xdims, seed=1)
+    rng = np.random.default_rng(2)
+    q = rand_query(net, beta, rng, kind="ellipsoid", radius=0.0)
+    ref = o.run_query(net, beta, q)
+    Z = np.triu(ref["Z"]) + np.triu(ref["Z"], 1).T
+    lay = nb.packed_layout(xdims, beta)
+    present = np.ones(len(lay["cells"]), dtype=np.uint8)
+    flat = nb.packed_unpack(xdims, beta, _pack_numpy(Z, lay, beta, present), present)
+    off = 0
+    for (Ck, _, _), blk in zip(ref["cliques"], o.clique_blocks(Z, ref["cliques"])):
+        n = len(Ck)
+        assert np.array_equal(flat[off:off + n * n].reshape(n, n).T, blk)
+        off += n * n
+
+
+def test_packed_api_argument_errors():
+    import ctypes as C
+    import nnsdp_b200 as nb
+    import nnsdp_b200._lib as L
+
+    xd = (L.c_i64 * 4)(2, 50, 50, 2)
+    n = L.c_i64(0)
+    assert L.lib.nnsdp_packed_layout(3, xd, 1, 0, None, None, None, None) == L.ERR_ARG          # ncells is required
+    assert L.lib.nnsdp_packed_layout(3, xd, -1, 0, None, C.byref(n), None, None) == L.ERR_ASSERT  # 0 <= beta
+    assert L.lib.nnsdp_packed_layout(3, xd, 1, 0, None, C.byref(n), None, None) == L.OK and n.value > 0
+    cells = (L.PackedCell * 1)()
+    assert L.lib.nnsdp_packed_layout(3, xd, 1, 1, cells, C.byref(n), None, None) == L.ERR_ARG   # table too small
+    rec = np.zeros(8)
+    pres = np.zeros(int(n.value), dtype=np.uint8)
+    out = np.zeros(8)
+    assert L.lib.nnsdp_packed_unpack(3, xd, 1, rec.ctypes.data_as(L.c_dp), pres.ctypes.data_as(C.POINTER(C.c_uint8)),
+                                     L.FORMAT_PACKED, out.ctypes.data_as(L.c_dp)) == L.ERR_ARG  # target must be dense
+    with pytest.raises(nb.NnsdpError):
+        nb.plan_stats([2, 50, 50, 2], 1, dense=3)
