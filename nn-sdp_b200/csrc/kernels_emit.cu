@@ -466,6 +466,15 @@ emit_fill_kernel(NetDev net, BatchDev b, GramDev g, PlanDev plan, int q0, int nq
     for (r += TR; r < row_end; r += TR) col[r] = (VALUE);                             \
   }
   if (prog == PROG_ZERO) {
+    if (BAND_INLINE && nrows + 3 <= TR) {
+      // narrow layers: one (masked) row per thread and column; the kernel is issue-bound there, so the general
+      // loop's second-row handling is left out
+      for (int c = cg; c < ncols; c += ncg, col += cstep) {
+        const int r = tr - (int)(((size_t)(col + row0) >> 3) & 3);
+        if ((unsigned)r < (unsigned)nrows) col[row0 + r] = 0.0;
+      }
+      return;
+    }
     NNSDP_STRIP_LOOP(0.0)
     return;
   }
