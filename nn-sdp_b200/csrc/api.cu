@@ -15,6 +15,8 @@
 #include <mutex>
 #include <thread>
 
+#include <cuda.h>  // CUtensorMap and its enums; cuTensorMapEncodeTiled is obtained through cudaGetDriverEntryPoint
+
 #include "internal.h"
 
 namespace nnsdp {
@@ -218,6 +220,7 @@ struct nnsdp_batch {
   bool packed = false;   // output = packed records (the block-sparse upper triangle of Z), see PackedLayout
   PackedLayout lay;
   DevBuf d_bands;
+  DevBuf d_tmaps, d_tmap_ok;  // tensor maps of the W matrices for the TMA staging of the CR window program
   int nbands = 0, band_max_m = 0;
   int64_t packed_emitted_bytes = 0, packed_present_cells = 0;  // of the last run
   nnsdp_sizes sz{};
@@ -285,7 +288,7 @@ struct nnsdp_batch {
     spans.clear();
   }
   std::vector<DevBuf*> all_bufs() {
-    return {&d_bands, &d_tiles, &d_strips, &d_mats, &d_goff, &d_ldG, &x1min, &x1max, &ymin, &ymax, &smin, &smax,
+    return {&d_bands, &d_tmaps, &d_tmap_ok, &d_tiles, &d_strips, &d_mats, &d_goff, &d_ldG, &x1min, &x1max, &ymin, &ymax, &smin, &smax,
             &gin, &gbnd, &gsec, &outS, &outvec, &outinvP, &gout, &xmin, &xmax, &acxmin, &acxmax,
             &smin_c, &smax_c, &d11, &Md, &T0, &Bt, &u, &aff, &part, &act, &cnt, &Z11, &Z1K, &U,
             &gram, &ringbuf, &flags, &cr_rowsA, &cr_rowsB, &cr_bias, &cr_prel, &cr_preu, &cr_du, &cr_bu, &cr_dl};
@@ -827,6 +830,47 @@ int32_t nnsdp_batch_create(nnsdp_ctx* ctx, int32_t dev_index, const nnsdp_net* n
     b->pd.n_edge = b->plan.n_edge;
     b->pd.tile_rows = b->plan.tile_rows;
     b->pd.per_query = b->plan.per_query_doubles;
+    b->pd.tmaps = nullptr;
+    b->pd.tmap_ok = nullptr;
+    if (b->plan.n_window > 0 && beta <= MAX_WINDOW_BETA) {
+      // One tensor map per layer: W_k as a 2-D tensor (neurons contiguous, then inputs), box (128 + 2 beta) x 32, zero
+      // fill outside.  A layer qualifies when its column pitch is a multiple of 16 bytes (an even number of neurons);
+      // boxes may stick out of the matrix on every side (tools/probe_tma.cu, profiles/r2_probe_tma.txt).
+      typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+      void* fn = nullptr;
+      cudaDriverEntryPointQueryResult qres;
+      static const bool no_tma = [] { const char* e = getenv("NNSDP_NO_TMA"); return e && e[0] == '1'; }();
+      if (!no_tma && cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) == cudaSuccess && fn &&
+          qres == cudaDriverEntryPointSuccess) {
+        std::vector<CUtensorMap> maps(sh.K);
+        std::vector<int> ok(sh.K, 0);
+        bool any = false;
+        for (int k = 0; k < sh.K; ++k) {
+          if (sh.n[k + 1] % 2 != 0) continue;
+          const cuuint64_t dims[2] = {(cuuint64_t)sh.n[k + 1], (cuuint64_t)sh.n[k]};
+          const cuuint64_t strides[1] = {(cuuint64_t)sh.n[k + 1] * 8};
+          const cuuint32_t box[2] = {(cuuint32_t)(128 + 2 * beta + 2), 32};  // CR_LDW(beta) of kernels_emit.cu
+          const cuuint32_t estr[2] = {1, 1};
+          const CUresult r = ((EncodeFn)fn)(&maps[k], CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, b->nd->M[k].p, dims, strides, box, estr,
+                                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                            CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+          ok[k] = (r == CUDA_SUCCESS);
+          any |= ok[k] != 0;
+        }
+        if (any) {
+          static_assert(sizeof(CUtensorMap) == 128, "CUtensorMap is 128 bytes");
+          NN_TRY(upload(b->d_tmaps, maps.data(), maps.size() * sizeof(CUtensorMap), b->st));
+          NN_TRY(upload(b->d_tmap_ok, ok.data(), ok.size() * 4, b->st));
+          NN_CUDA(cudaStreamSynchronize(b->st));
+          b->pd.tmaps = b->d_tmaps.p;
+          b->pd.tmap_ok = b->d_tmap_ok.as<int>();
+        }
+      } else {
+        cudaGetLastError();
+      }
+    }
     b->pd.packed = b->plan.skip_absent ? 1 : 0;
     b->pd.band_inline = b->plan.band_inline ? 1 : 0;
     b->gd.scratch = b->gram.as<double>();

@@ -298,6 +298,8 @@ struct PlanDev {
   int n_fill, n_window, n_edge;
   int tile_rows;
   long long per_query;       // doubles per query in the output
+  const void* tmaps;         // K tensor maps (CUtensorMap, 128 B each) of the W matrices for the CR window program, or null
+  const int* tmap_ok;        // K : layer k has a usable tensor map
   int packed;                // packed records: fill strips of an absent DIAG cell are skipped
   int band_inline;           // DIAG strips add the band term themselves (else the band kernel patches it in)
 };

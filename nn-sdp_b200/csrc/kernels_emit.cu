@@ -340,6 +340,34 @@ __device__ __forceinline__ void emit_rc(const NetDev& net, const BatchDev& b, co
   }
 }
 
+__host__ __device__ constexpr int CR_LDW(int beta) { return FAST_TR + 2 * beta + 2; }
+
+// ---- TMA (cp.async.bulk.tensor) staging of a W tile: one thread arms an mbarrier with the byte count and issues the
+// 2-D bulk tensor copy; rows / columns outside the matrix arrive as zeros (out-of-bounds fill of the tensor map)
+__device__ __forceinline__ void tma_load_tile_2d(double* smem_dst, unsigned long long* mbar, const void* tmap, int c0,
+                                                 int c1, unsigned bytes) {
+  const unsigned bar = (unsigned)__cvta_generic_to_shared(mbar);
+  const unsigned dst = (unsigned)__cvta_generic_to_shared(smem_dst);
+  if (threadIdx.x == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" ::"r"(bar));
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(bar), "r"(bytes) : "memory");
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];\n" ::"r"(dst),
+        "l"(tmap), "r"(c0), "r"(c1), "r"(bar)
+        : "memory");
+  }
+  __syncthreads();  // the barrier is initialised before anybody polls it
+  unsigned done = 0, spins = 0;
+  while (!done) {
+    asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\nselp.u32 %0, 1, 0, p;\n}\n"
+                 : "=r"(done)
+                 : "r"(bar)
+                 : "memory");
+    if (!done && ++spins > (1u << 24)) __trap();  // a copy that never completes must fail the launch, not hang the device
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // CR: out[jr, c] = sum_t W[jr - beta + t, c] * M[jr - beta + t, jr].  The (128 + 2 beta) x 32 tile of
 // W (neuron-contiguous) is staged once in shared memory; the taps depend on the row only and live
@@ -348,9 +376,9 @@ __device__ __forceinline__ void emit_rc(const NetDev& net, const BatchDev& b, co
 template <int BETA>
 __device__ __forceinline__ void emit_cr(const NetDev& net, const BatchDev& b, const PlanDev& plan,
                                         const TileDev& t, const MatDev& mat, int q0, int slot0,
-                                        int nslots, double* __restrict__ out, double* smem) {
+                                        int nslots, double* __restrict__ out, double* smem, unsigned long long* mbar) {
   constexpr int NTAP = 2 * BETA + 1;
-  constexpr int LDW = FAST_TR + 2 * BETA;  // rows per staged column
+  constexpr int LDW = CR_LDW(BETA);  // rows per staged column: 128 + 2 beta, + 2 so that a box can start on an even row
   const int n0 = net.n_in;
   const long long acdim = net.acdim;
   const int Bc = t.cblk;
@@ -358,19 +386,29 @@ __device__ __forceinline__ void emit_cr(const NetDev& net, const BatchDev& b, co
   const int jr0 = t.grow0 - n0, jr = jr0 + tr;
   const int cl0 = t.gcol0 - net.off[Bc];
   const int Lc0 = net.off[Bc + 1] - n0, nLc = net.n[Bc + 1];
-  const double* Wc0 = net.M[Bc] + (long long)cl0 * nLc;
-  for (int i = threadIdx.x; i < t.ncols * LDW; i += ETHREADS) {
-    const int c = i / LDW, ii = i - c * LDW;
-    const int j = jr0 - BETA + ii;
-    smem[i] = (j >= Lc0 && j < Lc0 + nLc) ? Wc0[(long long)c * nLc + (j - Lc0)] : 0.0;
+  int adj = 0;  // staged row ii holds neuron jr0 - BETA - adj + ii
+  if (plan.tmaps && plan.tmap_ok[Bc]) {
+    // The (128 + 2 beta + 2) x 32 box of W_Bc by TMA.  The start address of a box must be a multiple of 16 bytes
+    // (an odd start row of doubles faults with "illegal instruction", tools/probe_tma.cu), so the box starts one row
+    // early when jr0 - beta is odd; rows / columns outside the matrix arrive as zeros.
+    const int c0 = jr0 - BETA - Lc0;
+    adj = c0 & 1;
+    tma_load_tile_2d(smem, mbar, (const char*)plan.tmaps + 128 * Bc, c0 - adj, cl0, (unsigned)(FAST_TC * LDW * 8));
+  } else {
+    const double* Wc0 = net.M[Bc] + (long long)cl0 * nLc;
+    for (int i = threadIdx.x; i < t.ncols * LDW; i += ETHREADS) {
+      const int c = i / LDW, ii = i - c * LDW;
+      const int j = jr0 - BETA + ii;
+      smem[i] = (j >= Lc0 && j < Lc0 + nLc) ? Wc0[(long long)c * nLc + (j - Lc0)] : 0.0;
+    }
+    __syncthreads();
   }
-  __syncthreads();
   if (tr >= t.nrows) return;
   const int cbase = cg * FAST_NCOL;
   const long long ld = mat.ld;
   double* o0 = out + (long long)slot0 * plan.per_query + mat.out_off + (t.row0 + tr) + (long long)(t.col0 + cbase) * ld;
   const int ncl = min(FAST_NCOL, t.ncols - cbase);
-  const double* ws0 = smem + cbase * LDW + tr;
+  const double* ws0 = smem + cbase * LDW + tr + adj;
   const double* Md = b.Md + (long long)(q0 + slot0) * acdim;
   const double* Bt = b.Bt + (long long)(q0 + slot0) * BETA * acdim;
   // two queries per trip: the 2 beta + 1 values of W a column needs are read from shared memory once for both
@@ -550,8 +588,9 @@ template <int BETA>
 __global__ void __launch_bounds__(ETHREADS, 4)
 emit_window_kernel(NetDev net, BatchDev b, PlanDev plan, int tile0, int q0, int nq, int group, int group_major,
                    double* __restrict__ out) {
-  constexpr int RC_DOUBLES = SLOT_GROUP * (BETA + 1) * (FAST_TC + BETA + 1), CR_DOUBLES = FAST_TC * (FAST_TR + 2 * BETA);
-  __shared__ __align__(16) double smem[RC_DOUBLES > CR_DOUBLES ? RC_DOUBLES : CR_DOUBLES];
+  constexpr int RC_DOUBLES = SLOT_GROUP * (BETA + 1) * (FAST_TC + BETA + 1), CR_DOUBLES = FAST_TC * CR_LDW(BETA);
+  __shared__ __align__(128) double smem[RC_DOUBLES > CR_DOUBLES ? RC_DOUBLES : CR_DOUBLES];
+  __shared__ __align__(8) unsigned long long mbar;
   // slot group is the fastest grid index: CTAs that share a W tile run back to back (L2 reuse)
   const int ngroups = (nq + group - 1) / group;
   const int ti = group_major ? blockIdx.x % plan.n_window : blockIdx.x / ngroups;
@@ -564,7 +603,7 @@ emit_window_kernel(NetDev net, BatchDev b, PlanDev plan, int tile0, int q0, int 
     if (t.ncols == FAST_TC) emit_rc<BETA, true>(net, b, plan, t, mat, q0, slot0, nslots, out, smem);
     else emit_rc<BETA, false>(net, b, plan, t, mat, q0, slot0, nslots, out, smem);
   } else {
-    emit_cr<BETA>(net, b, plan, t, mat, q0, slot0, nslots, out, smem);
+    emit_cr<BETA>(net, b, plan, t, mat, q0, slot0, nslots, out, smem, &mbar);
   }
 }
 
