@@ -1044,9 +1044,34 @@ int32_t nnsdp_batch_prepare(nnsdp_batch* b) {
   for (int blk = 0; blk <= sh.K - 2; ++blk) max_rows = std::max(max_rows, (int)sh.n[blk]);
   const int all = affine_all_launch(nd.nd, sh.K, max_rows, b->bd.u, sh.acdim, b->bd.aff, sh.Zdim, (int)b->Q, b->st);
   launches += all;
+  // wide layers, many queries: the products of a run of layers [lb0, lb1) in ONE tensor-core launch (a single layer
+  // is 64 tiles at width 1000 and Q = 1024, under half of the SMs); the others one by one
+  int lb0 = 0, lb1 = 0;
+  if (all == 0) {
+    auto fits = [&](int blk) {
+      return sh.n[blk] >= 192 && sh.n[blk + 1] >= 128 && (sh.noff(blk + 1) & 1) == 0 && (sh.acdim & 1) == 0 &&
+             (((uintptr_t)b->bd.u) & 15) == 0;
+    };
+    int best0 = 0, best1 = 0;
+    for (int s = 0; s <= sh.K - 2;) {
+      if (!fits(s)) { ++s; continue; }
+      int e = s;
+      while (e <= sh.K - 2 && fits(e)) ++e;
+      if (e - s > best1 - best0) best0 = s, best1 = e;
+      s = e;
+    }
+    int rows = 0;
+    for (int blk = best0; blk < best1; ++blk) rows = std::max(rows, (int)sh.n[blk]);
+    if (best1 - best0 >= 2 && dgemm_dmma_affine_layers_launch(nd.nd, best0, best1 - best0, rows, b->bd.u, sh.acdim, b->bd.aff,
+                                                              sh.Zdim, (int)b->Q, b->st)) {
+      lb0 = best0, lb1 = best1;
+      ++launches;
+    }
+  }
   if (all == 0)
     for (int blk = 0; blk <= sh.K - 2; ++blk)
-      launches += affine_layer_launch(nd.Wt[blk].as<double>(), b->net->ldT[blk], (int)sh.n[blk],
+      if (blk < lb0 || blk >= lb1)
+        launches += affine_layer_launch(nd.Wt[blk].as<double>(), b->net->ldT[blk], (int)sh.n[blk],
                                       (int)sh.n[blk + 1], b->bd.u + sh.noff(blk + 1), sh.acdim,
                                       b->bd.aff + sh.off[blk], sh.Zdim, (int)b->Q, b->st);
   b->span_end(b->st, launches);

@@ -326,6 +326,9 @@ int ibp_all_launch(const NetDev& nd, int max_out, const double* x1min, long long
 // C (+)= A B on the FP64 tensor cores (kernels_dgemm.cu); 0 = operands not suitable, the caller falls back.
 int dgemm_dmma_launch(const double* A, int lda, int M, int K, const double* B, long long ldb, double* C, long long ldc,
                       int N, int accumulate, cudaStream_t st);
+// the affine-column products of all layers in one tensor-core launch (wide layers, many queries); 0 = not applicable
+int dgemm_dmma_affine_layers_launch(const NetDev& nd, int b0, int nb, int max_rows, const double* u, long long u_stride,
+                                    double* aff, long long aff_stride, int Q, cudaStream_t st);
 int ibp_chain_launch(const NetDev& nd, int max_w, const double* x1min, long long s_min, const double* x1max,
                      long long s_max, double* xmin, double* xmax, long long x_stride, double* acxmin, double* acxmax,
                      double* smin, double* smax, long long acx_stride, int Q, int* flag_bad, cudaStream_t st);

@@ -44,9 +44,8 @@ __device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b)
 }
 
 template <int ACC>  // 0: C = A B, 1: C += A B
-__global__ void __launch_bounds__(DTHREADS, 1)
-dgemm_dmma_kernel(const double* __restrict__ A, int lda, int M, int K, const double* __restrict__ B, long long ldb,
-                  double* __restrict__ C, long long ldc, int N) {
+__device__ __forceinline__ void dgemm_tile(const double* __restrict__ A, int lda, int M, int K, const double* __restrict__ B,
+                                           long long ldb, double* __restrict__ C, long long ldc, int N) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   DgemmSmem& sm = *reinterpret_cast<DgemmSmem*>(smem_raw);
   const int m0 = blockIdx.x * DT, n0 = blockIdx.y * DT;
@@ -126,7 +125,40 @@ dgemm_dmma_kernel(const double* __restrict__ A, int lda, int M, int K, const dou
   }
 }
 
+template <int ACC>
+__global__ void __launch_bounds__(DTHREADS, 1)
+dgemm_dmma_kernel(const double* __restrict__ A, int lda, int M, int K, const double* __restrict__ B, long long ldb,
+                  double* __restrict__ C, long long ldc, int N) {
+  dgemm_tile<ACC>(A, lda, M, K, B, ldb, C, ldc, N);
+}
+
+// The affine-column products of ALL layers in one launch (blockIdx.z = layer): aff[off_b ..] += Wt_b u_{b+1} for
+// b = 0 .. K-2.  The products are independent; one layer alone is 8 x 8 tiles at width 1000 and Q = 1024 -- 64 CTAs on
+// 148 SMs -- so launched layer by layer they run at 10 TFLOP/s.
+__global__ void __launch_bounds__(DTHREADS, 1)
+dgemm_dmma_affine_layers_kernel(NetDev net, int b0, const double* __restrict__ u, long long u_stride,
+                                double* __restrict__ aff, long long aff_stride, int Q) {
+  const int b = b0 + blockIdx.z;
+  const int M = net.n[b], Kd = net.n[b + 1];
+  if ((int)blockIdx.x * DT >= M) return;
+  dgemm_tile<1>(net.Wt[b], net.ldT[b], M, Kd, u + (net.off[b + 1] - net.n_in), u_stride, aff + net.off[b], aff_stride, Q);
+}
+
 }  // namespace
+
+// Layers b0 .. b0 + nb - 1; the caller has checked what dgemm_dmma_launch checks, for every one of them.
+int dgemm_dmma_affine_layers_launch(const NetDev& nd, int b0, int nb, int max_rows, const double* u, long long u_stride,
+                                    double* aff, long long aff_stride, int Q, cudaStream_t st) {
+  static const bool off = [] { const char* e = getenv("NNSDP_NO_DMMA_GEMM"); return e && atoi(e) != 0; }();
+  static const bool off2 = [] { const char* e = getenv("NNSDP_NO_AFFINE_LAYERS"); return e && atoi(e) != 0; }();
+  if (off || off2 || nb < 2 || Q < 128) return 0;
+  cudaFuncSetAttribute(dgemm_dmma_affine_layers_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DgemmSmem));
+  const dim3 grid((max_rows + DT - 1) / DT, (Q + DT - 1) / DT, nb);
+  dgemm_dmma_affine_layers_kernel<<<grid, DTHREADS, sizeof(DgemmSmem), st>>>(nd, b0, u, u_stride, aff, aff_stride, Q);
+  return 1;
+}
+
+
 
 // Returns 1 when the product was launched, 0 when the operands do not fit this kernel (the caller falls back).
 int dgemm_dmma_launch(const double* A, int lda, int M, int K, const double* B, long long ldb, double* C, long long ldc,
