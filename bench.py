@@ -40,6 +40,8 @@ WORKLOADS = {
     # BASELINE configs[3]: ACAS Xu shape 5 x (6 x 50) x 5 (exts/nnet_parser.jl), 45 safety queries (one vnnlib property
     # flattened over its boxes and half-spaces, experiments/vnnlib_utils.jl:18-56)
     "acas-5x50x6-beta2-Q45": dict(xdims=[5] + [50] * 6 + [5], beta=2, Q=45, ring=45, kind="acas"),
+    # alignment probe (profiles/r2_experiments.txt): clique blocks with ld = 3000, a multiple of four doubles
+    "probe-W999-D20-beta2-Q1024": dict(W=999, D=20, beta=2, Q=1024, ring=32),
 }
 EXTRA_WORKLOADS = ("mid-W100-D50-beta2-Q1024", "tiny-W10-D10-beta1-Q64", "reach-W20-D10-beta2-Q64", "acas-5x50x6-beta2-Q45")
 DEFAULT_WORKLOAD = "stress-W1000-D20-beta2-Q1024"

@@ -326,6 +326,10 @@ int ibp_all_launch(const NetDev& nd, int max_out, const double* x1min, long long
 // C (+)= A B on the FP64 tensor cores (kernels_dgemm.cu); 0 = operands not suitable, the caller falls back.
 int dgemm_dmma_launch(const double* A, int lda, int M, int K, const double* B, long long ldb, double* C, long long ldc,
                       int N, int accumulate, cudaStream_t st);
+// interval propagation of one wide layer for many boxes on the FP64 tensor cores; 0 = not applicable
+int ibp_dmma_launch(const double* Mk, int n_out_k, int n_in_k, const double* xin_min, const double* xin_max,
+                    long long x_stride, double* xout_min, double* xout_max, double* acx_min, double* acx_max,
+                    long long acx_stride, int Q, int relu, int write_x, int* flag_bad, cudaStream_t st);
 // the affine-column products of all layers in one tensor-core launch (wide layers, many queries); 0 = not applicable
 int dgemm_dmma_affine_layers_launch(const NetDev& nd, int b0, int nb, int max_rows, const double* u, long long u_stride,
                                     double* aff, long long aff_stride, int Q, cudaStream_t st);

@@ -596,6 +596,9 @@ int ibp_layer_launch(const double* Mk, int n_out_k, int n_in_k, const double* xi
         xout_max, x_stride, acx_min, acx_max, acx_stride, relu, write_x, flag_bad, st);
     return 1;
   }
+  if (ibp_dmma_launch(Mk, n_out_k, n_in_k, xin_min, xin_max, x_stride, xout_min, xout_max, acx_min, acx_max, acx_stride, Q,
+                      relu, write_x, flag_bad, st))
+    return 1;
   dim3 grid((n_out_k + BM - 1) / BM, (Q + BN - 1) / BN);
   gemm_nn_kernel<0><<<grid, GEMM_THREADS, 0, st>>>(
       Mk, n_out_k, n_out_k, n_in_k, xin_min, xin_max, x_stride, Q, Mk + (long long)n_in_k * n_out_k,

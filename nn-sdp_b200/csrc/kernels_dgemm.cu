@@ -17,11 +17,24 @@ namespace nnsdp {
 namespace {
 
 constexpr int DT = 128;         // tile side
-constexpr int DK = 16;          // contraction indices per stage
+#ifndef NNSDP_DGEMM_DK
+#define NNSDP_DGEMM_DK 16
+#endif
+constexpr int DK = NNSDP_DGEMM_DK;  // contraction indices per stage
 constexpr int DSTAGES = 3;
-constexpr int DLDA = DT + 8;    // As leading dimension (as in the Gram kernel)
+#ifndef NNSDP_DGEMM_LDA_PAD
+#define NNSDP_DGEMM_LDA_PAD 4
+#endif
+#ifndef NNSDP_DGEMM_WN
+#define NNSDP_DGEMM_WN 32
+#endif
+constexpr int DLDA = DT + NNSDP_DGEMM_LDA_PAD;  // As leading dimension: 4 (mod 16) puts the 4 x 4 (k, m) addresses of a half
+                                                // warp's fragment load in 16 distinct 8-byte banks (8 gives 2-way conflicts)
 constexpr int DLDB = DK + 4;    // Bs leading dimension
-constexpr int DTHREADS = 256;
+constexpr int DWN = NNSDP_DGEMM_WN;             // columns per warp tile (rows: 32)
+constexpr int DNJ = DWN / 8;
+constexpr int DTHREADS = 4 * (DT / DWN) * 32;   // 16 warps of 32 x 32: the DMMA issue cadence of a warp leaves the pipe half
+                                                // idle with 2 warps per scheduler (8 warps of 32 x 64)
 
 struct DgemmSmem {
   double A[DSTAGES][DK][DLDA];
@@ -50,7 +63,7 @@ __device__ __forceinline__ void dgemm_tile(const double* __restrict__ A, int lda
   DgemmSmem& sm = *reinterpret_cast<DgemmSmem*>(smem_raw);
   const int m0 = blockIdx.x * DT, n0 = blockIdx.y * DT;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int wm = (warp & 3) * 32, wn = (warp >> 2) * 64;
+  const int wm = (warp & 3) * 32, wn = (warp >> 2) * DWN;
   const int nsteps = (K + DK - 1) / DK;
 
   auto load_stage = [&](int stage, int step) {
@@ -71,11 +84,11 @@ __device__ __forceinline__ void dgemm_tile(const double* __restrict__ A, int lda
     }
   };
 
-  double acc[4][8][2];
+  double acc[4][DNJ][2];
 #pragma unroll
   for (int i = 0; i < 4; ++i)
 #pragma unroll
-    for (int j = 0; j < 8; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+    for (int j = 0; j < DNJ; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
 
   for (int s = 0; s < DSTAGES - 1; ++s) {
     if (s < nsteps) load_stage(s, s);
@@ -95,15 +108,15 @@ __device__ __forceinline__ void dgemm_tile(const double* __restrict__ A, int lda
 #pragma unroll
     for (int k4 = 0; k4 < DK; k4 += 4) {
       const int k = k4 + (lane & 3);
-      double af[4], bf[8];
+      double af[4], bf[DNJ];
 #pragma unroll
       for (int i = 0; i < 4; ++i) af[i] = As[k][wm + i * 8 + (lane >> 2)];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) bf[j] = Bs[wn + j * 8 + (lane >> 2)][k];
+      for (int j = 0; j < DNJ; ++j) bf[j] = Bs[wn + j * 8 + (lane >> 2)][k];
 #pragma unroll
       for (int i = 0; i < 4; ++i)
 #pragma unroll
-        for (int j = 0; j < 8; ++j) dmma(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+        for (int j = 0; j < DNJ; ++j) dmma(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
     }
   }
   cp_wait<0>();
@@ -112,7 +125,7 @@ __device__ __forceinline__ void dgemm_tile(const double* __restrict__ A, int lda
   for (int i = 0; i < 4; ++i) {
     const int r = m0 + wm + i * 8 + (lane >> 2);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
+    for (int j = 0; j < DNJ; ++j) {
 #pragma unroll
       for (int e = 0; e < 2; ++e) {
         const int c = n0 + wn + j * 8 + (lane & 3) * 2 + e;
@@ -144,6 +157,132 @@ dgemm_dmma_affine_layers_kernel(NetDev net, int b0, const double* __restrict__ u
   dgemm_tile<1>(net.Wt[b], net.ldT[b], M, Kd, u + (net.off[b + 1] - net.n_in), u_stride, aff + net.off[b], aff_stride, Q);
 }
 
+// ---------------------------------------------------------------------------------------------
+// Interval propagation of one wide layer for many boxes (intervalsWorstCase,
+// /root/reference/src/Intervals/intervals_easy.jl:21-33) on the FP64 tensor cores.  In centre / radius form
+//   ymin = W c + b - |W| r,   ymax = W c + b + |W| r,   c = (xmin + xmax) / 2,  r = (xmax - xmin) / 2
+// the two products share their A operand: a CTA owns 128 neurons x 64 boxes with TWO accumulator sets, loads the
+// fragment of W once and feeds it to the second product through fabs.  The tiles of xmin / xmax are staged as they
+// are (cp.async cannot transform) and turned into c / r when the B fragments are read.  The epilogue is the one of
+// the SIMT kernel (kernels_bounds.cu): bias, the ordering check, pre-activation bounds, ReLU'd post-activation bounds.
+// 16 warps of 32 x 16: at width 1000 and 1024 boxes that is 8 x 16 = 128 CTAs for 148 SMs in a single wave.
+// ---------------------------------------------------------------------------------------------
+constexpr int IT_N = 64;                     // boxes per CTA
+constexpr int ITHREADS = 512;
+
+struct IbpSmem {
+  double A[DSTAGES][DK][DLDA];
+  double Blo[DSTAGES][IT_N][DLDB];
+  double Bhi[DSTAGES][IT_N][DLDB];
+};
+
+__global__ void __launch_bounds__(ITHREADS, 1)
+ibp_dmma_kernel(const double* __restrict__ A, int lda, int M, int K, const double* __restrict__ Xlo,
+                const double* __restrict__ Xhi, long long ldb, int N, const double* __restrict__ bias,
+                double* __restrict__ C0, double* __restrict__ C1, long long ldc, double* __restrict__ D0,
+                double* __restrict__ D1, long long ldd, int relu, int write_x, int* __restrict__ flag_bad) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  IbpSmem& sm = *reinterpret_cast<IbpSmem*>(smem_raw);
+  const int m0 = blockIdx.x * DT, n0 = blockIdx.y * IT_N;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int wm = (warp & 3) * 32, wn = (warp >> 2) * 16;
+  const int nsteps = (K + DK - 1) / DK;
+
+  auto load_stage = [&](int stage, int step) {
+    const int k0 = step * DK;
+    for (int c = tid; c < DK * (DT / 2); c += ITHREADS) {
+      const int kk = c / (DT / 2), ch = c % (DT / 2);
+      const int m = m0 + ch * 2, k = k0 + kk;
+      const int rows = (k < K) ? max(0, min(2, M - m)) : 0;
+      cp16(&sm.A[stage][kk][ch * 2], rows ? A + (long long)k * lda + m : A, rows * 8);
+    }
+    for (int c = tid; c < 2 * IT_N * (DK / 2); c += ITHREADS) {
+      const int which = c / (IT_N * (DK / 2)), cc = c % (IT_N * (DK / 2));
+      const int nn = cc / (DK / 2), ch = cc % (DK / 2);
+      const int n = n0 + nn, k = k0 + ch * 2;
+      const int cnt = (n < N) ? max(0, min(2, K - k)) : 0;
+      const double* X = which ? Xhi : Xlo;
+      cp16(which ? &sm.Bhi[stage][nn][ch * 2] : &sm.Blo[stage][nn][ch * 2], cnt ? X + (long long)n * ldb + k : X, cnt * 8);
+    }
+  };
+
+  double acc0[4][2][2], acc1[4][2][2];   // W c and |W| r
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 2; ++j) acc0[i][j][0] = acc0[i][j][1] = acc1[i][j][0] = acc1[i][j][1] = 0.0;
+
+  for (int s = 0; s < DSTAGES - 1; ++s) {
+    if (s < nsteps) load_stage(s, s);
+    cp_commit();
+  }
+  for (int step = 0; step < nsteps; ++step) {
+    cp_wait<DSTAGES - 2>();
+    __syncthreads();
+    {
+      const int nxt = step + DSTAGES - 1;
+      if (nxt < nsteps) load_stage(nxt % DSTAGES, nxt);
+      cp_commit();
+    }
+    const int st = step % DSTAGES;
+    const double(*As)[DLDA] = sm.A[st];
+    const double(*Bl)[DLDB] = sm.Blo[st];
+    const double(*Bh)[DLDB] = sm.Bhi[st];
+#pragma unroll
+    for (int k4 = 0; k4 < DK; k4 += 4) {
+      const int k = k4 + (lane & 3);
+      double af[4], aa[4], bc[2], br[2];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        af[i] = As[k][wm + i * 8 + (lane >> 2)];
+        aa[i] = fabs(af[i]);
+      }
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const double lo = Bl[wn + j * 8 + (lane >> 2)][k], hi = Bh[wn + j * 8 + (lane >> 2)][k];
+        bc[j] = 0.5 * (lo + hi);
+        br[j] = 0.5 * (hi - lo);
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          dmma(acc0[i][j][0], acc0[i][j][1], af[i], bc[j]);
+          dmma(acc1[i][j][0], acc1[i][j][1], aa[i], br[j]);
+        }
+    }
+  }
+  cp_wait<0>();
+
+  bool bad = false;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int r = m0 + wm + i * 8 + (lane >> 2);
+    if (r >= M) continue;
+    const double bb = bias[r];
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int c = n0 + wn + j * 8 + (lane & 3) * 2 + e;
+        if (c >= N) continue;
+        const double mid = acc0[i][j][e] + bb;
+        const double ymin = mid - acc1[i][j][e], ymax = mid + acc1[i][j][e];
+        bad |= !(ymin <= ymax);
+        if (D0) {
+          D0[(long long)c * ldd + r] = ymin;
+          D1[(long long)c * ldd + r] = ymax;
+        }
+        if (write_x) {
+          C0[(long long)c * ldc + r] = relu ? fmax(ymin, 0.0) : ymin;
+          C1[(long long)c * ldc + r] = relu ? fmax(ymax, 0.0) : ymax;
+        }
+      }
+    }
+  }
+  if (bad && flag_bad) atomicOr(flag_bad, 1);
+}
+
 }  // namespace
 
 // Layers b0 .. b0 + nb - 1; the caller has checked what dgemm_dmma_launch checks, for every one of them.
@@ -159,6 +298,25 @@ int dgemm_dmma_affine_layers_launch(const NetDev& nd, int b0, int nb, int max_ro
 }
 
 
+
+// Interval propagation of one layer: Mk = [W_k b_k] (n_out x (n_in + 1), ld = n_out).  0 = operands not suitable.
+int ibp_dmma_launch(const double* Mk, int n_out_k, int n_in_k, const double* xin_min, const double* xin_max,
+                    long long x_stride, double* xout_min, double* xout_max, double* acx_min, double* acx_max,
+                    long long acx_stride, int Q, int relu, int write_x, int* flag_bad, cudaStream_t st) {
+  static const bool off = [] {
+    const char* e = getenv("NNSDP_NO_DMMA_GEMM"); const char* f = getenv("NNSDP_NO_DMMA_IBP");
+    return (e && atoi(e) != 0) || (f && atoi(f) != 0);
+  }();
+  if (off || n_out_k < 192 || Q < 128 || n_in_k < 128) return 0;
+  if (((uintptr_t)Mk | (uintptr_t)xin_min | (uintptr_t)xin_max) & 15) return 0;
+  if ((n_out_k & 1) || (x_stride & 1)) return 0;
+  cudaFuncSetAttribute(ibp_dmma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(IbpSmem));
+  const dim3 grid((n_out_k + DT - 1) / DT, (Q + IT_N - 1) / IT_N);
+  ibp_dmma_kernel<<<grid, ITHREADS, sizeof(IbpSmem), st>>>(Mk, n_out_k, n_out_k, n_in_k, xin_min, xin_max, x_stride, Q,
+                                                          Mk + (long long)n_in_k * n_out_k, xout_min, xout_max, x_stride,
+                                                          acx_min, acx_max, acx_stride, relu, write_x, flag_bad);
+  return 1;
+}
 
 // Returns 1 when the product was launched, 0 when the operands do not fit this kernel (the caller falls back).
 int dgemm_dmma_launch(const double* A, int lda, int M, int K, const double* B, long long ldb, double* C, long long ldc,

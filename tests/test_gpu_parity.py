@@ -1172,6 +1172,51 @@ def test_query_count_thresholds_of_the_bounds_and_affine_kernels(ctx, nq):
     b.close()
 
 
+@pytest.mark.parametrize("xdims,nq", [([2, 300, 260, 200, 2], 160), ([4, 194, 256, 131, 320, 3], 129),
+                                      ([2, 256, 250, 256, 2], 200)])
+def test_many_queries_on_wide_layers_use_the_tensor_core_bounds_and_affine_paths(ctx, xdims, nq):
+    """Q >= 128 on layers of >= 192 neurons: interval propagation as the two-accumulator FP64 tensor-core kernel
+    (centre / radius form of intervals_easy.jl:23-24) and the affine-column products of all layers in one launch.
+    Same bounds, sector slopes, affine column and blocks as the oracle; odd widths fall back layer by layer."""
+    import nnsdp_b200 as nb
+
+    beta = 2
+    net = rand_net(xdims, seed=31, sigma=0.15)
+    rng = np.random.default_rng(nq)
+    qs = [rand_query(net, beta, rng, kind="safety", radius=0.01 * (1 + i % 5)) for i in range(nq)]
+    dnet = nb.Net(ctx, net.xdims, net.Ms)
+    b = nb.Batch(dnet, beta, Qcap=nq, ring=4)
+    b.set_inputs(to_numeric_batch(nb, net, qs))
+    b.bounds()
+    b.prepare()
+    bd = b.get_bounds()
+    aff = b.get_affine()
+    for i in (0, 1, nq // 2, nq - 2, nq - 1):
+        _, xmin, xmax, amin, amax = _oracle_bounds(net, qs[i])
+        scale = max(np.abs(xmax).max(), np.abs(xmin).max(), 1.0)
+        assert np.abs(bd["xmin"][i] - xmin).max() <= TOL * scale
+        assert np.abs(bd["xmax"][i] - xmax).max() <= TOL * scale
+        assert np.abs(bd["acxmin"][i] - amin).max() <= TOL * scale
+        assert np.abs(bd["acxmax"][i] - amax).max() <= TOL * scale
+        rmin, rmax = o.make_sector_min_max(bd["acxmin"][i], bd["acxmax"][i])
+        assert np.array_equal(bd["smin"][i], rmin) and np.array_equal(bd["smax"][i], rmax)
+        ref = o.run_query(net, beta, qs[i])
+        assert relerr(aff[i], ref["Z"][:, -1]) <= TOL
+    # the same queries a few at a time (GEMV paths): same numbers to rounding
+    b8 = nb.Batch(dnet, beta, Qcap=8, ring=4)
+    b8.set_inputs(to_numeric_batch(nb, net, qs[:8]))
+    b8.bounds()
+    b8.prepare()
+    bd8, aff8 = b8.get_bounds(), b8.get_affine()
+    for key in ("xmin", "xmax", "acxmin", "acxmax"):
+        scale = max(np.abs(bd8[key]).max(), 1.0)
+        assert np.abs(bd8[key] - bd[key][:8]).max() <= 1e-13 * scale
+    assert np.array_equal(bd8["smin"], bd["smin"][:8]) and np.array_equal(bd8["smax"], bd["smax"][:8])
+    assert np.abs(aff8 - aff[:8]).max() <= 1e-12 * max(np.abs(aff8).max(), 1.0)
+    b.close()
+    b8.close()
+
+
 def test_recorded_optimum_minimiser_through_the_device_pipeline(ctx):
     """The reference's scale experiment on its shipped W10-D10 net (experiments/scale.jl: box [0.5, 1.5]^2,
     findEllipsoid), at the minimiser gamma* stored by oracle/sdp_crosscheck.py: the device pipeline -- CROWN bounds,
