@@ -20,11 +20,25 @@ namespace {
 // (four per DMMA, stage after stage) whatever the tile side, so the result does not depend on the choice.
 constexpr int GK = 16;         // neurons per pipeline stage
 constexpr int GSTAGES = 3;
-constexpr int GTHREADS = 256;  // 8 warps: 4 (rows) x 2 (cols), warp tile GT/4 x GT/2
+#ifndef NNSDP_GRAM_WARPS_N
+#define NNSDP_GRAM_WARPS_N 4
+#endif
+#ifndef NNSDP_GRAM_LD_PAD
+#define NNSDP_GRAM_LD_PAD 4
+#endif
+// 128 x 128 tiles: 16 warps, 4 (rows) x 4 (cols) of 32 x 32 (the DMMA cadence of one warp leaves the pipe half idle with
+// two warps per scheduler); 64 x 64 tiles: 8 warps, 4 x 2 of 16 x 32
+template <int GT>
+struct GramCfg {
+  static constexpr int WARPS_N = GT >= 128 ? NNSDP_GRAM_WARPS_N : 2;
+  static constexpr int THREADS = 4 * WARPS_N * 32;
+};
 
 template <int GT>
 struct GramSmem {
-  static constexpr int GLD = GT + 8;   // smem leading dimension: (k*GLD + row) hits 32 distinct banks pairs
+  // smem leading dimension: 4 (mod 16) puts the 4 x 8 (k, row) addresses of a fragment load in distinct 8-byte banks
+  // per half warp (GT + 8 gave two-way conflicts: k and k + 2 met in the same banks)
+  static constexpr int GLD = GT + NNSDP_GRAM_LD_PAD;
   double A[GSTAGES][GK][GLD];
   double B[GSTAGES][GK][GLD];
   double d[GSTAGES][GK];
@@ -48,9 +62,10 @@ __device__ __forceinline__ void dmma_m8n8k4(double& c0, double& c1, double a, do
 }
 
 template <int GT>
-__global__ void __launch_bounds__(GTHREADS, 1)
+__global__ void __launch_bounds__(GramCfg<GT>::THREADS, 1)
 gram_kernel(NetDev net, BatchDev b, GramDev g, int q0, const int* __restrict__ pairs) {
-  constexpr int GLD = GramSmem<GT>::GLD, WM = GT / 4, WN = GT / 2, NI = WM / 8, NJ = WN / 8;
+  constexpr int GTHREADS = GramCfg<GT>::THREADS;
+  constexpr int GLD = GramSmem<GT>::GLD, WM = GT / 4, WN = GT / GramCfg<GT>::WARPS_N, NI = WM / 8, NJ = WN / 8;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   GramSmem<GT>& sm = *reinterpret_cast<GramSmem<GT>*>(smem_raw);
 
@@ -164,7 +179,7 @@ static void launch_gram_t(const NetDev& net, const BatchDev& b, const GramDev& g
   cudaFuncSetAttribute(gram_kernel<GT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(GramSmem<GT>));
   const int ntile = (max_n + GT - 1) / GT;
   dim3 grid(npairs, ntile * (ntile + 1) / 2);  // grid.y <= 65535 is checked by launch_gram
-  gram_kernel<GT><<<grid, GTHREADS, sizeof(GramSmem<GT>), st>>>(net, b, g, q0, pairs);
+  gram_kernel<GT><<<grid, GramCfg<GT>::THREADS, sizeof(GramSmem<GT>), st>>>(net, b, g, q0, pairs);
 }
 
 int launch_gram(const NetDev& net, const BatchDev& b, const GramDev& g, int max_n, int q0, const int* pairs,
