@@ -1844,16 +1844,22 @@ int32_t crown_bounds_device(nnsdp_batch* b) {
   // queries per chunk: two row buffers of 2 * Qc * rows_cap * ld doubles, kept under ~1.5 GiB together
   int Qc = (int)std::max<int64_t>(1, std::min<int64_t>(b->Q, (int64_t(3) << 26) / std::max<int64_t>(1, 4 * rows_cap * ld)));
   Qc = std::min(Qc, 256);
-  // work buffers live in the batch; large ones (wide nets) are given back on return, small ones are kept so that
-  // repeated calls on narrow nets do not pay cudaMalloc / cudaFree (milliseconds, more than the kernels)
+  // work buffers live in the batch and are kept between calls (cudaMalloc + cudaFree of the ~0.5 GB row buffers of a
+  // wide net cost 50 .. 570 ms per call depending on the box, more than the 440 ms of kernels for 16 queries at width
+  // 1000); the chunk size above bounds them at ~1.5 GiB.  NNSDP_CROWN_KEEP_MB lowers the limit above which they are
+  // given back on return.
   DevBuf &rowsA = b->cr_rowsA, &rowsB = b->cr_rowsB, &bias = b->cr_bias, &prel = b->cr_prel, &preu = b->cr_preu,
          &du = b->cr_du, &bu = b->cr_bu, &dl = b->cr_dl;
+  static const size_t keep_cap = [] {
+    const char* e = getenv("NNSDP_CROWN_KEEP_MB");
+    return (size_t)(e ? std::max(0, atoi(e)) : 2048) << 20;
+  }();
   const size_t work_bytes = ((size_t)4 * Qc * rows_cap * ld + (size_t)2 * Qc * rows_cap + (size_t)5 * Qc * P) * 8;
   struct Rel {
     std::vector<DevBuf*> v;
     bool keep;
     ~Rel() { if (!keep) for (DevBuf* x : v) x->release(); }
-  } rel{{&rowsA, &rowsB, &bias, &prel, &preu, &du, &bu, &dl}, work_bytes <= ((size_t)64 << 20)};
+  } rel{{&rowsA, &rowsB, &bias, &prel, &preu, &du, &bu, &dl}, work_bytes <= keep_cap};
   NN_TRY(rowsA.ensure((size_t)2 * Qc * rows_cap * ld * 8));
   NN_TRY(rowsB.ensure((size_t)2 * Qc * rows_cap * ld * 8));
   NN_TRY(bias.ensure((size_t)2 * Qc * rows_cap * 8));
