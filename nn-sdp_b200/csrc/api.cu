@@ -225,7 +225,8 @@ struct nnsdp_batch {
   int64_t packed_emitted_bytes = 0, packed_present_cells = 0;  // of the last run
   nnsdp_sizes sz{};
   PlanHost plan;
-  DevBuf d_tiles, d_strips, d_mats, d_goff, d_ldG;
+  DevBuf d_tiles, d_strips, d_mats, d_panel, d_goff, d_ldG;
+  std::vector<int32_t> panel_host;
   std::vector<long long> goff;
   std::vector<int> ldG;
   long long gram_per_query = 0;
@@ -288,7 +289,7 @@ struct nnsdp_batch {
     spans.clear();
   }
   std::vector<DevBuf*> all_bufs() {
-    return {&d_bands, &d_tmaps, &d_tmap_ok, &d_tiles, &d_strips, &d_mats, &d_goff, &d_ldG, &x1min, &x1max, &ymin, &ymax, &smin, &smax,
+    return {&d_bands, &d_tmaps, &d_tmap_ok, &d_tiles, &d_strips, &d_mats, &d_panel, &d_goff, &d_ldG, &x1min, &x1max, &ymin, &ymax, &smin, &smax,
             &gin, &gbnd, &gsec, &outS, &outvec, &outinvP, &gout, &xmin, &xmax, &acxmin, &acxmax,
             &smin_c, &smax_c, &d11, &Md, &T0, &Bt, &u, &aff, &part, &act, &cnt, &Z11, &Z1K, &U,
             &gram, &ringbuf, &flags, &cr_rowsA, &cr_rowsB, &cr_bias, &cr_prel, &cr_preu, &cr_du, &cr_bu, &cr_dl};
@@ -824,6 +825,37 @@ int32_t nnsdp_batch_create(nnsdp_ctx* ctx, int32_t dev_index, const nnsdp_net* n
     b->pd.strips = b->d_strips.as<StripDev>();
     b->pd.tiles = b->d_tiles.as<TileDev>();
     b->pd.mats = b->d_mats.as<MatDev>();
+    b->pd.panel_items = nullptr;
+    b->pd.n_panel = 0;
+    {
+      // dense formats of wide nets: fill strips and window tiles in one launch, ordered by (matrix, 32-column panel,
+      // row) -- see emit_panel_kernel.  NNSDP_PANEL=0 keeps the two kernels.
+      static const int panel_env = [] { const char* e = getenv("NNSDP_PANEL"); return e ? atoi(e) : 1; }();
+      if (panel_env && !b->packed && !b->plan.band_inline && b->plan.n_window > 0 && beta <= MAX_WINDOW_BETA) {
+        struct Key { long long off; int panel, row0, col0, code; };
+        std::vector<Key> keys;
+        keys.reserve((size_t)b->plan.n_fill + b->plan.n_window);
+        for (int i = 0; i < b->plan.n_fill; ++i) {
+          const StripDev& d = b->plan.strips[i];
+          keys.push_back({d.out_off, d.col0 / 32, d.row0, d.col0, i});
+        }
+        for (int i = 0; i < b->plan.n_window; ++i) {
+          const TileDev& t = b->plan.tiles[b->plan.n_fill + i];
+          keys.push_back({b->plan.mats[t.mat].out_off, t.col0 / 32, t.row0, t.col0, ~i});
+        }
+        std::stable_sort(keys.begin(), keys.end(), [](const Key& x, const Key& y) {
+          if (x.off != y.off) return x.off < y.off;
+          if (x.panel != y.panel) return x.panel < y.panel;
+          if (x.col0 != y.col0) return x.col0 < y.col0;
+          return x.row0 < y.row0;
+        });
+        b->panel_host.resize(keys.size());
+        for (size_t i = 0; i < keys.size(); ++i) b->panel_host[i] = keys[i].code;
+        NN_TRY(upload(b->d_panel, b->panel_host.data(), b->panel_host.size() * 4, b->st));
+        b->pd.panel_items = b->d_panel.as<int>();
+        b->pd.n_panel = (int)keys.size();
+      }
+    }
     b->pd.ntiles = (int)b->plan.tiles.size();
     b->pd.n_fill = b->plan.n_fill;
     b->pd.n_window = b->plan.n_window;

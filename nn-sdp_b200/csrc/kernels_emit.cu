@@ -480,12 +480,11 @@ __device__ __forceinline__ double s22_entry(const double* WK, const double* U, i
 #define NNSDP_FILL_MINB 6
 #endif
 template <bool BAND_INLINE>  // DIAG strips add the band term themselves (narrow layers) or leave it to the band kernel
-__global__ void __launch_bounds__(ETHREADS, NNSDP_FILL_MINB)
-emit_fill_kernel(NetDev net, BatchDev b, GramDev g, PlanDev plan, int q0, int nq,
-                 double* __restrict__ out) {
-  const int4* dp = reinterpret_cast<const int4*>(plan.strips + blockIdx.x);
+__device__ __forceinline__ void fill_strip(const NetDev& net, const BatchDev& b, const GramDev& g, const PlanDev& plan,
+                                           int strip, int slot, int q0, double* __restrict__ out) {
+  const int4* dp = reinterpret_cast<const int4*>(plan.strips + strip);
   const int4 d0 = __ldg(dp), d1 = __ldg(dp + 1), d2 = __ldg(dp + 2);
-  const int slot = blockIdx.y, tid = threadIdx.x;
+  const int tid = threadIdx.x;
   const long long out_off = ((long long)(unsigned)d0.x) | ((long long)d0.y << 32);
   const long long ld = d1.x;
   const int row0 = d1.y, nrows = d1.z, col0 = d1.w, ncols = d2.x, prog = d2.w;
@@ -580,6 +579,13 @@ emit_fill_kernel(NetDev net, BatchDev b, GramDev g, PlanDev plan, int q0, int nq
 #undef NNSDP_STRIP_LOOP
 }
 
+template <bool BAND_INLINE>
+__global__ void __launch_bounds__(ETHREADS, NNSDP_FILL_MINB)
+emit_fill_kernel(NetDev net, BatchDev b, GramDev g, PlanDev plan, int q0, int nq,
+                 double* __restrict__ out) {
+  fill_strip<BAND_INLINE>(net, b, g, plan, blockIdx.x, blockIdx.y, q0, out);
+}
+
 // ---- kernel 2: RC / CR window sums (128 x 32 tiles, beta <= 4) ------------------------------------
 // One kernel for both programs: their CTAs interleave in plan order, so the rows a CR tile writes and the rows the
 // RC tile of the same columns writes reach DRAM close in time (dense formats: a column of a clique block is
@@ -596,6 +602,38 @@ emit_window_kernel(NetDev net, BatchDev b, PlanDev plan, int tile0, int q0, int 
   const int ti = group_major ? blockIdx.x % plan.n_window : blockIdx.x / ngroups;
   const int gi = group_major ? blockIdx.x / plan.n_window : blockIdx.x % ngroups;
   const TileDev t = plan.tiles[tile0 + ti];
+  const MatDev mat = plan.mats[t.mat];
+  const int slot0 = gi * group;
+  const int nslots = min(group, nq - slot0);
+  if (t.prog == PROG_RC) {
+    if (t.ncols == FAST_TC) emit_rc<BETA, true>(net, b, plan, t, mat, q0, slot0, nslots, out, smem);
+    else emit_rc<BETA, false>(net, b, plan, t, mat, q0, slot0, nslots, out, smem);
+  } else {
+    emit_cr<BETA>(net, b, plan, t, mat, q0, slot0, nslots, out, smem, &mbar);
+  }
+}
+
+// ---- kernels 1 + 2 as one launch in PANEL order (dense formats of wide nets) ----------------------------------
+// A column of a clique block is written by several programs: fill strips (zero / Gram / affine pieces) and window
+// tiles.  Launched one kernel after the other, the pieces of a column reach DRAM milliseconds apart and each launch
+// covers only part of every DRAM page it touches (tools/probe_write_bw.cu: two launches 5.7 TB/s, one launch with the
+// items ordered by 32-column panel 7.0 TB/s on pure stores).  Here the work items of both kernels are sorted by
+// (matrix, 32-column panel, row) and consecutive CTAs take consecutive items, so whole columns are written within
+// microseconds.  A strip CTA writes its strip for every ngroups-th query, a window CTA its tile for one query group.
+template <int BETA>
+__global__ void __launch_bounds__(ETHREADS, 4)
+emit_panel_kernel(NetDev net, BatchDev b, GramDev g, PlanDev plan, int q0, int nq, int group, double* __restrict__ out) {
+  constexpr int RC_DOUBLES = SLOT_GROUP * (BETA + 1) * (FAST_TC + BETA + 1), CR_DOUBLES = FAST_TC * CR_LDW(BETA);
+  __shared__ __align__(128) double smem[RC_DOUBLES > CR_DOUBLES ? RC_DOUBLES : CR_DOUBLES];
+  __shared__ __align__(8) unsigned long long mbar;
+  const int ngroups = (nq + group - 1) / group;
+  const int item = blockIdx.x / ngroups, gi = blockIdx.x % ngroups;
+  const int code = __ldg(plan.panel_items + item);   // >= 0: fill strip; < 0: window tile ~code
+  if (code >= 0) {
+    for (int slot = gi; slot < nq; slot += ngroups) fill_strip<false>(net, b, g, plan, code, slot, q0, out);
+    return;
+  }
+  const TileDev t = plan.tiles[plan.n_fill + ~code];
   const MatDev mat = plan.mats[t.mat];
   const int slot0 = gi * group;
   const int nslots = min(group, nq - slot0);
@@ -723,6 +761,22 @@ int launch_emit(const NetDev& net, const BatchDev& b, const GramDev& g, const Pl
   static const int egroup_env = [] { const char* e = getenv("NNSDP_EDGE_GROUP"); int v = e ? atoi(e) : 0; return v < 0 ? 0 : (v > SLOT_GROUP ? SLOT_GROUP : v); }();
   const int egroup = egroup_env > 0 ? egroup_env : (nq >= 64 ? SLOT_GROUP : (nq >= 16 ? 2 : 1));
   int launches = 0;
+  if (plan.n_panel > 0 && b.beta <= MAX_WINDOW_BETA) {   // fill strips and window tiles as one launch in panel order
+    if (which < 0 || which == 0) {
+      // queries per window CTA (a strip CTA then writes its strip for every ngroups-th query): 2 is the measured best
+      // (W1000-D20, 32-query pass: 7.57 ms against 7.75 ms with 4, 8.63 ms with 1; fill + window kernels 7.88 ms)
+      static const int pgroup = [] { const char* e = getenv("NNSDP_PANEL_GROUP"); int v = e ? atoi(e) : 2; return v < 1 ? 1 : (v > SLOT_GROUP ? SLOT_GROUP : v); }();
+      const dim3 grid((unsigned)plan.n_panel * ((nq + pgroup - 1) / pgroup));
+      switch (b.beta) {
+        case 0: emit_panel_kernel<0><<<grid, ETHREADS, 0, st>>>(net, b, g, plan, q0, nq, pgroup, out); break;
+        case 1: emit_panel_kernel<1><<<grid, ETHREADS, 0, st>>>(net, b, g, plan, q0, nq, pgroup, out); break;
+        case 2: emit_panel_kernel<2><<<grid, ETHREADS, 0, st>>>(net, b, g, plan, q0, nq, pgroup, out); break;
+        case 3: emit_panel_kernel<3><<<grid, ETHREADS, 0, st>>>(net, b, g, plan, q0, nq, pgroup, out); break;
+        default: emit_panel_kernel<4><<<grid, ETHREADS, 0, st>>>(net, b, g, plan, q0, nq, pgroup, out); break;
+      }
+      ++launches;
+    }
+  } else {
   if (plan.n_fill > 0 && (which < 0 || which == 0)) {
     if (plan.band_inline) emit_fill_kernel<true><<<dim3(plan.n_fill, nq), ETHREADS, 0, st>>>(net, b, g, plan, q0, nq, out);
     else emit_fill_kernel<false><<<dim3(plan.n_fill, nq), ETHREADS, 0, st>>>(net, b, g, plan, q0, nq, out);
@@ -745,6 +799,7 @@ int launch_emit(const NetDev& net, const BatchDev& b, const GramDev& g, const Pl
       default: return -1;  // the plan never emits window tiles for beta > MAX_WINDOW_BETA
     }
     ++launches;
+  }
   }
   if (plan.n_edge > 0 && (which < 0 || which == 2)) {
     emit_edge_kernel<<<dim3(plan.n_edge, (nq + egroup - 1) / egroup), ETHREADS, 0, st>>>(

@@ -1,5 +1,6 @@
 set -x
-timeout 300 python tools/sanitize_smoke.py > gpurun_out/san_plain.log 2>&1; tail -2 gpurun_out/san_plain.log
-timeout 1500 compute-sanitizer --tool memcheck --error-exitcode 9 python tools/sanitize_smoke.py > gpurun_out/san_memcheck.log 2>&1; echo memcheck rc=$?; tail -4 gpurun_out/san_memcheck.log
-timeout 1500 compute-sanitizer --tool racecheck --error-exitcode 9 python tools/sanitize_smoke.py > gpurun_out/san_racecheck.log 2>&1; echo racecheck rc=$?; tail -4 gpurun_out/san_racecheck.log
-timeout 600 python bench.py --steps 2 --warmup 3 --no-e2e > gpurun_out/g_bench.json 2> gpurun_out/g_bench.err; echo bench rc=$?
+export NNSDP_BENCH_RECAPTURE=1
+timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/f_pytest.log 2>&1; tail -2 gpurun_out/f_pytest.log
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:"emit_(panel|window|fill|edge|band)|gram_kernel" -s 12 -c 4 -o gpurun_out/f_emit_full python bench.py --steps 1 --warmup 3 --no-e2e --no-extras --queries 128 > gpurun_out/f_emit_full.log 2>&1
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -s 150 -c 300 --csv --log-file gpurun_out/f_launches.csv python bench.py --steps 2 --warmup 3 --no-e2e --no-extras > gpurun_out/f_launches.log 2>&1
+timeout 300 python bench.py --steps 3 --warmup 3 --no-e2e --no-extras > gpurun_out/f_quick.json 2> gpurun_out/f_quick.err
