@@ -1,6 +1,6 @@
-set -x
-export NNSDP_BENCH_RECAPTURE=1
-timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/f_pytest.log 2>&1; tail -2 gpurun_out/f_pytest.log
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:"emit_(panel|window|fill|edge|band)|gram_kernel" -s 12 -c 4 -o gpurun_out/f_emit_full python bench.py --steps 1 --warmup 3 --no-e2e --no-extras --queries 128 > gpurun_out/f_emit_full.log 2>&1
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -s 150 -c 300 --csv --log-file gpurun_out/f_launches.csv python bench.py --steps 2 --warmup 3 --no-e2e --no-extras > gpurun_out/f_launches.log 2>&1
-timeout 300 python bench.py --steps 3 --warmup 3 --no-e2e --no-extras > gpurun_out/f_quick.json 2> gpurun_out/f_quick.err
+run() { name=$1; shift; env "$@" timeout 300 python bench.py --steps 3 --warmup 3 --no-e2e --no-extras > gpurun_out/q_$name.json 2> gpurun_out/q_$name.err; }
+run base X=1
+run fs32 NNSDP_PANEL_FSPLIT=32
+run fs32g4 NNSDP_PANEL_FSPLIT=32 NNSDP_PANEL_GROUP=4
+run fs16g4 NNSDP_PANEL_FSPLIT=16 NNSDP_PANEL_GROUP=4
+run rowmaj NNSDP_PANEL_ROWMAJOR=1
