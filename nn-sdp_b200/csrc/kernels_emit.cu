@@ -759,7 +759,7 @@ int launch_emit(const NetDev& net, const BatchDev& b, const GramDev& g, const Pl
   static const int wgroup = [] { const char* e = getenv("NNSDP_WINDOW_GROUP"); int v = e ? atoi(e) : 4; return v < 1 ? 1 : (v > SLOT_GROUP ? SLOT_GROUP : v); }();
   // queries per edge CTA: one when a pass holds few queries (wide nets, 8 ring slots), eight when it holds many
   static const int egroup_env = [] { const char* e = getenv("NNSDP_EDGE_GROUP"); int v = e ? atoi(e) : 0; return v < 0 ? 0 : (v > SLOT_GROUP ? SLOT_GROUP : v); }();
-  const int egroup = egroup_env > 0 ? egroup_env : (nq >= 64 ? SLOT_GROUP : (nq >= 16 ? 2 : 1));
+  const int egroup = egroup_env > 0 ? egroup_env : (nq >= 64 ? SLOT_GROUP : (nq >= 16 ? 4 : 1));  // 32-query stress pass: 0.168 / 0.129 / 0.115 / 0.110 ms with 1 / 2 / 4 / 8
   int launches = 0;
   if (plan.n_panel > 0 && b.beta <= MAX_WINDOW_BETA) {   // fill strips and window tiles as one launch in panel order
     if (which < 0 || which == 0) {
