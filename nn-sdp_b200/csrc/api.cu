@@ -226,7 +226,7 @@ struct nnsdp_batch {
   nnsdp_sizes sz{};
   PlanHost plan;
   DevBuf d_tiles, d_strips, d_mats, d_panel, d_goff, d_ldG;
-  std::vector<int32_t> panel_host;
+  std::vector<StripDev> panel_host;
   std::vector<long long> goff;
   std::vector<int> ldG;
   long long gram_per_query = 0;
@@ -825,7 +825,7 @@ int32_t nnsdp_batch_create(nnsdp_ctx* ctx, int32_t dev_index, const nnsdp_net* n
     b->pd.strips = b->d_strips.as<StripDev>();
     b->pd.tiles = b->d_tiles.as<TileDev>();
     b->pd.mats = b->d_mats.as<MatDev>();
-    b->pd.panel_items = nullptr;
+    b->pd.panel_desc = nullptr;
     b->pd.n_panel = 0;
     {
       // dense formats of wide nets: fill strips and window tiles in one launch, ordered by (matrix, 32-column panel,
@@ -850,9 +850,24 @@ int32_t nnsdp_batch_create(nnsdp_ctx* ctx, int32_t dev_index, const nnsdp_net* n
           return x.row0 < y.row0;
         });
         b->panel_host.resize(keys.size());
-        for (size_t i = 0; i < keys.size(); ++i) b->panel_host[i] = keys[i].code;
-        NN_TRY(upload(b->d_panel, b->panel_host.data(), b->panel_host.size() * 4, b->st));
-        b->pd.panel_items = b->d_panel.as<int>();
+        for (size_t i = 0; i < keys.size(); ++i) {
+          const int code = keys[i].code;
+          if (code >= 0) {
+            b->panel_host[i] = b->plan.strips[code];
+            continue;
+          }
+          const TileDev& t = b->plan.tiles[b->plan.n_fill + ~code];
+          const MatDev& m = b->plan.mats[t.mat];
+          StripDev d{};
+          d.out_off = m.out_off;
+          d.ld = m.ld;
+          d.row0 = t.row0; d.nrows = t.nrows; d.col0 = t.col0; d.ncols = t.ncols;
+          d.grow0 = t.grow0; d.gcol0 = t.gcol0; d.prog = t.prog;
+          d.rblk = t.rblk; d.rl0 = t.cblk; d.cl0 = (int32_t)t.flags; d.ldG = m.n;
+          b->panel_host[i] = d;
+        }
+        NN_TRY(upload(b->d_panel, b->panel_host.data(), b->panel_host.size() * sizeof(StripDev), b->st));
+        b->pd.panel_desc = b->d_panel.as<StripDev>();
         b->pd.n_panel = (int)keys.size();
       }
     }

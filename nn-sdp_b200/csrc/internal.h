@@ -294,7 +294,8 @@ struct PlanDev {
   const StripDev* strips;    // n_fill entries, parallel to tiles[0 .. n_fill)
   const TileDev* tiles;
   const MatDev* mats;
-  const int* panel_items;    // n_panel work items of the panel-ordered launch: >= 0 fill strip, < 0 window tile ~code
+  const StripDev* panel_desc;  // n_panel work items of the panel-ordered launch: fill strips as they are; window tiles re-packed
+                             // (prog = PROG_RC / PROG_CR, rblk, rl0 = cblk, cl0 = flags, ldG = matrix order)
   int n_panel;               // 0: fill and window kernels run one after the other
   int ntiles;                // tiles are sorted: [fill | window | edge]
   int n_fill, n_window, n_edge;

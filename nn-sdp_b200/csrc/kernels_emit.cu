@@ -481,8 +481,8 @@ __device__ __forceinline__ double s22_entry(const double* WK, const double* U, i
 #endif
 template <bool BAND_INLINE>  // DIAG strips add the band term themselves (narrow layers) or leave it to the band kernel
 __device__ __forceinline__ void fill_strip(const NetDev& net, const BatchDev& b, const GramDev& g, const PlanDev& plan,
-                                           int strip, int slot, int q0, double* __restrict__ out) {
-  const int4* dp = reinterpret_cast<const int4*>(plan.strips + strip);
+                                           const StripDev* desc, int slot, int q0, double* __restrict__ out) {
+  const int4* dp = reinterpret_cast<const int4*>(desc);
   const int4 d0 = __ldg(dp), d1 = __ldg(dp + 1), d2 = __ldg(dp + 2);
   const int tid = threadIdx.x;
   const long long out_off = ((long long)(unsigned)d0.x) | ((long long)d0.y << 32);
@@ -583,7 +583,7 @@ template <bool BAND_INLINE>
 __global__ void __launch_bounds__(ETHREADS, NNSDP_FILL_MINB)
 emit_fill_kernel(NetDev net, BatchDev b, GramDev g, PlanDev plan, int q0, int nq,
                  double* __restrict__ out) {
-  fill_strip<BAND_INLINE>(net, b, g, plan, blockIdx.x, blockIdx.y, q0, out);
+  fill_strip<BAND_INLINE>(net, b, g, plan, plan.strips + blockIdx.x, blockIdx.y, q0, out);
 }
 
 // ---- kernel 2: RC / CR window sums (128 x 32 tiles, beta <= 4) ------------------------------------
@@ -628,13 +628,24 @@ emit_panel_kernel(NetDev net, BatchDev b, GramDev g, PlanDev plan, int q0, int n
   __shared__ __align__(8) unsigned long long mbar;
   const int ngroups = (nq + group - 1) / group;
   const int item = blockIdx.x / ngroups, gi = blockIdx.x % ngroups;
-  const int code = __ldg(plan.panel_items + item);   // >= 0: fill strip; < 0: window tile ~code
-  if (code >= 0) {
-    for (int slot = gi; slot < nq; slot += ngroups) fill_strip<false>(net, b, g, plan, code, slot, q0, out);
+  // one self-contained 64 B descriptor per item, in panel order: a fill strip as it is, a window tile re-packed into
+  // the same layout (no index -> tile -> matrix chain of dependent loads at the start of a short CTA)
+  const StripDev* desc = plan.panel_desc + item;
+  const int4* dp = reinterpret_cast<const int4*>(desc);
+  const int4 d2 = __ldg(dp + 2);
+  if (d2.w != PROG_RC && d2.w != PROG_CR) {
+    for (int slot = gi; slot < nq; slot += ngroups) fill_strip<false>(net, b, g, plan, desc, slot, q0, out);
     return;
   }
-  const TileDev t = plan.tiles[plan.n_fill + ~code];
-  const MatDev mat = plan.mats[t.mat];
+  const int4 d0 = __ldg(dp), d1 = __ldg(dp + 1), d3 = __ldg(dp + 3);
+  TileDev t;
+  t.mat = 0;
+  t.row0 = d1.y, t.nrows = d1.z, t.col0 = d1.w, t.ncols = d2.x, t.grow0 = d2.y, t.gcol0 = d2.z, t.prog = d2.w;
+  t.rblk = d3.x, t.cblk = d3.y, t.flags = (uint32_t)d3.z;
+  MatDev mat;
+  mat.out_off = ((long long)(unsigned)d0.x) | ((long long)d0.y << 32);
+  mat.ld = d1.x;
+  mat.n = d3.w;
   const int slot0 = gi * group;
   const int nslots = min(group, nq - slot0);
   if (t.prog == PROG_RC) {

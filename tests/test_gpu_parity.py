@@ -747,6 +747,53 @@ def test_wide_nets_all_programs(ctx, xdims, beta, kind):
             assert relerr(blk, rb) <= TOL
 
 
+_PANEL_SNIPPET = r"""
+import hashlib, os, sys
+import numpy as np
+root = sys.argv[1]
+for p in ("nn-sdp_b200", "oracle", "tests"):
+    sys.path.insert(0, os.path.join(root, p))
+import nnsdp_b200 as nb
+from helpers import rand_net, rand_query, to_numeric_batch
+ctx = nb.Context([0])
+for xdims, beta in (([2, 300, 270, 280, 2], 2), ([3, 150, 260, 140, 2], 4), ([2, 129, 128, 127, 300, 4], 3)):
+    net = rand_net(xdims, seed=3, sigma=0.1)
+    rng = np.random.default_rng(5)
+    qs = [rand_query(net, beta, rng, kind="ellipsoid", radius=0.004 * i) for i in range(7)]
+    dnet = nb.Net(ctx, net.xdims, net.Ms)
+    for ring in (3, 7):
+        b = nb.Batch(dnet, beta, Qcap=7, ring=ring)
+        b.set_inputs(to_numeric_batch(nb, net, qs))
+        out = np.full((7, b.per_query), np.nan)
+        b.run(out)
+        fill, window = b.stage_ms("emit_fill")[1], b.stage_ms("emit_window")[1]
+        b.close()
+        print(hashlib.sha256(out.tobytes()).hexdigest(), int(np.isnan(out).sum()), fill, window)
+"""
+
+
+def test_panel_ordered_launch_equals_the_separate_kernels(ctx, tmp_path):
+    """Dense blocks of wide nets: the fill strips and the window tiles as one panel-ordered launch (the default) and as
+    two kernels one after the other (NNSDP_PANEL=0) are the same programs on the same items -- the outputs must agree
+    bit for bit, for whole and ragged passes.  The switch is read once per process, hence the two subprocesses."""
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    script = tmp_path / "panel_ab.py"
+    script.write_text(_PANEL_SNIPPET)
+    outs = {}
+    for mode in ("1", "0"):
+        env = dict(os.environ, NNSDP_PANEL=mode)
+        r = subprocess.run([sys.executable, str(script), root], capture_output=True, text=True, env=env, timeout=600)
+        assert r.returncode == 0, r.stderr[-2000:]
+        outs[mode] = [ln.split() for ln in r.stdout.strip().splitlines()]
+    assert len(outs["1"]) == 6 and len(outs["0"]) == 6
+    for a, b_ in zip(outs["1"], outs["0"]):
+        assert a[0] == b_[0] and a[1] == b_[1] == "0"          # same bytes, every entry written
+        assert int(a[3]) == 0 and int(b_[3]) > 0               # one launch against two: the window span is empty / used
+
+
 def test_ragged_batches_and_rings(ctx):
     """Q not a multiple of the ring, ring of 1, Q = 1, more ring slots than queries."""
     import nnsdp_b200 as nb
