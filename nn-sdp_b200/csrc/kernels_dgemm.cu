@@ -168,35 +168,42 @@ dgemm_dmma_affine_layers_kernel(NetDev net, int b0, const double* __restrict__ u
 // 16 warps of 32 x 16: at width 1000 and 1024 boxes that is 8 x 16 = 128 CTAs for 148 SMs in a single wave.
 // ---------------------------------------------------------------------------------------------
 constexpr int IT_N = 64;                     // boxes per CTA
-constexpr int ITHREADS = 512;
 
+// WM = warps along the neurons: the CTA owns 32 WM neurons x 64 boxes with 4 WM warps of 32 x 16.  WM = 4 at the stress
+// size (128 CTAs for 1000 neurons x 1024 boxes); batches of a few hundred boxes take WM = 2 or 1 so that the launch
+// still covers the SMs (a CTA is bound by its own DMMA stream: 1000 neurons x 128 boxes as 16 CTAs of WM = 4 take
+// 0.19 ms per layer whatever the rest of the GPU does).
+template <int WM>
 struct IbpSmem {
-  double A[DSTAGES][DK][DLDA];
+  static constexpr int TM = 32 * WM, LDA = TM + 4;
+  double A[DSTAGES][DK][LDA];
   double Blo[DSTAGES][IT_N][DLDB];
   double Bhi[DSTAGES][IT_N][DLDB];
 };
 
-__global__ void __launch_bounds__(ITHREADS, 1)
+template <int WM>
+__global__ void __launch_bounds__(128 * WM, 1)
 ibp_dmma_kernel(const double* __restrict__ A, int lda, int M, int K, const double* __restrict__ Xlo,
                 const double* __restrict__ Xhi, long long ldb, int N, const double* __restrict__ bias,
                 double* __restrict__ C0, double* __restrict__ C1, long long ldc, double* __restrict__ D0,
                 double* __restrict__ D1, long long ldd, int relu, int write_x, int* __restrict__ flag_bad) {
+  constexpr int TM = IbpSmem<WM>::TM, NTHREADS = 128 * WM;
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  IbpSmem& sm = *reinterpret_cast<IbpSmem*>(smem_raw);
-  const int m0 = blockIdx.x * DT, n0 = blockIdx.y * IT_N;
+  IbpSmem<WM>& sm = *reinterpret_cast<IbpSmem<WM>*>(smem_raw);
+  const int m0 = blockIdx.x * TM, n0 = blockIdx.y * IT_N;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int wm = (warp & 3) * 32, wn = (warp >> 2) * 16;
+  const int wm = (warp % WM) * 32, wn = (warp / WM) * 16;
   const int nsteps = (K + DK - 1) / DK;
 
   auto load_stage = [&](int stage, int step) {
     const int k0 = step * DK;
-    for (int c = tid; c < DK * (DT / 2); c += ITHREADS) {
-      const int kk = c / (DT / 2), ch = c % (DT / 2);
+    for (int c = tid; c < DK * (TM / 2); c += NTHREADS) {
+      const int kk = c / (TM / 2), ch = c % (TM / 2);
       const int m = m0 + ch * 2, k = k0 + kk;
       const int rows = (k < K) ? max(0, min(2, M - m)) : 0;
       cp16(&sm.A[stage][kk][ch * 2], rows ? A + (long long)k * lda + m : A, rows * 8);
     }
-    for (int c = tid; c < 2 * IT_N * (DK / 2); c += ITHREADS) {
+    for (int c = tid; c < 2 * IT_N * (DK / 2); c += NTHREADS) {
       const int which = c / (IT_N * (DK / 2)), cc = c % (IT_N * (DK / 2));
       const int nn = cc / (DK / 2), ch = cc % (DK / 2);
       const int n = n0 + nn, k = k0 + ch * 2;
@@ -225,7 +232,7 @@ ibp_dmma_kernel(const double* __restrict__ A, int lda, int M, int K, const doubl
       cp_commit();
     }
     const int st = step % DSTAGES;
-    const double(*As)[DLDA] = sm.A[st];
+    const double(*As)[IbpSmem<WM>::LDA] = sm.A[st];
     const double(*Bl)[DLDB] = sm.Blo[st];
     const double(*Bh)[DLDB] = sm.Bhi[st];
 #pragma unroll
@@ -283,6 +290,18 @@ ibp_dmma_kernel(const double* __restrict__ A, int lda, int M, int K, const doubl
   if (bad && flag_bad) atomicOr(flag_bad, 1);
 }
 
+template <int WM>
+static void ibp_dmma_launch_t(const double* Mk, int n_out_k, int n_in_k, const double* xin_min, const double* xin_max,
+                              long long x_stride, double* xout_min, double* xout_max, double* acx_min, double* acx_max,
+                              long long acx_stride, int Q, int relu, int write_x, int* flag_bad, cudaStream_t st) {
+  cudaFuncSetAttribute(ibp_dmma_kernel<WM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(IbpSmem<WM>));
+  const dim3 grid((n_out_k + 32 * WM - 1) / (32 * WM), (Q + IT_N - 1) / IT_N);
+  ibp_dmma_kernel<WM><<<grid, 128 * WM, sizeof(IbpSmem<WM>), st>>>(Mk, n_out_k, n_out_k, n_in_k, xin_min, xin_max, x_stride, Q,
+                                                                 Mk + (long long)n_in_k * n_out_k, xout_min, xout_max,
+                                                                 x_stride, acx_min, acx_max, acx_stride, relu, write_x,
+                                                                 flag_bad);
+}
+
 }  // namespace
 
 // Layers b0 .. b0 + nb - 1; the caller has checked what dgemm_dmma_launch checks, for every one of them.
@@ -310,11 +329,15 @@ int ibp_dmma_launch(const double* Mk, int n_out_k, int n_in_k, const double* xin
   if (off || n_out_k < 192 || Q < 128 || n_in_k < 128) return 0;
   if (((uintptr_t)Mk | (uintptr_t)xin_min | (uintptr_t)xin_max) & 15) return 0;
   if ((n_out_k & 1) || (x_stride & 1)) return 0;
-  cudaFuncSetAttribute(ibp_dmma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(IbpSmem));
-  const dim3 grid((n_out_k + DT - 1) / DT, (Q + IT_N - 1) / IT_N);
-  ibp_dmma_kernel<<<grid, ITHREADS, sizeof(IbpSmem), st>>>(Mk, n_out_k, n_out_k, n_in_k, xin_min, xin_max, x_stride, Q,
-                                                          Mk + (long long)n_in_k * n_out_k, xout_min, xout_max, x_stride,
-                                                          acx_min, acx_max, acx_stride, relu, write_x, flag_bad);
+  // the largest tile whose grid still covers the SMs
+  const long long nt = (Q + IT_N - 1) / IT_N;
+  const int wm = ((n_out_k + 127) / 128) * nt >= 120 ? 4 : (((n_out_k + 63) / 64) * nt >= 120 ? 2 : 1);
+#define NNSDP_IBP(W) ibp_dmma_launch_t<W>(Mk, n_out_k, n_in_k, xin_min, xin_max, x_stride, xout_min, xout_max, acx_min, acx_max, \
+                                          acx_stride, Q, relu, write_x, flag_bad, st)
+  if (wm == 4) NNSDP_IBP(4);
+  else if (wm == 2) NNSDP_IBP(2);
+  else NNSDP_IBP(1);
+#undef NNSDP_IBP
   return 1;
 }
 
