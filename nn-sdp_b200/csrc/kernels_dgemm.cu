@@ -33,12 +33,21 @@ constexpr int DLDA = DT + NNSDP_DGEMM_LDA_PAD;  // As leading dimension: 4 (mod 
 constexpr int DLDB = DK + 4;    // Bs leading dimension
 constexpr int DWN = NNSDP_DGEMM_WN;             // columns per warp tile (rows: 32)
 constexpr int DNJ = DWN / 8;
-constexpr int DTHREADS = 4 * (DT / DWN) * 32;   // 16 warps of 32 x 32: the DMMA issue cadence of a warp leaves the pipe half
+#ifndef NNSDP_DGEMM_TN
+#define NNSDP_DGEMM_TN 64
+#endif
+#ifndef NNSDP_DGEMM_MINB
+#define NNSDP_DGEMM_MINB 2
+#endif
+constexpr int DTN = NNSDP_DGEMM_TN;             // tile columns (rows: DT).  128 x 64 tiles, 8 warps, two CTAs per SM: one CTA's
+                                                // barrier and pipeline fill hide under the other's DMMA stream (CROWN W1000-D20
+                                                // 68.3 -> 66.1 ms per 2 queries, affine launch 2.49 -> 2.31 ms against 128 x 128 x 1)
+constexpr int DTHREADS = 4 * (DTN / DWN) * 32;   // 16 warps of 32 x 32: the DMMA issue cadence of a warp leaves the pipe half
                                                 // idle with 2 warps per scheduler (8 warps of 32 x 64)
 
 struct DgemmSmem {
   double A[DSTAGES][DK][DLDA];
-  double B[DSTAGES][DT][DLDB];
+  double B[DSTAGES][DTN][DLDB];
 };
 
 __device__ __forceinline__ void cp16(void* smem, const void* gmem, int src_bytes) {
@@ -61,7 +70,7 @@ __device__ __forceinline__ void dgemm_tile(const double* __restrict__ A, int lda
                                            long long ldb, double* __restrict__ C, long long ldc, int N) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   DgemmSmem& sm = *reinterpret_cast<DgemmSmem*>(smem_raw);
-  const int m0 = blockIdx.x * DT, n0 = blockIdx.y * DT;
+  const int m0 = blockIdx.x * DT, n0 = blockIdx.y * DTN;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int wm = (warp & 3) * 32, wn = (warp >> 2) * DWN;
   const int nsteps = (K + DK - 1) / DK;
@@ -76,7 +85,7 @@ __device__ __forceinline__ void dgemm_tile(const double* __restrict__ A, int lda
       cp16(&sm.A[stage][kk][ch * 2], rows ? A + (long long)k * lda + m : A, rows * 8);
     }
     // B: 128 columns x 8 chunks of two contraction indices
-    for (int c = tid; c < DT * (DK / 2); c += DTHREADS) {
+    for (int c = tid; c < DTN * (DK / 2); c += DTHREADS) {
       const int nn = c / (DK / 2), ch = c % (DK / 2);
       const int n = n0 + nn, k = k0 + ch * 2;
       const int cnt = (n < N) ? max(0, min(2, K - k)) : 0;
@@ -139,7 +148,7 @@ __device__ __forceinline__ void dgemm_tile(const double* __restrict__ A, int lda
 }
 
 template <int ACC>
-__global__ void __launch_bounds__(DTHREADS, 1)
+__global__ void __launch_bounds__(DTHREADS, NNSDP_DGEMM_MINB)
 dgemm_dmma_kernel(const double* __restrict__ A, int lda, int M, int K, const double* __restrict__ B, long long ldb,
                   double* __restrict__ C, long long ldc, int N) {
   dgemm_tile<ACC>(A, lda, M, K, B, ldb, C, ldc, N);
@@ -148,7 +157,7 @@ dgemm_dmma_kernel(const double* __restrict__ A, int lda, int M, int K, const dou
 // The affine-column products of ALL layers in one launch (blockIdx.z = layer): aff[off_b ..] += Wt_b u_{b+1} for
 // b = 0 .. K-2.  The products are independent; one layer alone is 8 x 8 tiles at width 1000 and Q = 1024 -- 64 CTAs on
 // 148 SMs -- so launched layer by layer they run at 10 TFLOP/s.
-__global__ void __launch_bounds__(DTHREADS, 1)
+__global__ void __launch_bounds__(DTHREADS, NNSDP_DGEMM_MINB)
 dgemm_dmma_affine_layers_kernel(NetDev net, int b0, const double* __restrict__ u, long long u_stride,
                                 double* __restrict__ aff, long long aff_stride, int Q) {
   const int b = b0 + blockIdx.z;
@@ -311,7 +320,7 @@ int dgemm_dmma_affine_layers_launch(const NetDev& nd, int b0, int nb, int max_ro
   static const bool off2 = [] { const char* e = getenv("NNSDP_NO_AFFINE_LAYERS"); return e && atoi(e) != 0; }();
   if (off || off2 || nb < 2 || Q < 128) return 0;
   cudaFuncSetAttribute(dgemm_dmma_affine_layers_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DgemmSmem));
-  const dim3 grid((max_rows + DT - 1) / DT, (Q + DT - 1) / DT, nb);
+  const dim3 grid((max_rows + DT - 1) / DT, (Q + DTN - 1) / DTN, nb);
   dgemm_dmma_affine_layers_kernel<<<grid, DTHREADS, sizeof(DgemmSmem), st>>>(nd, b0, u, u_stride, aff, aff_stride, Q);
   return 1;
 }
@@ -350,7 +359,7 @@ int dgemm_dmma_launch(const double* A, int lda, int M, int K, const double* B, l
   if ((lda & 1) || (ldb & 1)) return 0;
   cudaFuncSetAttribute(dgemm_dmma_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DgemmSmem));
   cudaFuncSetAttribute(dgemm_dmma_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DgemmSmem));
-  const dim3 grid((M + DT - 1) / DT, (N + DT - 1) / DT);
+  const dim3 grid((M + DT - 1) / DT, (N + DTN - 1) / DTN);
   if (accumulate) dgemm_dmma_kernel<1><<<grid, DTHREADS, sizeof(DgemmSmem), st>>>(A, lda, M, K, B, ldb, C, ldc, N);
   else dgemm_dmma_kernel<0><<<grid, DTHREADS, sizeof(DgemmSmem), st>>>(A, lda, M, K, B, ldb, C, ldc, N);
   return 1;
