@@ -2,7 +2,7 @@
 // Used by the CROWN chain steps on wide layers (A = W_k', B = the stack of relaxed rows: N = 2 x queries x rows),
 // by the affine-column product of the QC preparation and by the factored matvec of the lambda_max check when
 // many queries share a launch.  tcgen05 has no f64 kind, so this is the DMMA path (mma.sync.m8n8k4.f64), the same
-// building block as the Gram kernel (kernels_gram.cu): 128 x 128 tiles, 8 warps of 32 x 64, 3 cp.async stages.
+// building block as the Gram kernel (kernels_gram.cu): 128 x 64 tiles, 8 warps of 32 x 32, two CTAs per SM, 3 cp.async stages.
 //   A tile: As[k][m]   (columns of A are contiguous in m: 16 B chunks along m)
 //   B tile: Bs[n][k]   (columns of B are contiguous in k: 16 B chunks along k; leading dimension 20 doubles puts
 //                       the 4 x 4 (k, n) addresses of a half warp's fragment load in 16 distinct 8-byte banks)
