@@ -178,8 +178,8 @@ dgemm_dmma_affine_layers_kernel(NetDev net, int b0, const double* __restrict__ u
 // ---------------------------------------------------------------------------------------------
 constexpr int IT_N = 64;                     // boxes per CTA
 
-// WM = warps along the neurons: the CTA owns 32 WM neurons x 64 boxes with 4 WM warps of 32 x 16.  WM = 4 at the stress
-// size (128 CTAs for 1000 neurons x 1024 boxes); batches of a few hundred boxes take WM = 2 or 1 so that the launch
+// WM = warps along the neurons: the CTA owns 32 WM neurons x 64 boxes with 4 WM warps of 32 x 16.  WM = 2 at the stress
+// size (256 CTAs for 1000 neurons x 1024 boxes, two per SM); batches of a few hundred boxes take WM = 1 so that the launch
 // still covers the SMs (a CTA is bound by its own DMMA stream: 1000 neurons x 128 boxes as 16 CTAs of WM = 4 take
 // 0.19 ms per layer whatever the rest of the GPU does).
 template <int WM>
@@ -340,7 +340,10 @@ int ibp_dmma_launch(const double* Mk, int n_out_k, int n_in_k, const double* xin
   if ((n_out_k & 1) || (x_stride & 1)) return 0;
   // the largest tile whose grid still covers the SMs
   const long long nt = (Q + IT_N - 1) / IT_N;
-  const int wm = ((n_out_k + 127) / 128) * nt >= 120 ? 4 : (((n_out_k + 63) / 64) * nt >= 120 ? 2 : 1);
+  static const int wm_env = [] { const char* e = getenv("NNSDP_IBP_WM"); return e ? atoi(e) : 0; }();
+  // 64-neuron tiles run two CTAs per SM (one CTA's barrier hides under the other's DMMA stream): 1000 neurons x 1024 boxes
+  // 3.94 ms per 20 layers against 4.14 ms with 128-neuron tiles and 4.50 ms with 32-neuron ones (NNSDP_IBP_WM forces one)
+  const int wm = wm_env ? wm_env : (((n_out_k + 63) / 64) * nt >= 120 ? 2 : 1);
 #define NNSDP_IBP(W) ibp_dmma_launch_t<W>(Mk, n_out_k, n_in_k, xin_min, xin_max, x_stride, xout_min, xout_max, acx_min, acx_max, \
                                           acx_stride, Q, relu, write_x, flag_bad, st)
   if (wm == 4) NNSDP_IBP(4);
