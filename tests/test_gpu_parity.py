@@ -1221,8 +1221,8 @@ def test_query_count_thresholds_of_the_bounds_and_affine_kernels(ctx, nq):
 
 @pytest.mark.parametrize("xdims,nq", [([2, 300, 260, 200, 2], 160), ([4, 194, 256, 131, 320, 3], 129),
                                       ([2, 256, 250, 256, 2], 200),
-                                      ([2, 960, 1000, 2], 512),     # 64-neuron tiles (two warps along the neurons)
-                                      ([2, 640, 768, 2], 1536)])    # 128-neuron tiles, as at the stress size
+                                      ([2, 960, 1000, 2], 512),     # 64-neuron tiles (the three above: 32-neuron tiles)
+                                      ([2, 640, 768, 2], 1536)])    # 64-neuron tiles, 24 column tiles
 def test_many_queries_on_wide_layers_use_the_tensor_core_bounds_and_affine_paths(ctx, xdims, nq):
     """Q >= 128 on layers of >= 192 neurons: interval propagation as the two-accumulator FP64 tensor-core kernel
     (centre / radius form of intervals_easy.jl:23-24) and the affine-column products of all layers in one launch.
