@@ -1,7 +1,14 @@
-run() { name=$1; shift; env "$@" timeout 300 python bench.py --steps 2 --warmup 2 --no-e2e --no-extras > gpurun_out/y_$name.json 2> gpurun_out/y_$name.err; }
-run r256 NNSDP_STRIP_ROWS=256
-run r1024 NNSDP_STRIP_ROWS=1024
-run r2048 NNSDP_STRIP_ROWS=2048
-run c16 NNSDP_STRIP_COLS=16
-run c32 NNSDP_STRIP_COLS=32
-run r1024c4 NNSDP_STRIP_ROWS=1024 NNSDP_STRIP_COLS=4
+# end-of-round measurement at one GPU: smoke, GPU tests, the default bench line, the reference arm, ncu launch list and
+# the --set full captures the roofline figures cite (profiles/README.md).  NNSDP_BENCH_RECAPTURE=1 lets bench.py run while
+# profiles/r2_emit_full.summary.csv is being re-captured.
+set -x
+export NNSDP_BENCH_RECAPTURE=1
+timeout 300 python __graft_entry__.py smoke > gpurun_out/f_smoke.log 2>&1; echo smoke rc=$?
+timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/f_pytest.log 2>&1; tail -2 gpurun_out/f_pytest.log
+timeout 900 python bench.py --steps 5 --warmup 3 > gpurun_out/f_bench_n1.json 2> gpurun_out/f_bench_n1.err; echo bench rc=$?
+timeout 600 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/f_bench_ref.json 2> gpurun_out/f_bench_ref.err; echo ref rc=$?
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -s 150 -c 300 --csv --log-file gpurun_out/f_launches.csv python bench.py --steps 2 --warmup 3 --no-e2e --no-extras > gpurun_out/f_launches.log 2>&1
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:"emit_(panel|window|fill|edge|band)|gram_kernel" -s 12 -c 4 -o gpurun_out/f_emit_full python bench.py --steps 1 --warmup 3 --no-e2e --no-extras --queries 128 > gpurun_out/f_emit_full.log 2>&1
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:"ibp_dmma|dgemm_dmma_affine" -s 19 -c 2 -o gpurun_out/f_fp64_full python bench.py --steps 1 --warmup 1 --no-e2e --no-extras > gpurun_out/f_fp64_full.log 2>&1
+timeout 300 python tools/crown_timing.py > gpurun_out/f_crown_timing.txt 2>&1
+timeout 300 python tools/latency_small.py > gpurun_out/f_latency_small.txt 2>&1
