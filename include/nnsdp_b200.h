@@ -174,6 +174,15 @@ int32_t nnsdp_plan_stats(int64_t K, const int64_t* xdims, int64_t beta, int32_t 
 int32_t nnsdp_plan_tiles(int64_t K, const int64_t* xdims, int64_t beta, int32_t dense_Z,
                          int64_t max_tiles, int32_t* tiles_out, int64_t* ntiles);
 
+/* The panel-ordered work list of the dense formats of wide nets (host only): the items of the fill and the window
+ * program classes as ONE list sorted by (output matrix, 32-column panel, first column, first row), so that all pieces
+ * of a column of a clique block are written by consecutive CTAs of one launch.  10 int64 per item {out_off, ld, row0,
+ * nrows, col0, ncols, grow0, gcol0, prog, rblk} (out_off = offset in doubles of the item's matrix inside one query's
+ * output; rows / columns local to that matrix).  *nitems == 0: this plan keeps the separate kernels (packed records,
+ * narrow layers, beta above the window programs).  items_out == NULL queries the count. */
+int32_t nnsdp_plan_panel(int64_t K, const int64_t* xdims, int64_t beta, int32_t dense_Z, int64_t max_items,
+                         int64_t* items_out, int64_t* nitems);
+
 /* The host-gather plan of nnsdp_batch_run_ex (host only, for inspection and tests): every output matrix cut at
  * block boundaries into cells, 8 int32 each {mat, row0, nrows, col0, ncols, kind, blk, pure_zero} with kind
  * 0 = never copied as a whole, 1 = always dense, 2 = dense when layer blk has a stably-active neuron,

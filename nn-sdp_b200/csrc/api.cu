@@ -226,7 +226,6 @@ struct nnsdp_batch {
   nnsdp_sizes sz{};
   PlanHost plan;
   DevBuf d_tiles, d_strips, d_mats, d_panel, d_goff, d_ldG;
-  std::vector<StripDev> panel_host;
   std::vector<long long> goff;
   std::vector<int> ldG;
   long long gram_per_query = 0;
@@ -663,6 +662,31 @@ int32_t nnsdp_plan_tiles(int64_t K, const int64_t* xdims, int64_t beta, int32_t 
   return NNSDP_OK;
 }
 
+int32_t nnsdp_plan_panel(int64_t K, const int64_t* xdims, int64_t beta, int32_t dense_Z, int64_t max_items,
+                         int64_t* items_out, int64_t* nitems) {
+  NN_CHECK(nitems != nullptr, NNSDP_ERR_ARG, "NULL argument");
+  Shape sh;
+  NN_TRY(shape_from_xdims(K, xdims, &sh));
+  nnsdp_sizes sz;
+  NN_TRY(fill_sizes(sh, beta, &sz));
+  std::vector<CliqueRanges> mats;
+  NN_TRY(format_mats(sh, beta, dense_Z, &mats));
+  PlanHost plan;
+  PackedLayout lay;
+  NN_TRY(build_plan(sh, beta, mats, true, &plan, dense_Z == NNSDP_FORMAT_PACKED ? &lay : nullptr));
+  *nitems = (int64_t)plan.panel.size();
+  if (items_out) {
+    NN_CHECK(max_items >= *nitems, NNSDP_ERR_ARG, "items_out too small");
+    for (size_t i = 0; i < plan.panel.size(); ++i) {
+      const StripDev& d = plan.panel[i];
+      int64_t* o = items_out + 10 * i;
+      o[0] = d.out_off; o[1] = d.ld; o[2] = d.row0; o[3] = d.nrows; o[4] = d.col0; o[5] = d.ncols;
+      o[6] = d.grow0; o[7] = d.gcol0; o[8] = d.prog; o[9] = d.rblk;
+    }
+  }
+  return NNSDP_OK;
+}
+
 /* The host-gather plan (host only): cells {mat, row0, nrows, col0, ncols, kind, blk, pure_zero} (8 int32 each;
  * kind 0 = never dense, 1 = always, 2 = Gram-active layers only, 3 = S22 only) and the thin-entry offsets
  * (doubles inside one query's output).  Either output may be NULL to query the counts. */
@@ -828,47 +852,13 @@ int32_t nnsdp_batch_create(nnsdp_ctx* ctx, int32_t dev_index, const nnsdp_net* n
     b->pd.panel_desc = nullptr;
     b->pd.n_panel = 0;
     {
-      // dense formats of wide nets: fill strips and window tiles in one launch, ordered by (matrix, 32-column panel,
-      // row) -- see emit_panel_kernel.  NNSDP_PANEL=0 keeps the two kernels.
+      // dense formats of wide nets: fill strips and window tiles in one launch in panel order (plan.cpp build_panel,
+      // emit_panel_kernel).  NNSDP_PANEL=0 keeps the two kernels.
       static const int panel_env = [] { const char* e = getenv("NNSDP_PANEL"); return e ? atoi(e) : 1; }();
-      if (panel_env && !b->packed && !b->plan.band_inline && b->plan.n_window > 0 && beta <= MAX_WINDOW_BETA) {
-        struct Key { long long off; int panel, row0, col0, code; };
-        std::vector<Key> keys;
-        keys.reserve((size_t)b->plan.n_fill + b->plan.n_window);
-        for (int i = 0; i < b->plan.n_fill; ++i) {
-          const StripDev& d = b->plan.strips[i];
-          keys.push_back({d.out_off, d.col0 / 32, d.row0, d.col0, i});
-        }
-        for (int i = 0; i < b->plan.n_window; ++i) {
-          const TileDev& t = b->plan.tiles[b->plan.n_fill + i];
-          keys.push_back({b->plan.mats[t.mat].out_off, t.col0 / 32, t.row0, t.col0, ~i});
-        }
-        std::stable_sort(keys.begin(), keys.end(), [](const Key& x, const Key& y) {
-          if (x.off != y.off) return x.off < y.off;
-          if (x.panel != y.panel) return x.panel < y.panel;
-          if (x.col0 != y.col0) return x.col0 < y.col0;
-          return x.row0 < y.row0;
-        });
-        b->panel_host.resize(keys.size());
-        for (size_t i = 0; i < keys.size(); ++i) {
-          const int code = keys[i].code;
-          if (code >= 0) {
-            b->panel_host[i] = b->plan.strips[code];
-            continue;
-          }
-          const TileDev& t = b->plan.tiles[b->plan.n_fill + ~code];
-          const MatDev& m = b->plan.mats[t.mat];
-          StripDev d{};
-          d.out_off = m.out_off;
-          d.ld = m.ld;
-          d.row0 = t.row0; d.nrows = t.nrows; d.col0 = t.col0; d.ncols = t.ncols;
-          d.grow0 = t.grow0; d.gcol0 = t.gcol0; d.prog = t.prog;
-          d.rblk = t.rblk; d.rl0 = t.cblk; d.cl0 = (int32_t)t.flags; d.ldG = m.n;
-          b->panel_host[i] = d;
-        }
-        NN_TRY(upload(b->d_panel, b->panel_host.data(), b->panel_host.size() * sizeof(StripDev), b->st));
+      if (panel_env && !b->packed && !b->plan.panel.empty()) {
+        NN_TRY(upload(b->d_panel, b->plan.panel.data(), b->plan.panel.size() * sizeof(StripDev), b->st));
         b->pd.panel_desc = b->d_panel.as<StripDev>();
-        b->pd.n_panel = (int)keys.size();
+        b->pd.n_panel = (int)b->plan.panel.size();
       }
     }
     b->pd.ntiles = (int)b->plan.tiles.size();

@@ -185,6 +185,11 @@ struct PlanHost {
   bool band_inline = true;       // see BandDev
   int n_fill = 0, n_window = 0, n_edge = 0;  // tiles are sorted by kernel class
   bool skip_absent = false;  // packed plans of wide nets: the fill strips of an absent DIAG cell are not written
+  // Dense formats of wide nets (separate band handling, window programs available): the work items of the fill and the
+  // window kernel as one list sorted by (matrix, 32-column panel, first column, first row) -- fill strips as they are,
+  // window tiles re-packed into the strip layout (prog = PROG_RC / PROG_CR, rl0 = cblk, cl0 = flags, ldG = matrix order).
+  // Empty when the plan keeps the two kernels.
+  std::vector<StripDev> panel;
 };
 
 // ---------------------------------------------------------------------------------

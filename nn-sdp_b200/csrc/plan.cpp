@@ -631,6 +631,47 @@ int32_t build_plan(const Shape& sh, int64_t beta, const std::vector<CliqueRanges
     const int c = cls(t);
     (c == 0 ? plan->n_fill : c == 1 ? plan->n_window : plan->n_edge)++;
   }
+  // ---- panel order (emit_panel_kernel): a column of a clique block is written by several programs; with the items of
+  // the fill and the window kernel in ONE list sorted by 32-column panel, all pieces of a column are written by
+  // consecutive CTAs of one launch.  Dense formats of wide nets only: packed cells are contiguous per program, and
+  // narrow layers are issue-bound, not locality-bound (profiles/r2_experiments.txt).
+  plan->panel.clear();
+  if (!packed && !plan->band_inline && plan->n_window > 0 && beta <= MAX_WINDOW_BETA) {
+    struct Key { long long off; int panel, row0, col0, code; };
+    std::vector<Key> keys;
+    keys.reserve((size_t)plan->n_fill + plan->n_window);
+    for (int i = 0; i < plan->n_fill; ++i) {
+      const StripDev& d = plan->strips[i];
+      keys.push_back({d.out_off, d.col0 / 32, d.row0, d.col0, i});
+    }
+    for (int i = 0; i < plan->n_window; ++i) {
+      const TileDev& t = plan->tiles[plan->n_fill + i];
+      keys.push_back({plan->mats[t.mat].out_off, t.col0 / 32, t.row0, t.col0, ~i});
+    }
+    std::stable_sort(keys.begin(), keys.end(), [](const Key& x, const Key& y) {
+      if (x.off != y.off) return x.off < y.off;
+      if (x.panel != y.panel) return x.panel < y.panel;
+      if (x.col0 != y.col0) return x.col0 < y.col0;
+      return x.row0 < y.row0;
+    });
+    plan->panel.resize(keys.size());
+    for (size_t i = 0; i < keys.size(); ++i) {
+      const int code = keys[i].code;
+      if (code >= 0) {
+        plan->panel[i] = plan->strips[code];
+        continue;
+      }
+      const TileDev& t = plan->tiles[plan->n_fill + ~code];
+      const MatDev& m = plan->mats[t.mat];
+      StripDev d{};
+      d.out_off = m.out_off;
+      d.ld = m.ld;
+      d.row0 = t.row0; d.nrows = t.nrows; d.col0 = t.col0; d.ncols = t.ncols;
+      d.grow0 = t.grow0; d.gcol0 = t.gcol0; d.prog = t.prog;
+      d.rblk = t.rblk; d.rl0 = t.cblk; d.cl0 = (int32_t)t.flags; d.ldG = m.n;
+      plan->panel[i] = d;
+    }
+  }
   return NNSDP_OK;
 }
 

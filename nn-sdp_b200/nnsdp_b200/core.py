@@ -160,6 +160,22 @@ def plan_stats(xdims: Sequence[int], beta: int, dense: bool = False) -> dict:
 TILE_FIELDS = ("mat", "row0", "nrows", "col0", "ncols", "grow0", "gcol0", "flags", "rblk", "cblk", "prog")
 
 
+PANEL_FIELDS = ("out_off", "ld", "row0", "nrows", "col0", "ncols", "grow0", "gcol0", "prog", "rblk")
+
+
+def plan_panel(xdims: Sequence[int], beta: int, dense: int = 0) -> np.ndarray:
+    """The panel-ordered work list of the emitter (fill strips + window tiles of the dense formats of wide nets) as an
+    (nitems, 10) int64 array (columns: PANEL_FIELDS); empty when the plan keeps the separate kernels.  Host only."""
+    K = len(xdims) - 1
+    xd = (L.c_i64 * (K + 1))(*[int(x) for x in xdims])
+    n = L.c_i64(0)
+    L.check(L.lib.nnsdp_plan_panel(K, xd, beta, int(dense), 0, None, C.byref(n)))
+    out = np.zeros((int(n.value), 10), dtype=np.int64)
+    if n.value:
+        L.check(L.lib.nnsdp_plan_panel(K, xd, beta, int(dense), int(n.value), out.ctypes.data_as(L.c_i64p), C.byref(n)))
+    return out
+
+
 def plan_tiles(xdims: Sequence[int], beta: int, dense: bool = False) -> np.ndarray:
     """The emission plan's tile list as an (ntiles, 11) int32 array (columns: TILE_FIELDS); host only."""
     K = len(xdims) - 1

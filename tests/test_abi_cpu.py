@@ -458,3 +458,67 @@ def test_vnnlib_reader_random_properties(n_in, n_out, seed):
         assert np.array_equal(got["x1min"][i], qi.x1min) and np.array_equal(got["x1max"][i], qi.x1max)
         S = np.asarray(qs.S)
         assert np.array_equal(got["S"][i], S) and np.array_equal(np.signbit(got["S"][i]), np.signbit(S))
+
+
+# ---------------------------------------------------------------------------------------------
+# Panel-ordered work list of the emitter (csrc/plan.cpp, emit_panel_kernel): dense formats of wide nets write the
+# clique blocks Z[C_k, C_k] (the blocks setupZksum! scatters, /root/reference/src/Methods/chordal_sdp.jl:60-93) with the
+# fill strips and the window tiles of one 32-column panel as consecutive work items of ONE launch.
+# ---------------------------------------------------------------------------------------------
+PANEL_SHAPES = [([2, 300, 270, 280, 2], 2, 0), ([3, 150, 260, 140, 2], 4, 0), ([2, 129, 128, 127, 300, 4], 3, 0),
+                ([2, 300, 270, 280, 2], 2, 1), ([2] + [1000] * 4 + [2], 2, 0)]
+
+
+@pytest.mark.parametrize("xdims,beta,dense", PANEL_SHAPES)
+def test_panel_work_list_covers_the_fill_and_window_entries_once(xdims, beta, dense):
+    import nnsdp_b200 as nb
+
+    items = nb.plan_panel(xdims, beta, dense=dense)
+    tiles = nb.plan_tiles(xdims, beta, dense=dense)
+    F = {n: i for i, n in enumerate(nb.core.TILE_FIELDS)}
+    P = {n: i for i, n in enumerate(nb.core.PANEL_FIELDS)}
+    assert len(items) > 0
+    PROG = dict(ZERO=0, SAME=1, RC=2, CR=3, MIXED=4, GENERAL=5, DIAG=6, AFF=7)
+    names = {v: k for k, v in PROG.items()}
+    st = nb.plan_stats(xdims, beta, dense=dense)
+    # the matrices of the output: offsets and sides from the tile list (mat -> local extents)
+    nmat = int(tiles[:, F["mat"]].max()) + 1
+    side = [int((tiles[tiles[:, F["mat"]] == m][:, F["row0"]] + tiles[tiles[:, F["mat"]] == m][:, F["nrows"]]).max()) for m in range(nmat)]
+    offs = np.concatenate([[0], np.cumsum([n * n for n in side])])
+    paint = [np.zeros((n, n), dtype=np.int8) for n in side]
+    ent = {k: 0 for k in PROG}
+    last_key = None
+    for it in items:
+        off, ld, r0, nr, c0, nc, prog = (int(it[P[k]]) for k in ("out_off", "ld", "row0", "nrows", "col0", "ncols", "prog"))
+        m = int(np.searchsorted(offs, off, side="right") - 1)
+        assert offs[m] == off and ld == side[m]
+        assert 0 <= r0 and r0 + nr <= side[m] and 0 <= c0 and c0 + nc <= side[m]
+        paint[m][r0:r0 + nr, c0:c0 + nc] += 1
+        ent[names[prog]] += nr * nc
+        key = (off, c0 // 32, c0, r0)          # the sort order: matrix, panel, first column, first row
+        assert last_key is None or key >= last_key
+        last_key = key
+    # every entry of the fill and window classes exactly once, nothing of the edge class
+    for k in ("ZERO", "RC", "CR", "AFF"):
+        assert ent[k] == st["entries"][k], k
+    assert ent["SAME"] + ent["DIAG"] == st["entries"]["SAME"] + st["entries"]["DIAG"]     # merged into DIAG strips
+    assert ent["MIXED"] == ent["GENERAL"] == 0
+    total = 0
+    for m in range(nmat):
+        assert paint[m].max() <= 1
+        total += int(paint[m].sum())
+    assert total + st["entries"]["MIXED"] + st["entries"]["GENERAL"] == sum(n * n for n in side)
+    # the entries the panel list leaves out are exactly the tiles of the edge class
+    for t in tiles:
+        if names[int(t[F["prog"]])] in ("MIXED", "GENERAL"):
+            m, r0, nr, c0, nc = (int(t[F[k]]) for k in ("mat", "row0", "nrows", "col0", "ncols"))
+            assert paint[m][r0:r0 + nr, c0:c0 + nc].sum() == 0
+
+
+@pytest.mark.parametrize("xdims,beta,dense", [([2, 100, 100, 100, 2], 2, 0), ([2, 10, 10, 2], 1, 0),
+                                              ([2, 300, 270, 280, 2], 2, 2), ([3, 150, 260, 140, 2], 6, 0)])
+def test_panel_work_list_is_empty_where_the_kernels_stay_separate(xdims, beta, dense):
+    """Narrow layers (inline band), small nets, packed records, beta beyond the window programs."""
+    import nnsdp_b200 as nb
+
+    assert len(nb.plan_panel(xdims, beta, dense=dense)) == 0
