@@ -108,18 +108,22 @@ def ncu_traffic(kernel):
     path = os.path.join(ROOT, "profiles", "r2_emit_full.summary.csv")
     if not os.path.exists(path):
         return None
-    rows = list(csv.reader(open(path)))
-    hdr = rows[0]
     unit = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    # the default pass (panel-ordered launch), then the capture with NNSDP_PANEL=0 (fill and window kernels on their own)
+    for p in (path, os.path.join(ROOT, "profiles", "r2_emit_full_separate_kernels.summary.csv")):
+        if not os.path.exists(p):
+            continue
+        rows = list(csv.reader(open(p)))
+        hdr = rows[0]
 
-    def col(prefix):
-        i = [j for j, h in enumerate(hdr) if h.startswith(prefix)][0]
-        return i, unit[hdr[i].split("[")[1].rstrip("]")]
+        def col(prefix):
+            i = [j for j, h in enumerate(hdr) if h.startswith(prefix)][0]
+            return i, unit[hdr[i].split("[")[1].rstrip("]")]
 
-    (ir, ur), (iw, uw) = col("dram__bytes_read.sum"), col("dram__bytes_write.sum")
-    for r in rows[1:]:
-        if r[0].split("<")[0] == kernel:
-            return float(r[ir]) * ur + float(r[iw]) * uw
+        (ir, ur), (iw, uw) = col("dram__bytes_read.sum"), col("dram__bytes_write.sum")
+        for r in rows[1:]:
+            if r[0].split("<")[0] == kernel:
+                return float(r[ir]) * ur + float(r[iw]) * uw
     if os.environ.get("NNSDP_BENCH_RECAPTURE") == "1":   # the run that re-captures the profile itself
         print(f"bench.py: {path} holds no launch of {kernel}; traffic = null in this run", file=sys.stderr)
         return None
