@@ -703,12 +703,9 @@ emit_edge_kernel(NetDev net, BatchDev b, GramDev g, PlanDev plan, int tile0, int
 // fill strips stored (plans with separate band handling; stream order makes this kernel the last writer; packed
 // records: only when the DIAG cell is present, upper triangle) and / or into the BAND cell of a packed record.
 namespace {
-__global__ void __launch_bounds__(ETHREADS)
-emit_band_kernel(NetDev net, BatchDev b, GramDev g, const BandDev* __restrict__ bands, long long per_query, int q0,
-                 double* __restrict__ out) {
-  const BandDev bd = bands[blockIdx.y];
-  const int slot = blockIdx.z, q = q0 + slot, K = net.K, beta = b.beta, nt = 2 * beta + 1;
-  const int idx = blockIdx.x * ETHREADS + threadIdx.x;
+__device__ __forceinline__ void band_entry(const NetDev& net, const BatchDev& b, const GramDev& g, const BandDev& bd,
+                                           long long per_query, int q0, int slot, int idx, double* __restrict__ out) {
+  const int q = q0 + slot, K = net.K, beta = b.beta, nt = 2 * beta + 1;
   if (idx >= bd.m * nt) return;
   const int i = idx / nt, t = idx - i * nt - beta, c = i + t;  // entry (i, c) of the range, |t| <= beta
   if (bd.upper_only && t < 0) return;
@@ -732,13 +729,25 @@ emit_band_kernel(NetDev net, BatchDev b, GramDev g, const BandDev* __restrict__ 
   if (bd.ld > 0 && (!bd.optional || copy || s22)) o[bd.out_off + (bd.row0 + i) + (long long)(bd.col0 + c) * bd.ld] = val;
   if (bd.band_off >= 0 && t >= 0) o[bd.band_off + t + (long long)(beta + 1) * i] = val;
 }
+
+__global__ void __launch_bounds__(ETHREADS)
+emit_band_kernel(NetDev net, BatchDev b, GramDev g, const BandDev* __restrict__ bands, long long per_query, int q0,
+                 int nq, int spc, double* __restrict__ out) {
+  const BandDev bd = bands[blockIdx.y];
+  const int idx = blockIdx.x * ETHREADS + threadIdx.x;
+  // spc queries per CTA (one entry per thread and query): a 32-query stress pass is 47,360 CTAs of one query each
+  for (int slot = blockIdx.z * spc; slot < min(nq, (blockIdx.z + 1) * spc); ++slot)
+    band_entry(net, b, g, bd, per_query, q0, slot, idx, out);
+}
 }  // namespace
 
 int launch_emit_band(const NetDev& net, const BatchDev& b, const GramDev& g, const BandDev* bands, int nbands,
                      int max_m, long long per_query, int q0, int nq, double* out, cudaStream_t st) {
   if (nbands <= 0 || nq <= 0 || max_m <= 0) return 0;
   const int nx = (max_m * (2 * b.beta + 1) + ETHREADS - 1) / ETHREADS;
-  emit_band_kernel<<<dim3(nx, nbands, nq), ETHREADS, 0, st>>>(net, b, g, bands, per_query, q0, out);
+  static const int spc_env = [] { const char* e = getenv("NNSDP_BAND_GROUP"); return e ? atoi(e) : 0; }();
+  const int spc = spc_env > 0 ? spc_env : (nq >= 16 ? 4 : 1);
+  emit_band_kernel<<<dim3(nx, nbands, (nq + spc - 1) / spc), ETHREADS, 0, st>>>(net, b, g, bands, per_query, q0, nq, spc, out);
   return 1;
 }
 
