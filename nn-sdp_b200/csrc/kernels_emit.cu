@@ -626,15 +626,23 @@ emit_panel_kernel(NetDev net, BatchDev b, GramDev g, PlanDev plan, int q0, int n
   constexpr int RC_DOUBLES = SLOT_GROUP * (BETA + 1) * (FAST_TC + BETA + 1), CR_DOUBLES = FAST_TC * CR_LDW(BETA);
   __shared__ __align__(128) double smem[RC_DOUBLES > CR_DOUBLES ? RC_DOUBLES : CR_DOUBLES];
   __shared__ __align__(8) unsigned long long mbar;
-  const int ngroups = (nq + group - 1) / group;
-  const int item = blockIdx.x / ngroups, gi = blockIdx.x % ngroups;
+  // CTA order: the queries of a pass go in sub-batches of `batch` (a multiple of group): all items for the first
+  // sub-batch, then all items for the next one.  Fewer queries in flight at a time = fewer DRAM pages open at a time:
+  // a 16-query pass runs at 5.75 TB/s and an 8-query pass at 5.83 TB/s where a 32-query pass reaches 5.58 TB/s.
+  const int batch = group >> 8;
+  group &= 255;
+  const int gb = batch / group;                         // CTAs per item and full sub-batch
+  const int per_batch = plan.n_panel * gb;
+  const int sb = blockIdx.x / per_batch, rem = blockIdx.x - sb * per_batch;
+  const int slot_lo = sb * batch, slot_hi = min(nq, slot_lo + batch);
+  const int item = rem / gb, g0 = rem - item * gb;
   // one self-contained 64 B descriptor per item, in panel order: a fill strip as it is, a window tile re-packed into
   // the same layout (no index -> tile -> matrix chain of dependent loads at the start of a short CTA)
   const StripDev* desc = plan.panel_desc + item;
   const int4* dp = reinterpret_cast<const int4*>(desc);
   const int4 d2 = __ldg(dp + 2);
   if (d2.w != PROG_RC && d2.w != PROG_CR) {
-    for (int slot = gi; slot < nq; slot += ngroups) fill_strip<false>(net, b, g, plan, desc, slot, q0, out);
+    for (int slot = slot_lo + g0; slot < slot_hi; slot += gb) fill_strip<false>(net, b, g, plan, desc, slot, q0, out);
     return;
   }
   const int4 d0 = __ldg(dp), d1 = __ldg(dp + 1), d3 = __ldg(dp + 3);
@@ -646,8 +654,9 @@ emit_panel_kernel(NetDev net, BatchDev b, GramDev g, PlanDev plan, int q0, int n
   mat.out_off = ((long long)(unsigned)d0.x) | ((long long)d0.y << 32);
   mat.ld = d1.x;
   mat.n = d3.w;
-  const int slot0 = gi * group;
-  const int nslots = min(group, nq - slot0);
+  const int slot0 = slot_lo + g0 * group;
+  const int nslots = min(group, slot_hi - slot0);
+  if (nslots <= 0) return;
   if (t.prog == PROG_RC) {
     if (t.ncols == FAST_TC) emit_rc<BETA, true>(net, b, plan, t, mat, q0, slot0, nslots, out, smem);
     else emit_rc<BETA, false>(net, b, plan, t, mat, q0, slot0, nslots, out, smem);
@@ -786,13 +795,18 @@ int launch_emit(const NetDev& net, const BatchDev& b, const GramDev& g, const Pl
       // queries per window CTA (a strip CTA then writes its strip for every ngroups-th query): 2 is the measured best
       // (W1000-D20, 32-query pass: 7.57 ms against 7.75 ms with 4, 8.63 ms with 1; fill + window kernels 7.88 ms)
       static const int pgroup = [] { const char* e = getenv("NNSDP_PANEL_GROUP"); int v = e ? atoi(e) : 2; return v < 1 ? 1 : (v > SLOT_GROUP ? SLOT_GROUP : v); }();
-      const dim3 grid((unsigned)plan.n_panel * ((nq + pgroup - 1) / pgroup));
+      // queries per sub-batch of the launch (a multiple of pgroup)
+      static const int pbatch_env = [] { const char* e = getenv("NNSDP_PANEL_BATCH"); return e ? atoi(e) : 8; }();
+      int pbatch = std::max(pgroup, (pbatch_env / pgroup) * pgroup);
+      if (pbatch > 255) pbatch = (255 / pgroup) * pgroup;
+      const int nbatches = (nq + pbatch - 1) / pbatch;
+      const dim3 grid((unsigned)plan.n_panel * (pbatch / pgroup) * nbatches);
       switch (b.beta) {
-        case 0: emit_panel_kernel<0><<<grid, ETHREADS, 0, st>>>(net, b, g, plan, q0, nq, pgroup, out); break;
-        case 1: emit_panel_kernel<1><<<grid, ETHREADS, 0, st>>>(net, b, g, plan, q0, nq, pgroup, out); break;
-        case 2: emit_panel_kernel<2><<<grid, ETHREADS, 0, st>>>(net, b, g, plan, q0, nq, pgroup, out); break;
-        case 3: emit_panel_kernel<3><<<grid, ETHREADS, 0, st>>>(net, b, g, plan, q0, nq, pgroup, out); break;
-        default: emit_panel_kernel<4><<<grid, ETHREADS, 0, st>>>(net, b, g, plan, q0, nq, pgroup, out); break;
+        case 0: emit_panel_kernel<0><<<grid, ETHREADS, 0, st>>>(net, b, g, plan, q0, nq, pgroup | (pbatch << 8), out); break;
+        case 1: emit_panel_kernel<1><<<grid, ETHREADS, 0, st>>>(net, b, g, plan, q0, nq, pgroup | (pbatch << 8), out); break;
+        case 2: emit_panel_kernel<2><<<grid, ETHREADS, 0, st>>>(net, b, g, plan, q0, nq, pgroup | (pbatch << 8), out); break;
+        case 3: emit_panel_kernel<3><<<grid, ETHREADS, 0, st>>>(net, b, g, plan, q0, nq, pgroup | (pbatch << 8), out); break;
+        default: emit_panel_kernel<4><<<grid, ETHREADS, 0, st>>>(net, b, g, plan, q0, nq, pgroup | (pbatch << 8), out); break;
       }
       ++launches;
     }
