@@ -619,7 +619,8 @@ emit_window_kernel(NetDev net, BatchDev b, PlanDev plan, int tile0, int q0, int 
 // covers only part of every DRAM page it touches (tools/probe_write_bw.cu: two launches 5.7 TB/s, one launch with the
 // items ordered by 32-column panel 7.0 TB/s on pure stores).  Here the work items of both kernels are sorted by
 // (matrix, 32-column panel, row) and consecutive CTAs take consecutive items, so whole columns are written within
-// microseconds.  A strip CTA writes its strip for every ngroups-th query, a window CTA its tile for one query group.
+// microseconds.  Inside a sub-batch of queries (see below) a window CTA writes its tile for `group` consecutive queries and
+// a strip CTA its strip for every (batch / group)-th query.
 template <int BETA>
 __global__ void __launch_bounds__(ETHREADS, 4)
 emit_panel_kernel(NetDev net, BatchDev b, GramDev g, PlanDev plan, int q0, int nq, int group, double* __restrict__ out) {
