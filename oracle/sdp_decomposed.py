@@ -325,9 +325,6 @@ def primal_dual(prob, y, U, tol=1e-9, max_iter=200, verbose=False, stop=None):
         dy, dS, dX, dsl, dsu, dxl, dxu = direction(sigma * mu)
         ap, ad = steps(dS, dX, dsl, dsu, dxl, dxu)
         ap, ad = min(1.0, 0.9 * ap), min(1.0, 0.9 * ad)
-        if verbose and os.environ.get("SDP_DEBUG"):
-            print(f"       sigma {sigma:.3f} ap {ap:.3e} ad {ad:.3e} |dy| {np.abs(dy).max():.2e} cond(Mat scaled) "
-                  f"{np.linalg.cond(dscale[:, None] * Mat * dscale[None, :]):.2e}", flush=True)
         y = y + ap * dy
         S = S_of(y)
         sl, su = y[:ng].copy(), U - y[:ng]
