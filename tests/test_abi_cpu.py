@@ -522,3 +522,29 @@ def test_panel_work_list_is_empty_where_the_kernels_stay_separate(xdims, beta, d
     import nnsdp_b200 as nb
 
     assert len(nb.plan_panel(xdims, beta, dense=dense)) == 0
+
+
+def test_library_holds_the_blackwell_instructions_the_design_names():
+    """SASS of the built library (no device needed): the CR window program stages its W tile by TMA (UTMALDG.2D against
+    an mbarrier: SYNCS.ARRIVE.TRANS64 / SYNCS.PHASECHK...TRYWAIT), the FP64 contractions run on the tensor cores
+    (DMMA.8x8x4, the only FP64 tensor instruction of sm_100a) fed by cp.async (LDGSTS), and every kernel is compiled for
+    sm_100a only."""
+    import shutil
+    import subprocess
+
+    import nnsdp_b200._lib as L
+
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(cuobjdump):
+        pytest.skip("cuobjdump not available")
+    lib = os.path.abspath(L.LIB_PATH)
+    sass = subprocess.run([cuobjdump, "-sass", lib], capture_output=True, text=True, timeout=300).stdout
+    assert sass.count("UTMALDG.2D") >= 5                      # emit_window_kernel<0..4> and emit_panel_kernel<0..4>
+    assert "SYNCS.ARRIVE.TRANS64" in sass and "TRYWAIT" in sass
+    assert sass.count("DMMA.8x8x4") >= 100                    # gram_kernel, dgemm tiles, ibp_dmma_kernel
+    assert "LDGSTS" in sass
+    archs = set(ln.split("=")[1].strip() for ln in sass.splitlines() if ln.strip().startswith("arch ="))
+    assert archs == {"sm_100a"}, archs
+    for name in ("emit_panel_kernel", "emit_fill_kernel", "emit_window_kernel", "emit_edge_kernel", "emit_band_kernel",
+                 "gram_kernel", "ibp_dmma_kernel", "dgemm_dmma_affine_layers_kernel", "crown_post_kernel"):
+        assert name in sass, name
