@@ -9,6 +9,9 @@
 #include <algorithm>
 
 #include "internal.h"
+#include <atomic>
+#include <cstring>
+#include <thread>
 
 namespace nnsdp {
 
@@ -676,62 +679,106 @@ int32_t build_plan(const Shape& sh, int64_t beta, const std::vector<CliqueRanges
 }
 
 
+// Expands one record into the dense matrices of `mats` (clique blocks or the dense Z), both triangles.  Host work at
+// memory speed: the upper-triangle part of a cell is copied column run by column run (contiguous on both sides), its
+// mirror image in 64 x 64 tiles (contiguous writes, cache-resident strided reads); the matrices are independent and are
+// expanded by several threads.  Cells are applied in the order DIAG, WINDOW, BAND, RECT (later ones are authoritative
+// where cells overlap), so the result does not depend on the number of threads.
+static void unpack_one(int64_t beta, const PackedLayout& lay, const CliqueRanges& ck, const double* record,
+                       const uint8_t* present, double* o) {
+  const int64_t n = ck.size();
+  std::memset(o, 0, (size_t)n * n * sizeof(double));
+  constexpr int64_t TB = 64;
+  // rows [r0, r1] x columns [c0, c1] of a cell (global, inclusive) restricted to the index set
+  auto copy_rect = [&](const PackedCell& c) {
+    const double* src = record + c.offset;
+    int64_t rbase = 0;
+    for (int sr = 0; sr < ck.nseg; rbase += ck.hi[sr] - ck.lo[sr] + 1, ++sr) {
+      const int64_t r0 = std::max(c.grow0, ck.lo[sr]), r1 = std::min(c.grow0 + c.nrows - 1, ck.hi[sr]);
+      if (r0 > r1) continue;
+      int64_t cbase = 0;
+      for (int sc = 0; sc < ck.nseg; cbase += ck.hi[sc] - ck.lo[sc] + 1, ++sc) {
+        const int64_t c0 = std::max(c.gcol0, ck.lo[sc]), c1 = std::min(c.gcol0 + c.ncols - 1, ck.hi[sc]);
+        if (c0 > c1 || r0 > c1) continue;               // nothing on or above the diagonal
+        const int64_t lr_of = rbase - ck.lo[sr], lc_of = cbase - ck.lo[sc];   // local = global + offset
+        for (int64_t gcb = std::max(c0, r0); gcb <= c1; gcb += TB) {
+          const int64_t gce = std::min(gcb + TB - 1, c1);
+          for (int64_t grb = r0; grb <= std::min(r1, gce); grb += TB) {
+            const int64_t gre = std::min(grb + TB - 1, r1);
+            // as stored: column runs of the upper triangle
+            for (int64_t gc = gcb; gc <= gce; ++gc) {
+              const int64_t rhi = std::min(gre, gc);
+              if (grb > rhi) continue;
+              const double* col = src + (gc - c.gcol0) * c.nrows - c.grow0;
+              std::memcpy(o + (lr_of + grb) + (lc_of + gc) * n, col + grb, (size_t)(rhi - grb + 1) * sizeof(double));
+            }
+            // mirrored: entry (gr, gc), gr <= gc, also at (gc, gr); row by row, so the writes are contiguous
+            for (int64_t gr = grb; gr <= gre; ++gr) {
+              const int64_t glo = std::max(gcb, gr);
+              if (glo > gce) continue;
+              double* dst = o + (lr_of + gr) * n + lc_of;             // o[lc + lr * n], lc = lc_of + gc
+              const double* s0 = src - c.grow0 + gr - c.gcol0 * c.nrows;
+              for (int64_t gc = glo; gc <= gce; ++gc) dst[gc] = s0[gc * c.nrows];
+            }
+          }
+        }
+      }
+    }
+  };
+  auto local = [&](int64_t g) -> int64_t {
+    int64_t base = 0;
+    for (int s = 0; s < ck.nseg; base += ck.hi[s] - ck.lo[s] + 1, ++s)
+      if (g >= ck.lo[s] && g <= ck.hi[s]) return base + g - ck.lo[s];
+    return -1;
+  };
+  for (int pass : {PK_DIAG, PK_WINDOW, PK_BAND, PK_RECT})  // later passes are authoritative where cells overlap
+    for (size_t i = 0; i < lay.cells.size(); ++i) {
+      const PackedCell& c = lay.cells[i];
+      if (c.kind != pass || !present[i]) continue;
+      if (c.kind != PK_BAND) {
+        copy_rect(c);
+        continue;
+      }
+      const double* src = record + c.offset;
+      for (int64_t j = 0; j < c.ncols; ++j) {
+        const int64_t lr = local(c.grow0 + j);
+        if (lr < 0) continue;
+        for (int64_t t = 0; t <= beta && j + t < c.ncols; ++t) {
+          const int64_t lc = local(c.grow0 + j + t);
+          if (lc < 0) continue;
+          const double v = src[t + (beta + 1) * j];
+          o[lr + lc * n] = v;
+          o[lc + lr * n] = v;
+        }
+      }
+    }
+}
+
 void unpack_record(const Shape& sh, int64_t beta, const PackedLayout& lay, const std::vector<CliqueRanges>& mats,
                    const double* record, const uint8_t* present, double* out) {
   (void)sh;
-  int64_t out_off = 0;
-  for (const CliqueRanges& ck : mats) {
-    const int64_t n = ck.size();
-    double* o = out + out_off;
-    std::fill(o, o + n * n, 0.0);
-    auto put = [&](int64_t lr, int64_t lc, double v) {
-      o[lr + lc * n] = v;
-      o[lc + lr * n] = v;
-    };
-    // rows [r0, r1] x columns [c0, c1] of a cell (global, inclusive) restricted to the index set
-    auto copy_rect = [&](const PackedCell& c) {
-      const double* src = record + c.offset;
-      int64_t rbase = 0;
-      for (int sr = 0; sr < ck.nseg; rbase += ck.hi[sr] - ck.lo[sr] + 1, ++sr) {
-        const int64_t r0 = std::max(c.grow0, ck.lo[sr]), r1 = std::min(c.grow0 + c.nrows - 1, ck.hi[sr]);
-        if (r0 > r1) continue;
-        int64_t cbase = 0;
-        for (int sc = 0; sc < ck.nseg; cbase += ck.hi[sc] - ck.lo[sc] + 1, ++sc) {
-          const int64_t c0 = std::max(c.gcol0, ck.lo[sc]), c1 = std::min(c.gcol0 + c.ncols - 1, ck.hi[sc]);
-          for (int64_t gc = c0; gc <= c1; ++gc) {
-            const double* col = src + (gc - c.gcol0) * c.nrows - c.grow0;
-            const int64_t lc = cbase + gc - ck.lo[sc];
-            for (int64_t gr = r0; gr <= std::min(r1, gc); ++gr) put(rbase + gr - ck.lo[sr], lc, col[gr]);
-          }
-        }
-      }
-    };
-    auto local = [&](int64_t g) -> int64_t {
-      int64_t base = 0;
-      for (int s = 0; s < ck.nseg; base += ck.hi[s] - ck.lo[s] + 1, ++s)
-        if (g >= ck.lo[s] && g <= ck.hi[s]) return base + g - ck.lo[s];
-      return -1;
-    };
-    for (int pass : {PK_DIAG, PK_WINDOW, PK_BAND, PK_RECT})  // later passes are authoritative where cells overlap
-      for (size_t i = 0; i < lay.cells.size(); ++i) {
-        const PackedCell& c = lay.cells[i];
-        if (c.kind != pass || !present[i]) continue;
-        if (c.kind != PK_BAND) {
-          copy_rect(c);
-          continue;
-        }
-        const double* src = record + c.offset;
-        for (int64_t j = 0; j < c.ncols; ++j) {
-          const int64_t lr = local(c.grow0 + j);
-          if (lr < 0) continue;
-          for (int64_t t = 0; t <= beta && j + t < c.ncols; ++t) {
-            const int64_t lc = local(c.grow0 + j + t);
-            if (lc >= 0) put(lr, lc, src[t + (beta + 1) * j]);
-          }
-        }
-      }
-    out_off += n * n;
+  std::vector<int64_t> off(mats.size() + 1, 0);
+  for (size_t m = 0; m < mats.size(); ++m) off[m + 1] = off[m] + mats[m].size() * mats[m].size();
+  int nthreads = 1;
+  if (mats.size() > 1 && off.back() >= (int64_t(1) << 20)) {     // small outputs: a thread start costs more than the copy
+    const char* e = getenv("NNSDP_HOST_THREADS");
+    const unsigned hw = std::thread::hardware_concurrency();
+    nthreads = e ? atoi(e) : (int)std::min<unsigned>(hw ? hw : 1, 16);
+    nthreads = std::max(1, std::min<int>(nthreads, (int)mats.size()));
   }
+  if (nthreads == 1) {
+    for (size_t m = 0; m < mats.size(); ++m) unpack_one(beta, lay, mats[m], record, present, out + off[m]);
+    return;
+  }
+  std::atomic<size_t> next{0};
+  auto work = [&] {
+    for (size_t m = next.fetch_add(1); m < mats.size(); m = next.fetch_add(1))
+      unpack_one(beta, lay, mats[m], record, present, out + off[m]);
+  };
+  std::vector<std::thread> th;
+  for (int t = 1; t < nthreads; ++t) th.emplace_back(work);
+  work();
+  for (auto& t : th) t.join();
 }
 
 int32_t build_gather_plan(const Shape& sh, int64_t beta, const std::vector<CliqueRanges>& mats,

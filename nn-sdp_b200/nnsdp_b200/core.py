@@ -219,12 +219,19 @@ def packed_layout(xdims: Sequence[int], beta: int) -> dict:
     return {"cells": cells, "record_doubles": int(rec.value), "always_doubles": int(alw.value)}
 
 
-def packed_unpack(xdims: Sequence[int], beta: int, record: np.ndarray, present: np.ndarray, dense_Z: bool = False) -> np.ndarray:
-    """One packed record -> the flat dense clique blocks (or the dense Z, column-major) through nnsdp_packed_unpack."""
+def packed_unpack(xdims: Sequence[int], beta: int, record: np.ndarray, present: np.ndarray, dense_Z: bool = False,
+                  out: Optional[np.ndarray] = None) -> np.ndarray:
+    """One packed record -> the flat dense clique blocks (or the dense Z, column-major) through nnsdp_packed_unpack.
+    `out` (float64, C-contiguous, the right size) is reused when given: a fresh 1.33 GB array costs more in page faults
+    than the expansion itself."""
     K = len(xdims) - 1
     xd = (L.c_i64 * (K + 1))(*[int(x) for x in xdims])
     sz = sizes_from_xdims(xdims, beta)
-    out = np.empty(sz["Zdim"] ** 2 if dense_Z else sz["sum_ck_sq"])
+    need = sz["Zdim"] ** 2 if dense_Z else sz["sum_ck_sq"]
+    if out is None:
+        out = np.empty(need)
+    if out.dtype != np.float64 or out.size != need or not out.flags["C_CONTIGUOUS"]:
+        raise ValueError(f"out must be a C-contiguous float64 array of {need} entries")
     record = np.ascontiguousarray(record, dtype=np.float64)
     present = np.ascontiguousarray(present, dtype=np.uint8)
     L.check(L.lib.nnsdp_packed_unpack(K, xd, beta, _dp(record), present.ctypes.data_as(C.POINTER(C.c_uint8)),
