@@ -67,7 +67,7 @@ def approx_ellipsoid_population(net, x1min, x1max, n=400):
     return P, yc
 
 
-def barrier_solve(Z0, A, c, x0, U, gap, stop=None, mu=5.0, max_newton=400):
+def barrier_solve(Z0, A, c, x0, U, gap, stop=None, mu=5.0, max_newton=400, t0=1.0, newton_tol=1e-4):
     """min c'x  s.t.  0 < x < U,  -(Z0 + sum_v x_v A_v) > 0: log-barrier path following, damped Newton in the
     variables scaled by the current iterate.  Returns (x, X = M^-1 / t, newton steps).  U only bounds the
     multipliers of constraints that never bind (they would drift to infinity); the optimum does not depend on it
@@ -88,7 +88,7 @@ def barrier_solve(Z0, A, c, x0, U, gap, stop=None, mu=5.0, max_newton=400):
         except np.linalg.LinAlgError:
             return False
 
-    t, it = 1.0, 0
+    t, it = float(t0), 0
     while True:
         for _ in range(max_newton):
             Minv = np.linalg.inv(M_of(x))
@@ -100,7 +100,7 @@ def barrier_solve(Z0, A, c, x0, U, gap, stop=None, mu=5.0, max_newton=400):
             du = -np.linalg.solve(Hs, gs)
             lam = np.sqrt(max(-gs @ du, 0.0))
             it += 1
-            if lam < 1e-4:
+            if lam < newton_tol:
                 break
             step = 1.0 if lam < 0.25 else 1.0 / (1.0 + lam)
             while not feasible(x + step * x * du) and step > 1e-14:

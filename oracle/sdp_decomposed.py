@@ -125,7 +125,8 @@ def problem_from_handoff(h, cliques, mode="single"):
         Z0 = Z0 + Z0.T - np.diag(np.diag(Z0))
         out_blocks.append({"idx": B, "V": V, "A": Aj, "Z0": Z0})
     cx = np.concatenate([c[kidx], np.zeros(ns)])
-    return {"blocks": out_blocks, "c": cx, "ng": ng, "ns": ns, "keep": keep, "nvar": nvar}
+    return {"blocks": out_blocks, "c": cx, "ng": ng, "ns": ns, "keep": keep, "nvar": nvar,
+            "split_id": split_id, "own": own, "ent_row": er, "ent_col": ec, "Zdim": Zdim}
 
 
 def block_matrices(prob, x):
@@ -380,6 +381,144 @@ def certificate(prob, x, X, xl, xu, U):
 
 
 # ------------------------------------------------------------------------------------------------
+# A certificate for the decomposed problem from a solve of the DENSE one (Agler's theorem, made constructive).
+#   * primal: Z(gamma*) <= 0 with the sparsity of the cover has a zero-fill factorisation  -Z = L D L'  in the natural
+#     order (eliminating an index of block x_k only touches later indices of clique k: the cliques of makeCliques,
+#     /root/reference/src/Methods/chordal_cliques.jl:13-59, are a perfect elimination ordering with the common tail
+#     x_K, 1 last).  The columns of L are grouped by the clique that owns their index, Z_k = -sum_i d_i l_i l_i': every
+#     Z_k is negative semidefinite, lies inside C_k x C_k, and they add up to Z.  The split variables of the block LMI
+#     are read off the Z_k.
+#   * dual: a multiplier X >= 0 of the dense LMI restricted to the blocks, X_j = X[B_j, B_j], is a multiplier of the
+#     decomposed one with the same dual objective and the same dual residual on gamma (and none on the splits).
+# Both sides are then checked by certificate() exactly like an interior-point solution: nothing here is trusted.
+# Used where the block interior-point method runs out of digits (W10-D20: bracket 2e-3).
+# ------------------------------------------------------------------------------------------------
+def dense_from_handoff(h, keep):
+    """(Z0, A) of the dense LMI  Z0 + sum_v x_v A_v <= 0  over the kept variables, symmetric Zdim x Zdim."""
+    er, ec = np.asarray(h["ent_row"]) - 1, np.asarray(h["ent_col"]) - 1
+    Zdim = int(ec.max()) + 1
+    nvar, nent = int(h["nvar"]), int(h["nent"])
+    A = sp.coo_matrix((h["coo_val"], (np.asarray(h["coo_ent"]) - 1, np.asarray(h["coo_var"]) - 1)), shape=(nent, nvar)).tocsc()
+    A.sum_duplicates()
+    kidx = np.nonzero(keep)[0]
+    Z0 = np.zeros((Zdim, Zdim))
+    Z0[er, ec] = np.asarray(h["z0"], dtype=float)
+    Z0 = Z0 + Z0.T - np.diag(np.diag(Z0))
+    Ad = np.zeros((len(kidx), Zdim, Zdim))
+    for i, v in enumerate(kidx):
+        col = A[:, v].tocoo()
+        Ad[i, er[col.row], ec[col.row]] = col.data
+        Ad[i] = Ad[i] + Ad[i].T - np.diag(np.diag(Ad[i]))
+    return Z0, Ad
+
+
+def chordal_split(Z, blocks, eps):
+    """Z (negative definite, pattern inside the union of blocks x blocks, blocks in clique order) -> [Z_k] with
+    sum_k embed(Z_k) = Z and every Z_k <= -eps I: zero-fill LDL' of -(Z + eps diag(multiplicity)) in the natural order,
+    columns grouped by the last block that holds their index."""
+    n = Z.shape[0]
+    mult = np.zeros(n)
+    for B in blocks:
+        mult[B] += 1.0
+    M = -(Z + eps * np.diag(mult))
+    owner = -np.ones(n, dtype=np.int64)            # the LAST block that contains the index: an index of x_b lies in the
+    for j in range(len(blocks)):                   # cliques b-2 (if within beta of the layer start), b-1 and b, and its
+        owner[blocks[j]] = j                       # later neighbours (in the filled graph) all lie in clique b
+    loc = []
+    for B in blocks:
+        l = -np.ones(n, dtype=np.int64)
+        l[B] = np.arange(len(B))
+        loc.append(l)
+    out = [-eps * np.eye(len(B)) for B in blocks]
+    W = M.copy()
+    for i in range(n):
+        d = W[i, i]
+        assert d > 0, ("not negative definite", i, d)
+        l = W[i:, i] / d
+        nz = i + np.nonzero(l)[0]
+        j = owner[i]
+        assert np.all(loc[j][nz] >= 0), ("fill outside the clique", i)
+        li = loc[j][nz]
+        out[j][np.ix_(li, li)] -= d * np.outer(l[nz - i], l[nz - i])
+        W[i:, i:] -= d * np.outer(l, l)
+        W[i, i:] = 0.0
+        W[i:, i] = 0.0
+    return out
+
+
+def certificate_from_dense(h, cliques, mode="single", U=1e4, gap=1e-7, verbose=False):
+    """Solves the dense LMI of the hand-off by the barrier method of sdp_crosscheck.py and turns the result into a
+    primal point and multipliers of the decomposed problem (see above).  Returns the dict solve() returns."""
+    import sdp_crosscheck as sc
+
+    prob = problem_from_handoff(h, cliques, mode)
+    ng, ns = prob["ng"], prob["ns"]
+    Z0, A = dense_from_handoff(h, prob["keep"])
+    c = prob["c"][:ng]
+    n, m = A.shape[0], Z0.shape[0]
+    A1 = np.concatenate([A, -np.eye(m)[None], np.eye(m)[None]], 0)          # phase I as in sdp_crosscheck.solve
+    c1 = np.zeros(n + 2)
+    c1[n], c1[n + 1] = 1.0, -1.0
+    s0 = np.linalg.eigvalsh(Z0 + np.tensordot(np.ones(n), A, 1)).max()
+    z0 = np.concatenate([np.ones(n), [max(s0, 0.0) + 2.0, 1.0]])
+    U = max(U, 4 * z0.max())
+    z, _, it1 = sc.barrier_solve(Z0, A1, c1, z0, U=U, gap=1e-3, stop=lambda z: z[n] - z[n + 1] < -1e-3)
+    g = z[:n]
+    gc, _, it2 = sc.barrier_solve(Z0, A, c, g, U=U, gap=1e-3)                # a centred point well inside the cone
+    g, Xd, it3 = sc.barrier_solve(Z0, A, c, gc, U=U, gap=gap)
+    # barrier_solve multiplies t by 5 from 1 until (2n + m) / t < gap: the parameter of its last centring step
+    t = 1.0
+    while (2 * n + m) / t >= gap:
+        t *= 5.0
+    # once more at that t with a tight Newton tolerance: X = M^-1 / t is then dual feasible to rounding
+    g, Xd, it4 = sc.barrier_solve(Z0, A, c, g, U=U, gap=gap, t0=t, newton_tol=1e-10, max_newton=30)
+    it2 += it3 + it4
+    # a step of 1e-3 back towards the centred point: the LMI then holds with a margin the factorisation below can
+    # afford (lambda_max(Z) ~ -1e-12 at the barrier's last iterate is below its rounding), for ~1e-6 of objective
+    dense_obj = float(c @ g)
+    g = g + 1e-3 * (gc - g)
+    Zg = Z0 + np.tensordot(g, A, 1)
+    lam = float(np.linalg.eigvalsh(Zg).max())
+    assert lam < 0, lam
+    blocks = [b["idx"] for b in prob["blocks"]]
+    mmax = max(np.bincount(np.concatenate(blocks)))
+    eps = -lam / (4.0 * mmax)
+    Zk = chordal_split(Zg, blocks, eps)
+    # the split variables: what every non-primary owner of a cover entry holds
+    x = np.zeros(ng + ns)
+    x[:ng] = g
+    er, ec, split_id = prob["ent_row"], prob["ent_col"], prob["split_id"]
+    for j, B in enumerate(blocks):
+        l = -np.ones(prob["Zdim"], dtype=np.int64)
+        l[B] = np.arange(len(B))
+        sel = np.nonzero(split_id[j] >= 0)[0]
+        x[split_id[j, sel]] = Zk[j][l[er[sel]], l[ec[sel]]]
+    X = [Xd[np.ix_(B, B)] for B in blocks]
+    # multipliers of the box: the barrier's dual estimates, then the residual on gamma is pushed into them
+    xl, xu = 1.0 / (t * g), 1.0 / (t * (U - g))
+    rd = c.copy()
+    for b, Xj in zip(prob["blocks"], X):
+        V = b["V"]
+        r = b["A"].reshape(len(V), -1) @ Xj.ravel()
+        rd[V[V < ng]] += r[V < ng]
+    rd += -xl + xu
+    # the residual on gamma goes into the box multipliers, which stay >= 0: rd > 0 raises xl (free: the lower bound is
+    # 0); rd < 0 first lowers xl as far as it goes, only the rest raises xu (which costs U per unit in the dual objective)
+    xl += np.maximum(rd, 0.0)
+    take = np.minimum(xl, np.maximum(-rd, 0.0))
+    xl -= take
+    xu += np.maximum(-rd, 0.0) - take
+    pobj, lmax, dobj, rdn, rdx = certificate(prob, x, X, xl, xu, U)
+    if verbose:
+        print(f"  dense barrier: {it1 + it2} Newton steps, objective {pobj:.10f}, lambda_max(Z) {lam:.2e}; blocks: "
+              f"lambda_max {lmax:.2e}, dual objective {dobj:.10f}, dual residual {rdn:.1e}", flush=True)
+    gamma = np.ones(prob["nvar"])
+    gamma[prob["keep"]] = g
+    return {"obj": pobj, "dual_obj": dobj, "gap": pobj - dobj, "dual_residual": rdn, "x": x, "gamma": gamma,
+            "newton": it1 + it2, "lambda_max": lmax, "U": U, "X": X, "xl": xl, "xu": xu, "dense_obj": dense_obj}
+
+
+# ------------------------------------------------------------------------------------------------
 # the hand-off in the library's format, from the ORACLE (for CPU development and as a second source)
 # ------------------------------------------------------------------------------------------------
 def handoff_from_oracle(net, beta, x1min, x1max, qc_out, intv_info=None):
@@ -428,14 +567,18 @@ def main():
     if "--start" in sys.argv:   # multipliers of the dense optimum (tests/golden/scale_W10_D10_optimum.json) as a start
         res = json.load(open(sys.argv[sys.argv.index("--start") + 1]))
         start = np.array(res["oracle_optimum"][str(int(d["beta"]))]["gamma"])
-    r = solve(prob, gamma_start=start, verbose="-v" in sys.argv)
+    if "--from-dense" in sys.argv:   # certificate built from a barrier solve of the dense LMI (see certificate_from_dense)
+        r = certificate_from_dense(d, cliques, mode, verbose="-v" in sys.argv)
+    else:
+        r = solve(prob, gamma_start=start, verbose="-v" in sys.argv)
     print(f"  optimum {r['obj']:.8f}  lambda_max over blocks {r['lambda_max']:.2e}  {r['newton']} Newton steps, "
           f"{time.time() - t0:.0f} s", flush=True)
     print(f"  dual objective {r['dual_obj']:.8f}  gap {r['gap']:.1e}  dual residual {r['dual_residual']:.1e}", flush=True)
     if len(sys.argv) > 3 and not sys.argv[3].startswith("-"):
+        extra = {"dense_obj": r["dense_obj"]} if "dense_obj" in r else {}
         np.savez_compressed(sys.argv[3], obj=r["obj"], dual_obj=r["dual_obj"], lambda_max=r["lambda_max"], U=r["U"],
                             iterations=r["newton"], mode=mode, x=r["x"], gamma=r["gamma"],
-                            X=np.concatenate([Xj.ravel() for Xj in r["X"]]), xl=r["xl"], xu=r["xu"])
+                            X=np.concatenate([Xj.ravel() for Xj in r["X"]]), xl=r["xl"], xu=r["xu"], **extra)
 
 
 if __name__ == "__main__":

@@ -102,3 +102,71 @@ def test_a_misplaced_entry_breaks_the_certificate():
     h["coo_ent"] = ent
     prob = sd.problem_from_handoff(h, cliques, "single")
     assert sd.lambda_max(prob, sol["x"]) > 1e-6
+
+
+FROM_DENSE = [n for n in ("W10-D10_beta2", "W10-D20_beta2")
+              if os.path.exists(os.path.join(GOLD, f"decomposed_{n}_single_from_dense.npz"))]
+
+
+@pytest.mark.parametrize("name", FROM_DENSE)
+def test_point_built_from_the_dense_optimum_is_feasible_for_the_decomposed_problem(name):
+    """Agler's theorem made constructive (oracle/sdp_decomposed.certificate_from_dense, tests/golden/make_from_dense.py):
+    the optimum of the DENSE LMI of the hand-off, factorised without fill along the cliques of makeCliques
+    (chordal_cliques.jl:13-59), gives blocks Z_k < 0 with Z .== Zksum (chordal_sdp.jl:60-93) -- a strictly feasible
+    point of the decomposed problem built from the library's hand-off at the dense optimum.  With the easy direction
+    (a decomposed-feasible point has sum_k Z_k = Z(gamma) <= 0, so the decomposed optimum cannot be below the dense
+    one) this pins  |decomposed optimum - dense optimum| <= 1e-6  without trusting a solver, also on W10-D20, where the
+    block interior-point method stalls at a bracket of 2e-3."""
+    h = np.load(os.path.join(GOLD, f"handoff_{name}.npz"))
+    sol = np.load(os.path.join(GOLD, f"decomposed_{name}_single_from_dense.npz"))
+    cliques = sd.cliques_from_npz(h)
+    prob = sd.problem_from_handoff(h, cliques, "single")
+    x, U = sol["x"], float(sol["U"])
+    ng = prob["ng"]
+    assert len(x) == ng + prob["ns"] and np.all(x[:ng] > 0) and np.all(x[:ng] < U)
+    X, o = [], 0
+    for b in prob["blocks"]:
+        m = len(b["idx"])
+        X.append(sol["X"][o:o + m * m].reshape(m, m))
+        o += m * m
+    pobj, lam, dobj, rd, rdx = sd.certificate(prob, x, X, sol["xl"], sol["xu"], U)
+    assert lam < 0.0, lam                                        # every block strictly negative definite
+    assert abs(pobj - float(sol["obj"])) <= 1e-12 * abs(pobj)
+    # the blocks add up to the dense Z(gamma) of the same hand-off, which is therefore negative semidefinite as well
+    Z0, A = sd.dense_from_handoff(h, prob["keep"])
+    Zg = Z0 + np.tensordot(x[:ng], A, 1)
+    Zsum = np.zeros_like(Zg)
+    for b, Zk in zip(prob["blocks"], sd.block_matrices(prob, x)):
+        Zsum[np.ix_(b["idx"], b["idx"])] += Zk
+    assert np.abs(Zsum - Zg).max() <= 1e-11 * max(1.0, np.abs(Zg).max())
+    assert np.linalg.eigvalsh(Zg).max() < 0.0
+    # at the dense optimum (the barrier's last iterate, moved 1e-3 of the way back to a centred point for the margin)
+    dense = float(sol["dense_obj"])
+    assert 0.0 <= pobj - dense <= 1e-6 * dense, (pobj, dense)
+    # the stored interior-point multipliers bound the optimum from below: a solver-free bracket around the dense optimum
+    assert rd <= 2e-6
+    lower = dobj - 10 * abs(rdx)
+    assert lower <= dense and (pobj - lower) / pobj <= (3e-5 if name.startswith("W10-D10") else 1.5e-3)
+    if name.startswith("W10-D10"):
+        ipm = np.load(os.path.join(GOLD, f"decomposed_{name}_single.npz"))
+        assert abs(pobj - float(ipm["obj"])) <= 5e-6 * pobj      # and the interior-point optimum is the same number
+    else:
+        assert abs(pobj - np.mean(REF_W10_D20_BETA2)) <= 2e-3 * np.mean(REF_W10_D20_BETA2)
+
+
+def test_chordal_split_of_a_random_banded_matrix():
+    """The factorisation behind it on its own: a random negative definite matrix with the pattern of overlapping
+    cliques plus a common tail splits into negative definite blocks that add up to it."""
+    rng = np.random.default_rng(3)
+    n, tail = 40, [38, 39]
+    blocks = [np.array(sorted(set(range(s, min(s + 14, 38))) | set(tail))) for s in range(0, 30, 6)]
+    M = np.zeros((n, n))
+    for B in blocks:
+        G = rng.standard_normal((len(B), len(B)))
+        M[np.ix_(B, B)] -= G @ G.T + 0.1 * np.eye(len(B))
+    parts = sd.chordal_split(M, blocks, eps=1e-6)
+    S = np.zeros_like(M)
+    for B, P in zip(blocks, parts):
+        assert np.linalg.eigvalsh(P).max() <= -0.5e-6
+        S[np.ix_(B, B)] += P
+    assert np.abs(S - M).max() <= 1e-10
