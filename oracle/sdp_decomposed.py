@@ -465,25 +465,41 @@ def certificate_from_dense(h, cliques, mode="single", U=1e4, gap=1e-7, verbose=F
     z, _, it1 = sc.barrier_solve(Z0, A1, c1, z0, U=U, gap=1e-3, stop=lambda z: z[n] - z[n + 1] < -1e-3)
     g = z[:n]
     gc, _, it2 = sc.barrier_solve(Z0, A, c, g, U=U, gap=1e-3)                # a centred point well inside the cone
-    g, Xd, it3 = sc.barrier_solve(Z0, A, c, gc, U=U, gap=gap)
+    tc = 1.0
+    while (2 * n + m) / tc >= 1e-3:
+        tc *= 5.0
+    if verbose:
+        print(f"  dense barrier: centred at t = {tc:.3g} after {it1 + it2} Newton steps, objective {float(c @ gc):.8f}", flush=True)
+    g, Xd, it3 = sc.barrier_solve(Z0, A, c, gc, U=U, gap=gap, t0=tc)         # on from there (not from t = 1 again)
+    if verbose:
+        print(f"  dense barrier: gap {gap:g} after {it3} more steps, objective {float(c @ g):.10f}", flush=True)
     # barrier_solve multiplies t by 5 from 1 until (2n + m) / t < gap: the parameter of its last centring step
     t = 1.0
     while (2 * n + m) / t >= gap:
         t *= 5.0
-    # once more at that t with a tight Newton tolerance: X = M^-1 / t is then dual feasible to rounding
-    g, Xd, it4 = sc.barrier_solve(Z0, A, c, g, U=U, gap=gap, t0=t, newton_tol=1e-10, max_newton=30)
-    it2 += it3 + it4
-    # a step of 1e-3 back towards the centred point: the LMI then holds with a margin the factorisation below can
-    # afford (lambda_max(Z) ~ -1e-12 at the barrier's last iterate is below its rounding), for ~1e-6 of objective
+    it2 += it3
+    if os.environ.get("SDP_SAVE_STATE"):          # an hour of Newton steps at W10-D20: keep the two points
+        np.savez(os.environ["SDP_SAVE_STATE"], gc=gc, g=g, Xd=Xd, U=U, t=t)
+    # a small step back towards the centred point: the LMI then holds with a margin the factorisation below can afford
+    # (lambda_max(Z) ~ -1e-12 at the barrier's last iterate is below its rounding), for ~1e-6 of objective; the
+    # smallest step that leaves every block negative definite by a quarter of the shift is taken
     dense_obj = float(c @ g)
-    g = g + 1e-3 * (gc - g)
-    Zg = Z0 + np.tensordot(g, A, 1)
-    lam = float(np.linalg.eigvalsh(Zg).max())
-    assert lam < 0, lam
+    g_star = g
     blocks = [b["idx"] for b in prob["blocks"]]
     mmax = max(np.bincount(np.concatenate(blocks)))
-    eps = -lam / (4.0 * mmax)
-    Zk = chordal_split(Zg, blocks, eps)
+    for back in (1e-3, 3e-3, 1e-2, 3e-2):
+        g = g_star + back * (gc - g_star)
+        Zg = Z0 + np.tensordot(g, A, 1)
+        lam = float(np.linalg.eigvalsh(Zg).max())
+        assert lam < 0, lam
+        eps = -lam / (4.0 * mmax)
+        Zk = chordal_split(Zg, blocks, eps)
+        worst = max(float(np.linalg.eigvalsh(0.5 * (M + M.T)).max()) for M in Zk)
+        if verbose:
+            print(f"  step back {back:g}: lambda_max(Z) {lam:.2e}, blocks {worst:.2e} (shift {eps:.1e}), "
+                  f"objective {float(c @ g):.10f}", flush=True)
+        if worst <= -0.25 * eps:
+            break
     # the split variables: what every non-primary owner of a cover entry holds
     x = np.zeros(ng + ns)
     x[:ng] = g
