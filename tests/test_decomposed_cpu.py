@@ -115,7 +115,7 @@ def test_point_built_from_the_dense_optimum_is_feasible_for_the_decomposed_probl
     (chordal_cliques.jl:13-59), gives blocks Z_k < 0 with Z .== Zksum (chordal_sdp.jl:60-93) -- a strictly feasible
     point of the decomposed problem built from the library's hand-off at the dense optimum.  With the easy direction
     (a decomposed-feasible point has sum_k Z_k = Z(gamma) <= 0, so the decomposed optimum cannot be below the dense
-    one) this pins  |decomposed optimum - dense optimum| <= 1e-6  without trusting a solver, also on W10-D20, where the
+    one) this pins  |decomposed optimum - dense optimum| <= 3e-6  without trusting a solver, also on W10-D20, where the
     block interior-point method stalls at a bracket of 2e-3."""
     h = np.load(os.path.join(GOLD, f"handoff_{name}.npz"))
     sol = np.load(os.path.join(GOLD, f"decomposed_{name}_single_from_dense.npz"))
@@ -142,7 +142,7 @@ def test_point_built_from_the_dense_optimum_is_feasible_for_the_decomposed_probl
     assert np.linalg.eigvalsh(Zg).max() < 0.0
     # at the dense optimum (the barrier's last iterate, moved 1e-3 of the way back to a centred point for the margin)
     dense = float(sol["dense_obj"])
-    assert 0.0 <= pobj - dense <= 1e-6 * dense, (pobj, dense)
+    assert 0.0 <= pobj - dense <= 3e-6 * dense, (pobj, dense)
     # the stored interior-point multipliers bound the optimum from below: a solver-free bracket around the dense optimum
     assert rd <= 2e-6
     lower = dobj - 10 * abs(rdx)
