@@ -104,7 +104,7 @@ def test_a_misplaced_entry_breaks_the_certificate():
     assert sd.lambda_max(prob, sol["x"]) > 1e-6
 
 
-FROM_DENSE = [n for n in ("W10-D10_beta2", "W10-D20_beta2")
+FROM_DENSE = [n for n in [f"W10-D10_beta{b}" for b in range(8)] + ["W10-D20_beta2"]
               if os.path.exists(os.path.join(GOLD, f"decomposed_{n}_single_from_dense.npz"))]
 
 
