@@ -207,3 +207,67 @@ def test_packed_api_argument_errors():
                                      L.FORMAT_PACKED, out.ctypes.data_as(L.c_dp)) == L.ERR_ARG  # target must be dense
     with pytest.raises(nb.NnsdpError):
         nb.plan_stats([2, 50, 50, 2], 1, dense=3)
+
+
+def _mask_from_cells(cells, present, beta, Zdim):
+    """Upper-triangle support the present cells define (numpy, from the cell table alone)."""
+    M = np.zeros((Zdim, Zdim), dtype=bool)
+    for i, c in enumerate(cells):
+        if not present[i]:
+            continue
+        r0, c0, nr, nc = int(c["row0"]) - 1, int(c["col0"]) - 1, int(c["nrows"]), int(c["ncols"])
+        if c["kind"] == 3:
+            for t in range(beta + 1):
+                idx = np.arange(nc - t)
+                M[r0 + idx, r0 + idx + t] = True
+        else:
+            gr = (r0 + np.arange(nr))[:, None]
+            gc = (c0 + np.arange(nc))[None, :]
+            M[r0:r0 + nr, c0:c0 + nc] |= gr <= gc
+    return M
+
+
+@pytest.mark.parametrize("drop_diag", [False, True])
+def test_unpack_on_several_host_threads(monkeypatch, drop_diag):
+    """Outputs of 2^20 doubles and more are expanded by several host threads, one clique matrix at a time
+    (plan.cpp unpack_record).  A record packed from a random symmetric matrix restricted to the cells' support must
+    come back as that matrix's clique blocks (scatter of /root/reference/src/Methods/chordal_sdp.jl:60-93), and the
+    result must not depend on the number of threads.  With the DIAG cells absent the band and the slivers the
+    other cells hold must still be there."""
+    import nnsdp_b200 as nb
+
+    xdims, beta = [3, 260, 300, 280, 256, 270, 2], 2
+    Zdim = sum(xdims[:-1]) + 1
+    lay = nb.packed_layout(xdims, beta)
+    cells = lay["cells"]
+    present = np.ones(len(cells), dtype=np.uint8)
+    if drop_diag:
+        for i, c in enumerate(cells):
+            if not c["always"]:
+                present[i] = 0
+        assert present.sum() < len(cells)
+    rng = np.random.default_rng(11)
+    A = rng.standard_normal((Zdim, Zdim))
+    M = _mask_from_cells(cells, present, beta, Zdim)
+    Zu = np.triu(A) * M
+    Z = Zu + np.triu(Zu, 1).T
+    rec = _pack_numpy(Z, lay, beta, present)
+    cliques = nb.cliques_from_xdims(xdims, beta)
+    assert sum(len(c[0]) ** 2 for c in cliques) >= 1 << 20 and len(cliques) > 1
+    outs = []
+    for nthreads in ("1", "3", "16"):
+        monkeypatch.setenv("NNSDP_HOST_THREADS", nthreads)
+        outs.append(nb.packed_unpack(xdims, beta, rec, present))
+    monkeypatch.delenv("NNSDP_HOST_THREADS")
+    outs.append(nb.packed_unpack(xdims, beta, rec, present))
+    buf = np.full(outs[0].size, np.nan)
+    assert nb.packed_unpack(xdims, beta, rec, present, out=buf) is buf
+    outs.append(buf)
+    for flat in outs:
+        off = 0
+        for ck in cliques:
+            C = np.asarray(ck[0]) - 1
+            n = len(C)
+            assert np.array_equal(flat[off:off + n * n].reshape(n, n).T, Z[np.ix_(C, C)])
+            off += n * n
+        assert off == flat.size
